@@ -1,0 +1,130 @@
+// Internal declarations shared by the translation units of libhpose.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/hpose.h"
+
+void hp_set_error(const char* fmt, ...);
+
+#define HP_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      hp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+      return HP_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define HP_REQUIRE(cond, code, ...)                                                           \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      hp_set_error(__VA_ARGS__);                                                              \
+      return (code);                                                                          \
+    }                                                                                         \
+  } while (0)
+
+#define HP_TRY(expr)                                                                          \
+  do {                                                                                        \
+    int rc_ = (expr);                                                                         \
+    if (rc_ != HP_OK) return rc_;                                                             \
+  } while (0)
+
+// Growable device buffer owned by a handle.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t n) {
+    if (n <= bytes) return HP_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    HP_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return HP_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  float* f() const { return (float*)p; }
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// TensorFlow "SAME" padding: out = ceil(n/s), extra padding goes after.
+static inline void same_pad(int n, int k, int s, int* out, int* before) {
+  int o = ceil_div(n, s);
+  int total = (o - 1) * s + k - n;
+  if (total < 0) total = 0;
+  *out = o;
+  *before = total / 2;
+}
+
+// ---------------------------------------------------------------------------- backbone
+struct BlockShape {
+  int cin, cout, stride;
+};
+extern const BlockShape kBlazeBlocks[16];
+static inline int chan_pad(int c) { return (c + 3) & ~3; }
+
+struct BlockWeights {
+  const float *dww, *dwb, *pww, *pwb;  // [9][CINP], [CINP], [CINP][COUTP], [COUTP] (zero padded)
+};
+
+struct Backbone {
+  bool loaded = false;
+  DevBuf arena;
+  const float* stem_w = nullptr;  // [75][24]
+  const float* stem_b = nullptr;
+  BlockWeights blk[16];
+  const float *det16_w = nullptr, *det16_b = nullptr;  // [88][36] = cls(2)|loc(32)|pad
+  const float *det8_w = nullptr, *det8_b = nullptr;    // [96][104] = cls(6)|loc(96)|pad
+  DevBuf act[2], dwtmp, feat16, feat8;
+};
+
+// ---------------------------------------------------------------------------- comm (NCCL via dlsym)
+struct Comm {
+  void* lib = nullptr;
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+struct hp_head;  // heads.cu
+
+struct hp_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int impl = HP_IMPL_FAST;
+  int64_t launches = 0;
+  Backbone bb;
+  Comm comm;
+  DevBuf pose16, pose8, cls, loc;  // unified-path internals
+  DevBuf scratch;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+// generic per-token dense layer used by detector heads and regressor heads (dense.cu)
+struct DenseOut {
+  float* ptr;            // destination for columns [col_begin, col_end)
+  int col_begin, col_end;
+  int rows_per_img;      // rows are grouped by image: dst = ptr + img*img_stride + row_in_img*row_stride + (c-col_begin)
+  long long img_stride;
+  int row_stride;
+};
+// y = act(x[M,K](ld=ldx) @ W[K][ldw] + b); transpose_w: use W^T stored as [N][ldw] (for dX = dY W^T)
+int hp_launch_dense(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b,
+                    int N, int act, bool transpose_w, const DenseOut* outs, int n_outs, bool accumulate,
+                    cudaStream_t st);
+
+int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat16, float* feat8, float* cls,
+                    float* loc, int stop_after_blk, float* dbg_dst, size_t dbg_floats, float* per_layer_ms,
+                    int prof_iters, cudaStream_t st);
+
+int hp_comm_allreduce_sum(hp_ctx* h, float* buf, size_t n, cudaStream_t st);

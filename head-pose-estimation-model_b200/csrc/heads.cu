@@ -1,0 +1,1015 @@
+// Regressor heads: forward, backward, loss and optimizers for the small fully-convolutional
+// yaw/pitch/roll regressors, executed as a register program (hp_head_op) compiled by the Python
+// layer from the Keras graphs of the reference:
+//   Model-88/attention_model.py:16-80   se_transformer_regr_head (SE gate, MHA, LayerNorm, FF, 1x1 convs)
+//   Model-88/attention_model.py:82-169  create_modelC, create_model_complex
+//   Model-88/train_88.py:66-253         create_model, create_model_skip_fc, bestmodelV1
+//   Model-96/train_96.py:65-110         create_model
+// Training semantics (loss, L2, SpatialDropout2D, SGD/Adam/Adamax) follow Keras 2.13 as listed in
+// SURVEY.md Appendix B.4-B.5; the step replaces the body of model.fit (train_96.py:175, train_88.py:355).
+//
+// All tensors are [rows][channels] float32 with rows = images*tokens (or images for per-image
+// registers).  Shapes are tiny (<= 128 channels), so kernels are CUDA-core code; the data-parallel
+// gradient exchange is one flat-buffer allreduce (comm.cu).
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+// ============================================================================ activations
+__device__ __forceinline__ float act_fwd(int act, float v) {
+  switch (act) {
+    case HP_ACT_RELU: return fmaxf(v, 0.f);
+    case HP_ACT_TANH: return tanhf(v);
+    case HP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case HP_ACT_SOFTSIGN: return v / (1.f + fabsf(v));
+    default: return v;
+  }
+}
+// derivative expressed with the OUTPUT y of the activation
+__device__ __forceinline__ float act_bwd(int act, float y) {
+  switch (act) {
+    case HP_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case HP_ACT_TANH: return 1.f - y * y;
+    case HP_ACT_SIGMOID: return y * (1.f - y);
+    case HP_ACT_SOFTSIGN: {
+      float t = 1.f - fabsf(y);
+      return t * t;
+    }
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// ============================================================================ generic dense
+#define DENSE_TM 64
+struct DenseKParams {
+  const float* x;
+  const float* W;
+  const float* b;
+  int M, K, ldx, ldw, N, act, transpose_w, accumulate;
+  int KP, NP, XS;
+  int n_outs;
+  DenseOut outs[2];
+};
+
+__global__ void __launch_bounds__(256) dense_kernel(DenseKParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;                 // [KP][NP]
+  float* bs = Ws + p.KP * p.NP;     // [NP]
+  float* xs = bs + p.NP;            // [TM][XS]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p.KP * p.NP; i += 256) {
+    const int k = i / p.NP, n = i - k * p.NP;
+    float v = 0.f;
+    if (k < p.K && n < p.N) v = p.transpose_w ? p.W[(long long)n * p.ldw + k] : p.W[(long long)k * p.ldw + n];
+    Ws[i] = v;
+  }
+  for (int i = tid; i < p.NP; i += 256) bs[i] = (p.b && i < p.N) ? p.b[i] : 0.f;
+  const int ngd = p.NP / 4;
+  const int RG = DENSE_TM / 4;  // 16 row groups; a thread's 4 rows are rg, rg+16, rg+32, rg+48
+  const int n_tiles = (p.M + DENSE_TM - 1) / DENSE_TM;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long m0 = (long long)tile * DENSE_TM;
+    __syncthreads();
+    for (int i = tid; i < DENSE_TM * p.KP; i += 256) {
+      const int r = i / p.KP, k = i - r * p.KP;
+      const long long m = m0 + r;
+      xs[r * p.XS + k] = (m < p.M && k < p.K) ? p.x[m * p.ldx + k] : 0.f;
+    }
+    __syncthreads();
+    for (int item = tid; item < RG * ngd; item += 256) {
+      const int cg = item % ngd, rg = item / ngd;
+      float4 acc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < p.KP; k += 4) {
+        const float4 w0 = ld4(Ws + (k + 0) * p.NP + cg * 4);
+        const float4 w1 = ld4(Ws + (k + 1) * p.NP + cg * 4);
+        const float4 w2 = ld4(Ws + (k + 2) * p.NP + cg * 4);
+        const float4 w3 = ld4(Ws + (k + 3) * p.NP + cg * 4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4 a = ld4(xs + (rg + r * RG) * p.XS + k);
+          acc[r].x = fmaf(a.x, w0.x, acc[r].x); acc[r].y = fmaf(a.x, w0.y, acc[r].y);
+          acc[r].z = fmaf(a.x, w0.z, acc[r].z); acc[r].w = fmaf(a.x, w0.w, acc[r].w);
+          acc[r].x = fmaf(a.y, w1.x, acc[r].x); acc[r].y = fmaf(a.y, w1.y, acc[r].y);
+          acc[r].z = fmaf(a.y, w1.z, acc[r].z); acc[r].w = fmaf(a.y, w1.w, acc[r].w);
+          acc[r].x = fmaf(a.z, w2.x, acc[r].x); acc[r].y = fmaf(a.z, w2.y, acc[r].y);
+          acc[r].z = fmaf(a.z, w2.z, acc[r].z); acc[r].w = fmaf(a.z, w2.w, acc[r].w);
+          acc[r].x = fmaf(a.w, w3.x, acc[r].x); acc[r].y = fmaf(a.w, w3.y, acc[r].y);
+          acc[r].z = fmaf(a.w, w3.z, acc[r].z); acc[r].w = fmaf(a.w, w3.w, acc[r].w);
+        }
+      }
+      const float4 bias = ld4(bs + cg * 4);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const long long m = m0 + rg + r * RG;
+        if (m >= p.M) continue;
+        float v[4] = {acc[r].x + bias.x, acc[r].y + bias.y, acc[r].z + bias.z, acc[r].w + bias.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = cg * 4 + j;
+          if (c >= p.N) continue;
+          const float val = act_fwd(p.act, v[j]);
+          for (int o = 0; o < p.n_outs; ++o) {
+            const DenseOut& d = p.outs[o];
+            if (c >= d.col_begin && c < d.col_end) {
+              const long long img = m / d.rows_per_img;
+              const int row = (int)(m - img * d.rows_per_img);
+              float* dst = d.ptr + img * d.img_stride + (long long)row * d.row_stride + (c - d.col_begin);
+              if (p.accumulate) *dst += val; else *dst = val;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+int hp_launch_dense(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b,
+                    int N, int act, bool transpose_w, const DenseOut* outs, int n_outs, bool accumulate,
+                    cudaStream_t st) {
+  if (M <= 0) return HP_OK;
+  HP_REQUIRE(n_outs >= 1 && n_outs <= 2, HP_ERR_INVALID, "dense: 1 or 2 output segments");
+  DenseKParams p;
+  p.x = x; p.W = W; p.b = b; p.M = M; p.K = K; p.ldx = ldx; p.ldw = ldw; p.N = N; p.act = act;
+  p.transpose_w = transpose_w ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
+  p.KP = round_up(K, 4); p.NP = round_up(N, 4);
+  p.XS = ((p.KP / 4) & 1) ? p.KP : p.KP + 4;
+  p.n_outs = n_outs;
+  for (int i = 0; i < n_outs; ++i) p.outs[i] = outs[i];
+  size_t smem = ((size_t)p.KP * p.NP + p.NP + (size_t)DENSE_TM * p.XS) * sizeof(float);
+  HP_REQUIRE(smem <= 200 * 1024, HP_ERR_UNSUPPORTED, "dense layer %dx%d too large for the head engine", K, N);
+  HP_CUDA(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int n_tiles = ceil_div(M, DENSE_TM);
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  long long grid = (long long)h->num_sms * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  dense_kernel<<<(unsigned)grid, 256, smem, st>>>(p);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}
+
+// gW[K][N] += x^T gz ; gb[N] += sum_rows gz       (gW/gb must be zeroed by the caller)
+#define WG_TM 32
+__global__ void __launch_bounds__(256) dense_wgrad_kernel(const float* __restrict__ x, int ldx,
+                                                          const float* __restrict__ gz, int ldg, float* gW, float* gb,
+                                                          int M, int K, int N) {
+  extern __shared__ float smem[];
+  float* xs = smem;            // [WG_TM][K]
+  float* gs = xs + WG_TM * K;  // [WG_TM][N]
+  const long long m0 = (long long)blockIdx.x * WG_TM;
+  const int rows = (int)((M - m0 < WG_TM) ? (M - m0) : WG_TM);
+  for (int i = threadIdx.x; i < WG_TM * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    xs[i] = (r < rows) ? x[(m0 + r) * ldx + k] : 0.f;
+  }
+  for (int i = threadIdx.x; i < WG_TM * N; i += 256) {
+    const int r = i / N, n = i - r * N;
+    gs[i] = (r < rows) ? gz[(m0 + r) * ldg + n] : 0.f;
+  }
+  __syncthreads();
+  const int total = K * N + N;
+  for (int e = threadIdx.x; e < total; e += 256) {
+    float acc = 0.f;
+    if (e < K * N) {
+      const int k = e / N, n = e - k * N;
+      for (int r = 0; r < WG_TM; ++r) acc = fmaf(xs[r * K + k], gs[r * N + n], acc);
+      atomicAdd(gW + e, acc);
+    } else if (gb) {
+      const int n = e - K * N;
+      for (int r = 0; r < WG_TM; ++r) acc += gs[r * N + n];
+      atomicAdd(gb + n, acc);
+    }
+  }
+}
+
+// ============================================================================ elementwise kernels
+#define EW_GRID(total) (unsigned)(((total) + 255) / 256 > 65535 * 16 ? 65535 * 16 : ((total) + 255) / 256)
+
+__global__ void act_fwd_kernel(const float* in, float* out, long long total, int act) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) out[i] = act_fwd(act, in[i]);
+}
+// g_in += g_out * act'(y)
+__global__ void act_bwd_acc_kernel(const float* y, const float* gy, float* gx, long long total, int act) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll)
+    gx[i] += gy[i] * act_bwd(act, y[i]);
+}
+// gz = gy * act'(y)  (in place allowed)
+__global__ void act_bwd_kernel(const float* y, const float* gy, float* gz, long long total, int act) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll)
+    gz[i] = gy[i] * act_bwd(act, y[i]);
+}
+// out = a + b with row broadcasting (rows_a/rows_b are either `rows` or rows/T)
+__global__ void add_kernel(const float* a, const float* b, float* out, long long rows, int C, int T, int a_img, int b_img) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    const float va = a[(a_img ? r / T : r) * C + c];
+    const float vb = b[(b_img ? r / T : r) * C + c];
+    out[i] = va + vb;
+  }
+}
+__global__ void acc_kernel(float* dst, const float* src, long long total) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) dst[i] += src[i];
+}
+// out[n,t,c] = x[n,t,c] * g[n,c]
+__global__ void mulch_kernel(const float* x, const float* g, float* out, long long rows, int C, int T) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    out[i] = x[i] * g[(r / T) * C + c];
+  }
+}
+// gx += gy * g ; gg[n,c] += sum_t gy*x          one thread per (n,c)
+__global__ void mulch_bwd_kernel(const float* x, const float* g, const float* gy, float* gx, float* gg, int n_img, int C,
+                                 int T) {
+  const long long total = (long long)n_img * C;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long n = i / C;
+    const int c = (int)(i - n * C);
+    const float gv = g[i];
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const long long j = (n * T + t) * C + c;
+      const float go = gy[j];
+      if (gx) gx[j] += go * gv;
+      s = fmaf(go, x[j], s);
+    }
+    gg[i] += s;
+  }
+}
+__global__ void gap_kernel(const float* x, float* out, int n_img, int C, int T) {
+  const long long total = (long long)n_img * C;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long n = i / C;
+    const int c = (int)(i - n * C);
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += x[(n * T + t) * C + c];
+    out[i] = s / (float)T;
+  }
+}
+__global__ void gap_bwd_kernel(const float* gy, float* gx, long long rows, int C, int T) {
+  const long long total = rows * C;
+  const float inv = 1.f / (float)T;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    gx[i] += gy[(r / T) * C + c] * inv;
+  }
+}
+
+__host__ __device__ inline uint32_t dropout_hash(uint64_t seed, uint32_t step, uint32_t op_id, uint32_t image,
+                                                 uint32_t channel) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(step + 1);
+  z ^= 0xBF58476D1CE4E5B9ull * (uint64_t)(op_id + 1);
+  z += (((uint64_t)image) << 32 | (uint64_t)channel) * 0x94D049BB133111EBull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__host__ __device__ inline bool dropout_keep(uint32_t u, float rate) {
+  return (float)(u >> 8) * (1.0f / 16777216.0f) >= rate;
+}
+// mode 0: out = x*m ; mode 1: gx += gy*m  (m = keep/(1-rate), mask over (image, channel))
+__global__ void dropout_kernel(const float* in, float* out, long long rows, int C, int T, int per_image, float rate,
+                               uint64_t seed, uint32_t step, uint32_t op_id, int mode) {
+  const long long total = rows * C;
+  const float scale = 1.f / (1.f - rate);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    const uint32_t img = (uint32_t)(per_image ? r : r / T);
+    const float m = dropout_keep(dropout_hash(seed, step, op_id, img, (uint32_t)c), rate) ? scale : 0.f;
+    if (mode == 0) out[i] = in[i] * m; else out[i] += in[i] * m;
+  }
+}
+
+// ============================================================================ LayerNorm (warp per row)
+__global__ void layernorm_kernel(const float* x, const float* gamma, const float* beta, float* out, float* stats,
+                                 long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* xr = x + r * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = xr[c] - mu;
+      v = fmaf(d, d, v);
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = 1.f / sqrtf(v / (float)C + eps);
+    for (int c = lane; c < C; c += 32) out[r * C + c] = (xr[c] - mu) * rstd * gamma[c] + beta[c];
+    if (stats && lane == 0) {
+      stats[2 * r] = mu;
+      stats[2 * r + 1] = rstd;
+    }
+  }
+}
+// gx += rstd*(gh - mean(gh) - xh*mean(gh*xh)), gh = gy*gamma ; ggamma += gy*xh ; gbeta += gy (atomics)
+__global__ void layernorm_bwd_kernel(const float* x, const float* gamma, const float* stats, const float* gy, float* gx,
+                                     float* ggamma, float* gbeta, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float mu = stats[2 * r], rstd = stats[2 * r + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (x[r * C + c] - mu) * rstd;
+      const float gh = gy[r * C + c] * gamma[c];
+      s1 += gh;
+      s2 = fmaf(gh, xh, s2);
+    }
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 / (float)C, m2 = s2 / (float)C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (x[r * C + c] - mu) * rstd;
+      const float g = gy[r * C + c];
+      const float gh = g * gamma[c];
+      if (gx) gx[r * C + c] += rstd * (gh - m1 - xh * m2);
+      atomicAdd(ggamma + c, g * xh);
+      atomicAdd(gbeta + c, g);
+    }
+  }
+}
+
+// ============================================================================ attention core
+// Q,K,V,O: [n_img*T][HD] with head h at columns [h*d, h*d+d).  One CTA per (image, head), 4 warps,
+// warp per query row.  scale = 1/sqrt(d) is applied to Q (Keras MultiHeadAttention).
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const float* Q, const float* K, const float* V, float* O, int T,
+                                                       int heads, int d, float scale, float* Pout, float* unused) {
+  extern __shared__ float smem[];
+  const int DS = d + 1;
+  float* Ks = smem;                  // [T][DS]
+  float* Vs = Ks + T * DS;           // [T][DS]
+  float* sc = Vs + T * DS;           // [4][T]
+  const int img = blockIdx.x / heads, hh = blockIdx.x - img * heads;
+  const int HD = heads * d;
+  const long long base = (long long)img * T * HD + hh * d;
+  for (int i = threadIdx.x; i < T * d; i += 128) {
+    const int s = i / d, j = i - s * d;
+    Ks[s * DS + j] = K[base + (long long)s * HD + j];
+    Vs[s * DS + j] = V[base + (long long)s * HD + j];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my = sc + warp * T;
+  for (int t = warp; t < T; t += 4) {
+    const float* q = Q + base + (long long)t * HD;
+    float mx = -INFINITY;
+    for (int s = lane; s < T; s += 32) {
+      float a = 0.f;
+      for (int j = 0; j < d; ++j) a = fmaf(q[j] * scale, Ks[s * DS + j], a);
+      my[s] = a;
+      mx = fmaxf(mx, a);
+    }
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int s = lane; s < T; s += 32) {
+      const float e = expf(my[s] - mx);
+      my[s] = e;
+      sum += e;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    __syncwarp();
+    if (Pout) {
+      float* pr = Pout + ((long long)blockIdx.x * T + t) * T;
+      for (int s = lane; s < T; s += 32) pr[s] = my[s] * inv;
+    }
+    for (int j = lane; j < d; j += 32) {
+      float a = 0.f;
+      for (int s = 0; s < T; ++s) a = fmaf(my[s], Vs[s * DS + j], a);
+      O[base + (long long)t * HD + j] = a * inv;
+    }
+    __syncwarp();
+  }
+}
+
+// pass A: per query row: dS = P*(dP - sum(P*dP)), dP = dO V^T ; dQ = scale * dS K ; writes dS to global
+__global__ void __launch_bounds__(128) attn_bwd_a_kernel(const float* K, const float* V, const float* dO,
+                                                         const float* P, float* dS, float* dQ, int T, int heads, int d,
+                                                         float scale) {
+  extern __shared__ float smem[];
+  const int DS = d + 1;
+  float* Ks = smem;
+  float* Vs = Ks + T * DS;
+  float* sc = Vs + T * DS;  // [4][T]
+  const int img = blockIdx.x / heads, hh = blockIdx.x - img * heads;
+  const int HD = heads * d;
+  const long long base = (long long)img * T * HD + hh * d;
+  for (int i = threadIdx.x; i < T * d; i += 128) {
+    const int s = i / d, j = i - s * d;
+    Ks[s * DS + j] = K[base + (long long)s * HD + j];
+    Vs[s * DS + j] = V[base + (long long)s * HD + j];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my = sc + warp * T;
+  for (int t = warp; t < T; t += 4) {
+    const float* go = dO + base + (long long)t * HD;
+    const float* pr = P + ((long long)blockIdx.x * T + t) * T;
+    float dot = 0.f;
+    for (int s = lane; s < T; s += 32) {
+      float a = 0.f;
+      for (int j = 0; j < d; ++j) a = fmaf(go[j], Vs[s * DS + j], a);
+      my[s] = a;
+      dot = fmaf(pr[s], a, dot);
+    }
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    float* dsr = dS + ((long long)blockIdx.x * T + t) * T;
+    for (int s = lane; s < T; s += 32) {
+      const float v = pr[s] * (my[s] - dot);
+      my[s] = v;
+      dsr[s] = v;
+    }
+    __syncwarp();
+    for (int j = lane; j < d; j += 32) {
+      float a = 0.f;
+      for (int s = 0; s < T; ++s) a = fmaf(my[s], Ks[s * DS + j], a);
+      dQ[base + (long long)t * HD + j] = a * scale;
+    }
+    __syncwarp();
+  }
+}
+// pass B: thread per key row s: dV[s] = sum_t P[t][s] dO[t] ; dK[s] = scale * sum_t dS[t][s] Q[t]
+#define ATTN_DMAX 64
+__global__ void __launch_bounds__(128) attn_bwd_b_kernel(const float* Q, const float* dO, const float* P,
+                                                         const float* dS, float* dK, float* dV, int T, int heads,
+                                                         int d, float scale) {
+  extern __shared__ float smem[];
+  float* Qs = smem;          // [T][d]
+  float* Gs = Qs + T * d;    // [T][d]
+  const int nh = blockIdx.x;
+  const int img = nh / heads, hh = nh - img * heads;
+  const int HD = heads * d;
+  const long long base = (long long)img * T * HD + hh * d;
+  for (int i = threadIdx.x; i < T * d; i += 128) {
+    const int s = i / d, j = i - s * d;
+    Qs[i] = Q[base + (long long)s * HD + j];
+    Gs[i] = dO[base + (long long)s * HD + j];
+  }
+  __syncthreads();
+  for (int s = blockIdx.y * 128 + threadIdx.x; s < T; s += gridDim.y * 128) {
+    float av[ATTN_DMAX], ak[ATTN_DMAX];
+#pragma unroll
+    for (int j = 0; j < ATTN_DMAX; ++j) { av[j] = 0.f; ak[j] = 0.f; }
+    for (int t = 0; t < T; ++t) {
+      const float pv = P[((long long)nh * T + t) * T + s];
+      const float dv = dS[((long long)nh * T + t) * T + s];
+#pragma unroll
+      for (int j = 0; j < ATTN_DMAX; ++j)
+        if (j < d) {
+          av[j] = fmaf(pv, Gs[t * d + j], av[j]);
+          ak[j] = fmaf(dv, Qs[t * d + j], ak[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < ATTN_DMAX; ++j)
+      if (j < d) {
+        dV[base + (long long)s * HD + j] = av[j];
+        dK[base + (long long)s * HD + j] = ak[j] * scale;
+      }
+  }
+}
+
+// ============================================================================ loss / optimizer
+// g = 2*(pred-y)*inv_count ; sums[0] += (pred-y)^2 ; sums[1] += |pred-y| ; sums[2] += 1 per element
+__global__ void mse_loss_kernel(const float* pred, const float* y, float* g, long long total, float inv_count,
+                                float* sums) {
+  float sq = 0.f, ab = 0.f, cnt = 0.f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const float d = pred[i] - y[i];
+    if (g) g[i] = 2.f * d * inv_count;
+    sq = fmaf(d, d, sq);
+    ab += fabsf(d);
+    cnt += 1.f;
+  }
+  for (int o = 16; o; o >>= 1) {
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  __shared__ float red[3][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = sq; red[1][warp] = ab; red[2][warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, s);
+  }
+}
+// sums[3] = sum l2coef*w^2 (single block)
+__global__ void l2_penalty_kernel(const float* w, const float* l2, int n, float* out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s = fmaf(l2[i] * w[i], w[i], s);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    *out = t;
+  }
+}
+// Keras 2.13 update rules.  g_total = g + 2*l2*w
+__global__ void optimizer_kernel(float* w, const float* g, const float* l2, float* m, float* v, int n, int kind,
+                                 float lr, float b1, float b2, float eps, float alpha_t, float lr_t) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const float wi = w[i];
+    const float gi = g[i] + 2.f * l2[i] * wi;
+    if (kind == HP_OPT_SGD) {
+      w[i] = wi - lr * gi;
+    } else if (kind == HP_OPT_ADAM) {
+      const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+      const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+      m[i] = mi;
+      v[i] = vi;
+      w[i] = wi - (mi * alpha_t) / (sqrtf(vi) + eps);
+    } else {
+      const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+      const float ui = fmaxf(b2 * v[i], fabsf(gi));
+      m[i] = mi;
+      v[i] = ui;
+      w[i] = wi - (lr_t * mi) / (ui + eps);
+    }
+  }
+}
+
+// ============================================================================ head object
+struct MhaWs {
+  size_t q, k, v, o, gq, gk, gv, go, p, ds;  // float offsets into hp_head::ws
+};
+struct hp_head {
+  std::vector<hp_head_op> ops;
+  std::vector<hp_head_reg> regs;
+  int out_reg = 0, n_params = 0, in_channels = 0;
+  DevBuf params, grads, m, v, l2coef;
+  DevBuf acts, gacts, ws;
+  std::vector<size_t> reg_off;        // float offsets into acts/gacts (reg 0 unused: external input)
+  std::vector<size_t> stat_off;       // per op: layer-norm stats offset in ws
+  std::vector<MhaWs> mha;             // per op
+  uint32_t step = 0;
+  bool has_state = false;
+  float last_sums[4] = {0, 0, 0, 0};
+};
+
+static long long reg_rows(const hp_head* hd, int r, int n_img, int T) {
+  return hd->regs[r].per_image ? n_img : (long long)n_img * T;
+}
+
+int hp_head_create_impl(hp_ctx* h, const hp_head_op* ops, int n_ops, const hp_head_reg* regs, int n_regs, int out_reg,
+                        int n_params, hp_head** out) {
+  HP_REQUIRE(ops && regs && out && n_ops > 0 && n_regs > 1, HP_ERR_INVALID, "hp_head_create: bad arguments");
+  HP_REQUIRE(out_reg > 0 && out_reg < n_regs, HP_ERR_INVALID, "hp_head_create: out_reg %d out of range", out_reg);
+  HP_REQUIRE(n_params > 0, HP_ERR_INVALID, "hp_head_create: n_params must be positive");
+  hp_head* hd = new hp_head();
+  hd->ops.assign(ops, ops + n_ops);
+  hd->regs.assign(regs, regs + n_regs);
+  hd->out_reg = out_reg;
+  hd->n_params = n_params;
+  hd->in_channels = regs[0].channels;
+  std::vector<float> l2(n_params, 0.f);
+  std::vector<char> written(n_regs, 0);
+  written[0] = 1;
+  for (int i = 0; i < n_ops; ++i) {
+    const hp_head_op& o = ops[i];
+    auto bad = [&](const char* why) {
+      hp_set_error("hp_head_create: op %d (%d): %s", i, o.op, why);
+      delete hd;
+      return HP_ERR_INVALID;
+    };
+    if (o.in0 < 0 || o.in0 >= n_regs || o.out <= 0 || o.out >= n_regs) return bad("register index out of range");
+    if (!written[o.in0]) return bad("input register read before it is written");
+    if (written[o.out]) return bad("registers are single-assignment");
+    const int cin = regs[o.in0].channels, cout = regs[o.out].channels;
+    switch (o.op) {
+      case HP_OP_DENSE:
+        if (o.cin != cin || o.cout != cout) return bad("dense shape mismatch");
+        if (o.w_off < 0 || o.w_off + (long long)cin * cout > n_params || o.b_off < 0 || o.b_off + cout > n_params)
+          return bad("parameter offsets out of range");
+        if (regs[o.in0].per_image != regs[o.out].per_image) return bad("dense keeps the row kind");
+        for (int j = 0; j < cin * cout; ++j) l2[o.w_off + j] = o.l2_w;
+        for (int j = 0; j < cout; ++j) l2[o.b_off + j] = o.l2_b;
+        break;
+      case HP_OP_ACT:
+      case HP_OP_DROPOUT:
+        if (cin != cout || regs[o.in0].per_image != regs[o.out].per_image) return bad("shape mismatch");
+        if (o.op == HP_OP_DROPOUT && !(o.fparam >= 0.f && o.fparam < 1.f)) return bad("dropout rate must be in [0,1)");
+        break;
+      case HP_OP_ADD:
+        if (o.in1 < 0 || o.in1 >= n_regs || !written[o.in1]) return bad("second input invalid");
+        if (regs[o.in1].channels != cin || cout != cin) return bad("add needs equal channel counts");
+        if (regs[o.out].per_image != (regs[o.in0].per_image && regs[o.in1].per_image)) return bad("add row kind");
+        break;
+      case HP_OP_MULCH:
+        if (o.in1 < 0 || o.in1 >= n_regs || !written[o.in1]) return bad("second input invalid");
+        if (!regs[o.in1].per_image || regs[o.in0].per_image || regs[o.out].per_image) return bad("mulch: x per token, gate per image");
+        if (regs[o.in1].channels != cin || cout != cin) return bad("mulch channel mismatch");
+        break;
+      case HP_OP_GAP:
+        if (regs[o.in0].per_image || !regs[o.out].per_image || cin != cout) return bad("gap shapes");
+        break;
+      case HP_OP_LAYERNORM:
+        if (cin != cout || o.w_off < 0 || o.w_off + cin > n_params || o.b_off < 0 || o.b_off + cin > n_params)
+          return bad("layernorm parameters");
+        break;
+      case HP_OP_MHA: {
+        const int hdm = o.heads * o.key_dim;
+        if (o.heads <= 0 || o.key_dim <= 0 || o.key_dim > ATTN_DMAX) return bad("heads/key_dim unsupported");
+        if (cin != cout || regs[o.in0].per_image || regs[o.out].per_image) return bad("mha shapes");
+        const long long need = 3ll * (cin * hdm + hdm) + (long long)hdm * cin + cin;
+        if (o.w_off < 0 || o.w_off + need > n_params) return bad("mha parameters out of range");
+        break;
+      }
+      default:
+        return bad("unknown opcode");
+    }
+    written[o.out] = 1;
+  }
+  if (!written[out_reg]) {
+    hp_set_error("hp_head_create: output register never written");
+    delete hd;
+    return HP_ERR_INVALID;
+  }
+  int rc = hd->params.ensure((size_t)n_params * sizeof(float));
+  if (rc == HP_OK) rc = hd->grads.ensure((size_t)(n_params + 4) * sizeof(float));
+  if (rc == HP_OK) rc = hd->l2coef.ensure((size_t)n_params * sizeof(float));
+  if (rc != HP_OK) { delete hd; return rc; }
+  cudaMemset(hd->params.p, 0, (size_t)n_params * sizeof(float));
+  cudaMemcpy(hd->l2coef.p, l2.data(), (size_t)n_params * sizeof(float), cudaMemcpyHostToDevice);
+  *out = hd;
+  return HP_OK;
+}
+
+void hp_head_free_impl(hp_head* hd) {
+  if (!hd) return;
+  hd->params.release(); hd->grads.release(); hd->m.release(); hd->v.release(); hd->l2coef.release();
+  hd->acts.release(); hd->gacts.release(); hd->ws.release();
+  delete hd;
+}
+
+// lay out activation / workspace arenas for (n_img, T)
+static int head_plan(hp_head* hd, int n_img, int T, bool training) {
+  const int n_regs = (int)hd->regs.size();
+  hd->reg_off.assign(n_regs, 0);
+  size_t off = 0;
+  for (int r = 1; r < n_regs; ++r) {
+    hd->reg_off[r] = off;
+    off += (size_t)round_up((int)std::min<long long>(reg_rows(hd, r, n_img, T) * hd->regs[r].channels, 1ll << 30), 4);
+    HP_REQUIRE(reg_rows(hd, r, n_img, T) * hd->regs[r].channels < (1ll << 30), HP_ERR_INVALID, "head batch too large");
+  }
+  HP_TRY(hd->acts.ensure(off * sizeof(float)));
+  if (training) HP_TRY(hd->gacts.ensure(off * sizeof(float)));
+  size_t woff = 0;
+  hd->stat_off.assign(hd->ops.size(), 0);
+  hd->mha.assign(hd->ops.size(), MhaWs());
+  const long long tok = (long long)n_img * T;
+  for (size_t i = 0; i < hd->ops.size(); ++i) {
+    const hp_head_op& o = hd->ops[i];
+    if (o.op == HP_OP_LAYERNORM) {
+      hd->stat_off[i] = woff;
+      woff += (size_t)round_up((int)(2 * reg_rows(hd, o.in0, n_img, T)), 4);
+    } else if (o.op == HP_OP_MHA) {
+      const size_t sz = (size_t)round_up((int)(tok * o.heads * o.key_dim), 4);
+      MhaWs& w = hd->mha[i];
+      w.q = woff; woff += sz; w.k = woff; woff += sz; w.v = woff; woff += sz; w.o = woff; woff += sz;
+      if (training) {
+        w.gq = woff; woff += sz; w.gk = woff; woff += sz; w.gv = woff; woff += sz; w.go = woff; woff += sz;
+        const size_t pp = (size_t)round_up((int)std::min<long long>((long long)n_img * o.heads * T * T, 1ll << 30), 4);
+        HP_REQUIRE((long long)n_img * o.heads * T * T < (1ll << 30), HP_ERR_INVALID, "attention training scratch too large");
+        w.p = woff; woff += pp; w.ds = woff; woff += pp;
+      }
+    }
+  }
+  HP_TRY(hd->ws.ensure((woff + 4) * sizeof(float)));
+  return HP_OK;
+}
+
+static size_t attn_smem(int T, int d) { return ((size_t)2 * T * (d + 1) + 4 * (size_t)T) * sizeof(float); }
+
+static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, int T, bool training, uint64_t seed,
+                        cudaStream_t st) {
+  float* A = hd->acts.f();
+  auto R = [&](int r) -> const float* { return r == 0 ? feat : A + hd->reg_off[r]; };
+  auto RW = [&](int r) -> float* { return A + hd->reg_off[r]; };
+  for (size_t i = 0; i < hd->ops.size(); ++i) {
+    const hp_head_op& o = hd->ops[i];
+    const long long rows_out = reg_rows(hd, o.out, n_img, T);
+    const int C = hd->regs[o.out].channels;
+    const long long total = rows_out * C;
+    switch (o.op) {
+      case HP_OP_DENSE: {
+        DenseOut d{RW(o.out), 0, o.cout, (int)std::max<long long>(rows_out, 1), 0, o.cout};
+        HP_TRY(hp_launch_dense(h, R(o.in0), (int)rows_out, o.cin, o.cin, hd->params.f() + o.w_off, o.cout,
+                               hd->params.f() + o.b_off, o.cout, o.act, false, &d, 1, false, st));
+        break;
+      }
+      case HP_OP_ACT:
+        act_fwd_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), RW(o.out), total, o.act);
+        h->launches++;
+        break;
+      case HP_OP_ADD:
+        add_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), R(o.in1), RW(o.out), rows_out, C, T,
+                                                   hd->regs[o.in0].per_image && !hd->regs[o.out].per_image,
+                                                   hd->regs[o.in1].per_image && !hd->regs[o.out].per_image);
+        h->launches++;
+        break;
+      case HP_OP_MULCH:
+        mulch_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), R(o.in1), RW(o.out), rows_out, C, T);
+        h->launches++;
+        break;
+      case HP_OP_GAP:
+        gap_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), RW(o.out), n_img, C, T);
+        h->launches++;
+        break;
+      case HP_OP_DROPOUT:
+        if (training && o.fparam > 0.f) {
+          dropout_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), RW(o.out), rows_out, C, T, hd->regs[o.out].per_image,
+                                                        o.fparam, seed, hd->step, (uint32_t)o.op_id, 0);
+        } else {
+          HP_CUDA(cudaMemcpyAsync(RW(o.out), R(o.in0), total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        h->launches++;
+        break;
+      case HP_OP_LAYERNORM: {
+        long long warps_needed = rows_out;
+        unsigned grid = (unsigned)std::min<long long>((warps_needed + 7) / 8, 65535ll * 8);
+        layernorm_kernel<<<grid, 256, 0, st>>>(R(o.in0), hd->params.f() + o.w_off, hd->params.f() + o.b_off, RW(o.out),
+                                               hd->ws.f() + hd->stat_off[i], rows_out, C, o.fparam);
+        h->launches++;
+        break;
+      }
+      case HP_OP_MHA: {
+        const int hdm = o.heads * o.key_dim;
+        const float* P = hd->params.f() + o.w_off;
+        const float *Wq = P, *bq = Wq + C * hdm, *Wk = bq + hdm, *bk = Wk + C * hdm, *Wv = bk + hdm, *bv = Wv + C * hdm,
+                    *Wo = bv + hdm, *bo = Wo + hdm * C;
+        const MhaWs& w = hd->mha[i];
+        float* ws = hd->ws.f();
+        const int rows = (int)rows_out;
+        DenseOut dq{ws + w.q, 0, hdm, rows, 0, hdm}, dk{ws + w.k, 0, hdm, rows, 0, hdm}, dv{ws + w.v, 0, hdm, rows, 0, hdm};
+        HP_TRY(hp_launch_dense(h, R(o.in0), rows, C, C, Wq, hdm, bq, hdm, HP_ACT_LINEAR, false, &dq, 1, false, st));
+        HP_TRY(hp_launch_dense(h, R(o.in0), rows, C, C, Wk, hdm, bk, hdm, HP_ACT_LINEAR, false, &dk, 1, false, st));
+        HP_TRY(hp_launch_dense(h, R(o.in0), rows, C, C, Wv, hdm, bv, hdm, HP_ACT_LINEAR, false, &dv, 1, false, st));
+        const size_t smem = attn_smem(T, o.key_dim);
+        HP_REQUIRE(smem <= 200 * 1024, HP_ERR_UNSUPPORTED, "attention over %d tokens does not fit shared memory", T);
+        HP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attn_fwd_kernel<<<n_img * o.heads, 128, smem, st>>>(ws + w.q, ws + w.k, ws + w.v, ws + w.o, T, o.heads, o.key_dim,
+                                                           1.f / sqrtf((float)o.key_dim), training ? ws + w.p : nullptr,
+                                                           nullptr);
+        h->launches++;
+        DenseOut dout{RW(o.out), 0, C, rows, 0, C};
+        HP_TRY(hp_launch_dense(h, ws + w.o, rows, hdm, hdm, Wo, C, bo, C, HP_ACT_LINEAR, false, &dout, 1, false, st));
+        break;
+      }
+    }
+    HP_CUDA(cudaGetLastError());
+  }
+  return HP_OK;
+}
+
+static int dense_backward(hp_ctx* h, const float* x, int rows, int K, const float* W, int N, const float* gz,
+                          float* gW, float* gb, float* gx, cudaStream_t st) {
+  if (rows <= 0) return HP_OK;
+  const size_t smem = (size_t)WG_TM * (K + N) * sizeof(float);
+  HP_REQUIRE(smem <= 96 * 1024, HP_ERR_UNSUPPORTED, "dense backward %dx%d too large", K, N);
+  HP_CUDA(cudaFuncSetAttribute(dense_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  dense_wgrad_kernel<<<ceil_div(rows, WG_TM), 256, smem, st>>>(x, K, gz, N, gW, gb, rows, K, N);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  if (gx) {
+    DenseOut d{gx, 0, K, rows, 0, K};
+    HP_TRY(hp_launch_dense(h, gz, rows, N, N, W, N, nullptr, K, HP_ACT_LINEAR, true, &d, 1, true, st));
+  }
+  return HP_OK;
+}
+
+static int head_backward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, int T, uint64_t seed, cudaStream_t st) {
+  float* A = hd->acts.f();
+  float* G = hd->gacts.f();
+  float* gp = hd->grads.f();
+  auto R = [&](int r) -> const float* { return r == 0 ? feat : A + hd->reg_off[r]; };
+  auto GR = [&](int r) -> float* { return r == 0 ? nullptr : G + hd->reg_off[r]; };
+  for (int i = (int)hd->ops.size() - 1; i >= 0; --i) {
+    const hp_head_op& o = hd->ops[i];
+    const long long rows_out = reg_rows(hd, o.out, n_img, T);
+    const int C = hd->regs[o.out].channels;
+    const long long total = rows_out * C;
+    float* gy = GR(o.out);
+    switch (o.op) {
+      case HP_OP_DENSE: {
+        if (o.act != HP_ACT_LINEAR) {
+          act_bwd_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.out), gy, gy, total, o.act);
+          h->launches++;
+        }
+        HP_TRY(dense_backward(h, R(o.in0), (int)rows_out, o.cin, hd->params.f() + o.w_off, o.cout, gy, gp + o.w_off,
+                              gp + o.b_off, GR(o.in0), st));
+        break;
+      }
+      case HP_OP_ACT:
+        if (GR(o.in0)) {
+          act_bwd_acc_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.out), gy, GR(o.in0), total, o.act);
+          h->launches++;
+        }
+        break;
+      case HP_OP_ADD: {
+        const int ins[2] = {o.in0, o.in1};
+        for (int k = 0; k < 2; ++k) {
+          float* gi = GR(ins[k]);
+          if (!gi) continue;
+          if (hd->regs[ins[k]].per_image && !hd->regs[o.out].per_image) {
+            hp_set_error("backward of broadcasting Add is not supported");
+            return HP_ERR_UNSUPPORTED;
+          }
+          acc_kernel<<<EW_GRID(total), 256, 0, st>>>(gi, gy, total);
+          h->launches++;
+        }
+        break;
+      }
+      case HP_OP_MULCH: {
+        const long long tg = (long long)n_img * C;
+        mulch_bwd_kernel<<<EW_GRID(tg), 256, 0, st>>>(R(o.in0), R(o.in1), gy, GR(o.in0), GR(o.in1), n_img, C, T);
+        h->launches++;
+        break;
+      }
+      case HP_OP_GAP:
+        if (GR(o.in0)) {
+          const long long rows_in = (long long)n_img * T;
+          gap_bwd_kernel<<<EW_GRID(rows_in * C), 256, 0, st>>>(gy, GR(o.in0), rows_in, C, T);
+          h->launches++;
+        }
+        break;
+      case HP_OP_DROPOUT:
+        if (GR(o.in0)) {
+          if (o.fparam > 0.f)
+            dropout_kernel<<<EW_GRID(total), 256, 0, st>>>(gy, GR(o.in0), rows_out, C, T, hd->regs[o.out].per_image,
+                                                          o.fparam, seed, hd->step, (uint32_t)o.op_id, 1);
+          else
+            acc_kernel<<<EW_GRID(total), 256, 0, st>>>(GR(o.in0), gy, total);
+          h->launches++;
+        }
+        break;
+      case HP_OP_LAYERNORM: {
+        unsigned grid = (unsigned)std::min<long long>((rows_out + 7) / 8, 65535ll * 8);
+        layernorm_bwd_kernel<<<grid, 256, 0, st>>>(R(o.in0), hd->params.f() + o.w_off, hd->ws.f() + hd->stat_off[i], gy,
+                                                   GR(o.in0), gp + o.w_off, gp + o.b_off, rows_out, C);
+        h->launches++;
+        break;
+      }
+      case HP_OP_MHA: {
+        const int hdm = o.heads * o.key_dim, d = o.key_dim;
+        const float* P = hd->params.f() + o.w_off;
+        const float *Wq = P, *Wk = Wq + C * hdm + hdm, *Wv = Wk + C * hdm + hdm, *Wo = Wv + C * hdm + hdm;
+        float* gP = gp + o.w_off;
+        float *gWq = gP, *gbq = gWq + C * hdm, *gWk = gbq + hdm, *gbk = gWk + C * hdm, *gWv = gbk + hdm,
+              *gbv = gWv + C * hdm, *gWo = gbv + hdm, *gbo = gWo + hdm * C;
+        const MhaWs& w = hd->mha[i];
+        float* ws = hd->ws.f();
+        const int rows = (int)rows_out;
+        const float scale = 1.f / sqrtf((float)d);
+        // output projection: out = O Wo + bo
+        HP_CUDA(cudaMemsetAsync(ws + w.go, 0, (size_t)rows * hdm * sizeof(float), st));
+        HP_TRY(dense_backward(h, ws + w.o, rows, hdm, Wo, C, gy, gWo, gbo, ws + w.go, st));
+        const size_t smem_a = attn_smem(T, d);
+        HP_CUDA(cudaFuncSetAttribute(attn_bwd_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attn_bwd_a_kernel<<<n_img * o.heads, 128, smem_a, st>>>(ws + w.k, ws + w.v, ws + w.go, ws + w.p, ws + w.ds,
+                                                               ws + w.gq, T, o.heads, d, scale);
+        h->launches++;
+        const size_t smem_b = (size_t)2 * T * d * sizeof(float);
+        HP_REQUIRE(smem_b <= 200 * 1024, HP_ERR_UNSUPPORTED, "attention backward over %d tokens too large", T);
+        HP_CUDA(cudaFuncSetAttribute(attn_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        dim3 gb(n_img * o.heads, ceil_div(T, 128));
+        attn_bwd_b_kernel<<<gb, 128, smem_b, st>>>(ws + w.q, ws + w.go, ws + w.p, ws + w.ds, ws + w.gk, ws + w.gv, T,
+                                                   o.heads, d, scale);
+        h->launches++;
+        HP_CUDA(cudaGetLastError());
+        float* gx = GR(o.in0);
+        HP_TRY(dense_backward(h, R(o.in0), rows, C, Wq, hdm, ws + w.gq, gWq, gbq, gx, st));
+        HP_TRY(dense_backward(h, R(o.in0), rows, C, Wk, hdm, ws + w.gk, gWk, gbk, gx, st));
+        HP_TRY(dense_backward(h, R(o.in0), rows, C, Wv, hdm, ws + w.gv, gWv, gbv, gx, st));
+        break;
+      }
+    }
+    HP_CUDA(cudaGetLastError());
+  }
+  return HP_OK;
+}
+
+// ============================================================================ entry points used by api.cu
+int hp_head_set_weights_impl(hp_head* hd, const float* src, int n) {
+  HP_REQUIRE(hd && src && n == hd->n_params, HP_ERR_INVALID, "hp_head_set_weights: expected %d params", hd ? hd->n_params : -1);
+  HP_CUDA(cudaMemcpy(hd->params.p, src, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  return HP_OK;
+}
+int hp_head_get_weights_impl(hp_head* hd, float* dst, int n) {
+  HP_REQUIRE(hd && dst && n == hd->n_params, HP_ERR_INVALID, "hp_head_get_weights: expected %d params", hd ? hd->n_params : -1);
+  HP_CUDA(cudaDeviceSynchronize());
+  HP_CUDA(cudaMemcpy(dst, hd->params.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return HP_OK;
+}
+int hp_head_get_grads_impl(hp_head* hd, float* dst, int n) {
+  HP_REQUIRE(hd && dst && n == hd->n_params, HP_ERR_INVALID, "hp_head_get_grads: expected %d params", hd ? hd->n_params : -1);
+  HP_CUDA(cudaDeviceSynchronize());
+  HP_CUDA(cudaMemcpy(dst, hd->grads.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return HP_OK;
+}
+int hp_head_in_channels(hp_head* hd) { return hd->in_channels; }
+int hp_head_out_channels(hp_head* hd) { return hd->regs[hd->out_reg].channels; }
+
+int hp_head_forward_impl(hp_ctx* h, hp_head* hd, const float* feat, int B, int H, int W, float* out, cudaStream_t st) {
+  HP_REQUIRE(hd && feat && out && B > 0 && H > 0 && W > 0, HP_ERR_INVALID, "hp_head_forward: bad arguments");
+  HP_REQUIRE(!hd->regs[hd->out_reg].per_image, HP_ERR_INVALID, "head output must be per token");
+  const int T = H * W;
+  HP_TRY(head_plan(hd, B, T, false));
+  HP_TRY(head_forward(h, hd, feat, B, T, false, 0, st));
+  const long long total = (long long)B * T * hd->regs[hd->out_reg].channels;
+  HP_CUDA(cudaMemcpyAsync(out, hd->acts.f() + hd->reg_off[hd->out_reg], total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return HP_OK;
+}
+
+int hp_head_train_step_impl(hp_ctx* h, hp_head* hd, const float* x, const float* y, int n, int H, int W, int n_global,
+                            const hp_opt_config* opt, uint64_t seed, float* loss_mae_host, bool update,
+                            cudaStream_t st) {
+  HP_REQUIRE(hd && x && y && n > 0 && H > 0 && W > 0, HP_ERR_INVALID, "hp_head_train_step: bad arguments");
+  HP_REQUIRE(!update || opt, HP_ERR_INVALID, "hp_head_train_step: optimizer config required");
+  HP_REQUIRE(n_global >= n, HP_ERR_INVALID, "n_global (%d) must be >= n (%d)", n_global, n);
+  const int T = H * W;
+  const int Cout = hd->regs[hd->out_reg].channels;
+  const int np = hd->n_params;
+  HP_TRY(head_plan(hd, n, T, update));
+  HP_CUDA(cudaMemsetAsync(hd->grads.p, 0, (size_t)(np + 4) * sizeof(float), st));
+  HP_TRY(head_forward(h, hd, x, n, T, update, seed, st));
+  const long long total = (long long)n * T * Cout;
+  float* sums = hd->grads.f() + np;
+  const float* pred = hd->acts.f() + hd->reg_off[hd->out_reg];
+  if (update) {
+    size_t arena = hd->gacts.bytes;
+    HP_CUDA(cudaMemsetAsync(hd->gacts.p, 0, arena, st));
+  }
+  const float inv_count = 1.f / ((float)n_global * (float)T * (float)Cout);
+  mse_loss_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 1024), 256, 0, st>>>(
+      pred, y, update ? hd->gacts.f() + hd->reg_off[hd->out_reg] : nullptr, total, inv_count, sums);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  if (update) {
+    HP_TRY(head_backward(h, hd, x, n, T, seed, st));
+    if (h->comm.comm) HP_TRY(hp_comm_allreduce_sum(h, hd->grads.f(), (size_t)np + 3, st));
+    if (opt->kind != HP_OPT_SGD && !hd->has_state) {
+      HP_TRY(hd->m.ensure((size_t)np * sizeof(float)));
+      HP_TRY(hd->v.ensure((size_t)np * sizeof(float)));
+      HP_CUDA(cudaMemsetAsync(hd->m.p, 0, (size_t)np * sizeof(float), st));
+      HP_CUDA(cudaMemsetAsync(hd->v.p, 0, (size_t)np * sizeof(float), st));
+      hd->has_state = true;
+    }
+  }
+  if (loss_mae_host || !update) {
+    l2_penalty_kernel<<<1, 256, 0, st>>>(hd->params.f(), hd->l2coef.f(), np, sums + 3);
+    h->launches++;
+    HP_CUDA(cudaMemcpyAsync(hd->last_sums, sums, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (update) {
+    const double t = (double)hd->step + 1.0;
+    const double b1 = opt->beta1, b2 = opt->beta2;
+    const float alpha_t = (float)(opt->lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t)));
+    const float lr_t = (float)(opt->lr / (1.0 - pow(b1, t)));
+    optimizer_kernel<<<ceil_div(np, 256), 256, 0, st>>>(hd->params.f(), hd->grads.f(), hd->l2coef.f(), hd->m.f(), hd->v.f(),
+                                                       np, opt->kind, opt->lr, opt->beta1, opt->beta2, opt->eps, alpha_t,
+                                                       lr_t);
+    h->launches++;
+    HP_CUDA(cudaGetLastError());
+    hd->step++;
+  }
+  if (loss_mae_host) {
+    HP_CUDA(cudaStreamSynchronize(st));
+    const float cnt = update ? (float)n_global * T * Cout : hd->last_sums[2];
+    loss_mae_host[0] = hd->last_sums[0] / cnt + (update ? hd->last_sums[3] : 0.f);
+    loss_mae_host[1] = hd->last_sums[1] / cnt;
+    if (!update) loss_mae_host[2] = hd->last_sums[3];
+  }
+  return HP_OK;
+}
+
+uint32_t hp_dropout_hash(uint64_t seed, uint32_t step, uint32_t op_id, uint32_t image, uint32_t channel) {
+  return dropout_hash(seed, step, op_id, image, channel);
+}

@@ -1,0 +1,210 @@
+/*
+ * hpose.h -- C ABI of libhpose.so, the B200 (sm_100a) implementation of the reference's
+ * batched head-pose hot path.
+ *
+ * The reference (Maaz77/Head-Pose-Estimation-Model) has no FFI layer: its seam is Python
+ * duck-typing on a Keras model.  Each entry point below cites the reference interface it
+ * replaces; INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative hp_status; hp_last_error() returns a
+ *     thread-local human readable message for the last failure;
+ *   - pointers are DEVICE pointers unless the parameter name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - handles are opaque, one per GPU, not thread-safe;
+ *   - all feature maps are NHWC float32, batch-major; there is NO CPU fallback anywhere.
+ */
+#ifndef HPOSE_H_
+#define HPOSE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hp_ctx* hp_handle;
+
+enum hp_status {
+  HP_OK = 0,
+  HP_ERR_INVALID = -1,   /* bad argument (mirrors the reference's ValueError sites)            */
+  HP_ERR_CUDA = -2,      /* CUDA runtime failure                                               */
+  HP_ERR_STATE = -3,     /* call order violated (e.g. forward before load_weights)             */
+  HP_ERR_NCCL = -4,      /* NCCL missing or failed                                             */
+  HP_ERR_UNSUPPORTED = -5
+};
+
+#define HP_BACKBONE_PARAMS 101390 /* stem + 16 BlazeBlocks + 4 detector heads */
+#define HP_MAX_FACES 100          /* MAX_FACE_NUM, blazeFaceDetectorH5.py:9                    */
+#define HP_KEYPOINTS 6            /* KEY_POINT_SIZE, blazeFaceDetectorH5.py:8                  */
+
+/* kernel family selector for the backbone: FAST = fused BlazeBlock kernels (product path),
+ * NAIVE = one-thread-per-output CUDA kernels kept as an on-device cross-check.  Both are CUDA. */
+enum hp_impl { HP_IMPL_FAST = 0, HP_IMPL_NAIVE = 1 };
+
+const char* hp_last_error(void);
+int hp_version(void);
+
+int hp_create(int device, hp_handle* out);
+int hp_destroy(hp_handle h);
+int hp_set_impl(hp_handle h, int impl);
+/* number of kernels this library has launched on the handle since creation (bench `gpu_launches`) */
+int64_t hp_launch_count(hp_handle h);
+
+/* ---------------------------------------------------------------- backbone (a1-a3)
+ * Replaces the Keras model call `self.interpreter(x)` (blazeFaceDetectorH5.py:272) for the
+ * detector part of the unified graph (layers conv2d .. conv2d_20).
+ *
+ * packed_host layout (layout_id 0, all float32, Keras memory order):
+ *   stem kernel[5][5][3][24], stem bias[24],
+ *   for blk in 0..15: dw kernel[3][3][Cin], dw bias[Cin], pw kernel[Cin][Cout], pw bias[Cout],
+ *   cls16 kernel[88][2], bias[2], cls8 kernel[96][6], bias[6],
+ *   loc16 kernel[88][32], bias[32], loc8 kernel[96][96], bias[96]          (HP_BACKBONE_PARAMS floats)
+ */
+int hp_backbone_load_weights(hp_handle h, const float* packed_host, size_t n_floats, int layout_id);
+
+/* anchors for an HxW input: A = ceil(H/8)*ceil(W/8)*2 + ceil(H/16)*ceil(W/16)*6 */
+int hp_num_anchors(int H, int W);
+
+/* x[B,H,W,3] in [-1,1] -> feat16[B,H/8,W/8,88] (re_lu_10), feat8[B,H/16,W/16,96] (re_lu_15),
+ * cls[B,A] raw logits, loc[B,A,16] raw box/keypoint regressions (anchor order of
+ * classificators_1|2 / regressors_1|2 concatenated as in blazeFaceDetectorH5.py:280-281).
+ * Any of the four outputs may be NULL (feature maps are then kept in internal buffers). */
+int hp_backbone_forward(hp_handle h, const float* x, int B, int H, int W,
+                        float* feat16, float* feat8, float* cls, float* loc, void* stream);
+
+/* debugging / parity hook: run the backbone on x up to BlazeBlock `blk` (0..15; -1 = stem only) and
+ * copy that activation into dst (real channel count, NHWC). */
+int hp_backbone_read_activation(hp_handle h, const float* x, int B, int H, int W, int blk, float* dst,
+                                size_t dst_floats, void* stream);
+
+/* ---------------------------------------------------------------- pre-processing
+ * Replaces prepareInputForInference (blazeFaceDetectorH5.py:247-269) for images that already
+ * have the network input size: BGR uint8 [B,H,W,3] -> RGB float32 ((v/255)-0.5)/0.5. */
+int hp_preprocess_u8(hp_handle h, const uint8_t* bgr, int B, int H, int W, float* x, void* stream);
+
+/* ---------------------------------------------------------------- regressor heads (a4-a6)
+ * A head is a small program over per-token tensors ("registers"); the Python layer compiles the
+ * Keras graph built by se_transformer_regr_head / create_model* (attention_model.py:16-169,
+ * train_88.py:66-253, train_96.py:65-110) into this form.  Register 0 is the input feature map.
+ */
+enum hp_head_opcode {
+  HP_OP_DENSE = 1,     /* out = act(in0 @ W[cin][cout] + b)   Conv2D 1x1 / Dense               */
+  HP_OP_ACT = 2,       /* out = act(in0)                                                        */
+  HP_OP_ADD = 3,       /* out = in0 + in1                                                       */
+  HP_OP_MULCH = 4,     /* out[n,t,c] = in0[n,t,c] * in1[n,c]  (SE gate broadcast)               */
+  HP_OP_GAP = 5,       /* out[n,c] = mean_t in0[n,t,c]        GlobalAveragePooling2D            */
+  HP_OP_DROPOUT = 6,   /* SpatialDropout2D: mask (n,c), scale 1/(1-rate); identity at inference */
+  HP_OP_LAYERNORM = 7, /* LayerNormalization over channels, gamma=w_off beta=b_off eps=fparam   */
+  HP_OP_MHA = 8        /* self-attention over tokens: params at w_off in the order
+                          Wq[C][h*d] bq[h*d] Wk bk Wv bv Wo[h*d][C] bo[C]                        */
+};
+enum hp_act { HP_ACT_LINEAR = 0, HP_ACT_RELU = 1, HP_ACT_TANH = 2, HP_ACT_SIGMOID = 3, HP_ACT_SOFTSIGN = 4 };
+
+typedef struct hp_head_op {
+  int32_t op, in0, in1, out;
+  int32_t cin, cout, act;
+  int32_t w_off, b_off;      /* offsets (floats) into the head's flat parameter vector          */
+  int32_t heads, key_dim;    /* HP_OP_MHA                                                       */
+  int32_t op_id;             /* stable id mixed into the dropout hash                           */
+  float fparam;              /* dropout rate | layer-norm epsilon                               */
+  float l2_w, l2_b;          /* Keras L2 regulariser coefficients for kernel / bias             */
+} hp_head_op;
+
+typedef struct hp_head_reg {
+  int32_t channels;
+  int32_t per_image;         /* 1: one vector per image (after GAP), 0: one per token           */
+} hp_head_reg;
+
+typedef struct hp_head* hp_head_t;
+
+int hp_head_create(hp_handle h, const hp_head_op* ops, int n_ops, const hp_head_reg* regs, int n_regs,
+                   int out_reg, int n_params, hp_head_t* out);
+int hp_head_destroy(hp_handle h, hp_head_t head);
+int hp_head_set_weights(hp_handle h, hp_head_t head, const float* params_host, int n_params);
+int hp_head_get_weights(hp_handle h, hp_head_t head, float* params_host, int n_params);
+
+/* model.predict / model.__call__ (test.py:34): feat[B,H,W,Cin] -> out[B,H,W,Cout]; tokens = H*W. */
+int hp_head_forward(hp_handle h, hp_head_t head, const float* feat, int B, int H, int W, float* out,
+                    void* stream);
+
+enum hp_optimizer { HP_OPT_SGD = 0, HP_OPT_ADAM = 1, HP_OPT_ADAMAX = 2 };
+typedef struct hp_opt_config {
+  int32_t kind;
+  float lr, beta1, beta2, eps;
+} hp_opt_config;
+
+/* One optimizer step of model.fit (train_96.py:175, train_88.py:355): forward with dropout,
+ * loss = mean((pred-y)^2) + sum l2*|w|^2, backward, [allreduce if hp_comm_init was called],
+ * optimizer update.  x[n,H,W,Cin], y[n,H,W,3] are this rank's shard; n_global = samples summed over
+ * all ranks (== n on one GPU).  loss_mae_host[2] receives {loss incl. L2, mae} of the GLOBAL batch
+ * (may be NULL to avoid the device->host sync).  seed/step select the dropout masks. */
+int hp_head_train_step(hp_handle h, hp_head_t head, const float* x, const float* y, int n, int H, int W,
+                       int n_global, const hp_opt_config* opt, uint64_t seed, float* loss_mae_host,
+                       void* stream);
+/* gradients of the last train step (after allreduce, before L2), for parity tests */
+int hp_head_get_grads(hp_handle h, hp_head_t head, float* grads_host, int n_params);
+/* model.evaluate (train_96.py:186): mse_mae_host[3] = {mse, mae, l2 penalty}; Keras reports
+ * loss = mse + l2 penalty.  No update. */
+int hp_head_evaluate(hp_handle h, hp_head_t head, const float* x, const float* y, int n, int H, int W,
+                     float* mse_mae_host, void* stream);
+/* SpatialDropout2D keep decision used by the train step (exposed so the oracle can replay it) */
+uint32_t hp_dropout_hash(uint64_t seed, uint32_t step, uint32_t op_id, uint32_t image, uint32_t channel);
+
+/* ---------------------------------------------------------------- decode + NMS (a7-a9)
+ * Replaces filterDetections (blazeFaceDetectorH5.py:319-327), extractDetections (:284-317) and
+ * filterWithNonMaxSupression (:329-357, tf.image.non_max_suppression + pose lookup) per image.
+ *   cls[B,A], loc[B,A,16], pose16[B,H16,W16,3], pose8[B,H8,W8,3]
+ *   logit_thr = (float)log(t/(1-t)); iou_thr as float32; max_out <= HP_MAX_FACES
+ * outputs (row-major, per image, in selection order = score descending):
+ *   out_cnt[B], out_anchor[B,max_out] (anchor ids), boxes[B,max_out,4] float64 [x1,y1,x2,y2],
+ *   kps[B,max_out,6,2] float64, scores[B,max_out] float32, poses[B,max_out,3] float32.
+ * boxes/kps/scores/poses may be NULL. */
+int hp_decode_nms(hp_handle h, const float* cls, const float* loc, const float* pose16, const float* pose8,
+                  int B, int H, int W, float logit_thr, float iou_thr, int max_out,
+                  int32_t* out_cnt, int32_t* out_anchor, double* boxes, double* kps, float* scores,
+                  float* poses, void* stream);
+
+/* The same three steps as separate calls, one per reference method (used by the facade's
+ * filterDetections / extractDetections / filterWithNonMaxSupression):
+ *   hp_filter_detections: cls[B,A] -> out_idx[B,A] (ascending anchor ids, first out_cnt[b] valid),
+ *                         out_scores[B,A] float32 sigmoid                       (blazeFaceDetectorH5.py:319-327)
+ *   hp_extract_detections: loc[A,16] of one image + idx[n] -> boxes[n,4], kps[n,6,2] float64 (:284-317)
+ *   hp_nms: boxes[n,4] float64 (cast to float32 like TensorFlow), scores[n] -> out_sel[<=max_out] indices
+ *           into the candidate list in selection order, *out_cnt                (:332)            */
+int hp_filter_detections(hp_handle h, const float* cls, int B, int A, float logit_thr, int32_t* out_idx,
+                         float* out_scores, int32_t* out_cnt, void* stream);
+int hp_extract_detections(hp_handle h, const float* loc, const int32_t* idx, int n, int H, int W,
+                          double* boxes, double* kps, void* stream);
+int hp_nms(hp_handle h, const double* boxes, const float* scores, int n, float iou_thr, int max_out,
+           int32_t* out_sel, int32_t* out_cnt, void* stream);
+
+/* ---------------------------------------------------------------- unified path (config 5)
+ * backbone + detector heads + two pose heads (JoinModels.py:5-90 output order) + decode + NMS.
+ * pose16/pose8 outputs [B,H16,W16,3] / [B,H8,W8,3] may be NULL (internal). */
+int hp_unified_forward(hp_handle h, hp_head_t head16, hp_head_t head8, const float* x, int B, int H, int W,
+                       float logit_thr, float iou_thr, int max_out,
+                       float* pose16, float* pose8,
+                       int32_t* out_cnt, int32_t* out_anchor, double* boxes, double* kps, float* scores,
+                       float* poses, void* stream);
+
+/* ---------------------------------------------------------------- data-parallel training
+ * nccl_unique_id_host: the 128-byte ncclUniqueId produced by hp_comm_unique_id on rank 0 and
+ * broadcast by the caller (torch.distributed / MPI / files). */
+int hp_comm_unique_id(void* id128_host);
+int hp_comm_init(hp_handle h, const void* nccl_unique_id_host, int rank, int nranks);
+int hp_comm_destroy(hp_handle h);
+
+/* ---------------------------------------------------------------- measurement helpers
+ * fp32 FMA micro-benchmark (SURVEY 8d asks for the measured CUDA-core peak): returns TFLOP/s.
+ * mode 0 = scalar FFMA, mode 1 = packed fma.rn.f32x2 */
+int hp_fma_peak(hp_handle h, int mode, double* tflops_out);
+/* average device time (ms) of the backbone kernels of the last hp_backbone_forward (CUDA events on
+ * the launch stream); per_layer_ms may be NULL or float[18] = stem, 16 blocks, det heads */
+int hp_backbone_profile(hp_handle h, const float* x, int B, int H, int W, int iters, float* per_layer_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPOSE_H_ */

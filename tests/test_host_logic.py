@@ -1,0 +1,223 @@
+"""CPU tests of the host layer: spec compiler, Keras-format IO, builders, ABI surface, callbacks."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+from helpers import head_oracle, rel_err, unified_fixture
+from oracle.keras_graph import KerasGraph, to_torch
+
+
+def test_library_builds_and_exports_every_declared_symbol(built_lib):
+    from hpose_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "hpose.h")).read()
+    declared = set(re.findall(r"\b(hp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"hp_status", "hp_impl"}
+    lib = ctypes.CDLL(built_lib)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/hpose.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    # the dropout hash is host-callable without a GPU and must be a pure function
+    lib.hp_dropout_hash.restype = ctypes.c_uint32
+    lib.hp_dropout_hash.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+    a = lib.hp_dropout_hash(42, 0, 1, 2, 3)
+    assert a == lib.hp_dropout_hash(42, 0, 1, 2, 3) and a != lib.hp_dropout_hash(42, 1, 1, 2, 3)
+
+
+def test_no_gpu_means_loud_failure(built_lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hpose_b200 import _lib
+    from hpose_b200.device import default_context
+    with pytest.raises(_lib.HposeError):
+        default_context()
+    h = ctypes.c_void_p()
+    rc = _lib.lib().hp_create(0, ctypes.byref(h))
+    assert rc != 0 and b"no CPU fallback" in _lib.lib().hp_last_error()
+
+
+def test_builders_match_reference_parameter_counts():
+    from hpose_b200 import attention_model as am, keras_spec as K, train_88, train_96
+    K.reset_names()
+    assert am.se_transformer_regr_head().count_params() == 47328
+    assert am.se_transformer_regr_head(88, 8, 4, 16, 64, 64).count_params() == 42502   # == 12uei1sn.h5
+    assert train_88.create_model().count_params() == 5891                  # == stoqa9pt.h5
+    assert am.create_modelC().count_params() == 979 + 1056 + 3738 + 129
+    train_96.config.update(num_filters=64, dropout_rate=0.0, regularizer_rate=1e-5)
+    m = train_96.create_model()
+    assert m.count_params() == 96 * 64 + 64 + 64 * 3 + 3 and m.optimizer.kind == "adam"
+    train_96.config.update(num_filters=-1)
+    with pytest.raises(ValueError):
+        train_96.create_model()
+    train_96.config.update(num_filters=64)
+
+
+def test_traced_config_is_keras_format_and_evaluates_in_oracle():
+    from hpose_b200 import attention_model as am, keras_spec as K
+    K.reset_names(); K.set_seed(3)
+    m = am.se_transformer_regr_head(input_channels=24, reduction=4, num_heads=2, key_dim=4, ff_dim=8, hidden_channels=8)
+    cfg = json.loads(m.to_json())
+    names = [l["class_name"] for l in cfg["config"]["layers"]]
+    assert names.count("MultiHeadAttention") == 1 and names.count("LayerNormalization") == 2 and names[0] == "InputLayer"
+    g, _ = head_oracle(m)
+    x = torch.randn(2, 3, 5, 24, dtype=torch.float64)
+    with torch.no_grad():
+        y = g(x)
+    assert tuple(y.shape) == (2, 3, 5, 3)
+    # flat parameter packing is a bijection
+    flat = m.get_flat_weights()
+    assert np.array_equal(m.program.pack(m.program.unpack(flat)), flat)
+
+
+def test_h5_roundtrip_and_loader_errors(tmp_path):
+    from hpose_b200 import keras_spec as K, train_88
+    K.reset_names(); K.set_seed(11)
+    m = train_88.create_model_skip_fc()
+    m.compile(optimizer=K.SGD(learning_rate=2.8e-4), loss="mse", metrics=["mae"])
+    p = str(tmp_path / "m.h5")
+    m.save(p)
+    m2 = K.load_model(p)
+    assert m2.count_params() == m.count_params() and m2.optimizer.kind == "sgd"
+    assert np.array_equal(m2.get_flat_weights(), m.get_flat_weights())
+    assert abs(m2.optimizer.learning_rate - 2.8e-4) < 1e-9
+    with pytest.raises(FileNotFoundError):
+        K.load_model(str(tmp_path / "missing.h5"))
+    # shipped checkpoints load and agree with the oracle's reading of the same file
+    for hid, n in (("stoqa9pt", 5891), ("hrchr82r", 3683), ("12uei1sn", 42502)):
+        mm = K.load_model(os.path.join(GOLDEN, "heads", f"{hid}.h5"))
+        assert mm.count_params() == n
+
+
+def test_generated_detector_graph_equals_shipped_graph():
+    """unified.blazeface_graph_config reproduces the reference's unified model_config semantics."""
+    from hpose_b200 import keras_spec as K
+    from hpose_b200.unified import UnifiedModel, blazeface_graph_config, pack_backbone, unpack_backbone
+    graph, w = unified_fixture()
+    heads = {l["name"]: l for l in graph["config"]["layers"] if l["class_name"] == "Functional"}
+    gen = blazeface_graph_config({"class_name": "Functional", "config": heads["model"]["config"]},
+                                 {"class_name": "Functional", "config": heads["model_10"]["config"]})
+    ref_names = [(l["class_name"], l["name"]) for l in graph["config"]["layers"]]
+    gen_names = [(l["class_name"], l["name"]) for l in gen["config"]["layers"]]
+    assert sorted(ref_names) == sorted(gen_names)
+    x = torch.tensor(np.load(os.path.join(GOLDEN, "unified_kat.npz"))["x"][:1], dtype=torch.float64)
+    wt = to_torch(w, torch.float64)
+    with torch.no_grad():
+        a = KerasGraph(graph, wt)(x)
+        b = KerasGraph(gen, wt)(x)
+    for s, t in zip(a, b):
+        assert torch.equal(s, t)
+    flat = pack_backbone(w)
+    assert flat.size == 101390
+    back = unpack_backbone(flat)
+    assert all(np.array_equal(back[k], w[k]) for k in back)
+    bad = dict(w); bad["conv2d_3/kernel"] = np.zeros((1, 1, 28, 31), np.float32)
+    with pytest.raises(ValueError):
+        pack_backbone(bad)
+
+
+def test_unified_model_save_load(tmp_path):
+    from hpose_b200 import keras_spec as K
+    from hpose_b200.unified import UnifiedModel
+    _, w = unified_fixture()
+    h16 = K.load_model(os.path.join(GOLDEN, "heads", "stoqa9pt.h5"))
+    h8 = K.load_model(os.path.join(GOLDEN, "heads", "hrchr82r.h5"))
+    # nested head weights inside the unified file are bit-identical to the stand-alone checkpoints
+    for k, v in h16.get_weights_dict().items():
+        assert np.array_equal(v, w[f"model/{k}"])
+    for k, v in h8.get_weights_dict().items():
+        assert np.array_equal(v, w[f"model_10/{k}"])
+    u = UnifiedModel(w, h16, h8)
+    assert u.count_params() == 110964
+    p = str(tmp_path / "unified.h5")
+    u.save(p)
+    u2 = UnifiedModel.load(p)
+    assert np.array_equal(u2.backbone_flat, u.backbone_flat)
+    assert np.array_equal(u2.head16.get_flat_weights(), h16.get_flat_weights())
+    assert np.array_equal(u2.head8.get_flat_weights(), h8.get_flat_weights())
+    with pytest.raises(FileNotFoundError):
+        UnifiedModel.load(str(tmp_path / "nope.h5"))
+    with pytest.raises(ValueError):
+        UnifiedModel(w, h8, h16)
+
+
+def test_join_models_errors(tmp_path):
+    from hpose_b200.JoinModels import extract_id_from_path, join_models
+    with pytest.raises(FileNotFoundError):
+        join_models("a.h5", "b.h5", "c.h5", "re_lu_10", "re_lu_15", None)
+    s = os.path.join(GOLDEN, "heads", "stoqa9pt.h5")
+    with pytest.raises(ValueError):
+        join_models(s, s, s, "re_lu_99", "re_lu_15", None)
+    with pytest.raises(ValueError):     # a head checkpoint is not a BlazeFace detector
+        join_models(s, s, s, "re_lu_10", "re_lu_15", None)
+    assert extract_id_from_path("/x/y/stoqa9pt.h5") == "stoqa9pt" and extract_id_from_path("x.txt") is None
+
+
+def test_spec_compiler_rejects_unsupported_graphs():
+    from hpose_b200 import keras_spec as K
+    K.reset_names()
+    with pytest.raises(ValueError):
+        K.Conv2D(8, kernel_size=3)
+    x = K.Input((None, None, 8))
+    with pytest.raises(ValueError):
+        K.MultiHeadAttention(2, 4, value_dim=8)
+    y = K.Conv2D(3, 1, activation="selu")(x)
+    with pytest.raises(ValueError):
+        K.Model(x, y)
+
+
+def test_callbacks_follow_keras_rules():
+    from hpose_b200 import keras_spec as K
+
+    class Fake:
+        stop_training = False
+        w = 0
+        saved = []
+
+        def get_flat_weights(self): return self.w
+        def set_flat_weights(self, w): self.w = w
+        def save(self, p): self.saved.append(p)
+
+    m = Fake()
+    es = K.EarlyStopping(monitor="val_loss", patience=2, min_delta=1e-3, restore_best_weights=True)
+    ck = K.ModelCheckpoint("best.h5", monitor="val_loss", save_best_only=True)
+    for cb in (es, ck):
+        cb.set_model(m); cb.on_train_begin()
+    vals = [1.0, 0.9, 0.8995, 0.8999, 0.95]     # improvements < min_delta do not reset patience
+    for e, v in enumerate(vals):
+        m.w = e
+        for cb in (es, ck):
+            cb.on_epoch_end(e, {"val_loss": v})
+        if m.stop_training:
+            break
+    assert m.stop_training and e == 3 and m.w == 1          # restored to the epoch-1 weights
+    assert len(m.saved) == 3                                 # 1.0, 0.9, 0.8995 were strict improvements
+
+
+def test_npz_contract(tmp_path):
+    from hpose_b200.utilities import load_dataset, load_dataset_with_weights, save_dataset
+    f = np.abs(np.random.default_rng(0).normal(size=(9, 96))).astype(np.float32)
+    p = np.array([[0, 0, 0], [70, 0, 0], [0, 65, 3]] * 3, dtype=np.float64)
+    path = str(tmp_path / "d.npz")
+    save_dataset(path, f, p)
+    ff, pp = load_dataset(path)
+    assert ff.dtype == np.float32 and pp.dtype == np.float64 and ff.shape == (9, 96) and pp.shape == (9, 3)
+    d = load_dataset_with_weights(path)
+    assert d["weights"][0] == 1.0 and abs(d["weights"][1] - 0.5 ** 2) < 1e-12 and abs(d["weights"][2] - 0.5) < 1e-9
+    with pytest.raises(FileNotFoundError):
+        load_dataset(str(tmp_path / "none.npz"))
+
+
+def test_shard_bounds_cover_everything():
+    from hpose_b200.parallel import shard_bounds
+    for n in (0, 1, 7, 128, 4096, 4099):
+        for world in (1, 2, 4, 8):
+            cuts = [shard_bounds(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
