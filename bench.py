@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Headline benchmark: pose inferences/sec on synthetic 96x96 crops (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU restatement (oracle)
+
+One step = one pass of the unified hot path over one batch of 4096 crops per GPU:
+  BlazeFace backbone -> taps 12x12x88 / 6x6x96 -> detector heads + pose heads
+  (Model-88 shipped shape 88->64(softsign)->3 on the 88-channel tap, se_transformer_regr_head(96) on
+  the 96-channel tap) -> threshold + anchor decode + NMS + pose lookup.
+`value`  : crops/s with the float32 inputs already resident in HBM (device-timed, max over ranks).
+`e2e`    : the same metric through the Python facade with HOST buffers: pinned uint8 BGR crops are
+           copied host->device every step, pre-processed on the GPU, and counts/boxes/keypoints/scores/poses
+           are read back to pinned host memory every step.
+`roofline`: per-kernel CUDA-event timings measured live (hp_backbone_profile) against the measured HBM
+           copy bandwidth in MEASURED_PEAKS.json; algorithmic bytes per SURVEY 8(d) / DESIGN.md.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCKS = [(24, 24, 1), (24, 28, 1), (28, 32, 2), (32, 36, 1), (36, 42, 1), (42, 48, 2), (48, 56, 1), (56, 64, 1),
+          (64, 72, 1), (72, 80, 1), (80, 88, 1), (88, 96, 2), (96, 96, 1), (96, 96, 1), (96, 96, 1), (96, 96, 1)]
+METRIC = "pose inferences/sec at 96x96 crops"
+UNIT = "crops/s"
+
+
+def layer_table(size):
+    """[(name, algorithmic bytes per crop, flops per crop)] -- stem + one read of the input and one write of the
+    output per BlazeBlock, fp32, weights excluded."""
+    rows = []
+    h = -(-size // 2)
+    rows.append(("stem", (size * size * 3 + h * h * 24) * 4, 2 * h * h * 24 * 75))
+    for i, (cin, cout, s) in enumerate(BLOCKS):
+        ho = -(-h // s)
+        rows.append((f"block{i}", (h * h * cin + ho * ho * cout) * 4, 2 * ho * ho * (9 * cin + cin * cout)))
+        h = ho
+    return rows
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_model(size):
+    from hpose_b200 import keras_spec as K, train_88
+    from hpose_b200.attention_model import se_transformer_regr_head
+    from hpose_b200.unified import UnifiedModel, random_backbone
+    K.reset_names(); K.set_seed(1234)
+    head16 = train_88.create_model()
+    K.reset_names()
+    head8 = se_transformer_regr_head(input_channels=96)
+    return UnifiedModel(random_backbone(seed=1234), head16, head8)
+
+
+def cpu_reference_run(size, sample, reps, threads):
+    """Times the CPU restatement (oracle) of the same path on `sample` crops; returns crops/s (best of reps)."""
+    import torch
+    from oracle import postproc as opp
+    from oracle.keras_graph import KerasGraph, to_torch
+    torch.set_num_threads(threads)
+    model = build_model(size)
+    w = {}
+    from hpose_b200.unified import unpack_backbone
+    w.update(unpack_backbone(model.backbone_flat))
+    for name, head in ((model.head16_name, model.head16), (model.head8_name, model.head8)):
+        for k, v in head.program.unpack(head._flat).items():
+            w[f"{name}/{k}"] = v
+    g = KerasGraph(model.config(), to_torch(w, torch.float32))
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(sample, size, size, 3), dtype=np.uint8)
+    anchors = opp.blazeface_anchors(size)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        x = ((img[..., ::-1].astype(np.float64) / 255.0).astype(np.float32) - np.float32(0.5)) / np.float32(0.5)
+        with torch.no_grad():
+            o = [t.numpy() for t in g(torch.from_numpy(x))]
+        for i in range(sample):
+            cls = np.concatenate([o[0][i, :, 0], o[1][i, :, 0]])
+            loc = np.concatenate([o[2][i], o[3][i]])
+            opp.detect_postprocess(cls, loc, o[4][i], o[5][i], anchors, 0.4, 0.3, input_size=size)
+        best = min(best, time.perf_counter() - t0)
+    return sample / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample
+    times = []
+    for _ in range(args.warmup):
+        cpu_reference_run(args.size, sample, 1, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cps, dt = cpu_reference_run(args.size, sample, 1, threads)
+        times.append(dt)
+    total = time.perf_counter() - t0
+    value = sample * args.steps / sum(times)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"unified head-pose path, {args.size}x{args.size} uint8 crops, batch {args.batch}/GPU "
+                                   f"(reference arm times a bounded sample of {sample} crops per step)",
+                       "batch_per_gpu": args.batch, "input": f"{args.size}x{args.size}x3"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} crops/step x {args.steps} steps; restated CPU path (TensorFlow/Keras "
+                                       "unavailable): torch-CPU fp32 graph + numpy decode/NMS"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": total}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="crops per GPU per step")
+    ap.add_argument("--size", type=int, default=96)
+    ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--max-faces", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from hpose_b200 import _lib
+    from hpose_b200.blazeFaceDetectorH5 import blazeFaceDetector
+    from hpose_b200.device import default_context
+    B, S = args.batch, args.size
+    model = build_model(S)
+    det = blazeFaceDetector(model=model, inputSize=S)
+    ctx = default_context()
+    dev = ctx.torch_device
+
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    u8 = torch.randint(0, 256, (B, S, S, 3), generator=gen, device=dev, dtype=torch.uint8)
+    x = det._preprocess_device(u8)        # float32 inputs resident in HBM for the device-timed region
+    host_u8 = torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory()
+    host_u8.copy_(u8.cpu())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return det.detect_device(x, args.max_faces, float_input=True)
+
+    host_out = {}
+
+    def step_e2e():
+        d_u8 = host_u8.to(dev, non_blocking=True)
+        out = det.detect_device(d_u8, args.max_faces)
+        for k in ("count", "boxes", "keypoints", "scores", "poses"):
+            if k not in host_out:
+                host_out[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+            host_out[k].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the facade with host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e_steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ems = e0.elapsed_time(e1)
+    t = torch.tensor([ems], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ems = float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    e2e_value = world * B * e_steps / (ems * 1e-3)
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+    if rank == 0:
+        # ---- per-kernel roofline (CUDA events on the launch stream, each kernel repeated back to back)
+        peak, peak_src = measured_peaks()
+        per = (np.zeros(18, np.float32))
+        _lib.check(_lib.lib().hp_backbone_profile(ctx.handle, x.data_ptr(), B, S, S, 5, per.ctypes.data))
+        rows = layer_table(S)
+        layers = []
+        for (name, byts, flops), t_ms in zip(rows, per[:17]):
+            gbs = byts * B / (t_ms * 1e-3) / 1e9
+            layers.append({"kernel": name, "ms": float(t_ms), "algorithmic_GBps": gbs, "frac": gbs / peak,
+                           "tflops": flops * B / (t_ms * 1e-3) / 1e12})
+        bb_ms = float(per[:17].sum())
+        bb_bytes = sum(r[1] for r in rows)
+        bb_flops = sum(r[2] for r in rows)
+        dom = max(layers, key=lambda r: r["ms"])
+        bb_gbs = bb_bytes * B / (bb_ms * 1e-3) / 1e9
+        try:
+            fma_scalar = ctx.fma_peak_tflops(False)
+            fma_packed = ctx.fma_peak_tflops(True)
+        except Exception:
+            fma_scalar = fma_packed = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"unified head-pose path (backbone + detector heads + Model-88 head 88->64->3 + "
+                                       f"se_transformer_regr_head(96) + decode/NMS/pose lookup), {S}x{S} crops, "
+                                       f"batch {B} per GPU, random-init weights seed 1234",
+                           "batch_per_gpu": B, "global_batch": B * world, "input": f"{S}x{S}x3", "max_faces": args.max_faces,
+                           "parallelism": f"dp{world} (batch sharded, no collective)",
+                           "l2_policy": f"inputs larger than L2 ({B * S * S * 3 * 4 / 1e6:.0f} MB fp32 per step vs 126 MB)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_u8.numel()), "d2h_bytes_per_step": int(d2h),
+                        "steps": e_steps, "ms_per_step": ems / e_steps,
+                        "api": "blazeFaceDetector.detect_device(pinned uint8 BGR crops) + readback of count/boxes/keypoints/scores/poses"},
+                "gpu_launches": int(launches),
+                "clocks": sampler.summary(),
+                "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_GBps"], "peak": peak,
+                             "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                             "ms_per_launch": dom["ms"], "share_of_backbone": dom["ms"] / bb_ms},
+                "roofline_backbone": {"bound": "hbm", "achieved": bb_gbs, "peak": peak, "unit": "GB/s", "frac": bb_gbs / peak,
+                                      "bytes_per_crop": bb_bytes, "flop_per_crop": bb_flops, "ms": bb_ms,
+                                      "fp32_tflops": bb_flops * B / (bb_ms * 1e-3) / 1e12,
+                                      "fma_peak_tflops_measured": {"scalar_ffma": fma_scalar, "packed_f32x2": fma_packed},
+                                      "det_heads_ms": float(per[17])},
+                "layers": layers}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cps, dt = cpu_reference_run(S, args.cpu_sample, 2, threads)
+            line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_sample} crops, best of 2; restated CPU path (TensorFlow/Keras "
+                                              "unavailable): torch-CPU fp32 graph + numpy decode/NMS"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

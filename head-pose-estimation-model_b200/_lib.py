@@ -118,6 +118,8 @@ _PROTOS = {
     "hp_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "hp_comm_destroy": (C.c_int, [C.c_void_p]),
     "hp_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "hp_debug_set_tile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "hp_debug_tile_report": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_backbone_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

@@ -110,6 +110,17 @@ int hp_backbone_profile(hp_handle h, const float* x, int B, int H, int W, int it
                          (cudaStream_t)0);
 }
 
+int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf) {
+  HP_REQUIRE(h && blk >= 0 && blk < 16, HP_ERR_INVALID, "hp_debug_set_tile: bad arguments");
+  h->tile_override[blk][0] = TH; h->tile_override[blk][1] = TW; h->tile_override[blk][2] = IMGS; h->tile_override[blk][3] = nbuf;
+  return HP_OK;
+}
+int hp_debug_tile_report(hp_handle h, int* report16x8) {
+  HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
+  h->tile_report = report16x8;
+  return HP_OK;
+}
+
 int hp_preprocess_u8(hp_handle h, const uint8_t* bgr, int B, int H, int W, float* x, void* stream) {
   HP_ENTER(h);
   return hp_preprocess_u8_impl(h, bgr, B, H, W, x, (cudaStream_t)stream);

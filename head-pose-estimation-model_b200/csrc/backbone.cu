@@ -457,46 +457,60 @@ static size_t block_smem_bytes(int CINP, int COUTP, int PG, int in_tile_floats, 
   return fl * sizeof(float);
 }
 
-static bool choose_tile(int B, int Hout, int Wout, int S, int CINP, int COUTP, TileCfg* best) {
+static bool fill_tile(int B, int Hout, int Wout, int S, int CINP, int COUTP, int TH, int TW, int IMGS, int nbuf,
+                      TileCfg* tc) {
   const int NG = COUTP / 4;
+  const int TP = TH * TW * IMGS;
+  if (TH < 1 || TW < 1 || IMGS < 1 || TP < 8 || TP > 256 || (nbuf != 1 && nbuf != 2)) return false;
+  const int PG = ceil_div(TP, 8);
+  const int threads = round_up(PG * NG, 32);
+  if (threads > 512 || threads < CINP / 4) return false;
+  const int IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3;
+  const size_t smem = block_smem_bytes(CINP, COUTP, PG, IMGS * IH * IW * CINP, nbuf);
+  if (smem > 227 * 1024) return false;
+  tc->TH = TH; tc->TW = TW; tc->IMGS = IMGS; tc->PG = PG; tc->threads = threads; tc->nbuf = nbuf;
+  tc->IH = IH; tc->IW = IW; tc->tiles_y = ceil_div(Hout, TH); tc->tiles_x = ceil_div(Wout, TW);
+  tc->n_tiles = tc->tiles_y * tc->tiles_x * ceil_div(B, IMGS);
+  tc->smem = smem;
+  return true;
+}
+
+// Heuristic cost: wasted pixel slots x halo re-read x an occupancy penalty (resident warps per SM).
+static bool choose_tile(int B, int Hout, int Wout, int S, int CINP, int COUTP, TileCfg* best) {
   const size_t kMaxSmem = 227 * 1024;
   double best_cost = 1e30;
   bool found = false;
   for (int pass = 0; pass < 2; ++pass) {
-    // pass 0: whole images per tile (several small images), pass 1: partial images
-    for (int TW = (pass == 0 ? Wout : 4); TW <= (pass == 0 ? Wout : (Wout < 64 ? Wout : 64)); ++TW) {
+    // pass 0: whole (small) images, several per tile; pass 1: one image split into TH x TW tiles
+    const int tw_lo = pass == 0 ? Wout : 4, tw_hi = pass == 0 ? Wout : (Wout < 64 ? Wout : 64);
+    for (int TW = tw_lo; TW <= tw_hi; ++TW) {
       for (int TH = (pass == 0 ? Hout : 1); TH <= Hout; ++TH) {
         for (int IMGS = 1; IMGS <= (pass == 0 ? 8 : 1); ++IMGS) {
-          const int TP = TH * TW * IMGS;
-          if (TP > 256 || TP < 32) continue;
-          if (IMGS > B && IMGS > 1) continue;
-          const int PG = ceil_div(TP, 8);
-          const int threads = round_up(PG * NG, 32);
-          if (threads > 512) continue;
-          const int IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3;
-          const int in_tile = IMGS * IH * IW * CINP;
+          if (TH * TW * IMGS < 32) continue;
+          if (IMGS > 1 && IMGS > B) continue;
           for (int nbuf = 2; nbuf >= 1; --nbuf) {
-            const size_t smem = block_smem_bytes(CINP, COUTP, PG, in_tile, nbuf);
-            if (smem > kMaxSmem) continue;
-            const int tiles_y = ceil_div(Hout, TH), tiles_x = ceil_div(Wout, TW);
-            const long long n_tiles = (long long)tiles_y * tiles_x * ceil_div(B, IMGS);
-            const double slots = (double)n_tiles * PG * 8;
+            TileCfg tc;
+            if (!fill_tile(B, Hout, Wout, S, CINP, COUTP, TH, TW, IMGS, nbuf, &tc)) continue;
+            const double slots = (double)tc.n_tiles * tc.PG * 8;
             const double waste = slots / ((double)B * Hout * Wout);
-            const double halo = (double)(IH * IW) / (double)(TH * TW * S * S);
-            const int ctas_by_smem = (int)(kMaxSmem / (smem + 1024));
-            const int warps = (threads / 32) * (ctas_by_smem > 4 ? 4 : ctas_by_smem);
-            double cost = waste * (1.0 + 0.12 * (halo - 1.0));
-            if (warps < 8) cost *= 1.5;
-            else if (warps < 12) cost *= 1.15;
-            if (nbuf == 1 && ctas_by_smem < 2) cost *= 1.3;
+            const double halo = (double)(tc.IH * tc.IW) / (double)(TH * TW * S * S);
+            int ctas = (int)(kMaxSmem / (tc.smem + 1024));
+            if (ctas > 2048 / tc.threads) ctas = 2048 / tc.threads;
+            if (ctas > 16) ctas = 16;
+            const int warps = ctas * (tc.threads / 32);
+            double occ = 1.0;
+            if (warps < 4) occ = 2.5;
+            else if (warps < 6) occ = 1.6;
+            else if (warps < 8) occ = 1.3;
+            else if (warps < 12) occ = 1.15;
+            else if (warps < 16) occ = 1.05;
+            double cost = waste * (1.0 + 0.10 * (halo - 1.0)) * occ;
+            if (nbuf == 1) cost *= (ctas >= 2 ? 1.04 : 1.3);
             if (cost < best_cost - 1e-9) {
               best_cost = cost;
               found = true;
-              best->TH = TH; best->TW = TW; best->IMGS = IMGS; best->PG = PG; best->threads = threads;
-              best->nbuf = nbuf; best->IH = IH; best->IW = IW; best->tiles_y = tiles_y; best->tiles_x = tiles_x;
-              best->n_tiles = (int)n_tiles; best->smem = smem;
+              *best = tc;
             }
-            break;  // prefer the deepest buffering that fits for this shape
           }
         }
       }
@@ -728,8 +742,18 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
     const int Hi = hs[i], Wi = ws[i], Ho = hs[i + 1], Wo = ws[i + 1];
     TileCfg tc;
     if (!naive) {
-      HP_REQUIRE(choose_tile(B, Ho, Wo, S, cinp, coutp, &tc), HP_ERR_UNSUPPORTED,
-                 "no tile configuration for block %d at %dx%d", i, Ho, Wo);
+      const int* ov = h->tile_override[i];
+      if (ov[0] > 0) {
+        HP_REQUIRE(fill_tile(B, Ho, Wo, S, cinp, coutp, ov[0], ov[1], ov[2], ov[3], &tc), HP_ERR_INVALID,
+                   "tile override %dx%dx%d nbuf %d is not valid for block %d", ov[0], ov[1], ov[2], ov[3], i);
+      } else {
+        HP_REQUIRE(choose_tile(B, Ho, Wo, S, cinp, coutp, &tc), HP_ERR_UNSUPPORTED,
+                   "no tile configuration for block %d at %dx%d", i, Ho, Wo);
+      }
+      if (h->tile_report) {
+        int* r = h->tile_report + 8 * i;
+        r[0] = tc.TH; r[1] = tc.TW; r[2] = tc.IMGS; r[3] = tc.nbuf; r[4] = tc.threads; r[5] = (int)tc.smem; r[6] = tc.n_tiles; r[7] = tc.PG;
+      }
     }
     for (int it = 0; it < iters; ++it) {
       if (prof && it == 0) HP_CUDA(cudaEventRecord(h->ev[0], st));

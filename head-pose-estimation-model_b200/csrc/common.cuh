@@ -108,6 +108,8 @@ struct hp_ctx {
   DevBuf pose16, pose8, cls, loc;  // unified-path internals
   DevBuf scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  int tile_override[16][4] = {};   // TH, TW, IMGS, nbuf per block (0 = automatic)
+  int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
 };
 
 // generic per-token dense layer used by detector heads and regressor heads (dense.cu)

@@ -204,6 +204,11 @@ int hp_fma_peak(hp_handle h, int mode, double* tflops_out);
  * the launch stream); per_layer_ms may be NULL or float[18] = stem, 16 blocks, det heads */
 int hp_backbone_profile(hp_handle h, const float* x, int B, int H, int W, int iters, float* per_layer_ms);
 
+/* tuning hooks: force the tile shape of one BlazeBlock kernel (TH=0 restores the heuristic) and have
+ * the forward pass record {TH,TW,IMGS,nbuf,threads,smem,n_tiles,PG} per block into report16x8 (host int[128]) */
+int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf);
+int hp_debug_tile_report(hp_handle h, int* report16x8);
+
 #ifdef __cplusplus
 }
 #endif

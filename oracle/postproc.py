@@ -113,21 +113,21 @@ def filter_detections(cls: np.ndarray, score_threshold: float):
 
 
 def extract_detections(loc: np.ndarray, good: np.ndarray, anchors: np.ndarray, input_size: int = 128):
+    """Float64 decode; elementwise numpy float64 ops round exactly like the reference's scalar ones."""
     n = good.shape[0]
-    boxes = np.zeros((n, 4), dtype=np.float64)
-    kps = np.zeros((n, KEY_POINTS, 2), dtype=np.float64)
     size = float(input_size)
-    for i, a in enumerate(good):
-        ax, ay = float(anchors[a, 0]), float(anchors[a, 1])
-        row = loc[a].astype(np.float64)
-        cx = (row[0] + ax * size) / size
-        cy = (row[1] + ay * size) / size
-        w = row[2] / size
-        h = row[3] / size
-        for j in range(KEY_POINTS):
-            kps[i, j, 0] = (row[4 + 2 * j] + ax * size) / size
-            kps[i, j, 1] = (row[5 + 2 * j] + ay * size) / size
-        boxes[i] = (cx - w * 0.5, cy - h * 0.5, cx + w * 0.5, cy + h * 0.5)
+    rows = loc[good].astype(np.float64).reshape(n, 16)
+    ax = anchors[good, 0].astype(np.float64)
+    ay = anchors[good, 1].astype(np.float64)
+    cx = (rows[:, 0] + ax * size) / size
+    cy = (rows[:, 1] + ay * size) / size
+    w = rows[:, 2] / size
+    h = rows[:, 3] / size
+    kps = np.zeros((n, KEY_POINTS, 2), dtype=np.float64)
+    for j in range(KEY_POINTS):
+        kps[:, j, 0] = (rows[:, 4 + 2 * j] + ax * size) / size
+        kps[:, j, 1] = (rows[:, 5 + 2 * j] + ay * size) / size
+    boxes = np.stack([cx - w * 0.5, cy - h * 0.5, cx + w * 0.5, cy + h * 0.5], axis=1).reshape(n, 4)
     return boxes, kps
 
 
@@ -147,23 +147,43 @@ def _iou32(a: np.ndarray, b: np.ndarray) -> np.float32:
     return f(inter / f(f(area_i + area_j) - inter))
 
 
-def tf_non_max_suppression(boxes, scores, max_output_size: int, iou_threshold: float) -> np.ndarray:
+def _iou32_many(a: np.ndarray, kept: np.ndarray) -> np.ndarray:
+    """_iou32 of one box against an (m,4) array; elementwise float32 numpy ops are IEEE, hence bit-identical
+    to the scalar version above (checked in tests/test_oracle_postproc.py)."""
+    f = np.float32
+    ymin_i, ymax_i = min(a[0], a[2]), max(a[0], a[2])
+    xmin_i, xmax_i = min(a[1], a[3]), max(a[1], a[3])
+    ymin_j, ymax_j = np.minimum(kept[:, 0], kept[:, 2]), np.maximum(kept[:, 0], kept[:, 2])
+    xmin_j, xmax_j = np.minimum(kept[:, 1], kept[:, 3]), np.maximum(kept[:, 1], kept[:, 3])
+    area_i = f(f(ymax_i - ymin_i) * f(xmax_i - xmin_i))
+    area_j = (ymax_j - ymin_j) * (xmax_j - xmin_j)
+    iy = np.maximum(np.minimum(ymax_i, ymax_j) - np.maximum(ymin_i, ymin_j), f(0.0))
+    ix = np.maximum(np.minimum(xmax_i, xmax_j) - np.maximum(xmin_i, xmin_j), f(0.0))
+    inter = iy * ix
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = inter / ((area_i + area_j) - inter)
+    iou = np.where((area_j <= 0) | (area_i <= 0), f(0.0), iou)
+    return iou.astype(f)
+
+
+def tf_non_max_suppression(boxes, scores, max_output_size: int, iou_threshold: float, scalar: bool = False) -> np.ndarray:
     """Greedy hard NMS with TensorFlow NonMaxSuppressionV3 semantics (see module docstring)."""
-    b = np.asarray(boxes).astype(np.float32)
+    b = np.asarray(boxes).astype(np.float32).reshape(-1, 4)
     s = np.asarray(scores).astype(np.float32)
     thr = np.float32(iou_threshold)
-    order = sorted(range(len(s)), key=lambda i: (-float(s[i]), i))
+    order = np.lexsort((np.arange(len(s)), -s.astype(np.float64)))   # score descending, ties -> lower index
     keep: List[int] = []
+    kept_boxes = np.zeros((max(max_output_size, 1), 4), np.float32)
     for i in order:
         if len(keep) >= max_output_size:
             break
-        ok = True
-        for j in reversed(keep):
-            if _iou32(b[i], b[j]) > thr:
-                ok = False
-                break
+        if scalar:
+            ok = not any(_iou32(b[i], b[j]) > thr for j in reversed(keep))
+        else:
+            ok = not (keep and bool(np.any(_iou32_many(b[i], kept_boxes[:len(keep)]) > thr)))
         if ok:
-            keep.append(i)
+            kept_boxes[len(keep)] = b[i]
+            keep.append(int(i))
     return np.asarray(keep, dtype=np.int32)
 
 

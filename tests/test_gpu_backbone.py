@@ -1,0 +1,164 @@
+"""GPU parity: CUDA backbone (fast and naive kernel families) vs the float64 oracle.
+Tolerance (north_star): feature maps within 1e-4 relative (max-abs error / max-abs value per map)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from helpers import rel_err, unified_fixture
+from oracle.keras_graph import KerasGraph, to_torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _ctx():
+    from hpose_b200.device import default_context
+    return default_context()
+
+
+def _oracle_taps(graph, w, x):
+    taps = {}
+    g = KerasGraph(graph, to_torch(w, torch.float64))
+    with torch.no_grad():
+        outs = g(torch.tensor(x, dtype=torch.float64), taps=taps)
+    return outs, taps
+
+
+def _read_act(ctx, xt, blk, shape):
+    from hpose_b200 import _lib
+    dst = torch.empty(shape, dtype=torch.float32, device=xt.device)
+    B, H, W, _ = xt.shape
+    _lib.check(_lib.lib().hp_backbone_read_activation(ctx.handle, xt.data_ptr(), B, H, W, blk, dst.data_ptr(),
+                                                      dst.numel(), ctx.stream_ptr()))
+    torch.cuda.synchronize()
+    return dst.cpu().numpy()
+
+
+@pytest.mark.parametrize("impl", ["naive", "fast"])
+def test_trained_weights_128_all_layers(impl):
+    """Shipped detector weights, reference input size; every block output is compared."""
+    from hpose_b200 import _lib
+    from hpose_b200.unified import pack_backbone
+    graph, w = unified_fixture()
+    kat = np.load(os.path.join(GOLDEN, "unified_kat.npz"))
+    x = kat["x"]
+    ctx = _ctx()
+    ctx.set_impl(_lib.HP_IMPL_NAIVE if impl == "naive" else _lib.HP_IMPL_FAST)
+    try:
+        flat = pack_backbone(w)
+        _lib.check(_lib.lib().hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
+        xt = torch.from_numpy(x).to(ctx.torch_device)
+        _, taps = _oracle_taps(graph, w, x)
+        errs = {}
+        want = taps["conv2d"].numpy()
+        errs["stem"] = rel_err(_read_act(ctx, xt, -1, want.shape), want)
+        for blk in range(16):
+            want = taps["re_lu" if blk == 0 else f"re_lu_{blk}"].numpy()
+            errs[f"blk{blk}"] = rel_err(_read_act(ctx, xt, blk, want.shape), want)
+        bad = {k: v for k, v in errs.items() if not v < TOL}
+        assert not bad, f"{impl}: per-layer relative errors {errs}"
+    finally:
+        ctx.set_impl(_lib.HP_IMPL_FAST)
+
+
+@pytest.mark.parametrize("size,batch", [(128, 2), (96, 5), (88, 3), (64, 1), (120, 2)])
+def test_unified_outputs_match_oracle(size, batch):
+    """All six outputs of the unified graph (trained weights) at several input sizes incl. odd maps (88 -> 11 -> 6)."""
+    from hpose_b200 import keras_spec as K
+    from hpose_b200.unified import UnifiedModel
+    graph, w = unified_fixture()
+    u = UnifiedModel(w, K.load_model(os.path.join(GOLDEN, "heads", "stoqa9pt.h5")),
+                     K.load_model(os.path.join(GOLDEN, "heads", "hrchr82r.h5")))
+    rng = np.random.default_rng(size)
+    x = rng.uniform(-1, 1, size=(batch, size, size, 3)).astype(np.float32)
+    got = u(x)
+    want, taps = _oracle_taps(graph, w, x)
+    names = ("cls16", "cls8", "loc16", "loc8", "pose16", "pose8")
+    errs = {n: rel_err(a, b.numpy()) for n, a, b in zip(names, got, want)}
+    assert all(v < TOL for v in errs.values()), errs
+    # angles within 0.01 degree (north_star)
+    assert np.abs(got[4] - want[4].numpy()).max() < 0.01 and np.abs(got[5] - want[5].numpy()).max() < 0.01
+    dev = u.forward_device(torch.from_numpy(x).cuda())
+    assert rel_err(dev["feat16"].cpu().numpy(), taps["re_lu_10"].numpy()) < TOL
+    assert rel_err(dev["feat8"].cpu().numpy(), taps["re_lu_15"].numpy()) < TOL
+
+
+def test_golden_unified_kat():
+    """Committed float64 known answers (tests/golden/unified_kat.npz, generated from the shipped .h5)."""
+    from hpose_b200 import keras_spec as K
+    from hpose_b200.unified import UnifiedModel
+    _, w = unified_fixture()
+    kat = np.load(os.path.join(GOLDEN, "unified_kat.npz"))
+    u = UnifiedModel(w, K.load_model(os.path.join(GOLDEN, "heads", "stoqa9pt.h5")),
+                     K.load_model(os.path.join(GOLDEN, "heads", "hrchr82r.h5")))
+    got = u(kat["x"])
+    for name, a in zip(("cls16", "cls8", "loc16", "loc8", "pose16", "pose8"), got):
+        assert rel_err(a, kat[name]) < TOL, name
+    assert np.abs(got[4] - kat["pose16"]).max() < 0.01 and np.abs(got[5] - kat["pose8"]).max() < 0.01
+
+
+def test_random_weights_fast_equals_naive_large_batch():
+    """Random-init weights (bench recipe) at B=67, 96x96: the fast kernels agree with the naive CUDA kernels
+    (size-independent cross-check at a batch the oracle would take long for) and with the oracle on 2 images."""
+    from hpose_b200 import _lib, keras_spec as K
+    from hpose_b200.unified import blazeface_graph_config, pack_backbone, random_backbone
+    ctx = _ctx()
+    w = random_backbone(seed=1234, bias_scale=0.05)
+    flat = pack_backbone(w)
+    _lib.check(_lib.lib().hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
+    B, S = 67, 96
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand((B, S, S, 3), generator=g, device="cuda") * 2 - 1
+    A = _lib.lib().hp_num_anchors(S, S)
+    res = {}
+    for impl in (_lib.HP_IMPL_NAIVE, _lib.HP_IMPL_FAST):
+        ctx.set_impl(impl)
+        f16 = torch.empty((B, 12, 12, 88), device="cuda"); f8 = torch.empty((B, 6, 6, 96), device="cuda")
+        cls = torch.empty((B, A), device="cuda"); loc = torch.empty((B, A, 16), device="cuda")
+        _lib.check(_lib.lib().hp_backbone_forward(ctx.handle, x.data_ptr(), B, S, S, f16.data_ptr(), f8.data_ptr(),
+                                                  cls.data_ptr(), loc.data_ptr(), ctx.stream_ptr()))
+        torch.cuda.synchronize()
+        res[impl] = [t.cpu().numpy() for t in (f16, f8, cls, loc)]
+    ctx.set_impl(_lib.HP_IMPL_FAST)
+    for a, b, n in zip(res[_lib.HP_IMPL_FAST], res[_lib.HP_IMPL_NAIVE], ("feat16", "feat8", "cls", "loc")):
+        assert rel_err(a, b) < 2e-5, n
+    # oracle on the first two images
+    K.reset_names()
+    dummy16 = K.Model(*(lambda i: (i, K.Conv2D(3, 1)(i)))(K.Input((None, None, 88))))
+    K.reset_names()
+    dummy8 = K.Model(*(lambda i: (i, K.Conv2D(3, 1)(i)))(K.Input((None, None, 96))))
+    cfg = blazeface_graph_config(dummy16._config, dummy8._config)
+    ww = dict(w)
+    for nm, d in (("model", dummy16), ("model_10", dummy8)):
+        for k, v in d.get_weights_dict().items():
+            ww[f"{nm}/{k}"] = v
+    taps = {}
+    with torch.no_grad():
+        KerasGraph(cfg, to_torch(ww, torch.float64))(x[:2].double().cpu(), taps=taps)
+    assert rel_err(res[_lib.HP_IMPL_FAST][0][:2], taps["re_lu_10"].numpy()) < TOL
+    assert rel_err(res[_lib.HP_IMPL_FAST][1][:2], taps["re_lu_15"].numpy()) < TOL
+
+
+def test_argument_errors():
+    from hpose_b200 import _lib
+    ctx = _ctx()
+    x = torch.zeros((1, 8, 8, 3), device="cuda")
+    rc = _lib.lib().hp_backbone_forward(ctx.handle, x.data_ptr(), 1, 8, 8, None, None, None, None, None)
+    assert rc == -1 and b"H, W >= 16" in _lib.lib().hp_last_error()
+    bad = np.zeros(10, np.float32)
+    assert _lib.lib().hp_backbone_load_weights(ctx.handle, bad.ctypes.data, 10, 0) == -1
+
+
+def test_preprocess_matches_reference_arithmetic():
+    from hpose_b200 import _lib
+    ctx = _ctx()
+    img = np.random.default_rng(1).integers(0, 256, size=(3, 40, 24, 3), dtype=np.uint8)
+    u8 = torch.from_numpy(img).cuda()
+    x = torch.empty((3, 40, 24, 3), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().hp_preprocess_u8(ctx.handle, u8.data_ptr(), 3, 40, 24, x.data_ptr(), ctx.stream_ptr()))
+    want = ((img[..., ::-1].astype(np.float64) / 255.0).astype(np.float32) - np.float32(0.5)) / np.float32(0.5)
+    assert np.array_equal(x.cpu().numpy(), want)

@@ -1,0 +1,160 @@
+"""GPU parity of threshold + decode + NMS + pose lookup: bit-exact against the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import postproc as opp
+
+pytestmark = pytest.mark.gpu
+
+
+def _stress(B, size, seed, sigma=2.0):
+    rng = np.random.default_rng(seed)
+    g16, g8 = -(-size // 8), -(-size // 16)
+    A = g16 * g16 * 2 + g8 * g8 * 6
+    cls = rng.normal(0, sigma, (B, A)).astype(np.float32)
+    loc = np.zeros((B, A, 16), np.float32)
+    loc[..., :2] = rng.uniform(-8, 8, (B, A, 2))
+    loc[..., 2:4] = rng.uniform(16, 64, (B, A, 2))
+    loc[..., 4:] = rng.uniform(-20, 20, (B, A, 12))
+    p16 = rng.normal(0, 20, (B, g16, g16, 3)).astype(np.float32)
+    p8 = rng.normal(0, 20, (B, g8, g8, 3)).astype(np.float32)
+    return cls, loc, p16, p8
+
+
+def _run_fused(cls, loc, p16, p8, size, score_thr=0.4, iou_thr=0.3, max_out=100):
+    from hpose_b200 import _lib
+    from hpose_b200.device import default_context
+    ctx = default_context()
+    B = cls.shape[0]
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tc, tl, t16, t8 = d(cls), d(loc), d(p16), d(p8)
+    cnt = torch.empty((B,), dtype=torch.int32, device="cuda")
+    anc = torch.empty((B, max_out), dtype=torch.int32, device="cuda")
+    boxes = torch.zeros((B, max_out, 4), dtype=torch.float64, device="cuda")
+    kps = torch.zeros((B, max_out, 12), dtype=torch.float64, device="cuda")
+    sc = torch.zeros((B, max_out), dtype=torch.float32, device="cuda")
+    po = torch.zeros((B, max_out, 3), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().hp_decode_nms(ctx.handle, tc.data_ptr(), tl.data_ptr(), t16.data_ptr(), t8.data_ptr(), B, size, size,
+                                        float(opp.logit_threshold(score_thr)), float(np.float32(iou_thr)), max_out,
+                                        cnt.data_ptr(), anc.data_ptr(), boxes.data_ptr(), kps.data_ptr(), sc.data_ptr(),
+                                        po.data_ptr(), ctx.stream_ptr()))
+    torch.cuda.synchronize()
+    return [t.cpu().numpy() for t in (cnt, anc, boxes, kps, sc, po)]
+
+
+@pytest.mark.parametrize("size,B,seed,sigma", [(128, 24, 7, 2.0), (96, 16, 8, 2.0), (88, 9, 9, 4.0), (128, 6, 10, 8.0)])
+def test_fused_decode_nms_bit_exact(size, B, seed, sigma):
+    cls, loc, p16, p8 = _stress(B, size, seed, sigma)
+    # force exact score ties and saturated scores (tie-break by lower anchor index)
+    cls[0, 10] = cls[0, 200] = cls[0, 5] = np.float32(3.25)
+    cls[1, :40] = np.float32(30.0)
+    cnt, anc, boxes, kps, sc, po = _run_fused(cls, loc, p16, p8, size)
+    anchors = opp.blazeface_anchors(size)
+    for i in range(B):
+        ref = opp.detect_postprocess(cls[i], loc[i], p16[i], p8[i], anchors, 0.4, 0.3, input_size=size)
+        k = len(ref["kept_anchor"])
+        assert cnt[i] == k, (i, cnt[i], k)
+        assert np.array_equal(anc[i, :k], ref["kept_anchor"]), i            # NMS kept-anchor indices bit-exact
+        assert np.all(anc[i, k:] == -1)
+        assert np.array_equal(boxes[i, :k], ref["boxes"])                   # float64 decode bit-exact
+        assert np.array_equal(kps[i, :k].reshape(k, 6, 2), ref["keypoints"])
+        assert np.array_equal(sc[i, :k], ref["scores"])                     # float32 sigmoid bit-exact
+        assert np.array_equal(po[i, :k], ref["poses"])
+
+
+def test_edge_cases_empty_single_and_cap():
+    size = 128
+    cls, loc, p16, p8 = _stress(4, size, 3)
+    cls[0, :] = -20                      # nothing passes
+    cls[1, :] = -20; cls[1, 777] = 2.0   # exactly one
+    cls[2, :] = 5.0                      # everything passes with identical scores -> first 100 non-overlapping by index
+    loc[2, :, 2:4] = 1.0                 # tiny boxes: no overlaps
+    cnt, anc, boxes, kps, sc, po = _run_fused(cls, loc, p16, p8, size)
+    anchors = opp.blazeface_anchors(size)
+    assert cnt[0] == 0 and np.all(anc[0] == -1)
+    assert cnt[1] == 1 and anc[1, 0] == 777
+    for i in (2, 3):
+        ref = opp.detect_postprocess(cls[i], loc[i], p16[i], p8[i], anchors, 0.4, 0.3, input_size=size)
+        assert cnt[i] == len(ref["kept_anchor"]) and np.array_equal(anc[i, :cnt[i]], ref["kept_anchor"])
+    assert cnt[2] == 100
+    c5 = _run_fused(cls, loc, p16, p8, size, max_out=5)
+    assert c5[0][2] == 5 and np.array_equal(c5[1][2], anc[2, :5])
+
+
+def test_other_thresholds():
+    size = 96
+    cls, loc, p16, p8 = _stress(8, size, 21, 3.0)
+    anchors = opp.blazeface_anchors(size)
+    for st, it in ((0.7, 0.5), (0.1, 0.05), (0.5, 0.9)):
+        cnt, anc, *_ = _run_fused(cls, loc, p16, p8, size, st, it)
+        for i in range(8):
+            ref = opp.detect_postprocess(cls[i], loc[i], p16[i], p8[i], anchors, st, it, input_size=size)
+            assert cnt[i] == len(ref["kept_anchor"]) and np.array_equal(anc[i, :cnt[i]], ref["kept_anchor"]), (st, it, i)
+
+
+def test_facade_steps_match_oracle_one_image():
+    """filterDetections / extractDetections / filterWithNonMaxSupression individually (reference method split)."""
+    import os
+    from conftest import GOLDEN
+    from helpers import unified_fixture
+    from hpose_b200 import keras_spec as K
+    from hpose_b200.blazeFaceDetectorH5 import blazeFaceDetector
+    from hpose_b200.unified import UnifiedModel
+    _, w = unified_fixture()
+    u = UnifiedModel(w, K.load_model(os.path.join(GOLDEN, "heads", "stoqa9pt.h5")),
+                     K.load_model(os.path.join(GOLDEN, "heads", "hrchr82r.h5")))
+    det = blazeFaceDetector(model=u)
+    assert len(det.anchors) == 896 and det.inputHeight == 128 and abs(det.sigmoidScoreThreshold - np.log(0.4 / 0.6)) < 1e-12
+    cls, loc, p16, p8 = _stress(1, 128, 33)
+    anchors = opp.blazeface_anchors(128)
+    scores, good = det.filterDetections(cls[0])
+    rs, rg = opp.filter_detections(cls[0], 0.4)
+    assert np.array_equal(good, rg) and np.array_equal(scores, rs)
+    boxes, kps = det.extractDetections(loc[0], good)
+    rb, rk = opp.extract_detections(loc[0], rg, anchors, 128)
+    assert boxes.dtype == np.float64 and np.array_equal(boxes, rb) and np.array_equal(kps, rk)
+    res = det.filterWithNonMaxSupression(boxes, kps, scores, good, p16[0], p8[0])
+    ref = opp.detect_postprocess(cls[0], loc[0], p16[0], p8[0], anchors)
+    assert np.array_equal(res.boxes, ref["boxes"]) and np.array_equal(res.keypoints, ref["keypoints"])
+    assert np.array_equal(res.scores, ref["scores"]) and np.array_equal(res.poses, ref["poses"])
+    empty = det.filterWithNonMaxSupression(boxes[:0], kps[:0], scores[:0], good[:0], p16[0], p8[0])
+    assert empty.poses.shape == (0, 3) and empty.boxes.shape == (0, 4)
+
+
+def test_detect_faces_end_to_end_vs_oracle():
+    """uint8 BGR image -> Results through detectFaces (reference flow) and detectFacesBatch (fused flow)."""
+    import os
+    from conftest import GOLDEN
+    from helpers import unified_fixture
+    from hpose_b200 import keras_spec as K
+    from hpose_b200.blazeFaceDetectorH5 import blazeFaceDetector
+    from hpose_b200.unified import UnifiedModel
+    from oracle.keras_graph import KerasGraph, to_torch
+    graph, w = unified_fixture()
+    u = UnifiedModel(w, K.load_model(os.path.join(GOLDEN, "heads", "stoqa9pt.h5")),
+                     K.load_model(os.path.join(GOLDEN, "heads", "hrchr82r.h5")))
+    det = blazeFaceDetector(scoreThreshold=0.4, iouThreshold=0.3, model=u)
+    rng = np.random.default_rng(4)
+    imgs = rng.integers(0, 256, size=(3, 128, 128, 3), dtype=np.uint8)
+    imgs[1, 30:100, 30:100] = 200          # a bright blob so that some anchors fire with trained weights
+    batch = det.detectFacesBatch(imgs)
+    single = [det.detectFaces(im) for im in imgs]
+    for a, b in zip(batch, single):
+        assert np.array_equal(a.boxes, b.boxes) and np.array_equal(a.scores, b.scores) and np.array_equal(a.poses, b.poses)
+    # oracle: same logits (from the CUDA path) through the numpy post-processing, and float64 graph for the poses
+    x = ((imgs[..., ::-1].astype(np.float64) / 255.0).astype(np.float32) - np.float32(0.5)) / np.float32(0.5)
+    out = u(x)
+    anchors = opp.blazeface_anchors(128)
+    with torch.no_grad():
+        o64 = KerasGraph(graph, to_torch(w, torch.float64))(torch.tensor(x, dtype=torch.float64))
+    for i in range(3):
+        cls = np.concatenate([out[0][i, :, 0], out[1][i, :, 0]])
+        loc = np.concatenate([out[2][i], out[3][i]])
+        ref = opp.detect_postprocess(cls, loc, out[4][i], out[5][i], anchors)
+        assert np.array_equal(batch[i].boxes, ref["boxes"]) and np.array_equal(batch[i].poses, ref["poses"])
+        ref64 = opp.detect_postprocess(cls, loc, o64[4][i].numpy(), o64[5][i].numpy(), anchors)
+        if len(ref64["poses"]):
+            assert np.abs(batch[i].poses - ref64["poses"]).max() < 0.01      # angles within 0.01 degree
+    with pytest.raises(ValueError):
+        det.detectFaces(np.zeros((64, 64, 3), np.uint8))

@@ -79,3 +79,18 @@ def test_detect_postprocess_empty_and_full():
     k = out["kept_anchor"]
     assert 0 < len(k) <= 100 and len(set(k.tolist())) == len(k)
     assert np.all(np.diff(out["scores"]) <= 0)          # selection order = score descending
+
+
+def test_vectorised_nms_equals_scalar_restatement():
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        n = int(rng.integers(1, 400))
+        c = rng.uniform(0, 1, (n, 2))
+        wh = rng.uniform(0.0, 0.4, (n, 2)) * (rng.random((n, 2)) > 0.05)     # some zero-area boxes
+        boxes = np.concatenate([c - wh / 2, c + wh / 2], axis=1)
+        if trial % 2:
+            boxes[:, [0, 2]] = boxes[:, [2, 0]]                              # flipped corners
+        scores = np.round(rng.random(n), 2).astype(np.float32)               # many ties
+        a = opp.tf_non_max_suppression(boxes, scores, 100, 0.3)
+        b = opp.tf_non_max_suppression(boxes, scores, 100, 0.3, scalar=True)
+        assert np.array_equal(a, b)
