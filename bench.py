@@ -311,7 +311,7 @@ def main():
             line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_sample} crops, best of 2; restated CPU path (TensorFlow/Keras "
                                               "unavailable): torch-CPU fp32 graph + numpy decode/NMS"}
-        print(json.dumps(line))
+        print(json.dumps(line, default=float))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

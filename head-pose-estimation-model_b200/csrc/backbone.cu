@@ -486,8 +486,7 @@ static bool choose_tile(int B, int Hout, int Wout, int S, int CINP, int COUTP, T
     for (int TW = tw_lo; TW <= tw_hi; ++TW) {
       for (int TH = (pass == 0 ? Hout : 1); TH <= Hout; ++TH) {
         for (int IMGS = 1; IMGS <= (pass == 0 ? 8 : 1); ++IMGS) {
-          if (TH * TW * IMGS < 32) continue;
-          if (IMGS > 1 && IMGS > B) continue;
+          if (TH * TW * IMGS < 32 && !(pass == 0 && IMGS == 8)) continue;
           for (int nbuf = 2; nbuf >= 1; --nbuf) {
             TileCfg tc;
             if (!fill_tile(B, Hout, Wout, S, CINP, COUTP, TH, TW, IMGS, nbuf, &tc)) continue;

@@ -359,8 +359,9 @@ extern "C" int hp_filter_detections(hp_handle h, const float* cls, int B, int A,
 
 extern "C" int hp_extract_detections(hp_handle h, const float* loc, const int32_t* idx, int n, int H, int W,
                                      double* boxes, double* kps, void* stream) {
-  HP_REQUIRE(h && loc && boxes && kps && n >= 0 && (n == 0 || idx), HP_ERR_INVALID, "hp_extract_detections: bad arguments");
+  HP_REQUIRE(h && n >= 0, HP_ERR_INVALID, "hp_extract_detections: bad arguments");
   if (n == 0) return HP_OK;
+  HP_REQUIRE(loc && boxes && kps && idx, HP_ERR_INVALID, "hp_extract_detections: null pointer");
   HP_CUDA(cudaSetDevice(h->device));
   NmsParams p;
   memset(&p, 0, sizeof(p));

@@ -329,7 +329,7 @@ def keras_train_step(graph: KerasGraph, params: Dict[str, torch.Tensor], x: np.n
     loss.backward()
     grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
     apply_optimizer(params, grads, opt, state)
-    return float(loss), float(mae), grads
+    return float(loss.detach()), float(mae.detach()), grads
 
 
 def apply_optimizer(params, grads, opt: dict, state: dict):

@@ -34,7 +34,10 @@ sweep128)
 refbench)
   timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "refbench exit $?"; cat gpurun_out/bench_ref.json ;;
 ncu)
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
-  ncu --set full --clock-control none --import-source on -k regex:blaze_block -s 20 -c 3 -o gpurun_out/prof_block python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?" ;;
+  python tools/profile_target.py 96 2048 > gpurun_out/profile_plain.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 64 --csv --log-file gpurun_out/launches.csv python tools/profile_target.py 96 2048 > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
+  python tools/profile_target.py 96 2048 > gpurun_out/profile_plain.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"stem_kernel|blaze_block" -c 17 -o gpurun_out/prof_backbone python tools/profile_target.py 96 2048 > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
+  ls -la gpurun_out/*.ncu-rep ;;
 esac
 done
