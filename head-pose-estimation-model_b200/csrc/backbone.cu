@@ -740,18 +740,34 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
     else out = bb.act[pp ^ 1].f();
     const int Hi = hs[i], Wi = ws[i], Ho = hs[i + 1], Wo = ws[i + 1];
     TileCfg tc;
+    Tile2Cfg tc2;
+    const bool v1 = (h->impl == HP_IMPL_CPASYNC);
     if (!naive) {
       const int* ov = h->tile_override[i];
-      if (ov[0] > 0) {
-        HP_REQUIRE(fill_tile(B, Ho, Wo, S, cinp, coutp, ov[0], ov[1], ov[2], ov[3], &tc), HP_ERR_INVALID,
-                   "tile override %dx%dx%d nbuf %d is not valid for block %d", ov[0], ov[1], ov[2], ov[3], i);
+      if (v1) {
+        if (ov[0] > 0) {
+          HP_REQUIRE(fill_tile(B, Ho, Wo, S, cinp, coutp, ov[0], ov[1], ov[2], ov[3], &tc), HP_ERR_INVALID,
+                     "tile override %dx%dx%d nbuf %d is not valid for block %d", ov[0], ov[1], ov[2], ov[3], i);
+        } else {
+          HP_REQUIRE(choose_tile(B, Ho, Wo, S, cinp, coutp, &tc), HP_ERR_UNSUPPORTED,
+                     "no tile configuration for block %d at %dx%d", i, Ho, Wo);
+        }
+        if (h->tile_report) {
+          int* r = h->tile_report + 8 * i;
+          r[0] = tc.TH; r[1] = tc.TW; r[2] = tc.IMGS; r[3] = tc.nbuf; r[4] = tc.threads; r[5] = (int)tc.smem; r[6] = tc.n_tiles; r[7] = 8;
+        }
       } else {
-        HP_REQUIRE(choose_tile(B, Ho, Wo, S, cinp, coutp, &tc), HP_ERR_UNSUPPORTED,
-                   "no tile configuration for block %d at %dx%d", i, Ho, Wo);
-      }
-      if (h->tile_report) {
-        int* r = h->tile_report + 8 * i;
-        r[0] = tc.TH; r[1] = tc.TW; r[2] = tc.IMGS; r[3] = tc.nbuf; r[4] = tc.threads; r[5] = (int)tc.smem; r[6] = tc.n_tiles; r[7] = tc.PG;
+        if (ov[0] > 0) {
+          HP_REQUIRE(hp_tile2_fill(B, Ho, Wo, S, cinp, coutp, ov[0], ov[1], ov[2], ov[3], ov[4] ? ov[4] : 8, &tc2), HP_ERR_INVALID,
+                     "tile override %dx%dx%d nbuf %d MT %d is not valid for block %d", ov[0], ov[1], ov[2], ov[3], ov[4], i);
+        } else {
+          HP_REQUIRE(hp_tile2_choose(B, Ho, Wo, S, cinp, coutp, &tc2), HP_ERR_UNSUPPORTED,
+                     "no tile configuration for block %d at %dx%d", i, Ho, Wo);
+        }
+        if (h->tile_report) {
+          int* r = h->tile_report + 8 * i;
+          r[0] = tc2.TH; r[1] = tc2.TW; r[2] = tc2.IMGS; r[3] = tc2.nbuf; r[4] = tc2.threads; r[5] = (int)tc2.smem; r[6] = tc2.n_tiles; r[7] = tc2.MT;
+        }
       }
     }
     for (int it = 0; it < iters; ++it) {
@@ -764,6 +780,8 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         pw_naive_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(bb.dwtmp.f(), cur, bb.blk[i].pww, bb.blk[i].pwb, out,
                                                                     B, Hi, Wi, Ho, Wo, cinp, coutp, S);
         h->launches += 2;
+      } else if (!v1) {
+        HP_TRY(hp_launch_block_tma(h, i, cur, out, B, Hi, Wi, Ho, Wo, pts[i], pls[i], bb.blk[i], tc2, st));
       } else {
         BlkParams bp;
         bp.in = cur; bp.out = out;

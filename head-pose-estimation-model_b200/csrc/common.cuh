@@ -108,7 +108,7 @@ struct hp_ctx {
   DevBuf pose16, pose8, cls, loc;  // unified-path internals
   DevBuf scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
-  int tile_override[16][4] = {};   // TH, TW, IMGS, nbuf per block (0 = automatic)
+  int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
   int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
 };
 
@@ -130,3 +130,15 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
                     int prof_iters, cudaStream_t st);
 
 int hp_comm_allreduce_sum(hp_ctx* h, float* buf, size_t n, cudaStream_t st);
+
+// blocks_tma.cu: second-generation fused BlazeBlock kernel (TMA tile load/store)
+struct Tile2Cfg {
+  int TH, TW, IMGS, MT, nbuf, PG, TP, threads, IH, IW, tiles_y, tiles_x, n_tiles, n_runs, rpr;
+  int in_tile_floats, off_w, off_tab, off_dw, off_in;
+  size_t smem;
+};
+bool hp_tile2_fill(int B, int Hout, int Wout, int S, int CINP, int COUTP, int TH, int TW, int IMGS, int nbuf, int MT,
+                   Tile2Cfg* tc);
+bool hp_tile2_choose(int B, int Hout, int Wout, int S, int CINP, int COUTP, Tile2Cfg* best);
+int hp_launch_block_tma(hp_ctx* h, int blk, const float* in, float* out, int B, int Hin, int Win, int Hout, int Wout,
+                        int pad_t, int pad_l, const BlockWeights& w, const Tile2Cfg& tc, cudaStream_t st);

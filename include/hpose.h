@@ -39,9 +39,10 @@ enum hp_status {
 #define HP_MAX_FACES 100          /* MAX_FACE_NUM, blazeFaceDetectorH5.py:9                    */
 #define HP_KEYPOINTS 6            /* KEY_POINT_SIZE, blazeFaceDetectorH5.py:8                  */
 
-/* kernel family selector for the backbone: FAST = fused BlazeBlock kernels (product path),
- * NAIVE = one-thread-per-output CUDA kernels kept as an on-device cross-check.  Both are CUDA. */
-enum hp_impl { HP_IMPL_FAST = 0, HP_IMPL_NAIVE = 1 };
+/* kernel family selector for the backbone (all CUDA): FAST = fused BlazeBlock kernels with TMA tile
+ * load/store (product path), NAIVE = one-thread-per-output kernels kept as an on-device cross-check,
+ * CPASYNC = first-generation fused kernels (cp.async tiles), kept for A/B measurements. */
+enum hp_impl { HP_IMPL_FAST = 0, HP_IMPL_NAIVE = 1, HP_IMPL_CPASYNC = 2 };
 
 const char* hp_last_error(void);
 int hp_version(void);
@@ -204,9 +205,10 @@ int hp_fma_peak(hp_handle h, int mode, double* tflops_out);
  * the launch stream); per_layer_ms may be NULL or float[18] = stem, 16 blocks, det heads */
 int hp_backbone_profile(hp_handle h, const float* x, int B, int H, int W, int iters, float* per_layer_ms);
 
-/* tuning hooks: force the tile shape of one BlazeBlock kernel (TH=0 restores the heuristic) and have
- * the forward pass record {TH,TW,IMGS,nbuf,threads,smem,n_tiles,PG} per block into report16x8 (host int[128]) */
-int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf);
+/* tuning hooks: force the tile shape of one BlazeBlock kernel (TH=0 restores the heuristic; MT = pixels
+ * per thread, 4 or 8) and have the forward pass record {TH,TW,IMGS,nbuf,threads,smem,n_tiles,MT} per block
+ * into report16x8 (host int[128]) */
+int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf, int MT);
 int hp_debug_tile_report(hp_handle h, int* report16x8);
 
 #ifdef __cplusplus

@@ -38,7 +38,7 @@ def _read_act(ctx, xt, blk, shape):
     return dst.cpu().numpy()
 
 
-@pytest.mark.parametrize("impl", ["naive", "fast"])
+@pytest.mark.parametrize("impl", ["naive", "fast", "cpasync"])
 def test_trained_weights_128_all_layers(impl):
     """Shipped detector weights, reference input size; every block output is compared."""
     from hpose_b200 import _lib
@@ -47,7 +47,7 @@ def test_trained_weights_128_all_layers(impl):
     kat = np.load(os.path.join(GOLDEN, "unified_kat.npz"))
     x = kat["x"]
     ctx = _ctx()
-    ctx.set_impl(_lib.HP_IMPL_NAIVE if impl == "naive" else _lib.HP_IMPL_FAST)
+    ctx.set_impl({"naive": _lib.HP_IMPL_NAIVE, "fast": _lib.HP_IMPL_FAST, "cpasync": _lib.HP_IMPL_CPASYNC}[impl])
     try:
         flat = pack_backbone(w)
         _lib.check(_lib.lib().hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
@@ -115,7 +115,7 @@ def test_random_weights_fast_equals_naive_large_batch():
     x = torch.rand((B, S, S, 3), generator=g, device="cuda") * 2 - 1
     A = _lib.lib().hp_num_anchors(S, S)
     res = {}
-    for impl in (_lib.HP_IMPL_NAIVE, _lib.HP_IMPL_FAST):
+    for impl in (_lib.HP_IMPL_NAIVE, _lib.HP_IMPL_FAST, _lib.HP_IMPL_CPASYNC):
         ctx.set_impl(impl)
         f16 = torch.empty((B, 12, 12, 88), device="cuda"); f8 = torch.empty((B, 6, 6, 96), device="cuda")
         cls = torch.empty((B, A), device="cuda"); loc = torch.empty((B, A, 16), device="cuda")
@@ -124,8 +124,9 @@ def test_random_weights_fast_equals_naive_large_batch():
         torch.cuda.synchronize()
         res[impl] = [t.cpu().numpy() for t in (f16, f8, cls, loc)]
     ctx.set_impl(_lib.HP_IMPL_FAST)
-    for a, b, n in zip(res[_lib.HP_IMPL_FAST], res[_lib.HP_IMPL_NAIVE], ("feat16", "feat8", "cls", "loc")):
-        assert rel_err(a, b) < 2e-5, n
+    for impl in (_lib.HP_IMPL_FAST, _lib.HP_IMPL_CPASYNC):
+        for a, b, n in zip(res[impl], res[_lib.HP_IMPL_NAIVE], ("feat16", "feat8", "cls", "loc")):
+            assert rel_err(a, b) < 2e-5, (impl, n)
     # oracle on the first two images
     K.reset_names()
     dummy16 = K.Model(*(lambda i: (i, K.Conv2D(3, 1)(i)))(K.Input((None, None, 88))))

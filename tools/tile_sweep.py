@@ -23,20 +23,28 @@ def cd(a, b):
     return -(-a // b)
 
 
-def valid(Hout, Wout, S, cin, cout, TH, TW, IMGS, nbuf):
+def au(v, a=32):
+    return cd(v, a) * a
+
+
+def valid(Hout, Wout, S, cin, cout, TH, TW, IMGS, nbuf, MT):
     CINP, COUTP = (cin + 3) & ~3, (cout + 3) & ~3
     NG, C4 = COUTP // 4, CINP // 4
     TP = TH * TW * IMGS
-    if TH < 1 or TW < 1 or TH > Hout or TW > Wout or TP < 32 or TP > 256:
+    if TH < 1 or TW < 1 or TH > Hout or TW > Wout or TP < 32 or TP > 512:
         return False
-    PG = cd(TP, 8)
+    PG = cd(TP, MT)
     thr = cd(PG * NG, 32) * 32
     if thr > 512 or thr < C4:
         return False
     IH, IW = (TH - 1) * S + 3, (TW - 1) * S + 3
     DWS = CINP if C4 & 1 else CINP + 4
-    smem = (CINP * COUTP + COUTP + 10 * CINP + PG * 8 * DWS + nbuf * IMGS * IH * IW * CINP) * 4
-    return smem <= 227 * 1024
+    off = 32
+    off = au(off + CINP * COUTP + COUTP + 10 * CINP)
+    off = au(off + 2 * IMGS * TH * cd(TW, 4) + PG * MT)
+    off = au(off + max(PG * MT * DWS, TP * COUTP))
+    off += nbuf * au(IMGS * IH * IW * CINP) + au((4 * S + 3) * CINP)
+    return off * 4 <= 227 * 1024
 
 
 def candidates(Hout, Wout, S, cin, cout):
@@ -45,12 +53,13 @@ def candidates(Hout, Wout, S, cin, cout):
     tws = {Wout, cd(Wout, 2), cd(Wout, 3), cd(Wout, 4), 4, 6, 8, 12, 16, 24, 32}
     for TH in ths:
         for TW in tws:
-            for IMGS in (1, 2, 3, 4, 6):
+            for IMGS in (1, 2, 3, 4, 6, 8):
                 if IMGS > 1 and (TH != Hout or TW != Wout):
                     continue
                 for nbuf in (1, 2):
-                    if valid(Hout, Wout, S, cin, cout, TH, TW, IMGS, nbuf):
-                        out.add((TH, TW, IMGS, nbuf))
+                    for MT in (4, 8):
+                        if valid(Hout, Wout, S, cin, cout, TH, TW, IMGS, nbuf, MT):
+                            out.add((TH, TW, IMGS, nbuf, MT))
     return sorted(out)
 
 
@@ -91,7 +100,7 @@ def main():
             c = cands[i][r % len(cands[i])]
             results[i][",".join(map(str, c))] = float(per[1 + i])
     for i in range(16):
-        lib.hp_debug_set_tile(ctx.handle, i, 0, 0, 0, 0)
+        lib.hp_debug_set_tile(ctx.handle, i, 0, 0, 0, 0, 0)
     best_total = float(per[0])
     summary = []
     for i in range(16):
@@ -99,7 +108,7 @@ def main():
         summary.append({"block": i, "heuristic_ms": base["per_layer_ms"][1 + i], "heuristic_tile": base["tiles"][i],
                         "best": ranked[:6], "worst": ranked[-2:]})
         best_total += ranked[0][1] if ranked else base["per_layer_ms"][1 + i]
-        print(i, BLOCKS[i], "heur", round(base["per_layer_ms"][1 + i], 4), base["tiles"][i][:4], "best", ranked[:4])
+        print(i, BLOCKS[i], "heur", round(base["per_layer_ms"][1 + i], 4), base["tiles"][i], "best", ranked[:4])
     print("stem", base["per_layer_ms"][0], "sum-of-best", best_total, "heuristic total", sum(base["per_layer_ms"][:17]))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"tile_sweep_{size}.json"), "w") as f:
