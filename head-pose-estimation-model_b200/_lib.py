@@ -14,14 +14,14 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhpose.so")
-SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "heads.cu", "postproc.cu", "comm.cu"]
+SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
 HP_BACKBONE_PARAMS = 101390
 HP_MAX_FACES = 100
 HP_KEYPOINTS = 6
-HP_IMPL_FAST, HP_IMPL_NAIVE, HP_IMPL_CPASYNC = 0, 1, 2
+HP_IMPL_FAST, HP_IMPL_NAIVE, HP_IMPL_CPASYNC, HP_IMPL_TMA = 0, 1, 2, 3
 (HP_OP_DENSE, HP_OP_ACT, HP_OP_ADD, HP_OP_MULCH, HP_OP_GAP, HP_OP_DROPOUT, HP_OP_LAYERNORM,
  HP_OP_MHA) = range(1, 9)
 HP_ACT = {"linear": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3, "softsign": 4}
@@ -120,6 +120,7 @@ _PROTOS = {
     "hp_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "hp_debug_set_tile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_debug_tile_report": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hp_debug_set_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_backbone_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

@@ -74,7 +74,7 @@ int hp_destroy(hp_handle h) {
 }
 
 int hp_set_impl(hp_handle h, int impl) {
-  HP_REQUIRE(h && impl >= HP_IMPL_FAST && impl <= HP_IMPL_CPASYNC, HP_ERR_INVALID, "hp_set_impl: bad arguments");
+  HP_REQUIRE(h && impl >= HP_IMPL_FAST && impl <= HP_IMPL_TMA, HP_ERR_INVALID, "hp_set_impl: bad arguments");
   h->impl = impl;
   return HP_OK;
 }
@@ -114,6 +114,11 @@ int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf, 
   HP_REQUIRE(h && blk >= 0 && blk < 16, HP_ERR_INVALID, "hp_debug_set_tile: bad arguments");
   h->tile_override[blk][0] = TH; h->tile_override[blk][1] = TW; h->tile_override[blk][2] = IMGS; h->tile_override[blk][3] = nbuf;
   h->tile_override[blk][4] = MT;
+  return HP_OK;
+}
+int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe) {
+  HP_REQUIRE(h && blk >= 0 && blk < 16, HP_ERR_INVALID, "hp_debug_set_tc: bad arguments");
+  h->tc_override[blk][0] = TR; h->tc_override[blk][1] = NSTG; h->tc_override[blk][2] = BH; h->tc_override[blk][3] = npipe;
   return HP_OK;
 }
 int hp_debug_tile_report(hp_handle h, int* report16x8) {

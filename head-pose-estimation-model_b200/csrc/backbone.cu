@@ -575,7 +575,7 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
   size_t o_stem_b = reserve(24);
   memcpy(&host[o_stem_b], src + cur, 24 * sizeof(float));
   cur += 24;
-  size_t o_dww[16], o_dwb[16], o_pww[16], o_pwb[16];
+  size_t o_dww[16], o_dwb[16], o_pww[16], o_pwb[16], o_bhi[16], o_blo[16];
   for (int i = 0; i < 16; ++i) {
     const int cin = kBlazeBlocks[i].cin, cout = kBlazeBlocks[i].cout;
     const int cinp = chan_pad(cin), coutp = chan_pad(cout);
@@ -593,6 +593,13 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
     o_pwb[i] = reserve(coutp);
     for (int c = 0; c < cout; ++c) host[o_pwb[i] + c] = src[cur + c];
     cur += cout;
+    const int ntc = hp_tc_weight_floats(cinp, coutp);
+    o_bhi[i] = reserve(ntc);
+    o_blo[i] = reserve(ntc);
+    {
+      std::vector<float> pw(host.begin() + o_pww[i], host.begin() + o_pww[i] + (size_t)cinp * coutp);
+      hp_tc_split_weights(pw.data(), cinp, coutp, &host[o_bhi[i]], &host[o_blo[i]]);
+    }
   }
   // detector heads: concatenate cls|loc per tap
   const float* cls16_k = src + cur; cur += 88 * 2;
@@ -630,6 +637,8 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
     bb.blk[i].dwb = base + o_dwb[i];
     bb.blk[i].pww = base + o_pww[i];
     bb.blk[i].pwb = base + o_pwb[i];
+    bb.blk[i].bhi = base + o_bhi[i];
+    bb.blk[i].blo = base + o_blo[i];
   }
   bb.det16_w = base + o_d16w;
   bb.det16_b = base + o_d16b;
@@ -741,8 +750,24 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
     const int Hi = hs[i], Wi = ws[i], Ho = hs[i + 1], Wo = ws[i + 1];
     TileCfg tc;
     Tile2Cfg tc2;
+    TcCfg tcc;
     const bool v1 = (h->impl == HP_IMPL_CPASYNC);
-    if (!naive) {
+    bool use_tc = false;
+    if (h->impl == HP_IMPL_FAST && S == 1 && h->tc_override[i][0] >= 0 && hp_tc_choose(i, Ho, Wo, &tcc)) {
+      use_tc = (i == 0 || i == 1 || i == 3 || i == 4);
+      const int* tv = h->tc_override[i];
+      if (use_tc && tv[0] > 0) {
+        tcc.TR = tv[0];
+        if (tv[1] > 0) tcc.NSTG = tv[1];
+        if (tv[2] > 0) tcc.BH = tv[2];
+        if (tv[3] > 0) tcc.npipe = tv[3];
+      }
+      if (use_tc && h->tile_report) {
+        int* r = h->tile_report + 8 * i;
+        r[0] = tcc.TR; r[1] = tcc.BH; r[2] = tcc.IWB; r[3] = tcc.NSTG; r[4] = tcc.npipe * 160; r[5] = 0; r[6] = 0; r[7] = -1;
+      }
+    }
+    if (!naive && !use_tc) {
       const int* ov = h->tile_override[i];
       if (v1) {
         if (ov[0] > 0) {
@@ -780,6 +805,8 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         pw_naive_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(bb.dwtmp.f(), cur, bb.blk[i].pww, bb.blk[i].pwb, out,
                                                                     B, Hi, Wi, Ho, Wo, cinp, coutp, S);
         h->launches += 2;
+      } else if (use_tc) {
+        HP_TRY(hp_launch_block_tc(h, i, cur, out, B, Ho, Wo, bb.blk[i], tcc, st));
       } else if (!v1) {
         HP_TRY(hp_launch_block_tma(h, i, cur, out, B, Hi, Wi, Ho, Wo, pts[i], pls[i], bb.blk[i], tc2, st));
       } else {

@@ -1,0 +1,529 @@
+// Fused BlazeBlock kernel, third generation: the pointwise 1x1 conv runs on the tcgen05 tensor cores as a
+// 3xTF32 GEMM (fp32-level accuracy), everything else of the block stays fused around it.
+//
+// Why: ncu on the CUDA-core kernels (profiles/r01) shows the backbone bound by fp32 FMA issue, not HBM: the
+// pointwise convs are 83 % of the MACs.  Moving them to the tensor pipe leaves the CUDA cores the depthwise 3x3
+// (9 FMA per element) and the HBM roofline becomes reachable.  Plain TF32 (10-bit mantissa) cannot meet the 1e-4
+// parity bound, so every product is split: a = a_hi + a_lo, w = w_hi + w_lo (each part TF32-representable),
+// D += a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation in TMEM; the dropped a_lo*w_lo term is ~2^-22.
+//
+// Per CTA (persistent, 1 per SM): NPIPE independent pipelines, each = 4 worker warps (thread <-> TMEM lane) + 1 issuer warp.
+//   tile     : one band of BH output rows x full width W of one image; lane l <-> (strip yq = l / W, column x = l % W),
+//              a lane owns the TR output pixels (yq*TR + t, x), t < TR; pixel t of every lane forms M-tile t.
+//   load     : one TMA (cp.async.bulk.tensor.4d) per tile: box {PS, IWB, BH+2, 1} at (0, -1, y0-1, img).  PS > C pads the
+//              pixel stride to an odd number of 16-byte chunks (bank-conflict-free column access), out-of-range
+//              rows / columns / channels are zero-filled by the hardware (= SAME padding).
+//   depthwise: per k-step (8 channels) each lane slides a 3x3 window down its column (TR+2 rows, 3 LDS.128 per row and
+//              chunk), splits the result into hi/lo and stores 16 columns per M-tile into a TMEM ring stage (tcgen05.st).
+//   pointwise: the issuer thread fires 3 x TR tcgen05.mma (A from TMEM, W_hi / W_lo from smem, K-major no-swizzle
+//              descriptors) per k-step into TR accumulators D_t[128 x N16]; tcgen05.commit frees the ring stage.
+//   epilogue : tcgen05.ld D_t -> + bias + skip (centre pixel of the halo tile) -> ReLU -> written IN PLACE over the centre
+//              pixel (PS >= COUTP) -> one TMA store of the band interior (box {PS, IWB, BH, 1}, clipped to C x W x H).
+//
+// Reference semantics: BlazeBlock = DepthwiseConv2D(3x3, SAME) -> Conv2D(1x1) -> Add(skip / channel-padded skip) -> ReLU
+// (graph called at BlazePoser/blazeFaceDetectorH5.py:272).  Stride-1 blocks only.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: never hang the device on a lost signal
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+               ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], tf32 inputs, fp32 accumulate, M = 128
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_addr, uint32_t a_addr, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_addr), "r"(a_addr), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+               "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(addr));
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+// ---------------------------------------------------------------------------- compile-time geometry
+template <int CINP, int COUTP>
+struct TcGeom {
+  static constexpr int C4 = CINP / 4;
+  static constexpr int NG = COUTP / 4;
+  static constexpr int K8 = (CINP + 7) / 8 * 8;
+  static constexpr int KS = K8 / 8;
+  static constexpr int N16 = (COUTP + 15) / 16 * 16;
+  static constexpr int PSC = ((C4 > NG ? C4 : NG) | 1);   // pixel stride in 16-byte chunks: odd, >= both channel counts
+  static constexpr int PS = PSC * 4;                      // ... in floats
+};
+
+struct TcParams {
+  const float *dww, *dwb, *pwb;   // depthwise [9][CINP], [CINP]; pointwise bias [COUTP]
+  const float *bhi, *blo;         // pointwise weights split hi / lo, each [K8/4][N16][4] (K-major core matrices)
+  int W, H, BH, IWB, row_pitch;   // row_pitch = IWB * PS floats
+  int bands_per_img, n_tiles, lanes, npipe;
+  uint32_t load_bytes;
+  int off_b, off_w, off_pipe, buf_floats;   // shared-memory layout in floats (buffers 1024-byte aligned)
+};
+
+#define TC_MAX_PIPE 2
+#define TC_MAX_STG 4
+
+template <int CINP, int COUTP, int TR, int NSTG>
+__global__ void __launch_bounds__(TC_MAX_PIPE * 160, 1)
+blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcParams p) {
+  using G = TcGeom<CINP, COUTP>;
+  constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
+  constexpr int TCOLS = TR * N16 + NSTG * TR * 16;   // TMEM columns per pipeline: TR accumulators + the A ring
+  static_assert(TC_MAX_PIPE * TCOLS <= 512 || TCOLS <= 512, "TMEM budget");
+  static_assert(NSTG <= TC_MAX_STG, "ring depth");
+
+  extern __shared__ __align__(1024) float smem[];
+  // barrier block (first 256 bytes): per pipeline full, d_full, a_full[NSTG], a_empty[NSTG]; tmem base at byte 248
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + 62;
+  float* s_bhi = smem + p.off_b;
+  float* s_blo = s_bhi + K8 * N16;
+  float* s_dww = smem + p.off_w;
+  float* s_dwb = s_dww + 9 * CINP;
+  float* s_pwb = s_dwb + CINP;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane_id = tid & 31;
+  const int npipe = p.npipe;
+  const int n_work_warps = 4 * npipe;
+
+  for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
+    st4(s_bhi + i, ld4(p.bhi + i));
+    st4(s_blo + i, ld4(p.blo + i));
+  }
+  for (int i = tid * 4; i < 9 * CINP; i += nthr * 4) st4(s_dww + i, ld4(p.dww + i));
+  for (int i = tid * 4; i < CINP; i += nthr * 4) st4(s_dwb + i, ld4(p.dwb + i));
+  for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
+  fence_async_smem();   // the tensor core reads s_bhi / s_blo through the async proxy
+  if (tid == 0) {
+    for (int q = 0; q < npipe; ++q) {
+      uint64_t* b = bars + q * (2 + 2 * TC_MAX_STG);
+      mbar_init(&b[0], 1);                                     // full: TMA load landed
+      mbar_init(&b[1], 1);                                     // d_full: all MMAs of the tile done
+      for (int s = 0; s < NSTG; ++s) {
+        mbar_init(&b[2 + s], 128);                             // a_full[s]: every worker stored its A rows
+        mbar_init(&b[2 + TC_MAX_STG + s], 1);                  // a_empty[s]: MMAs that read stage s are done
+      }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == n_work_warps) {   // first issuer warp owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+
+  const int tile_stride = gridDim.x * npipe;
+
+  if (warp < n_work_warps) {
+    // =============================================================== worker: depthwise -> TMEM, epilogue
+    const int pipe = warp >> 2;
+    const int wq = warp & 3;
+    const int wtid = tid - pipe * 128;           // 0..127 = TMEM lane
+    uint64_t* b = bars + pipe * (2 + 2 * TC_MAX_STG);
+    uint64_t* bar_full = &b[0];
+    uint64_t* bar_dfull = &b[1];
+    uint64_t* bar_afull = &b[2];
+    uint64_t* bar_aempty = &b[2 + TC_MAX_STG];
+    float* buf = smem + p.off_pipe + pipe * p.buf_floats;
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(pipe * TCOLS);
+    const uint32_t colA0 = TR * N16;
+    const bool active = wtid < p.lanes;
+    const bool warp_active = wq * 32 < p.lanes;
+    const int l = active ? wtid : 0;
+    const int yq = l / p.W;
+    const int x = l - yq * p.W;
+    const int row_pitch = p.row_pitch;
+    const int my_off = yq * TR * row_pitch + x * PS;    // top-left pixel of the 3x3 window of output row yq*TR
+    const int centre0 = my_off + row_pitch + PS;        // centre pixel of output row yq*TR
+
+    auto tile_coords = [&](int tile, int& img, int& y0) {
+      img = tile / p.bands_per_img;
+      y0 = (tile - img * p.bands_per_img) * p.BH;
+    };
+    auto issue_load = [&](int tile) {   // wtid == 0 only
+      int img, y0;
+      tile_coords(tile, img, y0);
+      mbar_expect_tx(bar_full, p.load_bytes);
+      tma_load_4d(buf, &tm_in, bar_full, 0, -1, y0 - 1, img);
+    };
+
+    int tile = blockIdx.x * npipe + pipe;
+    if (wtid == 0 && tile < p.n_tiles) issue_load(tile);
+    uint32_t use = 0;
+    for (int it = 0; tile < p.n_tiles; tile += tile_stride, ++it) {
+      const int next = tile + tile_stride;
+      mbar_wait(bar_full, it & 1);
+      if (wtid == 0 && next < p.n_tiles) {   // warm L2 for the next tile of this pipeline (its buffer is still in use)
+        int img, y0;
+        tile_coords(next, img, y0);
+        tma_prefetch_4d(&tm_in, 0, -1, y0 - 1, img);
+      }
+
+      // ---------------- depthwise 3x3 (+bias) -> hi/lo split -> TMEM ring stage, one k-step (8 channels) at a time
+#pragma unroll 1
+      for (int ks = 0; ks < KS; ++ks, ++use) {
+        const uint32_t s = use % NSTG;
+        if (use >= NSTG) {
+          mbar_wait(&bar_aempty[s], ((use / NSTG) - 1) & 1);
+          tc_fence_after();
+        }
+        if (warp_active) {
+          uint32_t av[TR][16];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int c4 = 2 * ks + half;
+            if (c4 < C4) {
+              const float* win = buf + my_off + c4 * 4;
+              float4 w[9];
+#pragma unroll
+              for (int k = 0; k < 9; ++k) w[k] = ld4(s_dww + k * CINP + c4 * 4);
+              const float4 bias = ld4(s_dwb + c4 * 4);
+              float4 acc[TR];
+#pragma unroll
+              for (int t = 0; t < TR; ++t) acc[t] = bias;
+#pragma unroll
+              for (int r = 0; r < TR + 2; ++r) {
+                const float* row = win + r * row_pitch;
+                const float4 v0 = ld4(row), v1 = ld4(row + PS), v2 = ld4(row + 2 * PS);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                  const int t = r - ky;
+                  if (t >= 0 && t < TR) {
+                    acc[t] = fma4(v0, w[ky * 3 + 0], acc[t]);
+                    acc[t] = fma4(v1, w[ky * 3 + 1], acc[t]);
+                    acc[t] = fma4(v2, w[ky * 3 + 2], acc[t]);
+                  }
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < TR; ++t) {
+                const float a[4] = {acc[t].x, acc[t].y, acc[t].z, acc[t].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t hi = to_tf32(a[e]);
+                  av[t][half * 4 + e] = hi;
+                  av[t][8 + half * 4 + e] = to_tf32(a[e] - __uint_as_float(hi));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < TR; ++t)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  av[t][half * 4 + e] = 0u;
+                  av[t][8 + half * 4 + e] = 0u;
+                }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < TR; ++t) tmem_st16(tlane + colA0 + (s * TR + t) * 16, av[t]);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        }
+        mbar_arrive(&bar_afull[s]);
+      }
+
+      // ---------------- epilogue: D_t + bias + skip -> ReLU -> in place over the centre pixel
+      mbar_wait(bar_dfull, it & 1);
+      tc_fence_after();
+      if (warp_active) {
+#pragma unroll
+        for (int t = 0; t < TR; ++t) {
+          float* cpix = buf + centre0 + t * row_pitch;
+#pragma unroll
+          for (int g = 0; g < N16 / 16; ++g) {
+            if (g * 4 < NG) {
+              uint32_t v[16];
+              tmem_ld16(tlane + t * N16 + g * 16, v);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = g * 4 + jj;
+                if (j < NG) {
+                  const float4 bb = ld4(s_pwb + j * 4);
+                  float4 o = make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
+                                         __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
+                  if (j < C4) {
+                    const float4 sk = ld4(cpix + j * 4);
+                    o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                  }
+                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                  if (active) st4(cpix + j * 4, o);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+      }
+      named_bar_sync(1 + pipe, 128);
+      if (wtid == 0) {
+        int img, y0;
+        tile_coords(tile, img, y0);
+        tma_store_4d(&tm_out, buf + row_pitch + PS, 0, 0, y0, img);
+        tma_store_commit();
+        tma_store_wait_read();            // the band has left shared memory: the buffer may be refilled
+        if (next < p.n_tiles) issue_load(next);
+      }
+    }
+    if (wtid == 0) tma_store_wait_all();
+  } else if (lane_id == 0) {
+    // =============================================================== issuer: tcgen05.mma for one pipeline
+    const int pipe = warp - n_work_warps;
+    uint64_t* b = bars + pipe * (2 + 2 * TC_MAX_STG);
+    uint64_t* bar_dfull = &b[1];
+    uint64_t* bar_afull = &b[2];
+    uint64_t* bar_aempty = &b[2 + TC_MAX_STG];
+    const uint32_t tcol = tmem_base + (uint32_t)(pipe * TCOLS);
+    const uint32_t colA0 = TR * N16;
+    // instruction descriptor: D fp32, A/B tf32, both K-major, N = N16, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // smem descriptor of a [N16 rows][8 k] slice: core matrix = 8 rows x 16 B; LBO (next 4 k) = N16*16 B, SBO (next 8 rows) = 128 B
+    const uint64_t desc_fixed = ((uint64_t)(((uint32_t)(N16 * 16) >> 4) & 0x3FFF) << 16) | ((uint64_t)((128u >> 4) & 0x3FFF) << 32) |
+                                ((uint64_t)1 << 46);
+    const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
+    uint32_t use = 0;
+    for (int tile = blockIdx.x * npipe + pipe; tile < p.n_tiles; tile += tile_stride) {
+#pragma unroll 1
+      for (int ks = 0; ks < KS; ++ks, ++use) {
+        const uint32_t s = use % NSTG;
+        mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+        tc_fence_after();
+        const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
+        const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
+        const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+#pragma unroll
+        for (int t = 0; t < TR; ++t) {
+          const uint32_t d = tcol + t * N16;
+          const uint32_t a = tcol + colA0 + (s * TR + t) * 16;
+          mma_tf32_ts(d, a, dhi, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32_ts(d, a, dlo, idesc, 1u);
+          mma_tf32_ts(d, a + 8, dhi, idesc, 1u);
+        }
+        tc_commit(&bar_aempty[s]);
+      }
+      tc_commit(bar_dfull);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == n_work_warps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+
+int get_encode() {
+  if (g_encode) return HP_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  HP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  HP_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, HP_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+  g_encode = (PFN_encodeTiled)fn;
+  return HP_OK;
+}
+
+// NHWC float tensor [N][H][W][C] with box [bn][bh][bw][bc]; bc may exceed C (padded pixel stride in smem)
+int make_map(CUtensorMap* tm, const float* base, int N, int H, int W, int C, int bn, int bh, int bw, int bc) {
+  HP_TRY(get_encode());
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HP_REQUIRE(r == CUDA_SUCCESS, HP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for tensor %dx%dx%dx%d box %dx%dx%dx%d", (int)r, N,
+             H, W, C, bn, bh, bw, bc);
+  return HP_OK;
+}
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+template <int CINP, int COUTP, int TR, int NSTG>
+int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
+  using G = TcGeom<CINP, COUTP>;
+  constexpr int TCOLS = TR * G::N16 + NSTG * TR * 16;
+  HP_REQUIRE(tc.npipe >= 1 && tc.npipe <= TC_MAX_PIPE && tc.npipe * TCOLS <= 512, HP_ERR_INVALID,
+             "tc block <%d,%d,%d,%d>: %d pipelines x %d TMEM columns exceed 512", CINP, COUTP, TR, NSTG, tc.npipe, TCOLS);
+  TcParams p;
+  p.dww = w.dww; p.dwb = w.dwb; p.pwb = w.pwb; p.bhi = w.bhi; p.blo = w.blo;
+  p.W = W; p.H = H; p.BH = tc.BH; p.IWB = tc.IWB; p.row_pitch = tc.IWB * G::PS;
+  p.bands_per_img = ceil_div(H, tc.BH);
+  p.n_tiles = B * p.bands_per_img;
+  p.lanes = (tc.BH / TR) * W;
+  p.npipe = tc.npipe;
+  p.load_bytes = (uint32_t)((size_t)G::PS * tc.IWB * (tc.BH + 2) * sizeof(float));
+  int off = 64;                                   // 256 bytes: barriers + tmem base
+  p.off_b = off;
+  off = align_up(off + 2 * G::K8 * G::N16, 32);
+  p.off_w = off;
+  off = align_up(off + 10 * CINP + COUTP, 256);
+  p.off_pipe = off;
+  p.buf_floats = align_up(G::PS * tc.IWB * (tc.BH + 2), 256);
+  const size_t smem = (size_t)(off + tc.npipe * p.buf_floats) * sizeof(float);
+  HP_REQUIRE(smem <= 227 * 1024, HP_ERR_INVALID, "tc block <%d,%d>: %zu bytes of shared memory needed", CINP, COUTP, smem);
+  HP_REQUIRE(p.lanes >= 1 && p.lanes <= 128 && tc.BH % TR == 0 && (tc.IWB + 1) % 8 == 0 && tc.IWB >= W + 2 && tc.IWB <= 256 &&
+                 tc.BH + 2 <= 256,
+             HP_ERR_INVALID, "tc block <%d,%d>: bad band geometry BH %d IWB %d W %d", CINP, COUTP, tc.BH, tc.IWB, W);
+  CUtensorMap tin, tout;
+  HP_TRY(make_map(&tin, in, B, H, W, CINP, 1, tc.BH + 2, tc.IWB, G::PS));
+  HP_TRY(make_map(&tout, out, B, H, W, COUTP, 1, tc.BH, tc.IWB, G::PS));
+  auto kern = blaze_block_tc_kernel<CINP, COUTP, TR, NSTG>;
+  HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  long long grid = h->num_sms;
+  const long long need = ceil_div(p.n_tiles, tc.npipe);
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, tc.npipe * 160, smem, st>>>(tin, tout, p);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}
+
+template <int CINP, int COUTP>
+int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc,
+                  cudaStream_t st) {
+  if (tc.TR == 4 && tc.NSTG == 1) return launch_tc<CINP, COUTP, 4, 1>(h, in, out, B, H, W, w, tc, st);
+  if (tc.TR == 4 && tc.NSTG == 2) return launch_tc<CINP, COUTP, 4, 2>(h, in, out, B, H, W, w, tc, st);
+  if (tc.TR == 2 && tc.NSTG == 2) return launch_tc<CINP, COUTP, 2, 2>(h, in, out, B, H, W, w, tc, st);
+  hp_set_error("tc block: no kernel for TR %d NSTG %d", tc.TR, tc.NSTG);
+  return HP_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+// Split pointwise weights [CINP][COUTP] (row-major, zero padded) into TF32 hi / lo parts laid out [K8/4][N16][4].
+void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, float* blo) {
+  const int K8 = (cinp + 7) / 8 * 8, N16 = (coutp + 15) / 16 * 16;
+  auto rna = [](float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;   // round to nearest, ties away (cvt.rna.tf32.f32)
+    u &= 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+  };
+  for (int k = 0; k < K8; ++k)
+    for (int n = 0; n < N16; ++n) {
+      const float wv = (k < cinp && n < coutp) ? pww[k * coutp + n] : 0.f;
+      const float hi = rna(wv), lo = rna(wv - hi);
+      const size_t idx = ((size_t)(k / 4) * N16 + n) * 4 + (k % 4);
+      bhi[idx] = hi;
+      blo[idx] = lo;
+    }
+}
+
+int hp_tc_weight_floats(int cinp, int coutp) { return ((cinp + 7) / 8 * 8) * ((coutp + 15) / 16 * 16); }
+
+// Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.
+bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
+  const int cinp = chan_pad(kBlazeBlocks[blk].cin), coutp = chan_pad(kBlazeBlocks[blk].cout);
+  if (kBlazeBlocks[blk].stride != 1 || W + 2 > 255 || W > 128 || H < 1) return false;
+  const int C4 = cinp / 4, NG = coutp / 4, N16 = (coutp + 15) / 16 * 16, K8 = (cinp + 7) / 8 * 8;
+  const int PS = ((C4 > NG ? C4 : NG) | 1) * 4;
+  const int TR = 4;
+  int NSTG = 2, npipe = 2;
+  if (npipe * TR * (N16 + 16 * NSTG) > 512) NSTG = 1;
+  if (npipe * TR * (N16 + 16 * NSTG) > 512) return false;   // wide blocks: not tuned yet, the CUDA-core kernel runs them
+  const int strips = ceil_div(H, TR);
+  const int max_strips = 128 / W;
+  if (max_strips < 1) return false;
+  const int bands = ceil_div(strips, max_strips);
+  const int BH = ceil_div(strips, bands) * TR;
+  const int IWB = ((W + 2 + 1 + 7) / 8) * 8 - 1;   // >= W + 2 and == 7 (mod 8): the band interior starts 128-byte aligned
+  const size_t fixed = (size_t)(64 + align_up(2 * K8 * N16, 32) + align_up(10 * cinp + coutp, 256)) * 4;
+  const size_t buf = (size_t)align_up(PS * IWB * (BH + 2), 256) * 4;
+  if (fixed + npipe * buf > 227 * 1024) npipe = 1;
+  if (fixed + npipe * buf > 227 * 1024) return false;
+  tc->TR = TR; tc->NSTG = NSTG; tc->BH = BH; tc->IWB = IWB; tc->npipe = npipe;
+  return true;
+}
+
+int hp_launch_block_tc(hp_ctx* h, int blk, const float* in, float* out, int B, int H, int W, const BlockWeights& w,
+                       const TcCfg& tc, cudaStream_t st) {
+  HP_REQUIRE(w.bhi && w.blo, HP_ERR_STATE, "tc block %d: split weights missing", blk);
+  switch (blk) {
+    case 0: return launch_tc_cfg<24, 24>(h, in, out, B, H, W, w, tc, st);
+    case 1: return launch_tc_cfg<24, 28>(h, in, out, B, H, W, w, tc, st);
+    case 3: return launch_tc_cfg<32, 36>(h, in, out, B, H, W, w, tc, st);
+    case 4: return launch_tc_cfg<36, 44>(h, in, out, B, H, W, w, tc, st);
+    default: break;
+  }
+  hp_set_error("tc block: block %d has no tensor-core instantiation", blk);
+  return HP_ERR_UNSUPPORTED;
+}

@@ -76,6 +76,7 @@ static inline int chan_pad(int c) { return (c + 3) & ~3; }
 
 struct BlockWeights {
   const float *dww, *dwb, *pww, *pwb;  // [9][CINP], [CINP], [CINP][COUTP], [COUTP] (zero padded)
+  const float *bhi, *blo;              // pointwise weights split into TF32 hi / lo parts, [K8/4][N16][4] (blocks_tc.cu)
 };
 
 struct Backbone {
@@ -109,6 +110,7 @@ struct hp_ctx {
   DevBuf scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
+  int tc_override[16][4] = {};     // tensor-core kernel: TR, NSTG, BH, npipe per block (TR 0 = automatic, -1 = do not use)
   int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
 };
 
@@ -142,3 +144,13 @@ bool hp_tile2_fill(int B, int Hout, int Wout, int S, int CINP, int COUTP, int TH
 bool hp_tile2_choose(int B, int Hout, int Wout, int S, int CINP, int COUTP, Tile2Cfg* best);
 int hp_launch_block_tma(hp_ctx* h, int blk, const float* in, float* out, int B, int Hin, int Win, int Hout, int Wout,
                         int pad_t, int pad_l, const BlockWeights& w, const Tile2Cfg& tc, cudaStream_t st);
+
+// blocks_tc.cu: third-generation fused BlazeBlock kernel (depthwise on CUDA cores -> TMEM, pointwise as 3xTF32 tcgen05 GEMM)
+struct TcCfg {
+  int TR, NSTG, BH, IWB, npipe;
+};
+void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, float* blo);
+int hp_tc_weight_floats(int cinp, int coutp);
+bool hp_tc_choose(int blk, int H, int W, TcCfg* tc);
+int hp_launch_block_tc(hp_ctx* h, int blk, const float* in, float* out, int B, int H, int W, const BlockWeights& w,
+                       const TcCfg& tc, cudaStream_t st);

@@ -42,7 +42,7 @@ enum hp_status {
 /* kernel family selector for the backbone (all CUDA): FAST = fused BlazeBlock kernels with TMA tile
  * load/store (product path), NAIVE = one-thread-per-output kernels kept as an on-device cross-check,
  * CPASYNC = first-generation fused kernels (cp.async tiles), kept for A/B measurements. */
-enum hp_impl { HP_IMPL_FAST = 0, HP_IMPL_NAIVE = 1, HP_IMPL_CPASYNC = 2 };
+enum hp_impl { HP_IMPL_FAST = 0, HP_IMPL_NAIVE = 1, HP_IMPL_CPASYNC = 2, HP_IMPL_TMA = 3 };
 
 const char* hp_last_error(void);
 int hp_version(void);
@@ -210,6 +210,9 @@ int hp_backbone_profile(hp_handle h, const float* x, int B, int H, int W, int it
  * into report16x8 (host int[128]) */
 int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf, int MT);
 int hp_debug_tile_report(hp_handle h, int* report16x8);
+/* tensor-core BlazeBlock kernel (HP_IMPL_FAST, stride-1 blocks): TR rows per lane, ring depth, band height, pipelines per
+ * CTA; TR = 0 restores the defaults, TR = -1 keeps the block on the CUDA-core kernel */
+int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe);
 
 #ifdef __cplusplus
 }

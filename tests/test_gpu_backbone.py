@@ -38,7 +38,7 @@ def _read_act(ctx, xt, blk, shape):
     return dst.cpu().numpy()
 
 
-@pytest.mark.parametrize("impl", ["naive", "fast", "cpasync"])
+@pytest.mark.parametrize("impl", ["naive", "fast", "cpasync", "tma"])
 def test_trained_weights_128_all_layers(impl):
     """Shipped detector weights, reference input size; every block output is compared."""
     from hpose_b200 import _lib
@@ -47,7 +47,7 @@ def test_trained_weights_128_all_layers(impl):
     kat = np.load(os.path.join(GOLDEN, "unified_kat.npz"))
     x = kat["x"]
     ctx = _ctx()
-    ctx.set_impl({"naive": _lib.HP_IMPL_NAIVE, "fast": _lib.HP_IMPL_FAST, "cpasync": _lib.HP_IMPL_CPASYNC}[impl])
+    ctx.set_impl({"naive": _lib.HP_IMPL_NAIVE, "fast": _lib.HP_IMPL_FAST, "cpasync": _lib.HP_IMPL_CPASYNC, "tma": _lib.HP_IMPL_TMA}[impl])
     try:
         flat = pack_backbone(w)
         _lib.check(_lib.lib().hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
