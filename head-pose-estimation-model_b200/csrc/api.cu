@@ -116,9 +116,9 @@ int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf, 
   h->tile_override[blk][4] = MT;
   return HP_OK;
 }
-int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe) {
+int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, int nsets) {
   HP_REQUIRE(h && blk >= 0 && blk < 16, HP_ERR_INVALID, "hp_debug_set_tc: bad arguments");
-  h->tc_override[blk][0] = TR; h->tc_override[blk][1] = NSTG; h->tc_override[blk][2] = BH; h->tc_override[blk][3] = npipe;
+  h->tc_override[blk][0] = TR; h->tc_override[blk][1] = NSTG; h->tc_override[blk][2] = BH; h->tc_override[blk][3] = npipe; h->tc_override[blk][4] = nsets;
   return HP_OK;
 }
 int hp_debug_tile_report(hp_handle h, int* report16x8) {

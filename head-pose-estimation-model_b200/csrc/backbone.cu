@@ -761,10 +761,11 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         if (tv[1] > 0) tcc.NSTG = tv[1];
         if (tv[2] > 0) tcc.BH = tv[2];
         if (tv[3] > 0) tcc.npipe = tv[3];
+        if (tv[4] > 0) tcc.nsets = tv[4];
       }
       if (use_tc && h->tile_report) {
         int* r = h->tile_report + 8 * i;
-        r[0] = tcc.TR; r[1] = tcc.BH; r[2] = tcc.IWB; r[3] = tcc.NSTG; r[4] = tcc.npipe * 160; r[5] = 0; r[6] = 0; r[7] = -1;
+        r[0] = tcc.TR; r[1] = tcc.BH; r[2] = tcc.IWB; r[3] = tcc.NSTG; r[4] = tcc.npipe * (128 * tcc.nsets + 32); r[5] = tcc.npipe; r[6] = tcc.nsets; r[7] = -1;
       }
     }
     if (!naive && !use_tc) {

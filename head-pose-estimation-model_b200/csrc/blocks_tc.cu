@@ -50,6 +50,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: never hang the device on a lost signal
   }
 }
+// spin used by the single issuer thread: try_wait suspends in hardware, no watchdog arithmetic in the loop
+__device__ __forceinline__ void mbar_wait_light(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -75,11 +86,10 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// TF32 split a = hi + lo: hi keeps the top 19 bits (truncation, 1 LOP3), lo = a - hi is exact in fp32 and |lo| < 2^-10 |a|;
+// the tensor core ignores the low 13 mantissa bits of lo, so the representation error is < 2^-20 |a| (cvt.rna.tf32
+// would cost ~5 SASS instructions per value for one more bit).
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
 // D[tmem] (+)= A[tmem] * B[smem descriptor], tf32 inputs, fp32 accumulate, M = 128
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_addr, uint32_t a_addr, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
@@ -119,27 +129,37 @@ struct TcParams {
   const float *dww, *dwb, *pwb;   // depthwise [9][CINP], [CINP]; pointwise bias [COUTP]
   const float *bhi, *blo;         // pointwise weights split hi / lo, each [K8/4][N16][4] (K-major core matrices)
   int W, H, BH, IWB, row_pitch;   // row_pitch = IWB * PS floats
-  int bands_per_img, n_tiles, lanes, npipe;
+  int bands_per_img, n_tiles, lanes;
   uint32_t load_bytes;
   int off_b, off_w, off_pipe, buf_floats;   // shared-memory layout in floats (buffers 1024-byte aligned)
 };
 
-#define TC_MAX_PIPE 2
+#define TC_MAX_PIPE 4
 #define TC_MAX_STG 4
+#define TC_BAR_FLOATS 128   // 512 bytes: barriers of all pipelines + the TMEM base address
 
-template <int CINP, int COUTP, int TR, int NSTG>
-__global__ void __launch_bounds__(TC_MAX_PIPE * 160, 1)
+__device__ __forceinline__ void tmem_st4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// NSETS warp sets (4 warps each) share one pipeline: the 4-channel chunks of a tile are dealt round-robin to the sets
+// (chunk c -> set c % NSETS), the accumulator rows of the epilogue likewise (row t -> set t % NSETS).  More warps per tile
+// without more TMEM or shared memory: the kernel is latency bound with one warp per SM sub-partition.
+template <int CINP, int COUTP, int TR, int NSTG, int NPIPE, int NSETS>
+__global__ void __launch_bounds__(NPIPE * (128 * NSETS + 32), 1)
 blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcParams p) {
   using G = TcGeom<CINP, COUTP>;
   constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
   constexpr int TCOLS = TR * N16 + NSTG * TR * 16;   // TMEM columns per pipeline: TR accumulators + the A ring
-  static_assert(TC_MAX_PIPE * TCOLS <= 512 || TCOLS <= 512, "TMEM budget");
-  static_assert(NSTG <= TC_MAX_STG, "ring depth");
+  constexpr int WTHREADS = 128 * NSETS;              // worker threads per pipeline
+  constexpr int BARS = 2 + 2 * TC_MAX_STG;           // mbarriers per pipeline
+  static_assert(NPIPE * TCOLS <= 512 && NPIPE <= TC_MAX_PIPE, "TMEM budget");
+  static_assert(NSTG <= TC_MAX_STG && NPIPE * BARS * 8 + 4 <= TC_BAR_FLOATS * 4, "barrier block");
 
   extern __shared__ __align__(1024) float smem[];
-  // barrier block (first 256 bytes): per pipeline full, d_full, a_full[NSTG], a_empty[NSTG]; tmem base at byte 248
+  // barrier block: per pipeline full, d_full, a_full[NSTG], a_empty[NSTG]; TMEM base in the last word
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + 62;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (TC_BAR_FLOATS - 1);
   float* s_bhi = smem + p.off_b;
   float* s_blo = s_bhi + K8 * N16;
   float* s_dww = smem + p.off_w;
@@ -148,8 +168,7 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane_id = tid & 31;
-  const int npipe = p.npipe;
-  const int n_work_warps = 4 * npipe;
+  constexpr int n_work_warps = 4 * NSETS * NPIPE;
 
   for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
     st4(s_bhi + i, ld4(p.bhi + i));
@@ -160,12 +179,12 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
   fence_async_smem();   // the tensor core reads s_bhi / s_blo through the async proxy
   if (tid == 0) {
-    for (int q = 0; q < npipe; ++q) {
-      uint64_t* b = bars + q * (2 + 2 * TC_MAX_STG);
+    for (int q = 0; q < NPIPE; ++q) {
+      uint64_t* b = bars + q * BARS;
       mbar_init(&b[0], 1);                                     // full: TMA load landed
       mbar_init(&b[1], 1);                                     // d_full: all MMAs of the tile done
       for (int s = 0; s < NSTG; ++s) {
-        mbar_init(&b[2 + s], 128);                             // a_full[s]: every worker stored its A rows
+        mbar_init(&b[2 + s], 256);                             // a_full[s]: both 4-channel halves of the k-step stored (128 lanes each)
         mbar_init(&b[2 + TC_MAX_STG + s], 1);                  // a_empty[s]: MMAs that read stage s are done
       }
     }
@@ -180,24 +199,26 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
 
-  const int tile_stride = gridDim.x * npipe;
+  const int tile_stride = gridDim.x * NPIPE;
 
   if (warp < n_work_warps) {
     // =============================================================== worker: depthwise -> TMEM, epilogue
-    const int pipe = warp >> 2;
+    const int pipe = warp / (4 * NSETS);
+    const int set = (warp >> 2) % NSETS;
     const int wq = warp & 3;
-    const int wtid = tid - pipe * 128;           // 0..127 = TMEM lane
-    uint64_t* b = bars + pipe * (2 + 2 * TC_MAX_STG);
+    const int lane = wq * 32 + lane_id;          // TMEM lane = column of pixels owned by this thread
+    const bool leader = (set == 0 && lane == 0);
+    uint64_t* b = bars + pipe * BARS;
     uint64_t* bar_full = &b[0];
     uint64_t* bar_dfull = &b[1];
     uint64_t* bar_afull = &b[2];
     uint64_t* bar_aempty = &b[2 + TC_MAX_STG];
     float* buf = smem + p.off_pipe + pipe * p.buf_floats;
     const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(pipe * TCOLS);
-    const uint32_t colA0 = TR * N16;
-    const bool active = wtid < p.lanes;
+    constexpr uint32_t colA0 = TR * N16;
+    const bool active = lane < p.lanes;
     const bool warp_active = wq * 32 < p.lanes;
-    const int l = active ? wtid : 0;
+    const int l = active ? lane : 0;
     const int yq = l / p.W;
     const int x = l - yq * p.W;
     const int row_pitch = p.row_pitch;
@@ -208,95 +229,86 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       img = tile / p.bands_per_img;
       y0 = (tile - img * p.bands_per_img) * p.BH;
     };
-    auto issue_load = [&](int tile) {   // wtid == 0 only
+    auto issue_load = [&](int tile) {   // leader only
       int img, y0;
       tile_coords(tile, img, y0);
       mbar_expect_tx(bar_full, p.load_bytes);
       tma_load_4d(buf, &tm_in, bar_full, 0, -1, y0 - 1, img);
     };
 
-    int tile = blockIdx.x * npipe + pipe;
-    if (wtid == 0 && tile < p.n_tiles) issue_load(tile);
-    uint32_t use = 0;
+    int tile = blockIdx.x * NPIPE + pipe;
+    if (leader && tile < p.n_tiles) issue_load(tile);
     for (int it = 0; tile < p.n_tiles; tile += tile_stride, ++it) {
       const int next = tile + tile_stride;
       mbar_wait(bar_full, it & 1);
-      if (wtid == 0 && next < p.n_tiles) {   // warm L2 for the next tile of this pipeline (its buffer is still in use)
+      if (leader && next < p.n_tiles) {   // warm L2 for the next tile of this pipeline (its buffer is still in use)
         int img, y0;
         tile_coords(next, img, y0);
         tma_prefetch_4d(&tm_in, 0, -1, y0 - 1, img);
       }
 
-      // ---------------- depthwise 3x3 (+bias) -> hi/lo split -> TMEM ring stage, one k-step (8 channels) at a time
+      // ---------------- depthwise 3x3 (+bias) -> hi/lo split -> TMEM ring stage; this set's chunks only
 #pragma unroll 1
-      for (int ks = 0; ks < KS; ++ks, ++use) {
+      for (int c4 = set; c4 < 2 * KS; c4 += NSETS) {
+        const int ks = c4 >> 1, half = c4 & 1;
+        const uint32_t use = (uint32_t)it * KS + ks;   // global k-step counter of this pipeline
         const uint32_t s = use % NSTG;
         if (use >= NSTG) {
           mbar_wait(&bar_aempty[s], ((use / NSTG) - 1) & 1);
           tc_fence_after();
         }
         if (warp_active) {
-          uint32_t av[TR][16];
+          const uint32_t acol = tlane + colA0 + s * (TR * 16) + half * 4;
+          if (c4 < C4) {
+            const float* win = buf + my_off + c4 * 4;
+            float4 w[9];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int c4 = 2 * ks + half;
-            if (c4 < C4) {
-              const float* win = buf + my_off + c4 * 4;
-              float4 w[9];
+            for (int k = 0; k < 9; ++k) w[k] = ld4(s_dww + k * CINP + c4 * 4);
+            const float4 bias = ld4(s_dwb + c4 * 4);
+            float4 acc[TR];
 #pragma unroll
-              for (int k = 0; k < 9; ++k) w[k] = ld4(s_dww + k * CINP + c4 * 4);
-              const float4 bias = ld4(s_dwb + c4 * 4);
-              float4 acc[TR];
+            for (int t = 0; t < TR; ++t) acc[t] = bias;
 #pragma unroll
-              for (int t = 0; t < TR; ++t) acc[t] = bias;
+            for (int r = 0; r < TR + 2; ++r) {
+              const float* row = win + r * row_pitch;
+              const float4 v0 = ld4(row), v1 = ld4(row + PS), v2 = ld4(row + 2 * PS);
 #pragma unroll
-              for (int r = 0; r < TR + 2; ++r) {
-                const float* row = win + r * row_pitch;
-                const float4 v0 = ld4(row), v1 = ld4(row + PS), v2 = ld4(row + 2 * PS);
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                  const int t = r - ky;
-                  if (t >= 0 && t < TR) {
-                    acc[t] = fma4(v0, w[ky * 3 + 0], acc[t]);
-                    acc[t] = fma4(v1, w[ky * 3 + 1], acc[t]);
-                    acc[t] = fma4(v2, w[ky * 3 + 2], acc[t]);
-                  }
+              for (int ky = 0; ky < 3; ++ky) {
+                const int t = r - ky;
+                if (t >= 0 && t < TR) {
+                  acc[t] = fma4(v0, w[ky * 3 + 0], acc[t]);
+                  acc[t] = fma4(v1, w[ky * 3 + 1], acc[t]);
+                  acc[t] = fma4(v2, w[ky * 3 + 2], acc[t]);
                 }
               }
+            }
 #pragma unroll
-              for (int t = 0; t < TR; ++t) {
-                const float a[4] = {acc[t].x, acc[t].y, acc[t].z, acc[t].w};
+            for (int t = 0; t < TR; ++t) {
+              const uint32_t h0 = tf32_hi(acc[t].x), h1 = tf32_hi(acc[t].y), h2 = tf32_hi(acc[t].z), h3 = tf32_hi(acc[t].w);
+              tmem_st4(acol + t * 16, h0, h1, h2, h3);
+              tmem_st4(acol + t * 16 + 8, __float_as_uint(acc[t].x - __uint_as_float(h0)), __float_as_uint(acc[t].y - __uint_as_float(h1)),
+                       __float_as_uint(acc[t].z - __uint_as_float(h2)), __float_as_uint(acc[t].w - __uint_as_float(h3)));
+            }
+          } else {   // K padding (odd number of chunks): zero columns
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const uint32_t hi = to_tf32(a[e]);
-                  av[t][half * 4 + e] = hi;
-                  av[t][8 + half * 4 + e] = to_tf32(a[e] - __uint_as_float(hi));
-                }
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < TR; ++t)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  av[t][half * 4 + e] = 0u;
-                  av[t][8 + half * 4 + e] = 0u;
-                }
+            for (int t = 0; t < TR; ++t) {
+              tmem_st4(acol + t * 16, 0u, 0u, 0u, 0u);
+              tmem_st4(acol + t * 16 + 8, 0u, 0u, 0u, 0u);
             }
           }
-#pragma unroll
-          for (int t = 0; t < TR; ++t) tmem_st16(tlane + colA0 + (s * TR + t) * 16, av[t]);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
         }
         mbar_arrive(&bar_afull[s]);
       }
 
-      // ---------------- epilogue: D_t + bias + skip -> ReLU -> in place over the centre pixel
+      // ---------------- epilogue: D_t + bias + skip -> ReLU -> in place over the centre pixel; this set's rows only
       mbar_wait(bar_dfull, it & 1);
       tc_fence_after();
       if (warp_active) {
 #pragma unroll
         for (int t = 0; t < TR; ++t) {
+          if (t % NSETS != set) continue;
           float* cpix = buf + centre0 + t * row_pitch;
 #pragma unroll
           for (int g = 0; g < N16 / 16; ++g) {
@@ -325,8 +337,8 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         tc_fence_before();
         fence_async_smem();
       }
-      named_bar_sync(1 + pipe, 128);
-      if (wtid == 0) {
+      named_bar_sync(1 + pipe, WTHREADS);
+      if (leader) {
         int img, y0;
         tile_coords(tile, img, y0);
         tma_store_4d(&tm_out, buf + row_pitch + PS, 0, 0, y0, img);
@@ -335,16 +347,16 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         if (next < p.n_tiles) issue_load(next);
       }
     }
-    if (wtid == 0) tma_store_wait_all();
+    if (leader) tma_store_wait_all();
   } else if (lane_id == 0) {
     // =============================================================== issuer: tcgen05.mma for one pipeline
     const int pipe = warp - n_work_warps;
-    uint64_t* b = bars + pipe * (2 + 2 * TC_MAX_STG);
+    uint64_t* b = bars + pipe * BARS;
     uint64_t* bar_dfull = &b[1];
     uint64_t* bar_afull = &b[2];
     uint64_t* bar_aempty = &b[2 + TC_MAX_STG];
     const uint32_t tcol = tmem_base + (uint32_t)(pipe * TCOLS);
-    const uint32_t colA0 = TR * N16;
+    constexpr uint32_t colA0 = TR * N16;
     // instruction descriptor: D fp32, A/B tf32, both K-major, N = N16, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // smem descriptor of a [N16 rows][8 k] slice: core matrix = 8 rows x 16 B; LBO (next 4 k) = N16*16 B, SBO (next 8 rows) = 128 B
@@ -352,11 +364,11 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
                                 ((uint64_t)1 << 46);
     const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
     uint32_t use = 0;
-    for (int tile = blockIdx.x * npipe + pipe; tile < p.n_tiles; tile += tile_stride) {
+    for (int tile = blockIdx.x * NPIPE + pipe; tile < p.n_tiles; tile += tile_stride) {
 #pragma unroll 1
       for (int ks = 0; ks < KS; ++ks, ++use) {
         const uint32_t s = use % NSTG;
-        mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+        mbar_wait_light(&bar_afull[s], (use / NSTG) & 1);
         tc_fence_after();
         const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
         const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
@@ -414,26 +426,30 @@ int make_map(CUtensorMap* tm, const float* base, int N, int H, int W, int C, int
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-template <int CINP, int COUTP, int TR, int NSTG>
+// shared-memory layout in floats: [barriers][B hi | B lo][dw weights, dw bias, pw bias][pipeline buffers ...]
+inline void tc_layout(int cinp, int coutp, int K8, int N16, int* off_b, int* off_w, int* off_pipe) {
+  int off = TC_BAR_FLOATS;
+  *off_b = off;
+  off = align_up(off + 2 * K8 * N16, 32);
+  *off_w = off;
+  off = align_up(off + 10 * cinp + coutp, 256);
+  *off_pipe = off;
+}
+
+template <int CINP, int COUTP, int TR, int NSTG, int NPIPE, int NSETS>
 int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
   using G = TcGeom<CINP, COUTP>;
   constexpr int TCOLS = TR * G::N16 + NSTG * TR * 16;
-  HP_REQUIRE(tc.npipe >= 1 && tc.npipe <= TC_MAX_PIPE && tc.npipe * TCOLS <= 512, HP_ERR_INVALID,
-             "tc block <%d,%d,%d,%d>: %d pipelines x %d TMEM columns exceed 512", CINP, COUTP, TR, NSTG, tc.npipe, TCOLS);
+  static_assert(NPIPE * TCOLS <= 512, "TMEM budget");
   TcParams p;
   p.dww = w.dww; p.dwb = w.dwb; p.pwb = w.pwb; p.bhi = w.bhi; p.blo = w.blo;
   p.W = W; p.H = H; p.BH = tc.BH; p.IWB = tc.IWB; p.row_pitch = tc.IWB * G::PS;
   p.bands_per_img = ceil_div(H, tc.BH);
   p.n_tiles = B * p.bands_per_img;
   p.lanes = (tc.BH / TR) * W;
-  p.npipe = tc.npipe;
   p.load_bytes = (uint32_t)((size_t)G::PS * tc.IWB * (tc.BH + 2) * sizeof(float));
-  int off = 64;                                   // 256 bytes: barriers + tmem base
-  p.off_b = off;
-  off = align_up(off + 2 * G::K8 * G::N16, 32);
-  p.off_w = off;
-  off = align_up(off + 10 * CINP + COUTP, 256);
-  p.off_pipe = off;
+  tc_layout(CINP, COUTP, G::K8, G::N16, &p.off_b, &p.off_w, &p.off_pipe);
+  const int off = p.off_pipe;
   p.buf_floats = align_up(G::PS * tc.IWB * (tc.BH + 2), 256);
   const size_t smem = (size_t)(off + tc.npipe * p.buf_floats) * sizeof(float);
   HP_REQUIRE(smem <= 227 * 1024, HP_ERR_INVALID, "tc block <%d,%d>: %zu bytes of shared memory needed", CINP, COUTP, smem);
@@ -443,12 +459,12 @@ int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const
   CUtensorMap tin, tout;
   HP_TRY(make_map(&tin, in, B, H, W, CINP, 1, tc.BH + 2, tc.IWB, G::PS));
   HP_TRY(make_map(&tout, out, B, H, W, COUTP, 1, tc.BH, tc.IWB, G::PS));
-  auto kern = blaze_block_tc_kernel<CINP, COUTP, TR, NSTG>;
+  auto kern = blaze_block_tc_kernel<CINP, COUTP, TR, NSTG, NPIPE, NSETS>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   const long long need = ceil_div(p.n_tiles, tc.npipe);
   if (grid > need) grid = need;
-  kern<<<(unsigned)grid, tc.npipe * 160, smem, st>>>(tin, tout, p);
+  kern<<<(unsigned)grid, NPIPE * (128 * NSETS + 32), smem, st>>>(tin, tout, p);
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;
@@ -457,10 +473,17 @@ int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const
 template <int CINP, int COUTP>
 int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc,
                   cudaStream_t st) {
-  if (tc.TR == 4 && tc.NSTG == 1) return launch_tc<CINP, COUTP, 4, 1>(h, in, out, B, H, W, w, tc, st);
-  if (tc.TR == 4 && tc.NSTG == 2) return launch_tc<CINP, COUTP, 4, 2>(h, in, out, B, H, W, w, tc, st);
-  if (tc.TR == 2 && tc.NSTG == 2) return launch_tc<CINP, COUTP, 2, 2>(h, in, out, B, H, W, w, tc, st);
-  hp_set_error("tc block: no kernel for TR %d NSTG %d", tc.TR, tc.NSTG);
+  constexpr int N16 = TcGeom<CINP, COUTP>::N16;
+#define TC_CASE(TR_, NSTG_, NPIPE_, NSETS_)                                              \
+  if constexpr (NPIPE_ * TR_ * (N16 + 16 * NSTG_) <= 512)                                \
+    if (tc.TR == TR_ && tc.NSTG == NSTG_ && tc.npipe == NPIPE_ && tc.nsets == NSETS_)    \
+      return launch_tc<CINP, COUTP, TR_, NSTG_, NPIPE_, NSETS_>(h, in, out, B, H, W, w, tc, st);
+  TC_CASE(4, 2, 2, 1) TC_CASE(4, 1, 2, 1) TC_CASE(4, 2, 2, 2) TC_CASE(4, 1, 2, 2) TC_CASE(4, 2, 1, 2) TC_CASE(4, 3, 1, 3)
+  TC_CASE(4, 2, 1, 1) TC_CASE(4, 1, 1, 1)
+  TC_CASE(2, 2, 3, 1) TC_CASE(2, 2, 3, 2) TC_CASE(2, 2, 2, 2) TC_CASE(2, 1, 3, 1) TC_CASE(2, 2, 4, 1) TC_CASE(2, 1, 4, 1)
+  TC_CASE(3, 2, 2, 1) TC_CASE(3, 2, 2, 2) TC_CASE(3, 1, 2, 2)
+#undef TC_CASE
+  hp_set_error("tc block: no kernel for TR %d NSTG %d npipe %d nsets %d", tc.TR, tc.NSTG, tc.npipe, tc.nsets);
   return HP_ERR_UNSUPPORTED;
 }
 
@@ -490,28 +513,42 @@ void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, floa
 
 int hp_tc_weight_floats(int cinp, int coutp) { return ((cinp + 7) / 8 * 8) * ((coutp + 15) / 16 * 16); }
 
-// Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.
-bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
+// Shared memory / TMEM feasibility of one geometry (the kernel instantiations are listed in launch_tc_cfg).
+bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc) {
   const int cinp = chan_pad(kBlazeBlocks[blk].cin), coutp = chan_pad(kBlazeBlocks[blk].cout);
-  if (kBlazeBlocks[blk].stride != 1 || W + 2 > 255 || W > 128 || H < 1) return false;
   const int C4 = cinp / 4, NG = coutp / 4, N16 = (coutp + 15) / 16 * 16, K8 = (cinp + 7) / 8 * 8;
   const int PS = ((C4 > NG ? C4 : NG) | 1) * 4;
-  const int TR = 4;
-  int NSTG = 2, npipe = 2;
-  if (npipe * TR * (N16 + 16 * NSTG) > 512) NSTG = 1;
-  if (npipe * TR * (N16 + 16 * NSTG) > 512) return false;   // wide blocks: not tuned yet, the CUDA-core kernel runs them
-  const int strips = ceil_div(H, TR);
-  const int max_strips = 128 / W;
-  if (max_strips < 1) return false;
-  const int bands = ceil_div(strips, max_strips);
-  const int BH = ceil_div(strips, bands) * TR;
-  const int IWB = ((W + 2 + 1 + 7) / 8) * 8 - 1;   // >= W + 2 and == 7 (mod 8): the band interior starts 128-byte aligned
-  const size_t fixed = (size_t)(64 + align_up(2 * K8 * N16, 32) + align_up(10 * cinp + coutp, 256)) * 4;
-  const size_t buf = (size_t)align_up(PS * IWB * (BH + 2), 256) * 4;
-  if (fixed + npipe * buf > 227 * 1024) npipe = 1;
-  if (fixed + npipe * buf > 227 * 1024) return false;
-  tc->TR = TR; tc->NSTG = NSTG; tc->BH = BH; tc->IWB = IWB; tc->npipe = npipe;
-  return true;
+  if (tc.TR < 1 || tc.BH < tc.TR || tc.BH % tc.TR || (tc.BH / tc.TR) * W > 128 || tc.BH + 2 > 256) return false;
+  if (tc.npipe * tc.TR * (N16 + 16 * tc.NSTG) > 512) return false;
+  if (tc.npipe * (128 * tc.nsets + 32) > 1024) return false;
+  int off_b, off_w, off_pipe;
+  tc_layout(cinp, coutp, K8, N16, &off_b, &off_w, &off_pipe);
+  const size_t buf = (size_t)align_up(PS * tc.IWB * (tc.BH + 2), 256) * 4;
+  return (size_t)off_pipe * 4 + tc.npipe * buf <= 227 * 1024;
+}
+
+// Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.
+// Order of preference measured with tools/tc_sweep.py (profiles/): more resident warps first.
+bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
+  if (kBlazeBlocks[blk].stride != 1 || W + 2 > 255 || W > 128 || H < 1) return false;
+  static const int pref[][4] = {{2, 2, 4, 1}, {2, 1, 4, 1}, {2, 2, 3, 2}, {2, 2, 3, 1}, {4, 2, 2, 2}, {4, 1, 2, 2}, {2, 2, 2, 2}, {4, 2, 1, 2}, {4, 1, 1, 1}};   // TR, NSTG, npipe, nsets
+  for (const auto& c : pref) {
+    TcCfg t;
+    t.TR = c[0]; t.NSTG = c[1]; t.npipe = c[2]; t.nsets = c[3];
+    t.IWB = ((W + 2 + 1 + 7) / 8) * 8 - 1;   // >= W + 2 and == 7 (mod 8): the band interior starts 128-byte aligned
+    const int strips = ceil_div(H, t.TR);
+    int max_strips = 128 / W;
+    if (max_strips < 1) return false;
+    for (; max_strips >= 1; --max_strips) {
+      const int bands = ceil_div(strips, max_strips);
+      t.BH = ceil_div(strips, bands) * t.TR;
+      if (hp_tc_fits(blk, H, W, t)) {
+        *tc = t;
+        return true;
+      }
+    }
+  }
+  return false;
 }
 
 int hp_launch_block_tc(hp_ctx* h, int blk, const float* in, float* out, int B, int H, int W, const BlockWeights& w,

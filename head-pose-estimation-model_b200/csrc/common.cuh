@@ -110,7 +110,7 @@ struct hp_ctx {
   DevBuf scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
-  int tc_override[16][4] = {};     // tensor-core kernel: TR, NSTG, BH, npipe per block (TR 0 = automatic, -1 = do not use)
+  int tc_override[16][5] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets per block (TR 0 = automatic, -1 = do not use)
   int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
 };
 
@@ -147,8 +147,9 @@ int hp_launch_block_tma(hp_ctx* h, int blk, const float* in, float* out, int B, 
 
 // blocks_tc.cu: third-generation fused BlazeBlock kernel (depthwise on CUDA cores -> TMEM, pointwise as 3xTF32 tcgen05 GEMM)
 struct TcCfg {
-  int TR, NSTG, BH, IWB, npipe;
+  int TR, NSTG, BH, IWB, npipe, nsets;
 };
+bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc);
 void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, float* blo);
 int hp_tc_weight_floats(int cinp, int coutp);
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc);

@@ -211,8 +211,8 @@ int hp_backbone_profile(hp_handle h, const float* x, int B, int H, int W, int it
 int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf, int MT);
 int hp_debug_tile_report(hp_handle h, int* report16x8);
 /* tensor-core BlazeBlock kernel (HP_IMPL_FAST, stride-1 blocks): TR rows per lane, ring depth, band height, pipelines per
- * CTA; TR = 0 restores the defaults, TR = -1 keeps the block on the CUDA-core kernel */
-int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe);
+ * CTA, warp sets per pipeline; TR = 0 restores the defaults, TR = -1 keeps the block on the CUDA-core kernel */
+int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, int nsets);
 
 #ifdef __cplusplus
 }
