@@ -116,9 +116,14 @@ int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf, 
   h->tile_override[blk][4] = MT;
   return HP_OK;
 }
-int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, int nsets) {
+int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, int nsets, int nbuf) {
   HP_REQUIRE(h && blk >= 0 && blk < 16, HP_ERR_INVALID, "hp_debug_set_tc: bad arguments");
-  h->tc_override[blk][0] = TR; h->tc_override[blk][1] = NSTG; h->tc_override[blk][2] = BH; h->tc_override[blk][3] = npipe; h->tc_override[blk][4] = nsets;
+  h->tc_override[blk][0] = TR; h->tc_override[blk][1] = NSTG; h->tc_override[blk][2] = BH; h->tc_override[blk][3] = npipe; h->tc_override[blk][4] = nsets; h->tc_override[blk][5] = nbuf;
+  return HP_OK;
+}
+int hp_debug_tc_trace(hp_handle h, long long* dev_buf, int max_tiles) {
+  HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
+  h->tc_trace = dev_buf; h->tc_trace_tiles = dev_buf ? max_tiles : 0;
   return HP_OK;
 }
 int hp_debug_tile_report(hp_handle h, int* report16x8) {

@@ -762,6 +762,7 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         if (tv[2] > 0) tcc.BH = tv[2];
         if (tv[3] > 0) tcc.npipe = tv[3];
         if (tv[4] > 0) tcc.nsets = tv[4];
+        tcc.nbuf = tv[5];
       }
       if (use_tc && h->tile_report) {
         int* r = h->tile_report + 8 * i;

@@ -39,15 +39,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Blocking wait with a watchdog.  try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware until the
+// phase completes instead of burning issue slots (ncu: un-hinted polling was ~25 % of all issued instructions); the clock
+// is read every 256 wake-ups only.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  long long t0 = clock64();
+  uint32_t done = 0, n = 0;
+  long long t0 = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: never hang the device on a lost signal
+    if ((++n & 255u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();   // ~2 s: never hang the device on a lost signal
+    }
   }
 }
 // spin used by the single issuer thread: try_wait suspends in hardware, no watchdog arithmetic in the loop
@@ -132,6 +139,8 @@ struct TcParams {
   int bands_per_img, n_tiles, lanes;
   uint32_t load_bytes;
   int off_b, off_w, off_pipe, buf_floats;   // shared-memory layout in floats (buffers 1024-byte aligned)
+  long long* trace;                         // optional per-tile clock64 stamps of CTA 0 (8 per tile), see hp_debug_tc_trace
+  int trace_tiles;
 };
 
 #define TC_MAX_PIPE 4
@@ -140,6 +149,102 @@ struct TcParams {
 
 __device__ __forceinline__ void tmem_st4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+
+// watchdog spin for single-thread roles: try_wait suspends in hardware; the clock is read every 256 polls only
+__device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, n = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if ((++n & 255u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+
+// Depthwise 3x3 (+bias) of one 4-channel chunk for the TR pixels of a lane (sliding window down the column).
+template <int CINP, int TR, int PS>
+__device__ __forceinline__ void tc_dw_compute(const float* win, const float* dww_c, const float* dwb_c, int row_pitch, float4 (&acc)[TR]) {
+  float4 w[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = ld4(dww_c + k * CINP);
+  const float4 bias = ld4(dwb_c);
+#pragma unroll
+  for (int t = 0; t < TR; ++t) acc[t] = bias;
+#pragma unroll
+  for (int r = 0; r < TR + 2; ++r) {
+    const float* row = win + r * row_pitch;
+    const float4 v0 = ld4(row), v1 = ld4(row + PS), v2 = ld4(row + 2 * PS);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int t = r - ky;
+      if (t >= 0 && t < TR) {
+        acc[t] = fma4(v0, w[ky * 3 + 0], acc[t]);
+        acc[t] = fma4(v1, w[ky * 3 + 1], acc[t]);
+        acc[t] = fma4(v2, w[ky * 3 + 2], acc[t]);
+      }
+    }
+  }
+}
+// TF32 hi / lo split of the chunk and store to the A ring stage: hi at columns [acol + 16 t, +4), lo 8 columns further.
+template <int TR>
+__device__ __forceinline__ void tc_dw_store(const float4 (&acc)[TR], uint32_t acol) {
+#pragma unroll
+  for (int t = 0; t < TR; ++t) {
+    const uint32_t h0 = tf32_hi(acc[t].x), h1 = tf32_hi(acc[t].y), h2 = tf32_hi(acc[t].z), h3 = tf32_hi(acc[t].w);
+    tmem_st4(acol + t * 16, h0, h1, h2, h3);
+    tmem_st4(acol + t * 16 + 8, __float_as_uint(acc[t].x - __uint_as_float(h0)), __float_as_uint(acc[t].y - __uint_as_float(h1)),
+             __float_as_uint(acc[t].z - __uint_as_float(h2)), __float_as_uint(acc[t].w - __uint_as_float(h3)));
+  }
+}
+template <int CINP, int TR, int PS>
+__device__ __forceinline__ void tc_dw_chunk(const float* win, const float* dww_c, const float* dwb_c, int row_pitch, uint32_t acol) {
+  float4 acc[TR];
+  tc_dw_compute<CINP, TR, PS>(win, dww_c, dwb_c, row_pitch, acc);
+  tc_dw_store<TR>(acc, acol);
+}
+template <int TR>
+__device__ __forceinline__ void tc_zero_chunk(uint32_t acol) {   // K padding (odd number of chunks): zero columns
+#pragma unroll
+  for (int t = 0; t < TR; ++t) {
+    tmem_st4(acol + t * 16, 0u, 0u, 0u, 0u);
+    tmem_st4(acol + t * 16 + 8, 0u, 0u, 0u, 0u);
+  }
+}
+// Epilogue of one pixel: accumulator row (N16 columns at dcol) + bias + skip -> ReLU -> in place over the centre pixel.
+// All column groups are requested before the single tcgen05.wait::ld (the TMEM load latency is paid once per pixel).
+template <int C4, int NG, int N16>
+__device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, const float* s_pwb, bool active) {
+  constexpr int NGRP = (NG + 3) / 4;   // 16-column groups that hold real output channels
+  uint32_t v[NGRP][16];
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) tmem_ld16(dcol + g * 16, v[g]);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = g * 4 + jj;
+      if (j < NG) {
+        const float4 bb = ld4(s_pwb + j * 4);
+        float4 o = make_float4(__uint_as_float(v[g][jj * 4 + 0]) + bb.x, __uint_as_float(v[g][jj * 4 + 1]) + bb.y,
+                               __uint_as_float(v[g][jj * 4 + 2]) + bb.z, __uint_as_float(v[g][jj * 4 + 3]) + bb.w);
+        if (j < C4) {
+          const float4 sk = ld4(cpix + j * 4);
+          o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+        }
+        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        if (active) st4(cpix + j * 4, o);
+      }
+    }
+  }
 }
 
 // NSETS warp sets (4 warps each) share one pipeline: the 4-channel chunks of a tile are dealt round-robin to the sets
@@ -259,43 +364,8 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         }
         if (warp_active) {
           const uint32_t acol = tlane + colA0 + s * (TR * 16) + half * 4;
-          if (c4 < C4) {
-            const float* win = buf + my_off + c4 * 4;
-            float4 w[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) w[k] = ld4(s_dww + k * CINP + c4 * 4);
-            const float4 bias = ld4(s_dwb + c4 * 4);
-            float4 acc[TR];
-#pragma unroll
-            for (int t = 0; t < TR; ++t) acc[t] = bias;
-#pragma unroll
-            for (int r = 0; r < TR + 2; ++r) {
-              const float* row = win + r * row_pitch;
-              const float4 v0 = ld4(row), v1 = ld4(row + PS), v2 = ld4(row + 2 * PS);
-#pragma unroll
-              for (int ky = 0; ky < 3; ++ky) {
-                const int t = r - ky;
-                if (t >= 0 && t < TR) {
-                  acc[t] = fma4(v0, w[ky * 3 + 0], acc[t]);
-                  acc[t] = fma4(v1, w[ky * 3 + 1], acc[t]);
-                  acc[t] = fma4(v2, w[ky * 3 + 2], acc[t]);
-                }
-              }
-            }
-#pragma unroll
-            for (int t = 0; t < TR; ++t) {
-              const uint32_t h0 = tf32_hi(acc[t].x), h1 = tf32_hi(acc[t].y), h2 = tf32_hi(acc[t].z), h3 = tf32_hi(acc[t].w);
-              tmem_st4(acol + t * 16, h0, h1, h2, h3);
-              tmem_st4(acol + t * 16 + 8, __float_as_uint(acc[t].x - __uint_as_float(h0)), __float_as_uint(acc[t].y - __uint_as_float(h1)),
-                       __float_as_uint(acc[t].z - __uint_as_float(h2)), __float_as_uint(acc[t].w - __uint_as_float(h3)));
-            }
-          } else {   // K padding (odd number of chunks): zero columns
-#pragma unroll
-            for (int t = 0; t < TR; ++t) {
-              tmem_st4(acol + t * 16, 0u, 0u, 0u, 0u);
-              tmem_st4(acol + t * 16 + 8, 0u, 0u, 0u, 0u);
-            }
-          }
+          if (c4 < C4) tc_dw_chunk<CINP, TR, PS>(buf + my_off + c4 * 4, s_dww + c4 * 4, s_dwb + c4 * 4, row_pitch, acol);
+          else tc_zero_chunk<TR>(acol);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
         }
@@ -309,30 +379,7 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 #pragma unroll
         for (int t = 0; t < TR; ++t) {
           if (t % NSETS != set) continue;
-          float* cpix = buf + centre0 + t * row_pitch;
-#pragma unroll
-          for (int g = 0; g < N16 / 16; ++g) {
-            if (g * 4 < NG) {
-              uint32_t v[16];
-              tmem_ld16(tlane + t * N16 + g * 16, v);
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = g * 4 + jj;
-                if (j < NG) {
-                  const float4 bb = ld4(s_pwb + j * 4);
-                  float4 o = make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
-                                         __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
-                  if (j < C4) {
-                    const float4 sk = ld4(cpix + j * 4);
-                    o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
-                  }
-                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                  if (active) st4(cpix + j * 4, o);
-                }
-              }
-            }
-          }
+          tc_epilogue_pixel<C4, NG, N16>(buf + centre0 + t * row_pitch, tlane + t * N16, s_pwb, active);
         }
         tc_fence_before();
         fence_async_smem();
@@ -393,6 +440,251 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------- deep (warp-specialised) variant
+// One pipeline per CTA, every stage of a tile in its own warps so that load, depthwise + MMA, epilogue and store of
+// consecutive tiles overlap (measured with tools/tma_bench: a TMA load + store of one band costs ~5000 clk of latency
+// when nothing else is in flight, the whole HBM budget of a band is ~3300 clk):
+//   loader  (1 thread) : TMA loads into a ring of NBUF halo buffers            free[b]  -> full[b]
+//   DW sets (NSETS x 4 warps): depthwise chunks -> TMEM A ring                 full[b], a_empty[s] -> a_full[s]
+//   issuer  (1 thread) : 3 x TR tcgen05.mma per k-step into D[i & 1]           a_full[s], d_empty[d] -> a_empty[s], d_full[d]
+//   epilogue (4 warps) : D[d] + bias + skip -> ReLU in place in buffer b       d_full[d] -> d_empty[d], epi_done[b]
+//   storer  (1 thread) : TMA store of the band interior, frees the buffer      epi_done[b] -> free[b]
+#define TCD_MAXB 4
+template <int CINP, int COUTP, int TR, int NSTG, int NSETS, int NBUF, int NESETS>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
+blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcParams p) {
+  using G = TcGeom<CINP, COUTP>;
+  constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
+  constexpr uint32_t colA0 = 2 * TR * N16;                        // TMEM: D[0], D[1] (TR * N16 columns each), then the A ring
+  static_assert(colA0 + NSTG * TR * 16 <= 512, "TMEM budget");
+  static_assert(NSTG <= TC_MAX_STG && NBUF <= TCD_MAXB, "ring depth");
+
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* bar_full = bars;                                       // [NBUF]
+  uint64_t* bar_free = bars + TCD_MAXB;                            // [NBUF]
+  uint64_t* bar_epi = bars + 2 * TCD_MAXB;                         // [NBUF]
+  uint64_t* bar_afull = bars + 3 * TCD_MAXB;                       // [NSTG]
+  uint64_t* bar_aempty = bar_afull + TC_MAX_STG;                   // [NSTG]
+  uint64_t* bar_dfull = bar_aempty + TC_MAX_STG;                   // [2]
+  uint64_t* bar_dempty = bar_dfull + 2;                            // [2]
+  static_assert((3 * TCD_MAXB + 2 * TC_MAX_STG + 4) * 8 + 4 <= TC_BAR_FLOATS * 4, "barrier block");
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (TC_BAR_FLOATS - 1);
+  float* s_bhi = smem + p.off_b;
+  float* s_blo = s_bhi + K8 * N16;
+  float* s_dww = smem + p.off_w;
+  float* s_dwb = s_dww + 9 * CINP;
+  float* s_pwb = s_dwb + CINP;
+  float* bufs = smem + p.off_pipe;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane_id = tid & 31;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1, W_STORE = W_ISSUE + 2;
+
+  for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
+    st4(s_bhi + i, ld4(p.bhi + i));
+    st4(s_blo + i, ld4(p.blo + i));
+  }
+  for (int i = tid * 4; i < 9 * CINP; i += nthr * 4) st4(s_dww + i, ld4(p.dww + i));
+  for (int i = tid * 4; i < CINP; i += nthr * 4) st4(s_dwb + i, ld4(p.dwb + i));
+  for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
+  fence_async_smem();
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&bar_full[b], 1);
+      mbar_init(&bar_free[b], 1);
+      mbar_init(&bar_epi[b], 128 * NESETS);
+    }
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(&bar_afull[s], 256);
+      mbar_init(&bar_aempty[s], 1);
+    }
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&bar_dfull[d], 1);
+      mbar_init(&bar_dempty[d], 128 * NESETS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+
+  auto tile_coords = [&](int tile, int& img, int& y0) {
+    img = tile / p.bands_per_img;
+    y0 = (tile - img * p.bands_per_img) * p.BH;
+  };
+  const int row_pitch = p.row_pitch;
+  // trace slots: 0 load issued, 1 DW sees full, 2 DW set 0 done, 3 epilogue sees d_full, 4 epilogue done, 5 store issued, 6 store read done,
+  // 7 MMAs issued, 8 last DW set done, 9 issuer sees last a_full, 10 issuer sees first a_full, 11 issuer has D free
+  auto stamp = [&](int i, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && i < p.trace_tiles) p.trace[i * 12 + slot] = clock64();
+  };
+
+  if (warp < W_ISSUE) {
+    // lane geometry shared by the depthwise and the epilogue warps
+    const int wq = warp & 3;
+    const int lane = wq * 32 + lane_id;
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const bool active = lane < p.lanes;
+    const bool warp_active = wq * 32 < p.lanes;
+    const int l = active ? lane : 0;
+    const int yq = l / p.W;
+    const int x = l - yq * p.W;
+    const int my_off = yq * TR * row_pitch + x * PS;
+    if (warp < W_EPI) {
+      // =============================================================== depthwise sets
+      // The TMEM stores of a chunk are waited for (and the chunk published) only after the next chunk has been
+      // computed: tcgen05.st latency and the a_empty round trip hide behind the LDS / FFMA work.
+      const int set = warp >> 2;
+      int i = 0;
+      uint64_t* pending = nullptr;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        const int b = i % NBUF;
+        const float* buf = bufs + b * p.buf_floats;
+        mbar_wait(&bar_full[b], (i / NBUF) & 1);
+        if (tid == 0) stamp(i, 1);
+#pragma unroll 1
+        for (int c4 = set; c4 < 2 * KS; c4 += NSETS) {
+          const int ks = c4 >> 1, half = c4 & 1;
+          const uint32_t use = (uint32_t)i * KS + ks;
+          const uint32_t s = use % NSTG;
+          float4 acc[TR];
+          if (warp_active && c4 < C4) tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4, s_dww + c4 * 4, s_dwb + c4 * 4, row_pitch, acc);
+          if (pending != nullptr) {
+            if (warp_active) {
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              tc_fence_before();
+            }
+            mbar_arrive(pending);
+          }
+          if (use >= NSTG) {
+            mbar_wait(&bar_aempty[s], ((use / NSTG) - 1) & 1);
+            tc_fence_after();
+          }
+          if (warp_active) {
+            const uint32_t acol = tlane + colA0 + s * (TR * 16) + half * 4;
+            if (c4 < C4) tc_dw_store<TR>(acc, acol);
+            else tc_zero_chunk<TR>(acol);
+          }
+          pending = &bar_afull[s];
+        }
+        if (pending != nullptr) {   // publish the last chunk of the tile before waiting for the next load
+          if (warp_active) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
+          mbar_arrive(pending);
+          pending = nullptr;
+        }
+        if (tid == 0) stamp(i, 2);
+        if (tid == (NSETS - 1) * 128) stamp(i, 8);
+      }
+    } else {
+      // =============================================================== epilogue warps
+      const int centre0 = my_off + row_pitch + PS;
+      const int eset = (warp - W_EPI) >> 2;
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        const int b = i % NBUF, d = i & 1;
+        float* buf = bufs + b * p.buf_floats;
+        mbar_wait(&bar_dfull[d], (i >> 1) & 1);
+        tc_fence_after();
+        if (tid == W_EPI * 32) stamp(i, 3);
+        mbar_wait(&bar_full[b], (i / NBUF) & 1);   // already complete; orders the TMA-written skip pixels for this thread
+        if (warp_active) {
+#pragma unroll
+          for (int t = 0; t < TR; ++t)
+            if (t % NESETS == eset)
+              tc_epilogue_pixel<C4, NG, N16>(buf + centre0 + t * row_pitch, tlane + d * (TR * N16) + t * N16, s_pwb, active);
+          tc_fence_before();
+          fence_async_smem();
+        }
+        mbar_arrive(&bar_dempty[d]);
+        mbar_arrive(&bar_epi[b]);
+        if (tid == W_EPI * 32) stamp(i, 4);
+      }
+    }
+  } else if (lane_id == 0) {
+    if (warp == W_ISSUE) {
+      // =============================================================== MMA issuer
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t desc_fixed = ((uint64_t)(((uint32_t)(N16 * 16) >> 4) & 0x3FFF) << 16) | ((uint64_t)((128u >> 4) & 0x3FFF) << 32) |
+                                  ((uint64_t)1 << 46);
+      const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
+      uint32_t use = 0;
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        const int d = i & 1;
+        if (i >= 2) {
+          mbar_wait_role(&bar_dempty[d], ((i >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        stamp(i, 11);
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ++ks, ++use) {
+          const uint32_t s = use % NSTG;
+          mbar_wait_role(&bar_afull[s], (use / NSTG) & 1);
+          tc_fence_after();
+          if (ks == 0) stamp(i, 10);
+          if (ks == KS - 1) stamp(i, 9);
+          const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
+          const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
+          const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int t = 0; t < TR; ++t) {
+            const uint32_t dc = tmem_base + d * (TR * N16) + t * N16;
+            const uint32_t a = tmem_base + colA0 + (s * TR + t) * 16;
+            mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+            mma_tf32_ts(dc, a, dlo, idesc, 1u);
+            mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          }
+          tc_commit(&bar_aempty[s]);
+        }
+        tc_commit(&bar_dfull[d]);
+        stamp(i, 7);
+      }
+    } else if (warp == W_LOAD) {
+      // =============================================================== TMA loader
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        const int b = i % NBUF;
+        if (i >= NBUF) mbar_wait_role(&bar_free[b], ((i / NBUF) - 1) & 1);
+        int img, y0;
+        tile_coords(tile, img, y0);
+        mbar_expect_tx(&bar_full[b], p.load_bytes);
+        tma_load_4d(bufs + b * p.buf_floats, &tm_in, &bar_full[b], 0, -1, y0 - 1, img);
+        stamp(i, 0);
+      }
+    } else if (warp == W_STORE) {
+      // =============================================================== TMA storer
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        const int b = i % NBUF;
+        mbar_wait_role(&bar_epi[b], (i / NBUF) & 1);
+        int img, y0;
+        tile_coords(tile, img, y0);
+        tma_store_4d(&tm_out, bufs + b * p.buf_floats + row_pitch + PS, 0, 0, y0, img);
+        tma_store_commit();
+        stamp(i, 5);
+        tma_store_wait_read();
+        stamp(i, 6);
+        mbar_arrive(&bar_free[b]);
+      }
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -448,6 +740,7 @@ int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const
   p.n_tiles = B * p.bands_per_img;
   p.lanes = (tc.BH / TR) * W;
   p.load_bytes = (uint32_t)((size_t)G::PS * tc.IWB * (tc.BH + 2) * sizeof(float));
+  p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
   tc_layout(CINP, COUTP, G::K8, G::N16, &p.off_b, &p.off_w, &p.off_pipe);
   const int off = p.off_pipe;
   p.buf_floats = align_up(G::PS * tc.IWB * (tc.BH + 2), 256);
@@ -470,10 +763,54 @@ int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const
   return HP_OK;
 }
 
+template <int CINP, int COUTP, int TR, int NSTG, int NSETS, int NBUF, int NESETS>
+int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
+  using G = TcGeom<CINP, COUTP>;
+  TcParams p;
+  p.dww = w.dww; p.dwb = w.dwb; p.pwb = w.pwb; p.bhi = w.bhi; p.blo = w.blo;
+  p.W = W; p.H = H; p.BH = tc.BH; p.IWB = tc.IWB; p.row_pitch = tc.IWB * G::PS;
+  p.bands_per_img = ceil_div(H, tc.BH);
+  p.n_tiles = B * p.bands_per_img;
+  p.lanes = (tc.BH / TR) * W;
+  p.load_bytes = (uint32_t)((size_t)G::PS * tc.IWB * (tc.BH + 2) * sizeof(float));
+  p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
+  tc_layout(CINP, COUTP, G::K8, G::N16, &p.off_b, &p.off_w, &p.off_pipe);
+  p.buf_floats = align_up(G::PS * tc.IWB * (tc.BH + 2), 256);
+  const size_t smem = (size_t)(p.off_pipe + NBUF * p.buf_floats) * sizeof(float);
+  HP_REQUIRE(smem <= 227 * 1024, HP_ERR_INVALID, "tc deep block <%d,%d>: %zu bytes of shared memory needed", CINP, COUTP, smem);
+  HP_REQUIRE(p.lanes >= 1 && p.lanes <= 128 && tc.BH % TR == 0 && (tc.IWB + 1) % 8 == 0 && tc.IWB >= W + 2 && tc.IWB <= 256 &&
+                 tc.BH + 2 <= 256,
+             HP_ERR_INVALID, "tc deep block <%d,%d>: bad band geometry BH %d IWB %d W %d", CINP, COUTP, tc.BH, tc.IWB, W);
+  CUtensorMap tin, tout;
+  HP_TRY(make_map(&tin, in, B, H, W, CINP, 1, tc.BH + 2, tc.IWB, G::PS));
+  HP_TRY(make_map(&tout, out, B, H, W, COUTP, 1, tc.BH, tc.IWB, G::PS));
+  auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSTG, NSETS, NBUF, NESETS>;
+  HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  long long grid = h->num_sms;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + 96, smem, st>>>(tin, tout, p);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}
+
 template <int CINP, int COUTP>
 int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc,
                   cudaStream_t st) {
   constexpr int N16 = TcGeom<CINP, COUTP>::N16;
+#define TCD_CASE(TR_, NSTG_, NSETS_, NBUF_, NESETS_)                                     \
+  if constexpr (2 * TR_ * N16 + NSTG_ * TR_ * 16 <= 512)                                 \
+    if (tc.TR == TR_ && tc.NSTG == NSTG_ && tc.nsets == NSETS_ && tc.nbuf == NBUF_ && tc.npipe == NESETS_) \
+      return launch_deep<CINP, COUTP, TR_, NSTG_, NSETS_, NBUF_, NESETS_>(h, in, out, B, H, W, w, tc, st);
+  if (tc.nbuf > 0) {   // warp-specialised kernel: npipe carries the number of epilogue warp sets
+    TCD_CASE(4, 2, 2, 3, 1) TCD_CASE(4, 2, 2, 3, 2) TCD_CASE(4, 2, 3, 3, 2) TCD_CASE(4, 3, 3, 3, 2) TCD_CASE(4, 4, 3, 3, 2) TCD_CASE(4, 4, 2, 3, 2)
+    TCD_CASE(4, 2, 3, 2, 2) TCD_CASE(4, 2, 2, 2, 2) TCD_CASE(4, 2, 3, 3, 1)
+    TCD_CASE(2, 4, 2, 4, 1) TCD_CASE(2, 4, 3, 4, 1) TCD_CASE(2, 4, 2, 3, 1) TCD_CASE(2, 4, 3, 3, 1) TCD_CASE(2, 2, 2, 2, 1) TCD_CASE(2, 4, 2, 2, 1)
+    TCD_CASE(2, 4, 2, 4, 2) TCD_CASE(2, 4, 3, 4, 2) TCD_CASE(2, 4, 3, 3, 2)
+    hp_set_error("tc deep block: no kernel for TR %d NSTG %d nsets %d nbuf %d esets %d", tc.TR, tc.NSTG, tc.nsets, tc.nbuf, tc.npipe);
+    return HP_ERR_UNSUPPORTED;
+  }
+#undef TCD_CASE
 #define TC_CASE(TR_, NSTG_, NPIPE_, NSETS_)                                              \
   if constexpr (NPIPE_ * TR_ * (N16 + 16 * NSTG_) <= 512)                                \
     if (tc.TR == TR_ && tc.NSTG == NSTG_ && tc.npipe == NPIPE_ && tc.nsets == NSETS_)    \
@@ -519,12 +856,16 @@ bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc) {
   const int C4 = cinp / 4, NG = coutp / 4, N16 = (coutp + 15) / 16 * 16, K8 = (cinp + 7) / 8 * 8;
   const int PS = ((C4 > NG ? C4 : NG) | 1) * 4;
   if (tc.TR < 1 || tc.BH < tc.TR || tc.BH % tc.TR || (tc.BH / tc.TR) * W > 128 || tc.BH + 2 > 256) return false;
-  if (tc.npipe * tc.TR * (N16 + 16 * tc.NSTG) > 512) return false;
-  if (tc.npipe * (128 * tc.nsets + 32) > 1024) return false;
+  if (tc.nbuf > 0) {
+    if (2 * tc.TR * N16 + tc.NSTG * tc.TR * 16 > 512 || 128 * tc.nsets + 128 * tc.npipe + 96 > 1024 || tc.npipe < 1 || tc.npipe > 2) return false;
+  } else {
+    if (tc.npipe * tc.TR * (N16 + 16 * tc.NSTG) > 512) return false;
+    if (tc.npipe * (128 * tc.nsets + 32) > 1024) return false;
+  }
   int off_b, off_w, off_pipe;
   tc_layout(cinp, coutp, K8, N16, &off_b, &off_w, &off_pipe);
   const size_t buf = (size_t)align_up(PS * tc.IWB * (tc.BH + 2), 256) * 4;
-  return (size_t)off_pipe * 4 + tc.npipe * buf <= 227 * 1024;
+  return (size_t)off_pipe * 4 + (size_t)(tc.nbuf > 0 ? tc.nbuf : tc.npipe) * buf <= 227 * 1024;
 }
 
 // Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.
@@ -534,7 +875,7 @@ bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
   static const int pref[][4] = {{2, 2, 4, 1}, {2, 1, 4, 1}, {2, 2, 3, 2}, {2, 2, 3, 1}, {4, 2, 2, 2}, {4, 1, 2, 2}, {2, 2, 2, 2}, {4, 2, 1, 2}, {4, 1, 1, 1}};   // TR, NSTG, npipe, nsets
   for (const auto& c : pref) {
     TcCfg t;
-    t.TR = c[0]; t.NSTG = c[1]; t.npipe = c[2]; t.nsets = c[3];
+    t.TR = c[0]; t.NSTG = c[1]; t.npipe = c[2]; t.nsets = c[3]; t.nbuf = 0;
     t.IWB = ((W + 2 + 1 + 7) / 8) * 8 - 1;   // >= W + 2 and == 7 (mod 8): the band interior starts 128-byte aligned
     const int strips = ceil_div(H, t.TR);
     int max_strips = 128 / W;

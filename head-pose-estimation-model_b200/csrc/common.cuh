@@ -110,8 +110,10 @@ struct hp_ctx {
   DevBuf scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
-  int tc_override[16][5] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets per block (TR 0 = automatic, -1 = do not use)
+  int tc_override[16][6] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets, nbuf per block (TR 0 = automatic, -1 = do not use)
   int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
+  long long* tc_trace = nullptr;   // optional device buffer for per-tile clock stamps of the deep tensor-core kernel
+  int tc_trace_tiles = 0;
 };
 
 // generic per-token dense layer used by detector heads and regressor heads (dense.cu)
@@ -147,7 +149,7 @@ int hp_launch_block_tma(hp_ctx* h, int blk, const float* in, float* out, int B, 
 
 // blocks_tc.cu: third-generation fused BlazeBlock kernel (depthwise on CUDA cores -> TMEM, pointwise as 3xTF32 tcgen05 GEMM)
 struct TcCfg {
-  int TR, NSTG, BH, IWB, npipe, nsets;
+  int TR, NSTG, BH, IWB, npipe, nsets, nbuf;   // nbuf > 0 selects the warp-specialised (deep) kernel with nbuf halo buffers
 };
 bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc);
 void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, float* blo);

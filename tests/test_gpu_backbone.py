@@ -163,3 +163,51 @@ def test_preprocess_matches_reference_arithmetic():
     _lib.check(_lib.lib().hp_preprocess_u8(ctx.handle, u8.data_ptr(), 3, 40, 24, x.data_ptr(), ctx.stream_ptr()))
     want = ((img[..., ::-1].astype(np.float64) / 255.0).astype(np.float32) - np.float32(0.5)) / np.float32(0.5)
     assert np.array_equal(x.cpu().numpy(), want)
+
+
+# (TR, NSTG, npipe, nsets, nbuf): pipelined (nbuf 0) and warp-specialised (nbuf > 0) tensor-core geometries
+# (for nbuf > 0 the npipe slot carries the number of epilogue warp sets)
+TC_GEOMETRIES = [(2, 2, 4, 1, 0), (2, 2, 3, 2, 0), (4, 2, 2, 2, 0), (4, 1, 2, 2, 0), (4, 1, 1, 1, 0), (4, 2, 1, 2, 3),
+                 (4, 2, 2, 3, 3), (4, 4, 2, 3, 3), (4, 2, 2, 3, 2), (2, 4, 1, 2, 4), (2, 4, 2, 3, 4), (2, 4, 2, 3, 3), (2, 2, 1, 2, 2)]
+
+
+@pytest.mark.parametrize("geom", TC_GEOMETRIES)
+@pytest.mark.parametrize("size,batch", [(96, 37), (88, 5), (128, 3)])
+def test_tensor_core_block_geometries(geom, size, batch):
+    """Every instantiated geometry of the tensor-core BlazeBlock kernel reproduces the naive CUDA kernels on blocks
+    0, 1, 3 and 4 (random-init weights; batch 37 gives every persistent CTA a different number of tiles, 88 gives
+    partial bands and odd widths).  Geometries that do not fit a block (TMEM / shared memory) must be refused."""
+    from hpose_b200 import _lib
+    from hpose_b200.unified import pack_backbone, random_backbone
+    ctx = _ctx()
+    lib = _lib.lib()
+    flat = pack_backbone(random_backbone(seed=99, bias_scale=0.1))
+    _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
+    g = torch.Generator(device="cuda").manual_seed(size)
+    x = torch.rand((batch, size, size, 3), generator=g, device="cuda") * 2 - 1
+    chans = {0: 24, 1: 28, 3: 36, 4: 42}
+    TR, NSTG, npipe, nsets, nbuf = geom
+    ran = 0
+    try:
+        for blk, c in chans.items():
+            H = -(-size // 2) if blk < 2 else -(-size // 4)
+            shape = (batch, H, H, c)
+            ctx.set_impl(_lib.HP_IMPL_NAIVE)
+            want = _read_act(ctx, x, blk, shape)
+            ctx.set_impl(_lib.HP_IMPL_FAST)
+            strips = -(-H // TR)
+            bands = -(-strips // max(1, 128 // H))
+            BH = -(-strips // bands) * TR
+            _lib.check(lib.hp_debug_set_tc(ctx.handle, blk, TR, NSTG, BH, npipe, nsets, nbuf))
+            try:
+                got = _read_act(ctx, x, blk, shape)
+            except _lib.HposeError as e:
+                assert e.code in (-1, -5), e          # refused: not instantiated / does not fit
+                continue
+            finally:
+                _lib.check(lib.hp_debug_set_tc(ctx.handle, blk, 0, 0, 0, 0, 0, 0))
+            ran += 1
+            assert rel_err(got, want) < 2e-5, (geom, blk, rel_err(got, want))
+    finally:
+        ctx.set_impl(_lib.HP_IMPL_FAST)
+    assert ran >= 1 or size == 128, f"geometry {geom} ran on no block"

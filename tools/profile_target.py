@@ -18,6 +18,10 @@ ctx = default_context()
 lib = _lib.lib()
 flat = pack_backbone(random_backbone(1234))
 _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
+# optional geometry override for the tensor-core block kernel: TC_GEOM="blk:TR,NSTG,BH,npipe,nsets,nbuf;blk:..."
+for item in filter(None, os.environ.get("TC_GEOM", "").split(";")):
+    blk, vals = item.split(":")
+    _lib.check(lib.hp_debug_set_tc(ctx.handle, int(blk), *[int(v) for v in vals.split(",")]))
 x = torch.rand((B, size, size, 3), device="cuda") * 2 - 1
 A = lib.hp_num_anchors(size, size)
 cls = torch.empty((B, A), device="cuda")

@@ -25,8 +25,10 @@ x = torch.rand((B, size, size, 3), device="cuda") * 2 - 1
 ms = np.zeros(18, dtype=np.float32)
 
 # candidates (TR, NSTG, npipe, nsets); the band height follows from TR and the map size
-CANDS = [(4, 2, 2, 1), (4, 2, 2, 2), (4, 1, 2, 2), (4, 2, 1, 2), (4, 3, 1, 3), (2, 2, 3, 1), (2, 2, 3, 2), (2, 2, 2, 2), (2, 2, 4, 1),
-         (2, 1, 4, 1), (3, 2, 2, 1), (3, 2, 2, 2), (3, 1, 2, 2)]
+# nbuf > 0: warp-specialised (deep) kernel, the npipe slot then carries the number of epilogue warp sets
+CANDS = [(2, 2, 4, 1, 0), (2, 2, 3, 2, 0),
+         (4, 2, 1, 2, 3), (4, 2, 2, 2, 3), (4, 2, 2, 3, 3), (4, 3, 2, 3, 3), (4, 4, 2, 3, 3), (4, 4, 2, 2, 3), (4, 2, 1, 3, 3), (4, 2, 2, 3, 2), (4, 2, 2, 2, 2),
+         (2, 4, 1, 2, 4), (2, 4, 1, 3, 4), (2, 4, 2, 2, 4), (2, 4, 2, 3, 4), (2, 4, 1, 3, 3), (2, 4, 2, 3, 3)]
 TC_BLOCKS = [int(b) for b in os.environ.get("TC_BLOCKS", "0,1,3,4").split(",")]
 HS = {0: size // 2, 1: size // 2, 3: size // 4, 4: size // 4, 6: size // 8, 7: size // 8, 8: size // 8, 9: size // 8, 10: size // 8,
       12: size // 16, 13: size // 16, 14: size // 16, 15: size // 16}
@@ -49,23 +51,23 @@ base = run()
 print("default:", " ".join(f"b{b}={base[1 + b]:.4f}" for b in TC_BLOCKS), flush=True)
 res = {"default": {f"block{b}": float(base[1 + b]) for b in TC_BLOCKS}}
 for b in TC_BLOCKS:
-    _lib.check(lib.hp_debug_set_tc(ctx.handle, b, -1, 0, 0, 0, 0))
+    _lib.check(lib.hp_debug_set_tc(ctx.handle, b, -1, 0, 0, 0, 0, 0))
 t = run()
 res["cuda_core"] = {f"block{b}": float(t[1 + b]) for b in TC_BLOCKS}
 print("cuda-core kernel:", " ".join(f"b{b}={t[1 + b]:.4f}" for b in TC_BLOCKS), flush=True)
 for b in TC_BLOCKS:
     for cand in CANDS:
-        TR, NSTG, npipe, nsets = cand
+        TR, NSTG, npipe, nsets, nbuf = cand
         BH = band_height(HS[b], HS[b], TR)
-        _lib.check(lib.hp_debug_set_tc(ctx.handle, b, TR, NSTG, BH, npipe, nsets))
+        _lib.check(lib.hp_debug_set_tc(ctx.handle, b, TR, NSTG, BH, npipe, nsets, nbuf))
         try:
             t = run()
             res.setdefault(f"block{b}", {})[str(cand)] = float(t[1 + b])
-            print(f"block{b} TR={TR} NSTG={NSTG} BH={BH} npipe={npipe} nsets={nsets}: {t[1 + b]:.4f} ms", flush=True)
+            print(f"block{b} TR={TR} NSTG={NSTG} BH={BH} npipe={npipe} nsets={nsets} nbuf={nbuf}: {t[1 + b]:.4f} ms", flush=True)
         except Exception as e:  # configuration not instantiated / does not fit
             print(f"block{b} {cand} failed: {str(e)[:120]}", flush=True)
-    _lib.check(lib.hp_debug_set_tc(ctx.handle, b, -1, 0, 0, 0, 0))
+    _lib.check(lib.hp_debug_set_tc(ctx.handle, b, -1, 0, 0, 0, 0, 0))
 for b in TC_BLOCKS:
-    _lib.check(lib.hp_debug_set_tc(ctx.handle, b, 0, 0, 0, 0, 0))
+    _lib.check(lib.hp_debug_set_tc(ctx.handle, b, 0, 0, 0, 0, 0, 0))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"tc_sweep_{size}.json"), "w"), indent=1)
