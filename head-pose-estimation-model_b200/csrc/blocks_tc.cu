@@ -171,10 +171,16 @@ __device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity) {
 
 // Depthwise 3x3 (+bias) of one 4-channel chunk for the TR pixels of a lane (sliding window down the column).
 template <int CINP, int TR, int PS>
-__device__ __forceinline__ void tc_dw_compute(const float* win, const float* dww_c, const float* dwb_c, int row_pitch, float4 (&acc)[TR]) {
+__device__ __forceinline__ void tc_dw_compute(const float* win, const float* dww_c, const float* dwb_c, int row_pitch, bool mask_l, bool mask_r,
+                                              float4 (&acc)[TR]) {
   float4 w[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) w[k] = ld4(dww_c + k * CINP);
+  // SAME padding at the image's left / right edge when the halo buffer has no padding column there: the tap reads a
+  // finite value of a neighbouring row and multiplies it by zero
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mask_l) { w[0] = z4; w[3] = z4; w[6] = z4; }
+  if (mask_r) { w[2] = z4; w[5] = z4; w[8] = z4; }
   const float4 bias = ld4(dwb_c);
 #pragma unroll
   for (int t = 0; t < TR; ++t) acc[t] = bias;
@@ -207,7 +213,7 @@ __device__ __forceinline__ void tc_dw_store(const float4 (&acc)[TR], uint32_t ac
 template <int CINP, int TR, int PS>
 __device__ __forceinline__ void tc_dw_chunk(const float* win, const float* dww_c, const float* dwb_c, int row_pitch, uint32_t acol) {
   float4 acc[TR];
-  tc_dw_compute<CINP, TR, PS>(win, dww_c, dwb_c, row_pitch, acc);
+  tc_dw_compute<CINP, TR, PS>(win, dww_c, dwb_c, row_pitch, false, false, acc);
   tc_dw_store<TR>(acc, acol);
 }
 template <int TR>
@@ -244,6 +250,27 @@ __device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, co
         if (active) st4(cpix + j * 4, o);
       }
     }
+  }
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+// Both 4-channel chunks of a k-step at once: 8 hi columns, then 8 lo columns per M-tile (the layout the MMA reads)
+template <int TR>
+__device__ __forceinline__ void tc_dw_store2(const float4 (&a0)[TR], const float4 (&a1)[TR], uint32_t acol) {
+#pragma unroll
+  for (int t = 0; t < TR; ++t) {
+    const float f[8] = {a0[t].x, a0[t].y, a0[t].z, a0[t].w, a1[t].x, a1[t].y, a1[t].z, a1[t].w};
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      hi[e] = tf32_hi(f[e]);
+      lo[e] = __float_as_uint(f[e] - __uint_as_float(hi[e]));
+    }
+    tmem_st8(acol + t * 16, hi);
+    tmem_st8(acol + t * 16 + 8, lo);
   }
 }
 
@@ -447,25 +474,39 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 //   loader  (1 thread) : TMA loads into a ring of NBUF halo buffers            free[b]  -> full[b]
 //   DW sets (NSETS x 4 warps): depthwise chunks -> TMEM A ring                 full[b], a_empty[s] -> a_full[s]
 //   issuer  (1 thread) : 3 x TR tcgen05.mma per k-step into D[i & 1]           a_full[s], d_empty[d] -> a_empty[s], d_full[d]
-//   epilogue (4 warps) : D[d] + bias + skip -> ReLU in place in buffer b       d_full[d] -> d_empty[d], epi_done[b]
+//   epilogue (NESETS x 4 warps): D[d] + bias + skip -> ReLU in place in buffer b   d_full[d] -> d_empty[d], epi_done[b]
 //   storer  (1 thread) : TMA store of the band interior, frees the buffer      epi_done[b] -> free[b]
+// Tile = NI images x one band of BH rows x full width.  The halo buffer has NO left halo column: the box starts at x = 0
+// and is IWB >= W pixels wide with IWB * PS * 4 a multiple of 128 bytes, so every row (and the store source, the second
+// row) is 128-byte aligned.  The left neighbour of x = 0 (and the right neighbour of x = W - 1 when IWB == W) is SAME
+// padding: the lane multiplies whatever finite value it reads there by a zeroed depthwise weight.
 #define TCD_MAXB 4
-template <int CINP, int COUTP, int TR, int NSTG, int NSETS, int NBUF, int NESETS>
+struct TcdParams {
+  const float *dww, *dwb, *pwb, *bhi, *blo;
+  int W, H, BH, IWB, row_pitch, img_pitch;   // pitches in floats; img_pitch = (BH + 2) * row_pitch
+  int NI, bands_per_img, n_tiles, lanes, lanes_per_img, B;
+  int nstg, nbuf;
+  uint32_t load_bytes;
+  int off_b, off_w, off_pipe, buf_floats;
+  long long* trace;
+  int trace_tiles;
+};
+
+template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT>
 __global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
-blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcParams p) {
+blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcdParams p) {
   using G = TcGeom<CINP, COUTP>;
   constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
   constexpr uint32_t colA0 = 2 * TR * N16;                        // TMEM: D[0], D[1] (TR * N16 columns each), then the A ring
-  static_assert(colA0 + NSTG * TR * 16 <= 512, "TMEM budget");
-  static_assert(NSTG <= TC_MAX_STG && NBUF <= TCD_MAXB, "ring depth");
+  static_assert(colA0 + 2 * TR * 16 <= 512, "TMEM budget");
 
   extern __shared__ __align__(1024) float smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* bar_full = bars;                                       // [NBUF]
-  uint64_t* bar_free = bars + TCD_MAXB;                            // [NBUF]
-  uint64_t* bar_epi = bars + 2 * TCD_MAXB;                         // [NBUF]
-  uint64_t* bar_afull = bars + 3 * TCD_MAXB;                       // [NSTG]
-  uint64_t* bar_aempty = bar_afull + TC_MAX_STG;                   // [NSTG]
+  uint64_t* bar_full = bars;                                       // [nbuf]
+  uint64_t* bar_free = bars + TCD_MAXB;                            // [nbuf]
+  uint64_t* bar_epi = bars + 2 * TCD_MAXB;                         // [nbuf]
+  uint64_t* bar_afull = bars + 3 * TCD_MAXB;                       // [nstg]
+  uint64_t* bar_aempty = bar_afull + TC_MAX_STG;                   // [nstg]
   uint64_t* bar_dfull = bar_aempty + TC_MAX_STG;                   // [2]
   uint64_t* bar_dempty = bar_dfull + 2;                            // [2]
   static_assert((3 * TCD_MAXB + 2 * TC_MAX_STG + 4) * 8 + 4 <= TC_BAR_FLOATS * 4, "barrier block");
@@ -480,6 +521,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane_id = tid & 31;
   constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1, W_STORE = W_ISSUE + 2;
+  const int NSTG = p.nstg, NBUF = p.nbuf;
 
   for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
     st4(s_bhi + i, ld4(p.bhi + i));
@@ -488,6 +530,9 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   for (int i = tid * 4; i < 9 * CINP; i += nthr * 4) st4(s_dww + i, ld4(p.dww + i));
   for (int i = tid * 4; i < CINP; i += nthr * 4) st4(s_dwb + i, ld4(p.dwb + i));
   for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
+  // masked taps read (and multiply by zero) floats just outside the rows of a buffer: make every such float finite
+  for (int i = p.off_w + 10 * CINP + COUTP + tid * 4; i < p.off_pipe + NBUF * p.buf_floats + 256; i += nthr * 4)
+    st4(smem + i, make_float4(0.f, 0.f, 0.f, 0.f));
   fence_async_smem();
   if (tid == 0) {
     for (int b = 0; b < NBUF; ++b) {
@@ -496,7 +541,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       mbar_init(&bar_epi[b], 128 * NESETS);
     }
     for (int s = 0; s < NSTG; ++s) {
-      mbar_init(&bar_afull[s], 256);
+      mbar_init(&bar_afull[s], UNIT == 2 ? 128 : 256);   // one set per k-step (UNIT 2) or one set per 4-channel half
       mbar_init(&bar_aempty[s], 1);
     }
     for (int d = 0; d < 2; ++d) {
@@ -514,9 +559,11 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
 
+  // tile -> (first image, first row); NI > 1 only with one band per image
   auto tile_coords = [&](int tile, int& img, int& y0) {
-    img = tile / p.bands_per_img;
-    y0 = (tile - img * p.bands_per_img) * p.BH;
+    const int q = tile / p.bands_per_img;
+    img = q * p.NI;
+    y0 = (tile - q * p.bands_per_img) * p.BH;
   };
   const int row_pitch = p.row_pitch;
   // trace slots: 0 load issued, 1 DW sees full, 2 DW set 0 done, 3 epilogue sees d_full, 4 epilogue done, 5 store issued, 6 store read done,
@@ -526,71 +573,96 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   };
 
   if (warp < W_ISSUE) {
-    // lane geometry shared by the depthwise and the epilogue warps
+    // lane geometry shared by the depthwise and the epilogue warps: lane -> (image in tile, strip, column)
     const int wq = warp & 3;
     const int lane = wq * 32 + lane_id;
     const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
     const bool active = lane < p.lanes;
     const bool warp_active = wq * 32 < p.lanes;
     const int l = active ? lane : 0;
-    const int yq = l / p.W;
-    const int x = l - yq * p.W;
-    const int my_off = yq * TR * row_pitch + x * PS;
+    const int im = l / p.lanes_per_img;
+    const int l2 = l - im * p.lanes_per_img;
+    const int yq = l2 / p.W;
+    const int x = l2 - yq * p.W;
+    const int my_off = im * p.img_pitch + yq * TR * row_pitch + (x - 1) * PS;   // top-left pixel of the 3x3 window of output row yq*TR
+    const bool mask_l = (x == 0), mask_r = (x == p.W - 1 && p.IWB == p.W);
     if (warp < W_EPI) {
       // =============================================================== depthwise sets
-      // The TMEM stores of a chunk are waited for (and the chunk published) only after the next chunk has been
-      // computed: tcgen05.st latency and the a_empty round trip hide behind the LDS / FFMA work.
+      // Work units (a 4-channel chunk, or with UNIT 2 both chunks of a k-step) are dealt round-robin to the sets over the
+      // GLOBAL unit counter of the CTA, not per tile: consecutive units of a set are then always NSETS units apart, which
+      // bounds how far one set can run ahead of the others (an mbarrier parity wait is only safe one phase ahead: the
+      // host checks that consecutive units of a set are at most NSTG k-steps apart).  The TMEM stores of a unit are waited for, and the unit published, only after
+      // the next unit has been computed: tcgen05.st latency and the a_empty round trip hide behind the LDS / FFMA work.
       const int set = warp >> 2;
-      int i = 0;
+      constexpr int UPT = (UNIT == 2) ? KS : 2 * KS;                       // units per tile
+      const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const uint32_t n_units = (uint32_t)my_tiles * UPT;
       uint64_t* pending = nullptr;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
-        const int b = i % NBUF;
-        const float* buf = bufs + b * p.buf_floats;
-        mbar_wait(&bar_full[b], (i / NBUF) & 1);
-        if (tid == 0) stamp(i, 1);
+      int cur_i = -1;
+      const float* buf = bufs;
 #pragma unroll 1
-        for (int c4 = set; c4 < 2 * KS; c4 += NSETS) {
-          const int ks = c4 >> 1, half = c4 & 1;
-          const uint32_t use = (uint32_t)i * KS + ks;
-          const uint32_t s = use % NSTG;
-          float4 acc[TR];
-          if (warp_active && c4 < C4) tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4, s_dww + c4 * 4, s_dwb + c4 * 4, row_pitch, acc);
-          if (pending != nullptr) {
-            if (warp_active) {
-              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-              tc_fence_before();
-            }
-            mbar_arrive(pending);
-          }
-          if (use >= NSTG) {
-            mbar_wait(&bar_aempty[s], ((use / NSTG) - 1) & 1);
-            tc_fence_after();
-          }
-          if (warp_active) {
-            const uint32_t acol = tlane + colA0 + s * (TR * 16) + half * 4;
-            if (c4 < C4) tc_dw_store<TR>(acc, acol);
-            else tc_zero_chunk<TR>(acol);
-          }
-          pending = &bar_afull[s];
+      for (uint32_t g = set; g < n_units; g += NSETS) {
+        const int i = (int)(g / UPT);
+        const int u = (int)(g - (uint32_t)i * UPT);
+        const int ks = (UNIT == 2) ? u : (u >> 1), half = (UNIT == 2) ? 0 : (u & 1);
+        const int c4 = (UNIT == 2) ? 2 * u : u;
+        const uint32_t use = (uint32_t)i * KS + ks;
+        const uint32_t s = use % NSTG;
+        if (i != cur_i) {                                                    // first unit of this set in tile i
+          cur_i = i;
+          const int b = i % NBUF;
+          buf = bufs + b * p.buf_floats;
+          mbar_wait(&bar_full[b], (i / NBUF) & 1);
+          if (tid == 0) stamp(i, 1);
         }
-        if (pending != nullptr) {   // publish the last chunk of the tile before waiting for the next load
+        float4 acc[TR], acc1[TR];
+        if (warp_active && c4 < C4)
+          tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4, s_dww + c4 * 4, s_dwb + c4 * 4, row_pitch, mask_l, mask_r, acc);
+        if (UNIT == 2) {
+          if (warp_active && c4 + 1 < C4) {
+            tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4 + 4, s_dww + c4 * 4 + 4, s_dwb + c4 * 4 + 4, row_pitch, mask_l, mask_r, acc1);
+          } else {
+#pragma unroll
+            for (int t = 0; t < TR; ++t) acc1[t] = make_float4(0.f, 0.f, 0.f, 0.f);   // K padding
+          }
+        }
+        if (pending != nullptr) {
+          if (warp_active) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
+          mbar_arrive(pending);
+        }
+        if (use >= (uint32_t)NSTG) {
+          mbar_wait(&bar_aempty[s], ((use / NSTG) - 1) & 1);
+          tc_fence_after();
+        }
+        if (warp_active) {
+          const uint32_t acol = tlane + colA0 + s * (TR * 16) + half * 4;
+          if (UNIT == 2) tc_dw_store2<TR>(acc, acc1, acol);
+          else if (c4 < C4) tc_dw_store<TR>(acc, acol);
+          else tc_zero_chunk<TR>(acol);
+        }
+        pending = &bar_afull[s];
+        if (g + NSETS >= n_units || (int)((g + NSETS) / UPT) != i) {
+          // last unit of this set in tile i: publish now (the next unit may have to wait for a TMA load)
           if (warp_active) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
           }
           mbar_arrive(pending);
           pending = nullptr;
+          if (tid == 0) stamp(i, 2);
+          if (tid == (NSETS - 1) * 128) stamp(i, 8);
         }
-        if (tid == 0) stamp(i, 2);
-        if (tid == (NSETS - 1) * 128) stamp(i, 8);
       }
     } else {
       // =============================================================== epilogue warps
       const int centre0 = my_off + row_pitch + PS;
       const int eset = (warp - W_EPI) >> 2;
-      int i = 0;
+      int i = 0, b = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
-        const int b = i % NBUF, d = i & 1;
+        const int d = i & 1;
         float* buf = bufs + b * p.buf_floats;
         mbar_wait(&bar_dfull[d], (i >> 1) & 1);
         tc_fence_after();
@@ -607,6 +679,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
         mbar_arrive(&bar_dempty[d]);
         mbar_arrive(&bar_epi[b]);
         if (tid == W_EPI * 32) stamp(i, 4);
+        if (++b == NBUF) b = 0;
       }
     }
   } else if (lane_id == 0) {
@@ -621,14 +694,14 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
         const int d = i & 1;
         if (i >= 2) {
-          mbar_wait_role(&bar_dempty[d], ((i >> 1) - 1) & 1);
+          mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
           tc_fence_after();
         }
         stamp(i, 11);
 #pragma unroll 1
         for (int ks = 0; ks < KS; ++ks, ++use) {
           const uint32_t s = use % NSTG;
-          mbar_wait_role(&bar_afull[s], (use / NSTG) & 1);
+          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
           if (ks == 0) stamp(i, 10);
           if (ks == KS - 1) stamp(i, 9);
@@ -650,30 +723,31 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       }
     } else if (warp == W_LOAD) {
       // =============================================================== TMA loader
-      int i = 0;
+      int i = 0, b = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
-        const int b = i % NBUF;
-        if (i >= NBUF) mbar_wait_role(&bar_free[b], ((i / NBUF) - 1) & 1);
+        if (i >= NBUF) mbar_wait(&bar_free[b], ((i / NBUF) - 1) & 1);
         int img, y0;
         tile_coords(tile, img, y0);
         mbar_expect_tx(&bar_full[b], p.load_bytes);
-        tma_load_4d(bufs + b * p.buf_floats, &tm_in, &bar_full[b], 0, -1, y0 - 1, img);
+        tma_load_4d(bufs + b * p.buf_floats, &tm_in, &bar_full[b], 0, 0, y0 - 1, img);
         stamp(i, 0);
+        if (++b == NBUF) b = 0;
       }
     } else if (warp == W_STORE) {
       // =============================================================== TMA storer
-      int i = 0;
+      int i = 0, b = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
-        const int b = i % NBUF;
-        mbar_wait_role(&bar_epi[b], (i / NBUF) & 1);
+        mbar_wait(&bar_epi[b], (i / NBUF) & 1);
         int img, y0;
         tile_coords(tile, img, y0);
-        tma_store_4d(&tm_out, bufs + b * p.buf_floats + row_pitch + PS, 0, 0, y0, img);
+        for (int im = 0; im < p.NI; ++im)
+          if (img + im < p.B) tma_store_4d(&tm_out, bufs + b * p.buf_floats + im * p.img_pitch + row_pitch, 0, 0, y0, img + im);
         tma_store_commit();
         stamp(i, 5);
         tma_store_wait_read();
         stamp(i, 6);
         mbar_arrive(&bar_free[b]);
+        if (++b == NBUF) b = 0;
       }
       tma_store_wait_all();
     }
@@ -763,28 +837,34 @@ int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const
   return HP_OK;
 }
 
-template <int CINP, int COUTP, int TR, int NSTG, int NSETS, int NBUF, int NESETS>
+template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT>
 int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
   using G = TcGeom<CINP, COUTP>;
-  TcParams p;
+  TcdParams p;
   p.dww = w.dww; p.dwb = w.dwb; p.pwb = w.pwb; p.bhi = w.bhi; p.blo = w.blo;
-  p.W = W; p.H = H; p.BH = tc.BH; p.IWB = tc.IWB; p.row_pitch = tc.IWB * G::PS;
+  p.W = W; p.H = H; p.BH = tc.BH; p.IWB = tc.IWB; p.row_pitch = tc.IWB * G::PS; p.img_pitch = (tc.BH + 2) * p.row_pitch;
+  p.NI = tc.ni; p.B = B;
   p.bands_per_img = ceil_div(H, tc.BH);
-  p.n_tiles = B * p.bands_per_img;
-  p.lanes = (tc.BH / TR) * W;
-  p.load_bytes = (uint32_t)((size_t)G::PS * tc.IWB * (tc.BH + 2) * sizeof(float));
+  p.n_tiles = ceil_div(B, tc.ni) * p.bands_per_img;
+  p.lanes_per_img = (tc.BH / TR) * W;
+  p.lanes = tc.ni * p.lanes_per_img;
+  p.nstg = tc.NSTG; p.nbuf = tc.nbuf;
+  p.load_bytes = (uint32_t)((size_t)G::PS * tc.IWB * (tc.BH + 2) * tc.ni * sizeof(float));
   p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
   tc_layout(CINP, COUTP, G::K8, G::N16, &p.off_b, &p.off_w, &p.off_pipe);
-  p.buf_floats = align_up(G::PS * tc.IWB * (tc.BH + 2), 256);
-  const size_t smem = (size_t)(p.off_pipe + NBUF * p.buf_floats) * sizeof(float);
+  p.buf_floats = align_up(G::PS * tc.IWB * (tc.BH + 2) * tc.ni, 256);
+  const size_t smem = (size_t)(p.off_pipe + tc.nbuf * p.buf_floats + 256) * sizeof(float);
   HP_REQUIRE(smem <= 227 * 1024, HP_ERR_INVALID, "tc deep block <%d,%d>: %zu bytes of shared memory needed", CINP, COUTP, smem);
-  HP_REQUIRE(p.lanes >= 1 && p.lanes <= 128 && tc.BH % TR == 0 && (tc.IWB + 1) % 8 == 0 && tc.IWB >= W + 2 && tc.IWB <= 256 &&
-                 tc.BH + 2 <= 256,
-             HP_ERR_INVALID, "tc deep block <%d,%d>: bad band geometry BH %d IWB %d W %d", CINP, COUTP, tc.BH, tc.IWB, W);
+  HP_REQUIRE(p.lanes >= 1 && p.lanes <= 128 && tc.BH % TR == 0 && (tc.IWB * G::PS) % 32 == 0 && tc.IWB >= W && tc.IWB <= 256 &&
+                 tc.BH + 2 <= 256 && tc.ni >= 1 && tc.ni <= 256 && (tc.ni == 1 || p.bands_per_img == 1) && tc.nbuf >= 2 &&
+                 tc.nbuf <= TCD_MAXB && tc.NSTG >= 2 && tc.NSTG <= TC_MAX_STG && 2 * TR * G::N16 + tc.NSTG * TR * 16 <= 512 &&
+                 (tc.IWB > W || W % 8 == 0) && tc.nsets <= tc.NSTG * (tc.unit == 2 ? 1 : 2),
+             HP_ERR_INVALID, "tc deep block <%d,%d>: bad geometry TR %d BH %d IWB %d W %d NI %d nbuf %d nstg %d", CINP, COUTP, TR, tc.BH,
+             tc.IWB, W, tc.ni, tc.nbuf, tc.NSTG);
   CUtensorMap tin, tout;
-  HP_TRY(make_map(&tin, in, B, H, W, CINP, 1, tc.BH + 2, tc.IWB, G::PS));
+  HP_TRY(make_map(&tin, in, B, H, W, CINP, tc.ni, tc.BH + 2, tc.IWB, G::PS));
   HP_TRY(make_map(&tout, out, B, H, W, COUTP, 1, tc.BH, tc.IWB, G::PS));
-  auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSTG, NSETS, NBUF, NESETS>;
+  auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSETS, NESETS, UNIT>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -798,16 +878,14 @@ template <int CINP, int COUTP>
 int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc,
                   cudaStream_t st) {
   constexpr int N16 = TcGeom<CINP, COUTP>::N16;
-#define TCD_CASE(TR_, NSTG_, NSETS_, NBUF_, NESETS_)                                     \
-  if constexpr (2 * TR_ * N16 + NSTG_ * TR_ * 16 <= 512)                                 \
-    if (tc.TR == TR_ && tc.NSTG == NSTG_ && tc.nsets == NSETS_ && tc.nbuf == NBUF_ && tc.npipe == NESETS_) \
-      return launch_deep<CINP, COUTP, TR_, NSTG_, NSETS_, NBUF_, NESETS_>(h, in, out, B, H, W, w, tc, st);
+#define TCD_CASE(TR_, NSETS_, NESETS_, UNIT_)                                            \
+  if constexpr (2 * TR_ * N16 + 2 * TR_ * 16 <= 512)                                     \
+    if (tc.TR == TR_ && tc.nsets == NSETS_ && tc.npipe == NESETS_ && tc.unit == UNIT_)   \
+      return launch_deep<CINP, COUTP, TR_, NSETS_, NESETS_, UNIT_>(h, in, out, B, H, W, w, tc, st);
   if (tc.nbuf > 0) {   // warp-specialised kernel: npipe carries the number of epilogue warp sets
-    TCD_CASE(4, 2, 2, 3, 1) TCD_CASE(4, 2, 2, 3, 2) TCD_CASE(4, 2, 3, 3, 2) TCD_CASE(4, 3, 3, 3, 2) TCD_CASE(4, 4, 3, 3, 2) TCD_CASE(4, 4, 2, 3, 2)
-    TCD_CASE(4, 2, 3, 2, 2) TCD_CASE(4, 2, 2, 2, 2) TCD_CASE(4, 2, 3, 3, 1)
-    TCD_CASE(2, 4, 2, 4, 1) TCD_CASE(2, 4, 3, 4, 1) TCD_CASE(2, 4, 2, 3, 1) TCD_CASE(2, 4, 3, 3, 1) TCD_CASE(2, 2, 2, 2, 1) TCD_CASE(2, 4, 2, 2, 1)
-    TCD_CASE(2, 4, 2, 4, 2) TCD_CASE(2, 4, 3, 4, 2) TCD_CASE(2, 4, 3, 3, 2)
-    hp_set_error("tc deep block: no kernel for TR %d NSTG %d nsets %d nbuf %d esets %d", tc.TR, tc.NSTG, tc.nsets, tc.nbuf, tc.npipe);
+    TCD_CASE(4, 2, 2, 1) TCD_CASE(4, 3, 2, 1) TCD_CASE(2, 2, 2, 1) TCD_CASE(2, 3, 2, 1) TCD_CASE(4, 2, 1, 1) TCD_CASE(2, 3, 1, 1)
+    TCD_CASE(2, 2, 2, 2) TCD_CASE(2, 3, 2, 2) TCD_CASE(2, 3, 1, 2) TCD_CASE(2, 4, 1, 2) TCD_CASE(4, 2, 2, 2) TCD_CASE(4, 3, 2, 2)
+    hp_set_error("tc deep block: no kernel for TR %d nsets %d esets %d unit %d", tc.TR, tc.nsets, tc.npipe, tc.unit);
     return HP_ERR_UNSUPPORTED;
   }
 #undef TCD_CASE
@@ -815,10 +893,9 @@ int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, c
   if constexpr (NPIPE_ * TR_ * (N16 + 16 * NSTG_) <= 512)                                \
     if (tc.TR == TR_ && tc.NSTG == NSTG_ && tc.npipe == NPIPE_ && tc.nsets == NSETS_)    \
       return launch_tc<CINP, COUTP, TR_, NSTG_, NPIPE_, NSETS_>(h, in, out, B, H, W, w, tc, st);
-  TC_CASE(4, 2, 2, 1) TC_CASE(4, 1, 2, 1) TC_CASE(4, 2, 2, 2) TC_CASE(4, 1, 2, 2) TC_CASE(4, 2, 1, 2) TC_CASE(4, 3, 1, 3)
-  TC_CASE(4, 2, 1, 1) TC_CASE(4, 1, 1, 1)
-  TC_CASE(2, 2, 3, 1) TC_CASE(2, 2, 3, 2) TC_CASE(2, 2, 2, 2) TC_CASE(2, 1, 3, 1) TC_CASE(2, 2, 4, 1) TC_CASE(2, 1, 4, 1)
-  TC_CASE(3, 2, 2, 1) TC_CASE(3, 2, 2, 2) TC_CASE(3, 1, 2, 2)
+  if constexpr (CINP <= 36) {   // pipelined variant: kept for the four early blocks only (comparison / fallback)
+    TC_CASE(4, 2, 2, 2) TC_CASE(4, 1, 2, 2) TC_CASE(4, 1, 1, 1) TC_CASE(2, 2, 3, 2) TC_CASE(2, 2, 4, 1) TC_CASE(2, 1, 4, 1)
+  }
 #undef TC_CASE
   hp_set_error("tc block: no kernel for TR %d NSTG %d npipe %d nsets %d", tc.TR, tc.NSTG, tc.npipe, tc.nsets);
   return HP_ERR_UNSUPPORTED;
@@ -850,45 +927,80 @@ void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, floa
 
 int hp_tc_weight_floats(int cinp, int coutp) { return ((cinp + 7) / 8 * 8) * ((coutp + 15) / 16 * 16); }
 
+// Row width (pixels) of a halo buffer of the warp-specialised kernel: no halo columns when W is a multiple of 8,
+// otherwise at least one zero column on the right and rows of a multiple of 128 bytes.
+static int tcd_row_pixels(int W) { return (W % 8 == 0) ? W : round_up(W + 1, 8); }
+
 // Shared memory / TMEM feasibility of one geometry (the kernel instantiations are listed in launch_tc_cfg).
 bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc) {
   const int cinp = chan_pad(kBlazeBlocks[blk].cin), coutp = chan_pad(kBlazeBlocks[blk].cout);
   const int C4 = cinp / 4, NG = coutp / 4, N16 = (coutp + 15) / 16 * 16, K8 = (cinp + 7) / 8 * 8;
   const int PS = ((C4 > NG ? C4 : NG) | 1) * 4;
-  if (tc.TR < 1 || tc.BH < tc.TR || tc.BH % tc.TR || (tc.BH / tc.TR) * W > 128 || tc.BH + 2 > 256) return false;
+  const int ni = tc.nbuf > 0 ? tc.ni : 1;
+  if (tc.TR < 1 || tc.BH < tc.TR || tc.BH % tc.TR || ni < 1 || (tc.BH / tc.TR) * W * ni > 128 || tc.BH + 2 > 256) return false;
   if (tc.nbuf > 0) {
     if (2 * tc.TR * N16 + tc.NSTG * tc.TR * 16 > 512 || 128 * tc.nsets + 128 * tc.npipe + 96 > 1024 || tc.npipe < 1 || tc.npipe > 2) return false;
+    if (tc.nbuf < 2 || tc.nbuf > TCD_MAXB || tc.NSTG < 2 || tc.NSTG > TC_MAX_STG || (ni > 1 && tc.BH < H)) return false;
+    if (tc.unit < 1 || tc.unit > 2 || tc.nsets > tc.NSTG * (tc.unit == 2 ? 1 : 2)) return false;   // a set may run at most one ring phase ahead
   } else {
     if (tc.npipe * tc.TR * (N16 + 16 * tc.NSTG) > 512) return false;
     if (tc.npipe * (128 * tc.nsets + 32) > 1024) return false;
   }
   int off_b, off_w, off_pipe;
   tc_layout(cinp, coutp, K8, N16, &off_b, &off_w, &off_pipe);
-  const size_t buf = (size_t)align_up(PS * tc.IWB * (tc.BH + 2), 256) * 4;
-  return (size_t)off_pipe * 4 + (size_t)(tc.nbuf > 0 ? tc.nbuf : tc.npipe) * buf <= 227 * 1024;
+  const size_t buf = (size_t)align_up(PS * tc.IWB * (tc.BH + 2) * ni, 256) * 4;
+  return (size_t)off_pipe * 4 + (size_t)(tc.nbuf > 0 ? tc.nbuf : tc.npipe) * buf + 1024 <= 227 * 1024;
+}
+
+// Geometry of the warp-specialised kernel for one (TR, nsets, esets): largest ring of halo buffers that fits, whole
+// images per tile when a whole image needs at most 128 lanes.
+bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg* tc) {
+  const int cinp = chan_pad(kBlazeBlocks[blk].cin), coutp = chan_pad(kBlazeBlocks[blk].cout);
+  const int N16 = (coutp + 15) / 16 * 16, K8 = (cinp + 7) / 8 * 8;
+  if (kBlazeBlocks[blk].stride != 1 || W > 128 || H < 1 || 2 * TR * N16 + 2 * TR * 16 > 512) return false;
+  TcCfg t;
+  t.TR = TR; t.nsets = nsets; t.npipe = esets; t.unit = 1;
+  t.NSTG = (512 - 2 * TR * N16) / (TR * 16);
+  if (t.NSTG > TC_MAX_STG) t.NSTG = TC_MAX_STG;
+  if (t.NSTG > K8 / 8 && K8 / 8 >= 2) t.NSTG = K8 / 8;
+  t.IWB = tcd_row_pixels(W);
+  const int strips = ceil_div(H, TR);
+  if (strips * W <= 128) {          // whole images: as many per tile as lanes and a ring of >= 3 (then >= 2) buffers allow
+    t.BH = strips * TR;
+    for (int want = 3; want >= 2; --want)
+      for (t.ni = 128 / (strips * W); t.ni >= 1; --t.ni)
+        for (t.nbuf = TCD_MAXB; t.nbuf >= want; --t.nbuf)
+          if (hp_tc_fits(blk, H, W, t)) {
+            *tc = t;
+            return true;
+          }
+    return false;
+  }
+  t.ni = 1;
+  for (int want = 3; want >= 2; --want)
+    for (int max_strips = 128 / W; max_strips >= 1; --max_strips) {
+      const int bands = ceil_div(strips, max_strips);
+      t.BH = ceil_div(strips, bands) * TR;
+      for (t.nbuf = TCD_MAXB; t.nbuf >= want; --t.nbuf)
+        if (hp_tc_fits(blk, H, W, t)) {
+          *tc = t;
+          return true;
+        }
+    }
+  return false;
 }
 
 // Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.
-// Order of preference measured with tools/tc_sweep.py (profiles/): more resident warps first.
+// Order of preference measured with tools/tc_sweep.py (profiles/).
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
-  if (kBlazeBlocks[blk].stride != 1 || W + 2 > 255 || W > 128 || H < 1) return false;
-  static const int pref[][4] = {{2, 2, 4, 1}, {2, 1, 4, 1}, {2, 2, 3, 2}, {2, 2, 3, 1}, {4, 2, 2, 2}, {4, 1, 2, 2}, {2, 2, 2, 2}, {4, 2, 1, 2}, {4, 1, 1, 1}};   // TR, NSTG, npipe, nsets
-  for (const auto& c : pref) {
-    TcCfg t;
-    t.TR = c[0]; t.NSTG = c[1]; t.npipe = c[2]; t.nsets = c[3]; t.nbuf = 0;
-    t.IWB = ((W + 2 + 1 + 7) / 8) * 8 - 1;   // >= W + 2 and == 7 (mod 8): the band interior starts 128-byte aligned
-    const int strips = ceil_div(H, t.TR);
-    int max_strips = 128 / W;
-    if (max_strips < 1) return false;
-    for (; max_strips >= 1; --max_strips) {
-      const int bands = ceil_div(strips, max_strips);
-      t.BH = ceil_div(strips, bands) * t.TR;
-      if (hp_tc_fits(blk, H, W, t)) {
-        *tc = t;
-        return true;
-      }
-    }
-  }
+  if (kBlazeBlocks[blk].stride != 1 || W > 128 || H < 1) return false;
+  const int chunks = chan_pad(kBlazeBlocks[blk].cin) / 4;
+  const int nsets = chunks >= 12 ? 3 : 2;
+  TcCfg a, b;
+  const bool ok4 = hp_tcd_geometry(blk, H, W, 4, nsets, 2, &a);
+  const bool ok2 = hp_tcd_geometry(blk, H, W, 2, nsets, 2, &b);
+  if (ok4 && (a.nbuf >= 3 || !ok2 || b.nbuf <= a.nbuf)) { *tc = a; return true; }
+  if (ok2) { *tc = b; return true; }
   return false;
 }
 
@@ -900,6 +1012,12 @@ int hp_launch_block_tc(hp_ctx* h, int blk, const float* in, float* out, int B, i
     case 1: return launch_tc_cfg<24, 28>(h, in, out, B, H, W, w, tc, st);
     case 3: return launch_tc_cfg<32, 36>(h, in, out, B, H, W, w, tc, st);
     case 4: return launch_tc_cfg<36, 44>(h, in, out, B, H, W, w, tc, st);
+    case 6: return launch_tc_cfg<48, 56>(h, in, out, B, H, W, w, tc, st);
+    case 7: return launch_tc_cfg<56, 64>(h, in, out, B, H, W, w, tc, st);
+    case 8: return launch_tc_cfg<64, 72>(h, in, out, B, H, W, w, tc, st);
+    case 9: return launch_tc_cfg<72, 80>(h, in, out, B, H, W, w, tc, st);
+    case 10: return launch_tc_cfg<80, 88>(h, in, out, B, H, W, w, tc, st);
+    case 12: case 13: case 14: case 15: return launch_tc_cfg<96, 96>(h, in, out, B, H, W, w, tc, st);
     default: break;
   }
   hp_set_error("tc block: block %d has no tensor-core instantiation", blk);

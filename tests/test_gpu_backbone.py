@@ -165,18 +165,21 @@ def test_preprocess_matches_reference_arithmetic():
     assert np.array_equal(x.cpu().numpy(), want)
 
 
-# (TR, NSTG, npipe, nsets, nbuf): pipelined (nbuf 0) and warp-specialised (nbuf > 0) tensor-core geometries
-# (for nbuf > 0 the npipe slot carries the number of epilogue warp sets)
-TC_GEOMETRIES = [(2, 2, 4, 1, 0), (2, 2, 3, 2, 0), (4, 2, 2, 2, 0), (4, 1, 2, 2, 0), (4, 1, 1, 1, 0), (4, 2, 1, 2, 3),
-                 (4, 2, 2, 3, 3), (4, 4, 2, 3, 3), (4, 2, 2, 3, 2), (2, 4, 1, 2, 4), (2, 4, 2, 3, 4), (2, 4, 2, 3, 3), (2, 2, 1, 2, 2)]
+# (TR, NSTG, npipe, nsets, nbuf): nbuf == 0 -> pipelined kernel (early blocks only); nbuf > 0 -> warp-specialised kernel, where the
+# npipe slot carries the number of epilogue warp sets, NSTG 0 = automatic and nbuf % 16 caps the ring of halo buffers
+TC_GEOMETRIES = [(2, 2, 4, 1, 0), (2, 2, 3, 2, 0), (4, 2, 2, 2, 0), (4, 1, 2, 2, 0), (4, 1, 1, 1, 0),
+                 (4, 0, 2, 2, 4), (4, 0, 2, 3, 3), (4, 2, 1, 2, 2), (2, 0, 2, 2, 4), (2, 0, 2, 3, 2), (2, 2, 1, 3, 4),
+                 (2, 0, 2, 2, 4 + 32), (2, 0, 2, 3, 4 + 32), (2, 0, 1, 4, 3 + 32), (4, 0, 2, 2, 4 + 32), (4, 0, 2, 3, 4 + 32)]   # + 32: k-step work units
+TC_BLOCK_CHANNELS = {0: 24, 1: 28, 3: 36, 4: 42, 6: 56, 7: 64, 8: 72, 9: 80, 10: 88, 12: 96, 15: 96}
 
 
 @pytest.mark.parametrize("geom", TC_GEOMETRIES)
 @pytest.mark.parametrize("size,batch", [(96, 37), (88, 5), (128, 3)])
 def test_tensor_core_block_geometries(geom, size, batch):
-    """Every instantiated geometry of the tensor-core BlazeBlock kernel reproduces the naive CUDA kernels on blocks
-    0, 1, 3 and 4 (random-init weights; batch 37 gives every persistent CTA a different number of tiles, 88 gives
-    partial bands and odd widths).  Geometries that do not fit a block (TMEM / shared memory) must be refused."""
+    """Every instantiated geometry of the tensor-core BlazeBlock kernels reproduces the naive CUDA kernels on every
+    stride-1 block (random-init weights; batch 37 gives the persistent CTAs different tile counts and a partial last
+    multi-image tile, 88 gives partial bands and odd widths).  Geometries that do not fit a block (TMEM / shared
+    memory / not instantiated) must be refused with an error, never run wrong."""
     from hpose_b200 import _lib
     from hpose_b200.unified import pack_backbone, random_backbone
     ctx = _ctx()
@@ -185,12 +188,14 @@ def test_tensor_core_block_geometries(geom, size, batch):
     _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
     g = torch.Generator(device="cuda").manual_seed(size)
     x = torch.rand((batch, size, size, 3), generator=g, device="cuda") * 2 - 1
-    chans = {0: 24, 1: 28, 3: 36, 4: 42}
     TR, NSTG, npipe, nsets, nbuf = geom
     ran = 0
     try:
-        for blk, c in chans.items():
-            H = -(-size // 2) if blk < 2 else -(-size // 4)
+        for blk, c in TC_BLOCK_CHANNELS.items():
+            H = -(-size // 2)
+            for b in (2, 5, 11):
+                if blk > b:
+                    H = -(-H // 2)
             shape = (batch, H, H, c)
             ctx.set_impl(_lib.HP_IMPL_NAIVE)
             want = _read_act(ctx, x, blk, shape)

@@ -24,7 +24,7 @@ H = size // 2 if blk < 2 else size // 4 if blk < 5 else size // 8 if blk < 11 el
 strips = -(-H // TR)
 bands = -(-strips // max(1, 128 // H))
 BH = -(-strips // bands) * TR
-_lib.check(lib.hp_debug_set_tc(ctx.handle, blk, TR, NSTG, BH, esets, nsets, nbuf))
+_lib.check(lib.hp_debug_set_tc(ctx.handle, blk, TR, NSTG, 0, esets, nsets, nbuf))
 x = torch.rand((B, size, size, 3), device="cuda") * 2 - 1
 NT = 40
 trace = torch.zeros((NT, 12), dtype=torch.int64, device="cuda")
