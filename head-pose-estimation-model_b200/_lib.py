@@ -14,7 +14,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhpose.so")
-SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
+SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "stem_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -57,7 +57,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"),
                                                        os.path.join(PKG_DIR, "..", "include", "hpose.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -120,6 +120,7 @@ _PROTOS = {
     "hp_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "hp_debug_set_tile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_debug_tile_report": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hp_debug_set_stem_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_debug_tc_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hp_debug_set_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_backbone_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

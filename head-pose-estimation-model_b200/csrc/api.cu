@@ -121,6 +121,11 @@ int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, i
   h->tc_override[blk][0] = TR; h->tc_override[blk][1] = NSTG; h->tc_override[blk][2] = BH; h->tc_override[blk][3] = npipe; h->tc_override[blk][4] = nsets; h->tc_override[blk][5] = nbuf % 16; h->tc_override[blk][6] = nbuf / 16;
   return HP_OK;
 }
+int hp_debug_set_stem_tc(hp_handle h, int BH, int nbuf, int nout, int nsets) {
+  HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
+  h->stem_tc_cfg[0] = BH; h->stem_tc_cfg[1] = nbuf; h->stem_tc_cfg[2] = nout; h->stem_tc_cfg[3] = nsets;
+  return HP_OK;
+}
 int hp_debug_tc_trace(hp_handle h, long long* dev_buf, int max_tiles) {
   HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
   h->tc_trace = dev_buf; h->tc_trace_tiles = dev_buf ? max_tiles : 0;

@@ -575,6 +575,11 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
   size_t o_stem_b = reserve(24);
   memcpy(&host[o_stem_b], src + cur, 24 * sizeof(float));
   cur += 24;
+  size_t o_stem_bhi = reserve(hp_stem_tc_weight_floats()), o_stem_blo = reserve(hp_stem_tc_weight_floats());
+  {
+    std::vector<float> sw(host.begin() + o_stem_w, host.begin() + o_stem_w + 75 * 24);
+    hp_stem_tc_split_weights(sw.data(), &host[o_stem_bhi], &host[o_stem_blo]);
+  }
   size_t o_dww[16], o_dwb[16], o_pww[16], o_pwb[16], o_bhi[16], o_blo[16];
   for (int i = 0; i < 16; ++i) {
     const int cin = kBlazeBlocks[i].cin, cout = kBlazeBlocks[i].cout;
@@ -632,6 +637,8 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
   const float* base = bb.arena.f();
   bb.stem_w = base + o_stem_w;
   bb.stem_b = base + o_stem_b;
+  bb.stem_bhi = base + o_stem_bhi;
+  bb.stem_blo = base + o_stem_blo;
   for (int i = 0; i < 16; ++i) {
     bb.blk[i].dww = base + o_dww[i];
     bb.blk[i].dwb = base + o_dwb[i];
@@ -714,6 +721,9 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         long long total = (long long)B * hs[0] * ws[0] * 24;
         stem_naive_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, bb.stem_w, bb.stem_b, cur, B, H, W, hs[0],
                                                                          ws[0], pt_stem, pl_stem);
+      } else if (h->impl == HP_IMPL_FAST && h->stem_tc_cfg[0] >= 0 && hp_stem_tc_supported(H, W)) {
+        HP_TRY(hp_launch_stem_tc(h, x, cur, B, H, W, bb.stem_bhi, bb.stem_blo, bb.stem_b, h->stem_tc_cfg, st));
+        h->launches--;   // counted below
       } else {
         StemParams sp;
         sp.x = x; sp.w = bb.stem_w; sp.b = bb.stem_b; sp.y = cur;

@@ -22,103 +22,9 @@
 //
 // Reference semantics: BlazeBlock = DepthwiseConv2D(3x3, SAME) -> Conv2D(1x1) -> Add(skip / channel-padded skip) -> ReLU
 // (graph called at BlazePoser/blazeFaceDetectorH5.py:272).  Stride-1 blocks only.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
-
-// ---------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Blocking wait with a watchdog.  try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware until the
-// phase completes instead of burning issue slots (ncu: un-hinted polling was ~25 % of all issued instructions); the clock
-// is read every 256 wake-ups only.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0, n = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) break;
-    if ((++n & 255u) == 0u) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();   // ~2 s: never hang the device on a lost signal
-    }
-  }
-}
-// spin used by the single issuer thread: try_wait suspends in hardware, no watchdog arithmetic in the loop
-__device__ __forceinline__ void mbar_wait_light(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}" ::"r"(addr), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
-               ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// TF32 split a = hi + lo: hi keeps the top 19 bits (truncation, 1 LOP3), lo = a - hi is exact in fp32 and |lo| < 2^-10 |a|;
-// the tensor core ignores the low 13 mantissa bits of lo, so the representation error is < 2^-20 |a| (cvt.rna.tf32
-// would cost ~5 SASS instructions per value for one more bit).
-__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
-// D[tmem] (+)= A[tmem] * B[smem descriptor], tf32 inputs, fp32 accumulate, M = 128
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_addr, uint32_t a_addr, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-               ::"r"(d_addr), "r"(a_addr), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-               ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-               "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(addr));
-}
-
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
-  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
-}
 
 // ---------------------------------------------------------------------------- compile-time geometry
 template <int CINP, int COUTP>
@@ -147,9 +53,6 @@ struct TcParams {
 #define TC_MAX_STG 4
 #define TC_BAR_FLOATS 128   // 512 bytes: barriers of all pipelines + the TMEM base address
 
-__device__ __forceinline__ void tmem_st4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 
 
 // watchdog spin for single-thread roles: try_wait suspends in hardware; the clock is read every 256 polls only
@@ -253,10 +156,6 @@ __device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, co
   }
 }
 
-__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
 // Both 4-channel chunks of a k-step at once: 8 hi columns, then 8 lo columns per M-tile (the layout the MMA reads)
 template <int TR>
 __device__ __forceinline__ void tc_dw_store2(const float4 (&a0)[TR], const float4 (&a1)[TR], uint32_t acol) {
@@ -991,16 +890,22 @@ bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg*
 }
 
 // Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.
-// Order of preference measured with tools/tc_sweep.py (profiles/).
+// Choices measured with tools/tc_sweep.py (profiles/): k-step work units everywhere; 4 rows per lane where two accumulator
+// sets of 4 x N16 columns fit TMEM next to a ring of >= 2 stages (N16 <= 48), else 2; maps narrower than 8 pixels (the
+// 6 x 6 blocks at 96 x 96 input) stay on the CUDA-core kernel, which is faster there.
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
-  if (kBlazeBlocks[blk].stride != 1 || W > 128 || H < 1) return false;
-  const int chunks = chan_pad(kBlazeBlocks[blk].cin) / 4;
-  const int nsets = chunks >= 12 ? 3 : 2;
-  TcCfg a, b;
-  const bool ok4 = hp_tcd_geometry(blk, H, W, 4, nsets, 2, &a);
-  const bool ok2 = hp_tcd_geometry(blk, H, W, 2, nsets, 2, &b);
-  if (ok4 && (a.nbuf >= 3 || !ok2 || b.nbuf <= a.nbuf)) { *tc = a; return true; }
-  if (ok2) { *tc = b; return true; }
+  if (kBlazeBlocks[blk].stride != 1 || W > 128 || W < 8 || H < 1) return false;
+  TcCfg a;
+  if (hp_tcd_geometry(blk, H, W, 4, 2, 2, &a)) {
+    a.unit = 2;
+    if (hp_tc_fits(blk, H, W, a)) { *tc = a; return true; }
+  }
+  if (hp_tcd_geometry(blk, H, W, 2, 3, 2, &a)) {
+    a.unit = 2;
+    if (hp_tc_fits(blk, H, W, a)) { *tc = a; return true; }
+    a.unit = 1;
+    if (hp_tc_fits(blk, H, W, a)) { *tc = a; return true; }
+  }
   return false;
 }
 

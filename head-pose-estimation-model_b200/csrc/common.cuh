@@ -84,6 +84,7 @@ struct Backbone {
   DevBuf arena;
   const float* stem_w = nullptr;  // [75][24]
   const float* stem_b = nullptr;
+  const float *stem_bhi = nullptr, *stem_blo = nullptr;  // stem kernel split into TF32 hi / lo parts in GEMM layout (stem_tc.cu)
   BlockWeights blk[16];
   const float *det16_w = nullptr, *det16_b = nullptr;  // [88][36] = cls(2)|loc(32)|pad
   const float *det8_w = nullptr, *det8_b = nullptr;    // [96][104] = cls(6)|loc(96)|pad
@@ -110,6 +111,7 @@ struct hp_ctx {
   DevBuf scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
+  int stem_tc_cfg[4] = {};         // tensor-core stem: band height, input buffers, output stages, gather sets (0 = automatic, [0] = -1: off)
   int tc_override[16][7] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets, nbuf per block (TR 0 = automatic, -1 = do not use)
   int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
   long long* tc_trace = nullptr;   // optional device buffer for per-tile clock stamps of the deep tensor-core kernel
@@ -159,3 +161,10 @@ int hp_tc_weight_floats(int cinp, int coutp);
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc);
 int hp_launch_block_tc(hp_ctx* h, int blk, const float* in, float* out, int B, int H, int W, const BlockWeights& w,
                        const TcCfg& tc, cudaStream_t st);
+
+// stem_tc.cu: stem conv as an implicit 3xTF32 GEMM (tcgen05), warp-specialised
+int hp_stem_tc_weight_floats();
+void hp_stem_tc_split_weights(const float* w75x24, float* bhi, float* blo);
+bool hp_stem_tc_supported(int H, int W);
+int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W, const float* bhi, const float* blo, const float* bias,
+                      const int* cfg, cudaStream_t st);

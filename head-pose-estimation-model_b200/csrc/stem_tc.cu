@@ -1,0 +1,407 @@
+// Stem (Conv2D 5x5, stride 2, SAME, 3 -> 24, + bias, ReLU) as an implicit 3xTF32 GEMM on the tcgen05 tensor cores.
+//
+// Reference semantics: first layer `conv2d` of the Keras graph in BlazePoser/UnifiedModels/*.h5,
+// called at BlazePoser/blazeFaceDetectorH5.py:272.  The CUDA-core stem (backbone.cu) runs at 17 % of the HBM roofline
+// because 1800 MACs per output pixel sit on the fp32 pipe; here they go to the tensor pipe and the CUDA cores only
+// gather and split the operands.
+//
+// GEMM view: M = output pixels, N = 24 (padded to 32), K = 80.  With NHWC and 3 input channels the 5 x 3 taps of one
+// kernel row are 15 CONTIGUOUS floats of an input row, so the A row of an output pixel is 5 runs of 16 floats (the 15
+// taps preceded by one zero-weighted float that keeps the run 8-byte aligned): k = ky * 16 + 1 + kx * 3 + ci.  No
+// im2col buffer exists: each lane copies its runs from the input band in shared memory (LDS.64, conflict free)
+// straight into the TMEM A ring, split into TF32 hi / lo parts.
+//
+// Warp-specialised pipeline per CTA (persistent, 1 per SM), same scheme as blaze_block_deep_kernel:
+//   loader   (1 thread): TMA load of the input band (2 BH + 3 rows x W x 3) into a ring of NBUF buffers; rows above /
+//                        below the image are zero-filled by the hardware (SAME padding), left / right padding is
+//                        applied in registers (lanes x == 0 and x == Wo - 1)
+//   gather sets (NSETS x 4 warps): lane <-> output column x of a strip of TR output rows; unit = one k-step (8 floats of a run)
+//   issuer   (1 thread): 3 x TR tcgen05.mma per k-step into D[i & 1]
+//   epilogue (NESETS x 4 warps): D + bias -> ReLU -> output staging ring (pixel stride 28 floats: conflict free)
+//   storer   (1 thread): TMA store of the staged band (box wider than the 24 channels: clipped by the hardware)
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int ST_K8 = 80, ST_KS = 10, ST_N16 = 32, ST_COUT = 24, ST_PSO = 28;
+constexpr int ST_MAXB = 4, ST_MAXO = 3, ST_MAXSTG = 4;
+constexpr int ST_BAR_FLOATS = 128;
+
+struct StemTcParams {
+  const float *bhi, *blo, *bias;   // weights [K8/4][32][4] hi / lo, bias [24]
+  int W, H, Wo, Ho, BH, IR;        // IR = 2 BH + 3 input rows per band
+  int row_floats;                  // W * 3
+  int bands_per_img, n_tiles, lanes;
+  int nstg, nbuf, nout;
+  int IWBO;                        // staged output row width in pixels (multiple of 8, >= Wo)
+  uint32_t load_bytes;
+  int off_b, off_bias, off_in, in_floats, off_out, out_floats;
+};
+
+template <int TR, int NSETS, int NESETS>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, StemTcParams p) {
+  constexpr uint32_t colA0 = 2 * TR * ST_N16;
+  static_assert(colA0 + 2 * TR * 16 <= 512, "TMEM budget");
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* bar_full = bars;                       // [nbuf]  input band landed
+  uint64_t* bar_infree = bars + ST_MAXB;           // [nbuf]  all gather threads are done with the band
+  uint64_t* bar_epi = bars + 2 * ST_MAXB;          // [nout]  staged output complete
+  uint64_t* bar_outfree = bar_epi + ST_MAXO;       // [nout]  staged output has left shared memory
+  uint64_t* bar_afull = bar_outfree + ST_MAXO;     // [nstg]
+  uint64_t* bar_aempty = bar_afull + ST_MAXSTG;    // [nstg]
+  uint64_t* bar_dfull = bar_aempty + ST_MAXSTG;    // [2]
+  uint64_t* bar_dempty = bar_dfull + 2;            // [2]
+  static_assert((2 * ST_MAXB + 2 * ST_MAXO + 2 * ST_MAXSTG + 4) * 8 + 4 <= ST_BAR_FLOATS * 4, "barrier block");
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (ST_BAR_FLOATS - 1);
+  float* s_bhi = smem + p.off_b;
+  float* s_blo = s_bhi + ST_K8 * ST_N16;
+  float* s_bias = smem + p.off_bias;
+  float* in_bufs = smem + p.off_in;
+  float* out_bufs = smem + p.off_out;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane_id = tid & 31;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1, W_STORE = W_ISSUE + 2;
+  const int NSTG = p.nstg, NBUF = p.nbuf, NOUT = p.nout;
+
+  for (int i = tid * 4; i < ST_K8 * ST_N16; i += nthr * 4) {
+    st4(s_bhi + i, ld4(p.bhi + i));
+    st4(s_blo + i, ld4(p.blo + i));
+  }
+  if (tid < ST_N16) s_bias[tid] = tid < ST_COUT ? p.bias[tid] : 0.f;
+  // the zero-weighted lead float of a run and masked taps may lie just outside a band buffer: make those floats finite
+  for (int i = p.off_bias + ST_N16 + tid; i < p.off_in; i += nthr) smem[i] = 0.f;
+  for (int i = p.off_in + tid * 4; i < p.off_in + NBUF * p.in_floats; i += nthr * 4) st4(smem + i, make_float4(0.f, 0.f, 0.f, 0.f));
+  fence_async_smem();
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&bar_full[b], 1);
+      mbar_init(&bar_infree[b], 128 * NSETS);
+    }
+    for (int o = 0; o < NOUT; ++o) {
+      mbar_init(&bar_epi[o], 128 * NESETS);
+      mbar_init(&bar_outfree[o], 1);
+    }
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(&bar_afull[s], 128);
+      mbar_init(&bar_aempty[s], 1);
+    }
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&bar_dfull[d], 1);
+      mbar_init(&bar_dempty[d], 128 * NESETS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+
+  auto tile_coords = [&](int tile, int& img, int& y0) {
+    img = tile / p.bands_per_img;
+    y0 = (tile - img * p.bands_per_img) * p.BH;
+  };
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp < W_ISSUE) {
+    const int wq = warp & 3;
+    const int lane = wq * 32 + lane_id;
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const bool active = lane < p.lanes;
+    const bool warp_active = wq * 32 < p.lanes;
+    const int l = active ? lane : 0;
+    const int yq = l / p.Wo;
+    const int x = l - yq * p.Wo;
+    if (warp < W_EPI) {
+      // =============================================================== gather sets: input band -> TF32 hi / lo -> TMEM A ring
+      const int set = warp >> 2;
+      const uint32_t n_units = (uint32_t)my_tiles * ST_KS;
+      // run of kernel row ky for output row t: band row 2 (yq TR + t) + ky, floats [6 x - 4, 6 x + 12)
+      const int base_off = (2 * yq * TR) * p.row_floats + 6 * x - 4;
+      const bool first_col = (x == 0), last_col = (x == p.Wo - 1);
+      uint64_t* pending = nullptr;
+      int cur_i = -1, cur_b = 0;
+      const float* buf = in_bufs;
+#pragma unroll 1
+      for (uint32_t g = set; g < n_units; g += NSETS) {
+        const int i = (int)(g / ST_KS);
+        const int ks = (int)(g - (uint32_t)i * ST_KS);
+        const int ky = ks >> 1, h = ks & 1;
+        const uint32_t use = g;
+        const uint32_t s = use % NSTG;
+        if (i != cur_i) {
+          cur_i = i;
+          cur_b = i % NBUF;
+          buf = in_bufs + cur_b * p.in_floats;
+          mbar_wait(&bar_full[cur_b], (i / NBUF) & 1);
+        }
+        float f[TR][8];
+        if (warp_active) {
+          const float* src = buf + base_off + ky * p.row_floats + 8 * h;
+#pragma unroll
+          for (int t = 0; t < TR; ++t) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 v = *reinterpret_cast<const float2*>(src + t * 2 * p.row_floats + 2 * e);
+              f[t][2 * e] = v.x;
+              f[t][2 * e + 1] = v.y;
+            }
+            if (h == 0) {
+              f[t][0] = 0.f;                                           // zero-weighted lead float: keep it finite
+              if (first_col) { f[t][1] = 0.f; f[t][2] = 0.f; f[t][3] = 0.f; }   // kx = 0 taps left of the image
+            } else if (last_col) {
+#pragma unroll
+              for (int e = 2; e < 8; ++e) f[t][e] = 0.f;               // kx = 3, 4 taps right of the image
+            }
+          }
+        }
+        if (pending != nullptr) {
+          if (warp_active) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
+          mbar_arrive(pending);
+        }
+        if (use >= (uint32_t)NSTG) {
+          mbar_wait(&bar_aempty[s], ((use / NSTG) - 1) & 1);
+          tc_fence_after();
+        }
+        if (warp_active) {
+          const uint32_t acol = tlane + colA0 + s * (TR * 16);
+#pragma unroll
+          for (int t = 0; t < TR; ++t) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              hi[e] = tf32_hi(f[t][e]);
+              lo[e] = __float_as_uint(f[t][e] - __uint_as_float(hi[e]));
+            }
+            tmem_st8(acol + t * 16, hi);
+            tmem_st8(acol + t * 16 + 8, lo);
+          }
+        }
+        pending = &bar_afull[s];
+        if (g + NSETS >= n_units || (int)((g + NSETS) / ST_KS) != i) {
+          // last unit of this set in tile i: publish it and release the band (this thread reads nothing more from it)
+          if (warp_active) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
+          mbar_arrive(pending);
+          pending = nullptr;
+          mbar_arrive(&bar_infree[cur_b]);
+        }
+      }
+    } else {
+      // =============================================================== epilogue warps
+      const int eset = (warp - W_EPI) >> 2;
+      int o = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int d = i & 1;
+        float* ob = out_bufs + o * p.out_floats;
+        mbar_wait(&bar_dfull[d], (i >> 1) & 1);
+        tc_fence_after();
+        if (i >= NOUT) mbar_wait(&bar_outfree[o], ((i / NOUT) - 1) & 1);
+        if (warp_active) {
+#pragma unroll
+          for (int t = 0; t < TR; ++t) {
+            if (t % NESETS != eset) continue;
+            uint32_t v[2][16];
+            tmem_ld16(tlane + d * (TR * ST_N16) + t * ST_N16, v[0]);
+            tmem_ld16(tlane + d * (TR * ST_N16) + t * ST_N16 + 16, v[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float* dst = ob + ((yq * TR + t) * p.IWBO + x) * ST_PSO;
+#pragma unroll
+            for (int j = 0; j < ST_COUT / 4; ++j) {
+              const float4 bb = ld4(s_bias + j * 4);
+              const uint32_t* vv = &v[j / 4][(j % 4) * 4];
+              float4 r4 = make_float4(fmaxf(__uint_as_float(vv[0]) + bb.x, 0.f), fmaxf(__uint_as_float(vv[1]) + bb.y, 0.f),
+                                      fmaxf(__uint_as_float(vv[2]) + bb.z, 0.f), fmaxf(__uint_as_float(vv[3]) + bb.w, 0.f));
+              if (active) st4(dst + j * 4, r4);
+            }
+          }
+          tc_fence_before();
+          fence_async_smem();
+        }
+        mbar_arrive(&bar_dempty[d]);
+        mbar_arrive(&bar_epi[o]);
+        if (++o == NOUT) o = 0;
+      }
+    }
+  } else if (lane_id == 0) {
+    if (warp == W_ISSUE) {
+      // =============================================================== MMA issuer
+      const uint32_t idesc = tc_idesc_tf32(ST_N16);
+      const uint64_t desc_fixed = tc_bdesc_fixed(ST_N16);
+      const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
+      uint32_t use = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int d = i & 1;
+        if (i >= 2) {
+          mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int ks = 0; ks < ST_KS; ++ks, ++use) {
+          const uint32_t s = use % NSTG;
+          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          tc_fence_after();
+          const uint32_t koff = (uint32_t)ks * 2u * ST_N16 * 16u;
+          const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
+          const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int t = 0; t < TR; ++t) {
+            const uint32_t dc = tmem_base + d * (TR * ST_N16) + t * ST_N16;
+            const uint32_t a = tmem_base + colA0 + (s * TR + t) * 16;
+            mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+            mma_tf32_ts(dc, a, dlo, idesc, 1u);
+            mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          }
+          tc_commit(&bar_aempty[s]);
+        }
+        tc_commit(&bar_dfull[d]);
+      }
+    } else if (warp == W_LOAD) {
+      // =============================================================== TMA loader
+      int b = 0, i = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        if (i >= NBUF) mbar_wait(&bar_infree[b], ((i / NBUF) - 1) & 1);
+        int img, y0;
+        tile_coords(tile, img, y0);
+        mbar_expect_tx(&bar_full[b], p.load_bytes);
+        tma_load_4d(in_bufs + b * p.in_floats, &tm_in, &bar_full[b], 0, 0, 2 * y0 - 1, img);
+        if (++b == NBUF) b = 0;
+      }
+    } else if (warp == W_STORE) {
+      // =============================================================== TMA storer
+      int o = 0, i = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        mbar_wait(&bar_epi[o], (i / NOUT) & 1);
+        int img, y0;
+        tile_coords(tile, img, y0);
+        tma_store_4d(&tm_out, out_bufs + o * p.out_floats, 0, 0, y0, img);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&bar_outfree[o]);
+        if (++o == NOUT) o = 0;
+      }
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+}  // namespace
+
+int hp_stem_tc_weight_floats() { return ST_K8 * ST_N16; }
+
+// Stem kernel [5][5][3][24] (HWIO, = packed rows (ky*5+kx)*3+ci) -> TF32 hi / lo parts in the GEMM layout [K8/4][32][4],
+// k = ky * 16 + 1 + kx * 3 + ci (k = ky * 16 is the zero-weighted alignment float).
+void hp_stem_tc_split_weights(const float* w75x24, float* bhi, float* blo) {
+  auto rna = [](float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;
+    u &= 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+  };
+  for (int i = 0; i < ST_K8 * ST_N16; ++i) bhi[i] = blo[i] = 0.f;
+  for (int ky = 0; ky < 5; ++ky)
+    for (int j = 0; j < 15; ++j)
+      for (int n = 0; n < ST_COUT; ++n) {
+        const int k = ky * 16 + 1 + j;
+        const float wv = w75x24[(ky * 15 + j) * ST_COUT + n];
+        const float hi = rna(wv), lo = rna(wv - hi);
+        const size_t idx = ((size_t)(k / 4) * ST_N16 + n) * 4 + (k % 4);
+        bhi[idx] = hi;
+        blo[idx] = lo;
+      }
+}
+
+bool hp_stem_tc_supported(int H, int W) {
+  // even sizes (pad 1 before / 2 after in both directions), rows of whole 4-pixel groups for the TMA box
+  return H >= 4 && W >= 8 && H % 2 == 0 && W % 4 == 0 && W / 2 <= 128 && W / 4 <= 256;
+}
+
+int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W, const float* bhi, const float* blo, const float* bias,
+                      const int* cfg, cudaStream_t st) {
+  HP_REQUIRE(hp_stem_tc_supported(H, W), HP_ERR_UNSUPPORTED, "stem tc: unsupported input size %dx%d", H, W);
+  constexpr int TR = 4;
+  const int Ho = H / 2, Wo = W / 2;
+  StemTcParams p;
+  p.bhi = bhi; p.blo = blo; p.bias = bias;
+  p.W = W; p.H = H; p.Wo = Wo; p.Ho = Ho;
+  const int strips = ceil_div(Ho, TR);
+  const int max_strips = 128 / Wo;
+  const int bands = ceil_div(strips, max_strips);
+  p.BH = ceil_div(strips, bands) * TR;
+  if (cfg && cfg[0] > 0) p.BH = cfg[0];
+  HP_REQUIRE(p.BH % TR == 0 && (p.BH / TR) * Wo <= 128 && p.BH >= TR, HP_ERR_INVALID, "stem tc: bad band height %d", p.BH);
+  p.IR = 2 * p.BH + 3;
+  p.row_floats = W * 3;
+  p.bands_per_img = ceil_div(Ho, p.BH);
+  p.n_tiles = B * p.bands_per_img;
+  p.lanes = (p.BH / TR) * Wo;
+  p.nstg = 4;
+  p.IWBO = round_up(Wo, 8);
+  p.load_bytes = (uint32_t)((size_t)p.row_floats * p.IR * sizeof(float));
+  int off = ST_BAR_FLOATS;
+  p.off_b = off;
+  off += 2 * ST_K8 * ST_N16;
+  p.off_bias = off;
+  off = tc_align_up(off + ST_N16 + 16, 256);      // >= 16 zeroed floats in front of the first band buffer
+  p.off_in = off;
+  p.in_floats = tc_align_up(p.row_floats * p.IR + 16, 256);
+  p.out_floats = tc_align_up(p.BH * p.IWBO * ST_PSO, 256);
+  p.nbuf = (cfg && cfg[1] > 0) ? cfg[1] : ST_MAXB;
+  p.nout = (cfg && cfg[2] > 0) ? cfg[2] : ST_MAXO;
+  auto total = [&]() { return (size_t)(p.off_in + p.nbuf * p.in_floats + p.nout * p.out_floats) * sizeof(float); };
+  while (total() > 227 * 1024 && p.nout > 2) --p.nout;
+  while (total() > 227 * 1024 && p.nbuf > 2) --p.nbuf;
+  HP_REQUIRE(total() <= 227 * 1024 && p.nbuf >= 2 && p.nbuf <= ST_MAXB && p.nout >= 2 && p.nout <= ST_MAXO, HP_ERR_UNSUPPORTED,
+             "stem tc: %zu bytes of shared memory needed for %dx%d", total(), H, W);
+  p.off_out = p.off_in + p.nbuf * p.in_floats;
+  // input seen as [B][H][W/4][12 floats]: a band row is W/4 contiguous 48-byte groups
+  CUtensorMap tin, tout;
+  {
+    const cuuint64_t dims[4] = {12, (cuuint64_t)(W / 4), (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {48, (cuuint64_t)W * 12, (cuuint64_t)H * W * 12};
+    const cuuint32_t box[4] = {12, (cuuint32_t)(W / 4), (cuuint32_t)p.IR, 1};
+    HP_TRY(tc_make_map4(&tin, x, dims, strides, box));
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)ST_COUT, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)ST_COUT * 4, (cuuint64_t)Wo * ST_COUT * 4, (cuuint64_t)Ho * Wo * ST_COUT * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)ST_PSO, (cuuint32_t)p.IWBO, (cuuint32_t)p.BH, 1};
+    HP_TRY(tc_make_map4(&tout, out, dims, strides, box));
+  }
+  const int nsets = (cfg && cfg[3] > 0) ? cfg[3] : 3;
+  long long grid = h->num_sms;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  const size_t smem = total();
+#define STEM_CASE(NSETS_, NESETS_)                                                                                     \
+  if (nsets == NSETS_) {                                                                                               \
+    auto kern = stem_tc_kernel<TR, NSETS_, NESETS_>;                                                                   \
+    HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                      \
+    kern<<<(unsigned)grid, 128 * NSETS_ + 128 * NESETS_ + 96, smem, st>>>(tin, tout, p);                               \
+    h->launches++;                                                                                                     \
+    HP_CUDA(cudaGetLastError());                                                                                       \
+    return HP_OK;                                                                                                      \
+  }
+  STEM_CASE(2, 2) STEM_CASE(3, 2) STEM_CASE(4, 1)
+#undef STEM_CASE
+  hp_set_error("stem tc: no kernel for %d gather sets", nsets);
+  return HP_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,150 @@
+// Device-side PTX helpers shared by the tensor-core kernels (blocks_tc.cu, stem_tc.cu): mbarrier, TMA, tcgen05.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Blocking wait with a watchdog.  try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware until the
+// phase completes instead of burning issue slots (ncu: un-hinted polling was ~25 % of all issued instructions); the clock
+// is read every 256 wake-ups only.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, n = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if ((++n & 255u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();   // ~2 s: never hang the device on a lost signal
+    }
+  }
+}
+// spin used by the single issuer thread: try_wait suspends in hardware, no watchdog arithmetic in the loop
+__device__ __forceinline__ void mbar_wait_light(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+               ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// TF32 split a = hi + lo: hi keeps the top 19 bits (truncation, 1 LOP3), lo = a - hi is exact in fp32 and |lo| < 2^-10 |a|;
+// the tensor core ignores the low 13 mantissa bits of lo, so the representation error is < 2^-20 |a| (cvt.rna.tf32
+// would cost ~5 SASS instructions per value for one more bit).
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+// D[tmem] (+)= A[tmem] * B[smem descriptor], tf32 inputs, fp32 accumulate, M = 128
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_addr, uint32_t a_addr, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_addr), "r"(a_addr), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+               "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(addr));
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+
+// 8-column TMEM store, 128-bit shared-memory access helpers
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// instruction descriptor of tcgen05.mma kind::tf32: D fp32, A / B tf32, both K-major, M = 128, N = n16
+__device__ __forceinline__ uint32_t tc_idesc_tf32(int n16) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// shared-memory descriptor (without the start address) of a K-major no-swizzle B slice [n16 rows][8 k] stored as
+// [k / 4][n16][4]: core matrix = 8 rows x 16 B, LBO (next 4 k) = n16 * 16 B, SBO (next 8 rows) = 128 B, version 1
+__device__ __forceinline__ uint64_t tc_bdesc_fixed(int n16) {
+  return ((uint64_t)(((uint32_t)(n16 * 16) >> 4) & 0x3FFF) << 16) | ((uint64_t)((128u >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+
+typedef CUresult (*PFN_tcEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline int tc_get_encode(PFN_tcEncodeTiled* out) {
+  static PFN_tcEncodeTiled fn_cached = nullptr;
+  if (!fn_cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    HP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    HP_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, HP_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+    fn_cached = (PFN_tcEncodeTiled)fn;
+  }
+  *out = fn_cached;
+  return HP_OK;
+}
+// fp32 tensor map of rank 4 (dims / box innermost first; strides in bytes for dims 1..3); out-of-range elements read as zero
+inline int tc_make_map4(CUtensorMap* tm, const float* base, const cuuint64_t dims[4], const cuuint64_t strides[3], const cuuint32_t box[4]) {
+  PFN_tcEncodeTiled enc;
+  HP_TRY(tc_get_encode(&enc));
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HP_REQUIRE(r == CUDA_SUCCESS, HP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu box %u %u %u %u", (int)r,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3], box[0], box[1],
+             box[2], box[3]);
+  return HP_OK;
+}
+inline int tc_align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace

@@ -216,3 +216,31 @@ def test_tensor_core_block_geometries(geom, size, batch):
     finally:
         ctx.set_impl(_lib.HP_IMPL_FAST)
     assert ran >= 1 or size == 128, f"geometry {geom} ran on no block"
+
+
+@pytest.mark.parametrize("cfg", [(0, 0, 0, 0), (0, 2, 2, 2), (4, 3, 2, 3), (0, 4, 2, 4)])
+@pytest.mark.parametrize("size,batch", [(96, 37), (88, 5), (128, 3), (64, 2), (120, 2)])
+def test_tensor_core_stem(cfg, size, batch):
+    """The implicit-GEMM (tcgen05, 3xTF32) stem reproduces the naive CUDA stem for every pipeline geometry
+    (band height, input buffers, output stages, gather warp sets); 88 and 120 give partial last bands."""
+    from hpose_b200 import _lib
+    from hpose_b200.unified import pack_backbone, random_backbone
+    ctx = _ctx()
+    lib = _lib.lib()
+    flat = pack_backbone(random_backbone(seed=5, bias_scale=0.2))
+    _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
+    g = torch.Generator(device="cuda").manual_seed(size + 1)
+    x = torch.rand((batch, size, size, 3), generator=g, device="cuda") * 2 - 1
+    shape = (batch, size // 2, size // 2, 24)
+    try:
+        ctx.set_impl(_lib.HP_IMPL_NAIVE)
+        want = _read_act(ctx, x, -1, shape)
+        ctx.set_impl(_lib.HP_IMPL_FAST)
+        _lib.check(lib.hp_debug_set_stem_tc(ctx.handle, *cfg))
+        got = _read_act(ctx, x, -1, shape)
+        assert rel_err(got, want) < 2e-5, rel_err(got, want)
+        _lib.check(lib.hp_debug_set_stem_tc(ctx.handle, -1, 0, 0, 0))       # CUDA-core stem still agrees
+        assert rel_err(_read_act(ctx, x, -1, shape), want) < 2e-5
+    finally:
+        _lib.check(lib.hp_debug_set_stem_tc(ctx.handle, 0, 0, 0, 0))
+        ctx.set_impl(_lib.HP_IMPL_FAST)
