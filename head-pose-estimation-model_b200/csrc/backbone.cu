@@ -773,10 +773,11 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
           if (tv[1] > 0) tcc.NSTG = tv[1];
           if (tv[5] < tcc.nbuf) tcc.nbuf = tv[5];
           if (tv[6] > 0) tcc.unit = tv[6];
+          if (tv[7] > 0) tcc.niss = tv[7];
           HP_REQUIRE(hp_tc_fits(i, Ho, Wo, tcc), HP_ERR_INVALID, "tc override for block %d does not fit (TR %d NSTG %d nsets %d unit %d nbuf %d)", i,
                      tcc.TR, tcc.NSTG, tcc.nsets, tcc.unit, tcc.nbuf);
         } else {                            // pipelined kernel (halo columns, IWB = 7 mod 8)
-          tcc.TR = tv[0]; tcc.nbuf = 0; tcc.ni = 1; tcc.unit = 1;
+          tcc.TR = tv[0]; tcc.nbuf = 0; tcc.ni = 1; tcc.unit = 1; tcc.niss = 1;
           tcc.IWB = ((Wo + 2 + 1 + 7) / 8) * 8 - 1;
           if (tv[1] > 0) tcc.NSTG = tv[1];
           if (tv[2] > 0) tcc.BH = tv[2];

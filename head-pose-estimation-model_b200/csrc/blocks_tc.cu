@@ -391,8 +391,10 @@ struct TcdParams {
   int trace_tiles;
 };
 
-template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT>
-__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
+// NISS issuer warps: one thread can only issue a tcgen05.mma every ~46-55 clk whatever its size (tools/mma_rate.cu), the
+// tensor pipe itself needs 128 * N / 256 clk; the accumulator rows are therefore dealt to NISS issuing threads (t % NISS).
+template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 32 * (NISS + 2), 1)
 blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcdParams p) {
   using G = TcGeom<CINP, COUTP>;
   constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
@@ -419,7 +421,8 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane_id = tid & 31;
-  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1, W_STORE = W_ISSUE + 2;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + NISS, W_STORE = W_LOAD + 1;
+  static_assert(NISS >= 1 && NISS <= TR, "issuer warps");
   const int NSTG = p.nstg, NBUF = p.nbuf;
 
   for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
@@ -441,10 +444,10 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
     }
     for (int s = 0; s < NSTG; ++s) {
       mbar_init(&bar_afull[s], UNIT == 2 ? 128 : 256);   // one set per k-step (UNIT 2) or one set per 4-channel half
-      mbar_init(&bar_aempty[s], 1);
+      mbar_init(&bar_aempty[s], NISS);                   // one tcgen05.commit per issuer
     }
     for (int d = 0; d < 2; ++d) {
-      mbar_init(&bar_dfull[d], 1);
+      mbar_init(&bar_dfull[d], NISS);
       mbar_init(&bar_dempty[d], 128 * NESETS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -582,11 +585,11 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       }
     }
   } else if (lane_id == 0) {
-    if (warp == W_ISSUE) {
-      // =============================================================== MMA issuer
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint64_t desc_fixed = ((uint64_t)(((uint32_t)(N16 * 16) >> 4) & 0x3FFF) << 16) | ((uint64_t)((128u >> 4) & 0x3FFF) << 32) |
-                                  ((uint64_t)1 << 46);
+    if (warp >= W_ISSUE && warp < W_ISSUE + NISS) {
+      // =============================================================== MMA issuers (accumulator rows t % NISS == issuer)
+      const int issuer = warp - W_ISSUE;
+      const uint32_t idesc = tc_idesc_tf32(N16);
+      const uint64_t desc_fixed = tc_bdesc_fixed(N16);
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
       uint32_t use = 0;
       int i = 0;
@@ -596,19 +599,20 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
           mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
           tc_fence_after();
         }
-        stamp(i, 11);
+        if (issuer == 0) stamp(i, 11);
 #pragma unroll 1
         for (int ks = 0; ks < KS; ++ks, ++use) {
           const uint32_t s = use % NSTG;
           mbar_wait(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
-          if (ks == 0) stamp(i, 10);
-          if (ks == KS - 1) stamp(i, 9);
+          if (issuer == 0 && ks == 0) stamp(i, 10);
+          if (issuer == 0 && ks == KS - 1) stamp(i, 9);
           const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
           const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
           const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
+            if (t % NISS != issuer) continue;
             const uint32_t dc = tmem_base + d * (TR * N16) + t * N16;
             const uint32_t a = tmem_base + colA0 + (s * TR + t) * 16;
             mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
@@ -618,7 +622,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
           tc_commit(&bar_aempty[s]);
         }
         tc_commit(&bar_dfull[d]);
-        stamp(i, 7);
+        if (issuer == 0) stamp(i, 7);
       }
     } else if (warp == W_LOAD) {
       // =============================================================== TMA loader
@@ -736,7 +740,7 @@ int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const
   return HP_OK;
 }
 
-template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT>
+template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS>
 int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
   using G = TcGeom<CINP, COUTP>;
   TcdParams p;
@@ -763,11 +767,11 @@ int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, con
   CUtensorMap tin, tout;
   HP_TRY(make_map(&tin, in, B, H, W, CINP, tc.ni, tc.BH + 2, tc.IWB, G::PS));
   HP_TRY(make_map(&tout, out, B, H, W, COUTP, 1, tc.BH, tc.IWB, G::PS));
-  auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSETS, NESETS, UNIT>;
+  auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSETS, NESETS, UNIT, NISS>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + 96, smem, st>>>(tin, tout, p);
+  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + 32 * (NISS + 2), smem, st>>>(tin, tout, p);
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;
@@ -777,14 +781,15 @@ template <int CINP, int COUTP>
 int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc,
                   cudaStream_t st) {
   constexpr int N16 = TcGeom<CINP, COUTP>::N16;
-#define TCD_CASE(TR_, NSETS_, NESETS_, UNIT_)                                            \
+#define TCD_CASE(TR_, NSETS_, NESETS_, UNIT_, NISS_)                                     \
   if constexpr (2 * TR_ * N16 + 2 * TR_ * 16 <= 512)                                     \
-    if (tc.TR == TR_ && tc.nsets == NSETS_ && tc.npipe == NESETS_ && tc.unit == UNIT_)   \
-      return launch_deep<CINP, COUTP, TR_, NSETS_, NESETS_, UNIT_>(h, in, out, B, H, W, w, tc, st);
+    if (tc.TR == TR_ && tc.nsets == NSETS_ && tc.npipe == NESETS_ && tc.unit == UNIT_ && tc.niss == NISS_) \
+      return launch_deep<CINP, COUTP, TR_, NSETS_, NESETS_, UNIT_, NISS_>(h, in, out, B, H, W, w, tc, st);
   if (tc.nbuf > 0) {   // warp-specialised kernel: npipe carries the number of epilogue warp sets
-    TCD_CASE(4, 2, 2, 1) TCD_CASE(4, 3, 2, 1) TCD_CASE(2, 2, 2, 1) TCD_CASE(2, 3, 2, 1) TCD_CASE(4, 2, 1, 1) TCD_CASE(2, 3, 1, 1)
-    TCD_CASE(2, 2, 2, 2) TCD_CASE(2, 3, 2, 2) TCD_CASE(2, 3, 1, 2) TCD_CASE(2, 4, 1, 2) TCD_CASE(4, 2, 2, 2) TCD_CASE(4, 3, 2, 2)
-    hp_set_error("tc deep block: no kernel for TR %d nsets %d esets %d unit %d", tc.TR, tc.nsets, tc.npipe, tc.unit);
+    TCD_CASE(4, 2, 2, 1, 1) TCD_CASE(4, 3, 2, 1, 1) TCD_CASE(2, 2, 2, 1, 1) TCD_CASE(2, 3, 2, 1, 1) TCD_CASE(4, 2, 1, 1, 1) TCD_CASE(2, 3, 1, 1, 1)
+    TCD_CASE(2, 2, 2, 2, 1) TCD_CASE(2, 3, 2, 2, 1) TCD_CASE(2, 4, 1, 2, 1) TCD_CASE(4, 2, 2, 2, 1) TCD_CASE(4, 3, 2, 2, 1)
+    TCD_CASE(4, 2, 2, 2, 2) TCD_CASE(4, 2, 2, 2, 4) TCD_CASE(4, 3, 2, 2, 2) TCD_CASE(2, 3, 2, 2, 2) TCD_CASE(2, 2, 2, 2, 2) TCD_CASE(2, 3, 2, 1, 2)
+    hp_set_error("tc deep block: no kernel for TR %d nsets %d esets %d unit %d issuers %d", tc.TR, tc.nsets, tc.npipe, tc.unit, tc.niss);
     return HP_ERR_UNSUPPORTED;
   }
 #undef TCD_CASE
@@ -838,7 +843,9 @@ bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc) {
   const int ni = tc.nbuf > 0 ? tc.ni : 1;
   if (tc.TR < 1 || tc.BH < tc.TR || tc.BH % tc.TR || ni < 1 || (tc.BH / tc.TR) * W * ni > 128 || tc.BH + 2 > 256) return false;
   if (tc.nbuf > 0) {
-    if (2 * tc.TR * N16 + tc.NSTG * tc.TR * 16 > 512 || 128 * tc.nsets + 128 * tc.npipe + 96 > 1024 || tc.npipe < 1 || tc.npipe > 2) return false;
+    if (2 * tc.TR * N16 + tc.NSTG * tc.TR * 16 > 512 || tc.niss < 1 || tc.niss > tc.TR || 128 * tc.nsets + 128 * tc.npipe + 32 * (tc.niss + 2) > 1024 ||
+        tc.npipe < 1 || tc.npipe > 2)
+      return false;
     if (tc.nbuf < 2 || tc.nbuf > TCD_MAXB || tc.NSTG < 2 || tc.NSTG > TC_MAX_STG || (ni > 1 && tc.BH < H)) return false;
     if (tc.unit < 1 || tc.unit > 2 || tc.nsets > tc.NSTG * (tc.unit == 2 ? 1 : 2)) return false;   // a set may run at most one ring phase ahead
   } else {
@@ -858,7 +865,7 @@ bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg*
   const int N16 = (coutp + 15) / 16 * 16, K8 = (cinp + 7) / 8 * 8;
   if (kBlazeBlocks[blk].stride != 1 || W > 128 || H < 1 || 2 * TR * N16 + 2 * TR * 16 > 512) return false;
   TcCfg t;
-  t.TR = TR; t.nsets = nsets; t.npipe = esets; t.unit = 1;
+  t.TR = TR; t.nsets = nsets; t.npipe = esets; t.unit = 1; t.niss = 1;
   t.NSTG = (512 - 2 * TR * N16) / (TR * 16);
   if (t.NSTG > TC_MAX_STG) t.NSTG = TC_MAX_STG;
   if (t.NSTG > K8 / 8 && K8 / 8 >= 2) t.NSTG = K8 / 8;
@@ -897,10 +904,11 @@ bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
   if (kBlazeBlocks[blk].stride != 1 || W > 128 || W < 8 || H < 1) return false;
   TcCfg a;
   if (hp_tcd_geometry(blk, H, W, 4, 2, 2, &a)) {
-    a.unit = 2;
+    a.unit = 2; a.niss = 2;
     if (hp_tc_fits(blk, H, W, a)) { *tc = a; return true; }
   }
   if (hp_tcd_geometry(blk, H, W, 2, 3, 2, &a)) {
+    a.niss = 2;
     a.unit = 2;
     if (hp_tc_fits(blk, H, W, a)) { *tc = a; return true; }
     a.unit = 1;

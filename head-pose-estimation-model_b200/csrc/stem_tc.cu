@@ -36,6 +36,8 @@ struct StemTcParams {
   int IWBO;                        // staged output row width in pixels (multiple of 8, >= Wo)
   uint32_t load_bytes;
   int off_b, off_bias, off_in, in_floats, off_out, out_floats;
+  long long* trace;                // optional per-tile clock64 stamps of CTA 0 (12 per tile, same slots as the block kernel)
+  int trace_tiles;
 };
 
 template <int TR, int NSETS, int NESETS>
@@ -108,6 +110,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     y0 = (tile - img * p.bands_per_img) * p.BH;
   };
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto stamp = [&](int i, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && i < p.trace_tiles) p.trace[i * 12 + slot] = clock64();
+  };
 
   if (warp < W_ISSUE) {
     const int wq = warp & 3;
@@ -140,6 +145,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           cur_b = i % NBUF;
           buf = in_bufs + cur_b * p.in_floats;
           mbar_wait(&bar_full[cur_b], (i / NBUF) & 1);
+          if (tid == 0) stamp(i, 1);
         }
         float f[TR][8];
         if (warp_active) {
@@ -196,6 +202,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           mbar_arrive(pending);
           pending = nullptr;
           mbar_arrive(&bar_infree[cur_b]);
+          if (tid == 0) stamp(i, 2);
+          if (tid == (NSETS - 1) * 128) stamp(i, 8);
         }
       }
     } else {
@@ -207,7 +215,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         float* ob = out_bufs + o * p.out_floats;
         mbar_wait(&bar_dfull[d], (i >> 1) & 1);
         tc_fence_after();
+        if (tid == W_EPI * 32) stamp(i, 3);
         if (i >= NOUT) mbar_wait(&bar_outfree[o], ((i / NOUT) - 1) & 1);
+        if (tid == W_EPI * 32) stamp(i, 11);
         if (warp_active) {
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
@@ -231,6 +241,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         }
         mbar_arrive(&bar_dempty[d]);
         mbar_arrive(&bar_epi[o]);
+        if (tid == W_EPI * 32) stamp(i, 4);
         if (++o == NOUT) o = 0;
       }
     }
@@ -252,6 +263,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           const uint32_t s = use % NSTG;
           mbar_wait(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
+          if (issuer == 0 && ks == 0) stamp(i, 10);
+          if (issuer == 0 && ks == ST_KS - 1) stamp(i, 9);
           const uint32_t koff = (uint32_t)ks * 2u * ST_N16 * 16u;
           const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
           const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
@@ -266,6 +279,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           tc_commit(&bar_aempty[s]);
         }
         tc_commit(&bar_dfull[d]);
+        if (issuer == 0) stamp(i, 7);
       }
     } else if (warp == W_LOAD) {
       // =============================================================== TMA loader
@@ -276,6 +290,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         tile_coords(tile, img, y0);
         mbar_expect_tx(&bar_full[b], p.load_bytes);
         tma_load_4d(in_bufs + b * p.in_floats, &tm_in, &bar_full[b], 0, 0, 2 * y0 - 1, img);
+        stamp(i, 0);
         if (++b == NBUF) b = 0;
       }
     } else if (warp == W_STORE) {
@@ -287,7 +302,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         tile_coords(tile, img, y0);
         tma_store_4d(&tm_out, out_bufs + o * p.out_floats, 0, 0, y0, img);
         tma_store_commit();
+        stamp(i, 5);
         tma_store_wait_read();
+        stamp(i, 6);
         mbar_arrive(&bar_outfree[o]);
         if (++o == NOUT) o = 0;
       }
@@ -342,6 +359,7 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
   const int Ho = H / 2, Wo = W / 2;
   StemTcParams p;
   p.bhi = bhi; p.blo = blo; p.bias = bias;
+  p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
   p.W = W; p.H = H; p.Wo = Wo; p.Ho = Ho;
   const int strips = ceil_div(Ho, TR);
   const int max_strips = 128 / Wo;
@@ -373,12 +391,16 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
   HP_REQUIRE(total() <= 227 * 1024 && p.nbuf >= 2 && p.nbuf <= ST_MAXB && p.nout >= 2 && p.nout <= ST_MAXO, HP_ERR_UNSUPPORTED,
              "stem tc: %zu bytes of shared memory needed for %dx%d", total(), H, W);
   p.off_out = p.off_in + p.nbuf * p.in_floats;
-  // input seen as [B][H][W/4][12 floats]: a band row is W/4 contiguous 48-byte groups
+  // input seen as [B][H][g][W*3/g floats]: a band row is g contiguous pieces (as few as the 256-element box limit allows)
   CUtensorMap tin, tout;
   {
-    const cuuint64_t dims[4] = {12, (cuuint64_t)(W / 4), (cuuint64_t)H, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {48, (cuuint64_t)W * 12, (cuuint64_t)H * W * 12};
-    const cuuint32_t box[4] = {12, (cuuint32_t)(W / 4), (cuuint32_t)p.IR, 1};
+    int g = 1;
+    while (g <= 16 && !((W * 3) % g == 0 && (W * 3 / g) <= 256 && (W * 3 / g) % 4 == 0)) ++g;
+    HP_REQUIRE(g <= 16, HP_ERR_UNSUPPORTED, "stem tc: cannot split a row of %d floats into TMA boxes", W * 3);
+    const int inner = W * 3 / g;
+    const cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)g, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)inner * 4, (cuuint64_t)W * 12, (cuuint64_t)H * W * 12};
+    const cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)g, (cuuint32_t)p.IR, 1};
     HP_TRY(tc_make_map4(&tin, x, dims, strides, box));
   }
   {

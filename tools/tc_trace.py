@@ -20,15 +20,18 @@ ctx = default_context()
 lib = _lib.lib()
 flat = pack_backbone(random_backbone(1234))
 _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
-H = size // 2 if blk < 2 else size // 4 if blk < 5 else size // 8 if blk < 11 else size // 16
+H = size // 2 if blk < 2 else size // 4 if blk < 5 else size // 8 if blk < 11 else size // 16   # blk -1 = stem
 strips = -(-H // TR)
 bands = -(-strips // max(1, 128 // H))
 BH = -(-strips // bands) * TR
-_lib.check(lib.hp_debug_set_tc(ctx.handle, blk, TR, NSTG, 0, esets, nsets, nbuf))
+if blk >= 0:
+    _lib.check(lib.hp_debug_set_tc(ctx.handle, blk, TR, NSTG, 0, esets, nsets, nbuf))
+else:
+    _lib.check(lib.hp_debug_set_stem_tc(ctx.handle, 0, nbuf, 0, nsets))
 x = torch.rand((B, size, size, 3), device="cuda") * 2 - 1
 NT = 40
 trace = torch.zeros((NT, 12), dtype=torch.int64, device="cuda")
-c = (24, 28, 32, 36, 42, 48, 56, 64, 72, 80, 88, 96, 96, 96, 96, 96)[blk]
+c = (24, 28, 32, 36, 42, 48, 56, 64, 72, 80, 88, 96, 96, 96, 96, 96)[blk] if blk >= 0 else 24
 dst = torch.empty((B, H, H, c), device="cuda")
 for rep in range(2):
     _lib.check(lib.hp_debug_tc_trace(ctx.handle, trace.data_ptr() if rep == 1 else None, NT))
