@@ -131,16 +131,25 @@ __device__ __forceinline__ void tc_zero_chunk(uint32_t acol) {   // K padding (o
 // All column groups are requested before the single tcgen05.wait::ld (the TMEM load latency is paid once per pixel).
 template <int C4, int NG, int N16>
 __device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, const float* s_pwb, bool active) {
-  constexpr int NGRP = (NG + 3) / 4;   // 16-column groups that hold real output channels
-  uint32_t v[NGRP][16];
+  constexpr int NGRP = (NG + 7) / 8;   // 32-column groups that hold real output channels
+  uint32_t v[NGRP][32];
 #pragma unroll
-  for (int g = 0; g < NGRP; ++g) tmem_ld16(dcol + g * 16, v[g]);
+  for (int g = 0; g < NGRP; ++g) {
+    if (g * 32 + 32 <= N16) {
+      tmem_ld32(dcol + g * 32, v[g]);
+    } else {                             // N16 is a multiple of 16 only: the last group may be half
+      uint32_t h[16];
+      tmem_ld16(dcol + g * 32, h);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[g][e] = h[e];
+    }
+  }
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int g = 0; g < NGRP; ++g) {
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = g * 4 + jj;
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = g * 8 + jj;
       if (j < NG) {
         const float4 bb = ld4(s_pwb + j * 4);
         float4 o = make_float4(__uint_as_float(v[g][jj * 4 + 0]) + bb.x, __uint_as_float(v[g][jj * 4 + 1]) + bb.y,
@@ -156,20 +165,18 @@ __device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, co
   }
 }
 
-// Both 4-channel chunks of a k-step at once: 8 hi columns, then 8 lo columns per M-tile (the layout the MMA reads)
 template <int TR>
 __device__ __forceinline__ void tc_dw_store2(const float4 (&a0)[TR], const float4 (&a1)[TR], uint32_t acol) {
 #pragma unroll
   for (int t = 0; t < TR; ++t) {
     const float f[8] = {a0[t].x, a0[t].y, a0[t].z, a0[t].w, a1[t].x, a1[t].y, a1[t].z, a1[t].w};
-    uint32_t hi[8], lo[8];
+    uint32_t v[16];   // [hi 8 | lo 8] = the 16 columns of the stage row: one tcgen05.st (each costs ~40 clk of issue)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      hi[e] = tf32_hi(f[e]);
-      lo[e] = __float_as_uint(f[e] - __uint_as_float(hi[e]));
+      v[e] = tf32_hi(f[e]);
+      v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
     }
-    tmem_st8(acol + t * 16, hi);
-    tmem_st8(acol + t * 16 + 8, lo);
+    tmem_st16(acol + t * 16, v);
   }
 }
 

@@ -16,7 +16,7 @@
 //                        below the image are zero-filled by the hardware (SAME padding), left / right padding is
 //                        applied in registers (lanes x == 0 and x == Wo - 1)
 //   gather sets (NSETS x 4 warps): lane <-> output column x of a strip of TR output rows; unit = one k-step (8 floats of a run)
-//   issuer   (1 thread): 3 x TR tcgen05.mma per k-step into D[i & 1]
+//   issuers  (NISS threads in NISS warps): 3 tcgen05.mma per k-step and accumulator row into D[i & 1]
 //   epilogue (NESETS x 4 warps): D + bias -> ReLU -> output staging ring (pixel stride 28 floats: conflict free)
 //   storer   (1 thread): TMA store of the staged band (box wider than the 24 channels: clipped by the hardware)
 #include "tc_common.cuh"
@@ -40,8 +40,8 @@ struct StemTcParams {
   int trace_tiles;
 };
 
-template <int TR, int NSETS, int NESETS>
-__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
+template <int TR, int NSETS, int NESETS, int NISS>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 32 * (NISS + 2), 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, StemTcParams p) {
   constexpr uint32_t colA0 = 2 * TR * ST_N16;
   static_assert(colA0 + 2 * TR * 16 <= 512, "TMEM budget");
@@ -65,7 +65,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane_id = tid & 31;
-  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1, W_STORE = W_ISSUE + 2;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + NISS, W_STORE = W_LOAD + 1;
   const int NSTG = p.nstg, NBUF = p.nbuf, NOUT = p.nout;
 
   for (int i = tid * 4; i < ST_K8 * ST_N16; i += nthr * 4) {
@@ -88,10 +88,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     }
     for (int s = 0; s < NSTG; ++s) {
       mbar_init(&bar_afull[s], 128);
-      mbar_init(&bar_aempty[s], 1);
+      mbar_init(&bar_aempty[s], NISS);
     }
     for (int d = 0; d < 2; ++d) {
-      mbar_init(&bar_dfull[d], 1);
+      mbar_init(&bar_dfull[d], NISS);
       mbar_init(&bar_dempty[d], 128 * NESETS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -126,20 +126,22 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     if (warp < W_EPI) {
       // =============================================================== gather sets: input band -> TF32 hi / lo -> TMEM A ring
       const int set = warp >> 2;
-      const uint32_t n_units = (uint32_t)my_tiles * ST_KS;
+      // work unit = one kernel row ky = 2 k-steps (16 floats per output row): every tcgen05 / mbarrier instruction costs tens
+      // of cycles of issue whatever it carries, so a unit is as large as the registers allow
+      constexpr int UPT = ST_KS / 2;
+      const uint32_t n_units = (uint32_t)my_tiles * UPT;
       // run of kernel row ky for output row t: band row 2 (yq TR + t) + ky, floats [6 x - 4, 6 x + 12)
       const int base_off = (2 * yq * TR) * p.row_floats + 6 * x - 4;
       const bool first_col = (x == 0), last_col = (x == p.Wo - 1);
-      uint64_t* pending = nullptr;
+      uint64_t *pending0 = nullptr, *pending1 = nullptr;
       int cur_i = -1, cur_b = 0;
       const float* buf = in_bufs;
 #pragma unroll 1
       for (uint32_t g = set; g < n_units; g += NSETS) {
-        const int i = (int)(g / ST_KS);
-        const int ks = (int)(g - (uint32_t)i * ST_KS);
-        const int ky = ks >> 1, h = ks & 1;
-        const uint32_t use = g;
-        const uint32_t s = use % NSTG;
+        const int i = (int)(g / UPT);
+        const int ky = (int)(g - (uint32_t)i * UPT);
+        const uint32_t use = 2 * g;                 // first of the two k-steps
+        const uint32_t s0 = use % NSTG, s1 = (use + 1) % NSTG;
         if (i != cur_i) {
           cur_i = i;
           cur_b = i % NBUF;
@@ -147,60 +149,65 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           mbar_wait(&bar_full[cur_b], (i / NBUF) & 1);
           if (tid == 0) stamp(i, 1);
         }
-        float f[TR][8];
+        float f[TR][16];
         if (warp_active) {
-          const float* src = buf + base_off + ky * p.row_floats + 8 * h;
+          const float* src = buf + base_off + ky * p.row_floats;
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 8; ++e) {
               const float2 v = *reinterpret_cast<const float2*>(src + t * 2 * p.row_floats + 2 * e);
               f[t][2 * e] = v.x;
               f[t][2 * e + 1] = v.y;
             }
-            if (h == 0) {
-              f[t][0] = 0.f;                                           // zero-weighted lead float: keep it finite
-              if (first_col) { f[t][1] = 0.f; f[t][2] = 0.f; f[t][3] = 0.f; }   // kx = 0 taps left of the image
-            } else if (last_col) {
+            f[t][0] = 0.f;                                             // zero-weighted lead float: keep it finite
+            if (first_col) { f[t][1] = 0.f; f[t][2] = 0.f; f[t][3] = 0.f; }   // kx = 0 taps left of the image
+            if (last_col) {
 #pragma unroll
-              for (int e = 2; e < 8; ++e) f[t][e] = 0.f;               // kx = 3, 4 taps right of the image
+              for (int e = 10; e < 16; ++e) f[t][e] = 0.f;             // kx = 3, 4 taps right of the image
             }
           }
         }
-        if (pending != nullptr) {
+        if (pending0 != nullptr) {
           if (warp_active) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
           }
-          mbar_arrive(pending);
+          mbar_arrive(pending0);
+          mbar_arrive(pending1);
         }
-        if (use >= (uint32_t)NSTG) {
-          mbar_wait(&bar_aempty[s], ((use / NSTG) - 1) & 1);
+        if (use + 1 >= (uint32_t)NSTG) {
+          // the later stage was used later: its release (all issuers commit in k-step order) implies the earlier one's
+          mbar_wait(&bar_aempty[s1], (((use + 1) / NSTG) - 1) & 1);
           tc_fence_after();
         }
         if (warp_active) {
-          const uint32_t acol = tlane + colA0 + s * (TR * 16);
 #pragma unroll
-          for (int t = 0; t < TR; ++t) {
-            uint32_t hi[8], lo[8];
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t acol = tlane + colA0 + (hh == 0 ? s0 : s1) * (TR * 16);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              hi[e] = tf32_hi(f[t][e]);
-              lo[e] = __float_as_uint(f[t][e] - __uint_as_float(hi[e]));
+            for (int t = 0; t < TR; ++t) {
+              uint32_t v[16];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                v[e] = tf32_hi(f[t][hh * 8 + e]);
+                v[8 + e] = __float_as_uint(f[t][hh * 8 + e] - __uint_as_float(v[e]));
+              }
+              tmem_st16(acol + t * 16, v);
             }
-            tmem_st8(acol + t * 16, hi);
-            tmem_st8(acol + t * 16 + 8, lo);
           }
         }
-        pending = &bar_afull[s];
-        if (g + NSETS >= n_units || (int)((g + NSETS) / ST_KS) != i) {
+        pending0 = &bar_afull[s0];
+        pending1 = &bar_afull[s1];
+        if (g + NSETS >= n_units || (int)((g + NSETS) / UPT) != i) {
           // last unit of this set in tile i: publish it and release the band (this thread reads nothing more from it)
           if (warp_active) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
           }
-          mbar_arrive(pending);
-          pending = nullptr;
+          mbar_arrive(pending0);
+          mbar_arrive(pending1);
+          pending0 = nullptr;
           mbar_arrive(&bar_infree[cur_b]);
           if (tid == 0) stamp(i, 2);
           if (tid == (NSETS - 1) * 128) stamp(i, 8);
@@ -222,15 +229,14 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
             if (t % NESETS != eset) continue;
-            uint32_t v[2][16];
-            tmem_ld16(tlane + d * (TR * ST_N16) + t * ST_N16, v[0]);
-            tmem_ld16(tlane + d * (TR * ST_N16) + t * ST_N16 + 16, v[1]);
+            uint32_t v[32];
+            tmem_ld32(tlane + d * (TR * ST_N16) + t * ST_N16, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float* dst = ob + ((yq * TR + t) * p.IWBO + x) * ST_PSO;
 #pragma unroll
             for (int j = 0; j < ST_COUT / 4; ++j) {
               const float4 bb = ld4(s_bias + j * 4);
-              const uint32_t* vv = &v[j / 4][(j % 4) * 4];
+              const uint32_t* vv = &v[j * 4];
               float4 r4 = make_float4(fmaxf(__uint_as_float(vv[0]) + bb.x, 0.f), fmaxf(__uint_as_float(vv[1]) + bb.y, 0.f),
                                       fmaxf(__uint_as_float(vv[2]) + bb.z, 0.f), fmaxf(__uint_as_float(vv[3]) + bb.w, 0.f));
               if (active) st4(dst + j * 4, r4);
@@ -246,8 +252,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       }
     }
   } else if (lane_id == 0) {
-    if (warp == W_ISSUE) {
-      // =============================================================== MMA issuer
+    if (warp >= W_ISSUE && warp < W_ISSUE + NISS) {
+      // =============================================================== MMA issuers: accumulator rows t % NISS == issuer (one thread
+      // issues a tcgen05.mma only every ~46-55 clk, the tensor pipe needs 16 clk at N = 32: tools/mma_rate.cu)
+      const int issuer = warp - W_ISSUE;
       const uint32_t idesc = tc_idesc_tf32(ST_N16);
       const uint64_t desc_fixed = tc_bdesc_fixed(ST_N16);
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
@@ -270,6 +278,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
+            if (t % NISS != issuer) continue;
             const uint32_t dc = tmem_base + d * (TR * ST_N16) + t * ST_N16;
             const uint32_t a = tmem_base + colA0 + (s * TR + t) * 16;
             mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
@@ -409,21 +418,24 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
     const cuuint32_t box[4] = {(cuuint32_t)ST_PSO, (cuuint32_t)p.IWBO, (cuuint32_t)p.BH, 1};
     HP_TRY(tc_make_map4(&tout, out, dims, strides, box));
   }
-  const int nsets = (cfg && cfg[3] > 0) ? cfg[3] : 3;
+  const int nsets = (cfg && cfg[3] > 0) ? cfg[3] % 16 : 2;
+  const int niss = (cfg && cfg[3] >= 16) ? cfg[3] / 16 : 4;
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
   const size_t smem = total();
-#define STEM_CASE(NSETS_, NESETS_)                                                                                     \
-  if (nsets == NSETS_) {                                                                                               \
-    auto kern = stem_tc_kernel<TR, NSETS_, NESETS_>;                                                                   \
+#define STEM_CASE(NSETS_, NESETS_, NISS_)                                                                              \
+  if (nsets == NSETS_ && niss == NISS_) {                                                                              \
+    auto kern = stem_tc_kernel<TR, NSETS_, NESETS_, NISS_>;                                                            \
     HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                      \
-    kern<<<(unsigned)grid, 128 * NSETS_ + 128 * NESETS_ + 96, smem, st>>>(tin, tout, p);                               \
+    kern<<<(unsigned)grid, 128 * NSETS_ + 128 * NESETS_ + 32 * (NISS_ + 2), smem, st>>>(tin, tout, p);                 \
     h->launches++;                                                                                                     \
     HP_CUDA(cudaGetLastError());                                                                                       \
     return HP_OK;                                                                                                      \
   }
-  STEM_CASE(2, 2) STEM_CASE(3, 2) STEM_CASE(4, 1)
+  // consecutive units of a gather set are 2 * nsets k-steps apart: at most the ring depth (see blaze_block_deep_kernel)
+  HP_REQUIRE(2 * nsets <= p.nstg, HP_ERR_INVALID, "stem tc: %d gather sets need a ring of %d stages", nsets, 2 * nsets);
+  STEM_CASE(2, 2, 4) STEM_CASE(2, 2, 2) STEM_CASE(1, 2, 4)
 #undef STEM_CASE
-  hp_set_error("stem tc: no kernel for %d gather sets", nsets);
+  hp_set_error("stem tc: no kernel for %d gather sets, %d issuers", nsets, niss);
   return HP_ERR_UNSUPPORTED;
 }
