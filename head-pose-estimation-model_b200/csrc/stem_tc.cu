@@ -126,22 +126,23 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     if (warp < W_EPI) {
       // =============================================================== gather sets: input band -> TF32 hi / lo -> TMEM A ring
       const int set = warp >> 2;
-      // work unit = one kernel row ky = 2 k-steps (16 floats per output row): every tcgen05 / mbarrier instruction costs tens
-      // of cycles of issue whatever it carries, so a unit is as large as the registers allow
-      constexpr int UPT = ST_KS / 2;
+      // work unit = one k-step (8 floats of a run per output row); units are dealt round-robin to the sets over the global
+      // unit counter (see blaze_block_deep_kernel: consecutive units of a set must be at most NSTG k-steps apart)
+      constexpr int UPT = ST_KS;
       const uint32_t n_units = (uint32_t)my_tiles * UPT;
       // run of kernel row ky for output row t: band row 2 (yq TR + t) + ky, floats [6 x - 4, 6 x + 12)
       const int base_off = (2 * yq * TR) * p.row_floats + 6 * x - 4;
       const bool first_col = (x == 0), last_col = (x == p.Wo - 1);
-      uint64_t *pending0 = nullptr, *pending1 = nullptr;
+      uint64_t* pending = nullptr;
       int cur_i = -1, cur_b = 0;
       const float* buf = in_bufs;
 #pragma unroll 1
       for (uint32_t g = set; g < n_units; g += NSETS) {
         const int i = (int)(g / UPT);
-        const int ky = (int)(g - (uint32_t)i * UPT);
-        const uint32_t use = 2 * g;                 // first of the two k-steps
-        const uint32_t s0 = use % NSTG, s1 = (use + 1) % NSTG;
+        const int ks = (int)(g - (uint32_t)i * UPT);
+        const int ky = ks >> 1, h = ks & 1;
+        const uint32_t use = g;
+        const uint32_t s = use % NSTG;
         if (i != cur_i) {
           cur_i = i;
           cur_b = i % NBUF;
@@ -149,65 +150,57 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           mbar_wait(&bar_full[cur_b], (i / NBUF) & 1);
           if (tid == 0) stamp(i, 1);
         }
-        float f[TR][16];
+        uint32_t v[TR][16];   // per output row: [hi 8 | lo 8] = the 16 columns of the stage row
         if (warp_active) {
-          const float* src = buf + base_off + ky * p.row_floats;
+          const float* src = buf + base_off + ky * p.row_floats + 8 * h;
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 q = *reinterpret_cast<const float2*>(src + t * 2 * p.row_floats + 2 * e);
+              f[2 * e] = q.x;
+              f[2 * e + 1] = q.y;
+            }
+            if (h == 0) {
+              f[0] = 0.f;                                              // zero-weighted lead float: keep it finite
+              if (first_col) { f[1] = 0.f; f[2] = 0.f; f[3] = 0.f; }   // kx = 0 taps left of the image
+            } else if (last_col) {
+#pragma unroll
+              for (int e = 2; e < 8; ++e) f[e] = 0.f;                  // kx = 3, 4 taps right of the image
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float2 v = *reinterpret_cast<const float2*>(src + t * 2 * p.row_floats + 2 * e);
-              f[t][2 * e] = v.x;
-              f[t][2 * e + 1] = v.y;
-            }
-            f[t][0] = 0.f;                                             // zero-weighted lead float: keep it finite
-            if (first_col) { f[t][1] = 0.f; f[t][2] = 0.f; f[t][3] = 0.f; }   // kx = 0 taps left of the image
-            if (last_col) {
-#pragma unroll
-              for (int e = 10; e < 16; ++e) f[t][e] = 0.f;             // kx = 3, 4 taps right of the image
+              v[t][e] = tf32_hi(f[e]);
+              v[t][8 + e] = __float_as_uint(f[e] - __uint_as_float(v[t][e]));
             }
           }
         }
-        if (pending0 != nullptr) {
+        if (pending != nullptr) {
           if (warp_active) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
           }
-          mbar_arrive(pending0);
-          mbar_arrive(pending1);
+          mbar_arrive(pending);
         }
-        if (use + 1 >= (uint32_t)NSTG) {
-          // the later stage was used later: its release (all issuers commit in k-step order) implies the earlier one's
-          mbar_wait(&bar_aempty[s1], (((use + 1) / NSTG) - 1) & 1);
+        if (use >= (uint32_t)NSTG) {
+          mbar_wait(&bar_aempty[s], ((use / NSTG) - 1) & 1);
           tc_fence_after();
         }
         if (warp_active) {
+          const uint32_t acol = tlane + colA0 + s * (TR * 16);
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const uint32_t acol = tlane + colA0 + (hh == 0 ? s0 : s1) * (TR * 16);
-#pragma unroll
-            for (int t = 0; t < TR; ++t) {
-              uint32_t v[16];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                v[e] = tf32_hi(f[t][hh * 8 + e]);
-                v[8 + e] = __float_as_uint(f[t][hh * 8 + e] - __uint_as_float(v[e]));
-              }
-              tmem_st16(acol + t * 16, v);
-            }
-          }
+          for (int t = 0; t < TR; ++t) tmem_st16(acol + t * 16, v[t]);
         }
-        pending0 = &bar_afull[s0];
-        pending1 = &bar_afull[s1];
+        pending = &bar_afull[s];
         if (g + NSETS >= n_units || (int)((g + NSETS) / UPT) != i) {
           // last unit of this set in tile i: publish it and release the band (this thread reads nothing more from it)
           if (warp_active) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
           }
-          mbar_arrive(pending0);
-          mbar_arrive(pending1);
-          pending0 = nullptr;
+          mbar_arrive(pending);
+          pending = nullptr;
           mbar_arrive(&bar_infree[cur_b]);
           if (tid == 0) stamp(i, 2);
           if (tid == (NSETS - 1) * 128) stamp(i, 8);
@@ -418,7 +411,7 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
     const cuuint32_t box[4] = {(cuuint32_t)ST_PSO, (cuuint32_t)p.IWBO, (cuuint32_t)p.BH, 1};
     HP_TRY(tc_make_map4(&tout, out, dims, strides, box));
   }
-  const int nsets = (cfg && cfg[3] > 0) ? cfg[3] % 16 : 2;
+  const int nsets = (cfg && cfg[3] > 0) ? cfg[3] % 16 : 4;
   const int niss = (cfg && cfg[3] >= 16) ? cfg[3] / 16 : 4;
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -432,9 +425,9 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
     HP_CUDA(cudaGetLastError());                                                                                       \
     return HP_OK;                                                                                                      \
   }
-  // consecutive units of a gather set are 2 * nsets k-steps apart: at most the ring depth (see blaze_block_deep_kernel)
-  HP_REQUIRE(2 * nsets <= p.nstg, HP_ERR_INVALID, "stem tc: %d gather sets need a ring of %d stages", nsets, 2 * nsets);
-  STEM_CASE(2, 2, 4) STEM_CASE(2, 2, 2) STEM_CASE(1, 2, 4)
+  // consecutive units of a gather set are nsets k-steps apart: at most the ring depth (see blaze_block_deep_kernel)
+  HP_REQUIRE(nsets <= p.nstg, HP_ERR_INVALID, "stem tc: %d gather sets need a ring of %d stages", nsets, nsets);
+  STEM_CASE(4, 1, 4) STEM_CASE(4, 1, 2) STEM_CASE(3, 1, 4) STEM_CASE(3, 2, 2) STEM_CASE(2, 2, 4) STEM_CASE(2, 2, 2)
 #undef STEM_CASE
   hp_set_error("stem tc: no kernel for %d gather sets, %d issuers", nsets, niss);
   return HP_ERR_UNSUPPORTED;

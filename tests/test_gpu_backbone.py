@@ -219,7 +219,7 @@ def test_tensor_core_block_geometries(geom, size, batch):
     assert ran >= 1 or size == 128, f"geometry {geom} ran on no block"
 
 
-@pytest.mark.parametrize("cfg", [(0, 0, 0, 0), (0, 2, 2, 2 + 32), (4, 3, 2, 1), (0, 4, 3, 2)])   # BH, nbuf, nout, nsets (+ 16 x issuers)
+@pytest.mark.parametrize("cfg", [(0, 0, 0, 0), (0, 2, 2, 2 + 32), (4, 3, 2, 3 + 32), (0, 4, 3, 4 + 32), (0, 0, 0, 3)])   # BH, nbuf, nout, nsets (+ 16 x issuers)
 @pytest.mark.parametrize("size,batch", [(96, 37), (88, 5), (128, 3), (64, 2), (120, 2)])
 def test_tensor_core_stem(cfg, size, batch):
     """The implicit-GEMM (tcgen05, 3xTF32) stem reproduces the naive CUDA stem for every pipeline geometry
