@@ -1,4 +1,4 @@
-// Stem (Conv2D 5x5, stride 2, SAME, 3 -> 24, + bias, ReLU) as an implicit 3xTF32 GEMM on the tcgen05 tensor cores.
+// Stem (Conv2D 5x5, stride 2, SAME, 3 -> 24, + bias, ReLU) as an implicit split-fp16 GEMM on the tcgen05 tensor cores.
 //
 // Reference semantics: first layer `conv2d` of the Keras graph in BlazePoser/UnifiedModels/*.h5,
 // called at BlazePoser/blazeFaceDetectorH5.py:272.  The CUDA-core stem (backbone.cu) runs at 17 % of the HBM roofline
@@ -9,7 +9,13 @@
 // kernel row are 15 CONTIGUOUS floats of an input row, so the A row of an output pixel is 5 runs of 16 floats (the 15
 // taps preceded by one zero-weighted float that keeps the run 8-byte aligned): k = ky * 16 + 1 + kx * 3 + ci.  No
 // im2col buffer exists: each lane copies its runs from the input band in shared memory (LDS.64, conflict free)
-// straight into the TMEM A ring, split into TF32 hi / lo parts.
+// straight into the TMEM A ring, split into fp16 hi / lo parts.
+//
+// Precision: x = x_hi + x_lo and w = w_hi + w_lo with all four parts in fp16 (11-bit significands, lo parts may be fp16
+// subnormals: absolute error <= 2^-25), D += x_hi w_hi + x_hi w_lo + x_lo w_hi in fp32.  fp16 rather than TF32 because one
+// thread can issue a tcgen05.mma only every ~45 clk whatever its size (tools/mma_rate.cu) and kind::f16 covers K = 16 per
+// instruction instead of 8: 60 instead of 120 MMAs per band.  fp16 needs |x| <= 65504: inputs are normalised pixels
+// ([-1, 1], blazeFaceDetectorH5.py:247-269); larger magnitudes must use the CUDA-core stem (hp_debug_set_stem_tc(-1)).
 //
 // Warp-specialised pipeline per CTA (persistent, 1 per SM), same scheme as blaze_block_deep_kernel:
 //   loader   (1 thread): TMA load of the input band (2 BH + 3 rows x W x 3) into a ring of NBUF buffers; rows above /
@@ -19,16 +25,18 @@
 //   issuers  (NISS threads in NISS warps): 3 tcgen05.mma per k-step and accumulator row into D[i & 1]
 //   epilogue (NESETS x 4 warps): D + bias -> ReLU -> output staging ring (pixel stride 28 floats: conflict free)
 //   storer   (1 thread): TMA store of the staged band (box wider than the 24 channels: clipped by the hardware)
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int ST_K8 = 80, ST_KS = 10, ST_N16 = 32, ST_COUT = 24, ST_PSO = 28;
+constexpr int ST_K8 = 80, ST_KS = 5, ST_N16 = 32, ST_COUT = 24, ST_PSO = 28;   // ST_KS k-steps of 16 (one kernel row each)
 constexpr int ST_MAXB = 4, ST_MAXO = 3, ST_MAXSTG = 4;
 constexpr int ST_BAR_FLOATS = 128;
 
 struct StemTcParams {
-  const float *bhi, *blo, *bias;   // weights [K8/4][32][4] hi / lo, bias [24]
+  const float *bhi, *blo, *bias;   // weights as fp16 [K/8][32][8] hi / lo (each 1280 floats of storage), bias [24]
   int W, H, Wo, Ho, BH, IR;        // IR = 2 BH + 3 input rows per band
   int row_floats;                  // W * 3
   int bands_per_img, n_tiles, lanes;
@@ -58,7 +66,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   static_assert((2 * ST_MAXB + 2 * ST_MAXO + 2 * ST_MAXSTG + 4) * 8 + 4 <= ST_BAR_FLOATS * 4, "barrier block");
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (ST_BAR_FLOATS - 1);
   float* s_bhi = smem + p.off_b;
-  float* s_blo = s_bhi + ST_K8 * ST_N16;
+  float* s_blo = s_bhi + ST_K8 * ST_N16 / 2;
   float* s_bias = smem + p.off_bias;
   float* in_bufs = smem + p.off_in;
   float* out_bufs = smem + p.off_out;
@@ -68,7 +76,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + NISS, W_STORE = W_LOAD + 1;
   const int NSTG = p.nstg, NBUF = p.nbuf, NOUT = p.nout;
 
-  for (int i = tid * 4; i < ST_K8 * ST_N16; i += nthr * 4) {
+  for (int i = tid * 4; i < ST_K8 * ST_N16 / 2; i += nthr * 4) {
     st4(s_bhi + i, ld4(p.bhi + i));
     st4(s_blo + i, ld4(p.blo + i));
   }
@@ -126,8 +134,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     if (warp < W_EPI) {
       // =============================================================== gather sets: input band -> TF32 hi / lo -> TMEM A ring
       const int set = warp >> 2;
-      // work unit = one k-step (8 floats of a run per output row); units are dealt round-robin to the sets over the global
-      // unit counter (see blaze_block_deep_kernel: consecutive units of a set must be at most NSTG k-steps apart)
+      // work unit = one k-step = one kernel row (16 floats per output row); units are dealt round-robin to the sets over the
+      // global unit counter (see blaze_block_deep_kernel: consecutive units of a set must be at most NSTG k-steps apart)
       constexpr int UPT = ST_KS;
       const uint32_t n_units = (uint32_t)my_tiles * UPT;
       // run of kernel row ky for output row t: band row 2 (yq TR + t) + ky, floats [6 x - 4, 6 x + 12)
@@ -139,8 +147,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll 1
       for (uint32_t g = set; g < n_units; g += NSETS) {
         const int i = (int)(g / UPT);
-        const int ks = (int)(g - (uint32_t)i * UPT);
-        const int ky = ks >> 1, h = ks & 1;
+        const int ky = (int)(g - (uint32_t)i * UPT);
         const uint32_t use = g;
         const uint32_t s = use % NSTG;
         if (i != cur_i) {
@@ -150,29 +157,23 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           mbar_wait(&bar_full[cur_b], (i / NBUF) & 1);
           if (tid == 0) stamp(i, 1);
         }
-        uint32_t v[TR][16];   // per output row: [hi 8 | lo 8] = the 16 columns of the stage row
+        uint32_t v[TR][16];   // per output row: 8 columns of fp16 pairs hi (k = 2c, 2c + 1), then 8 columns lo
         if (warp_active) {
-          const float* src = buf + base_off + ky * p.row_floats + 8 * h;
+          const float* src = buf + base_off + ky * p.row_floats;
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 q = *reinterpret_cast<const float2*>(src + t * 2 * p.row_floats + 2 * e);
-              f[2 * e] = q.x;
-              f[2 * e + 1] = q.y;
-            }
-            if (h == 0) {
-              f[0] = 0.f;                                              // zero-weighted lead float: keep it finite
-              if (first_col) { f[1] = 0.f; f[2] = 0.f; f[3] = 0.f; }   // kx = 0 taps left of the image
-            } else if (last_col) {
-#pragma unroll
-              for (int e = 2; e < 8; ++e) f[e] = 0.f;                  // kx = 3, 4 taps right of the image
-            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              v[t][e] = tf32_hi(f[e]);
-              v[t][8 + e] = __float_as_uint(f[e] - __uint_as_float(v[t][e]));
+              float2 q = *reinterpret_cast<const float2*>(src + t * 2 * p.row_floats + 2 * e);
+              if (e == 0) q.x = 0.f;                                        // zero-weighted lead float: keep it finite
+              if (first_col && e == 0) q.y = 0.f;                           // kx = 0 taps (floats 1..3) left of the image
+              if (first_col && e == 1) q = make_float2(0.f, 0.f);
+              if (last_col && e >= 5) q = make_float2(0.f, 0.f);            // kx = 3, 4 taps (floats 10..15) right of the image
+              const __half2 hi = __floats2half2_rn(q.x, q.y);
+              const float2 back = __half22float2(hi);
+              const __half2 lo = __floats2half2_rn(q.x - back.x, q.y - back.y);
+              v[t][e] = *reinterpret_cast<const uint32_t*>(&hi);
+              v[t][8 + e] = *reinterpret_cast<const uint32_t*>(&lo);
             }
           }
         }
@@ -249,7 +250,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       // =============================================================== MMA issuers: accumulator rows t % NISS == issuer (one thread
       // issues a tcgen05.mma only every ~46-55 clk, the tensor pipe needs 16 clk at N = 32: tools/mma_rate.cu)
       const int issuer = warp - W_ISSUE;
-      const uint32_t idesc = tc_idesc_tf32(ST_N16);
+      // kind::f16: A / B fp16 (format 0), D fp32, K = 16 per instruction; B slice [32 rows][16 k] = 2 core matrices of 8 rows x 16 B
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(ST_N16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t desc_fixed = tc_bdesc_fixed(ST_N16);
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
       uint32_t use = 0;
@@ -274,9 +276,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             if (t % NISS != issuer) continue;
             const uint32_t dc = tmem_base + d * (TR * ST_N16) + t * ST_N16;
             const uint32_t a = tmem_base + colA0 + (s * TR + t) * 16;
-            mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
-            mma_tf32_ts(dc, a, dlo, idesc, 1u);
-            mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+            mma_f16_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+            mma_f16_ts(dc, a, dlo, idesc, 1u);
+            mma_f16_ts(dc, a + 8, dhi, idesc, 1u);
           }
           tc_commit(&bar_aempty[s]);
         }
@@ -322,28 +324,62 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
 }  // namespace
 
-int hp_stem_tc_weight_floats() { return ST_K8 * ST_N16; }
+int hp_stem_tc_weight_floats() { return ST_K8 * ST_N16 / 2; }   // fp16 elements stored two per float slot
 
-// Stem kernel [5][5][3][24] (HWIO, = packed rows (ky*5+kx)*3+ci) -> TF32 hi / lo parts in the GEMM layout [K8/4][32][4],
-// k = ky * 16 + 1 + kx * 3 + ci (k = ky * 16 is the zero-weighted alignment float).
-void hp_stem_tc_split_weights(const float* w75x24, float* bhi, float* blo) {
-  auto rna = [](float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;
-    u &= 0xFFFFE000u;
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
-  };
-  for (int i = 0; i < ST_K8 * ST_N16; ++i) bhi[i] = blo[i] = 0.f;
+static uint16_t f32_to_f16_rn(float f) {   // round to nearest even, subnormals kept, overflow to infinity
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7FFFFFFFu;
+  if (x >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | (x > 0x7F800000u ? 0x200u : 0u));
+  if (x >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                       // rounds to >= 65520: infinity
+  if (x < 0x38800000u) {                                                         // below 2^-14: subnormal half
+    if (x < 0x33000000u) return (uint16_t)sign;                                  // below 2^-25: zero
+    const int e = (int)(x >> 23);
+    const uint32_t m = (x & 0x7FFFFFu) | 0x800000u;
+    const int shift = 126 - e;                                                   // 14 .. 24
+    uint32_t h = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((x - 0x38000000u) >> 13);
+  const uint32_t rem = x & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return (uint16_t)(sign | h);
+}
+static float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+  uint32_t x;
+  if (e == 0) {
+    if (m == 0) x = sign;
+    else {
+      int sh = 0;
+      uint32_t mm = m;
+      while (!(mm & 0x400u)) { mm <<= 1; ++sh; }
+      x = sign | ((uint32_t)(113 - sh) << 23) | ((mm & 0x3FFu) << 13);
+    }
+  } else if (e == 31) x = sign | 0x7F800000u | (m << 13);
+  else x = sign | ((e + 112u) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &x, 4);
+  return f;
+}
+
+// Stem kernel [5][5][3][24] (HWIO, = packed rows (ky*5+kx)*3+ci) -> fp16 hi / lo parts in the GEMM layout [K/8][32][8 halves]
+// (K-major core matrices of 8 rows x 16 bytes), k = ky * 16 + 1 + kx * 3 + ci (k = ky * 16 is the zero-weighted alignment float).
+void hp_stem_tc_split_weights(const float* w75x24, float* bhi_f, float* blo_f) {
+  uint16_t* bhi = reinterpret_cast<uint16_t*>(bhi_f);
+  uint16_t* blo = reinterpret_cast<uint16_t*>(blo_f);
+  for (int i = 0; i < ST_K8 * ST_N16; ++i) bhi[i] = blo[i] = 0;
   for (int ky = 0; ky < 5; ++ky)
     for (int j = 0; j < 15; ++j)
       for (int n = 0; n < ST_COUT; ++n) {
         const int k = ky * 16 + 1 + j;
         const float wv = w75x24[(ky * 15 + j) * ST_COUT + n];
-        const float hi = rna(wv), lo = rna(wv - hi);
-        const size_t idx = ((size_t)(k / 4) * ST_N16 + n) * 4 + (k % 4);
+        const uint16_t hi = f32_to_f16_rn(wv);
+        const uint16_t lo = f32_to_f16_rn(wv - f16_to_f32(hi));
+        const size_t idx = ((size_t)(k / 8) * ST_N16 + n) * 8 + (k % 8);
         bhi[idx] = hi;
         blo[idx] = lo;
       }
@@ -379,7 +415,7 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
   p.load_bytes = (uint32_t)((size_t)p.row_floats * p.IR * sizeof(float));
   int off = ST_BAR_FLOATS;
   p.off_b = off;
-  off += 2 * ST_K8 * ST_N16;
+  off += ST_K8 * ST_N16;          // hi + lo, fp16
   p.off_bias = off;
   off = tc_align_up(off + ST_N16 + 16, 256);      // >= 16 zeroed floats in front of the first band buffer
   p.off_in = off;
@@ -411,8 +447,8 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
     const cuuint32_t box[4] = {(cuuint32_t)ST_PSO, (cuuint32_t)p.IWBO, (cuuint32_t)p.BH, 1};
     HP_TRY(tc_make_map4(&tout, out, dims, strides, box));
   }
-  const int nsets = (cfg && cfg[3] > 0) ? cfg[3] % 16 : 4;
-  const int niss = (cfg && cfg[3] >= 16) ? cfg[3] / 16 : 4;
+  const int nsets = (cfg && cfg[3] > 0) ? cfg[3] % 16 : 2;
+  const int niss = (cfg && cfg[3] >= 16) ? cfg[3] / 16 : 2;
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
   const size_t smem = total();

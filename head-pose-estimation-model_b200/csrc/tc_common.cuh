@@ -80,6 +80,11 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_addr, uint32_t a_addr, ui
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d_addr), "r"(a_addr), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with fp16 inputs (two per 32-bit TMEM column), K = 16
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_addr, uint32_t a_addr, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_addr), "r"(a_addr), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
