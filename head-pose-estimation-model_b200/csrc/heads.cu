@@ -44,22 +44,35 @@ __device__ __forceinline__ float act_bwd(int act, float y) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // ============================================================================ generic dense
-#define DENSE_TM 64
+// y = act(x W + b) for row-major x [M][K]: persistent CTAs, 128-row tiles.
+//   x tile   : cp.async 16-byte chunks (coalesced) into smem rows of XS floats (XS / 4 odd: conflict-free row access)
+//   compute  : register tile 8 rows x 4 columns per thread (weights as conflict-free LDS.128, activations as broadcast
+//              LDS.128); layers with fewer than 16 output columns use one thread per row instead
+//   epilogue : bias + activation into a staging tile that reuses the x tile, then coalesced stores per output segment
+//              (the detector heads scatter cls | loc columns of one GEMM to two tensors in anchor order)
+#define DENSE_TM 128
 struct DenseKParams {
   const float* x;
   const float* W;
   const float* b;
   int M, K, ldx, ldw, N, act, transpose_w, accumulate;
-  int KP, NP, XS;
+  int KP, NP, XS, OS;        // OS = staging row stride
+  int vec_x;                 // x rows can be fetched with 16-byte cp.async
   int n_outs;
   DenseOut outs[2];
+  unsigned magic[2];         // ceil(2^32 / width) of each output segment
 };
 
-__global__ void __launch_bounds__(256) dense_kernel(DenseKParams p) {
+__device__ __forceinline__ void dense_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+
+__global__ void __launch_bounds__(256, 2) dense_kernel(DenseKParams p) {
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;                 // [KP][NP]
   float* bs = Ws + p.KP * p.NP;     // [NP]
-  float* xs = bs + p.NP;            // [TM][XS]
+  float* xs = bs + p.NP;            // [TM][XS]; reused as the staging tile [TM][OS]
   const int tid = threadIdx.x;
   for (int i = tid; i < p.KP * p.NP; i += 256) {
     const int k = i / p.NP, n = i - k * p.NP;
@@ -69,61 +82,112 @@ __global__ void __launch_bounds__(256) dense_kernel(DenseKParams p) {
   }
   for (int i = tid; i < p.NP; i += 256) bs[i] = (p.b && i < p.N) ? p.b[i] : 0.f;
   const int ngd = p.NP / 4;
-  const int RG = DENSE_TM / 4;  // 16 row groups; a thread's 4 rows are rg, rg+16, rg+32, rg+48
+  constexpr int RG = DENSE_TM / 8;  // 16 row groups; a thread's 8 rows are rg + 16 r
   const int n_tiles = (p.M + DENSE_TM - 1) / DENSE_TM;
+  const int kc = p.KP / 4;          // 16-byte chunks per row
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long m0 = (long long)tile * DENSE_TM;
-    __syncthreads();
-    for (int i = tid; i < DENSE_TM * p.KP; i += 256) {
-      const int r = i / p.KP, k = i - r * p.KP;
-      const long long m = m0 + r;
-      xs[r * p.XS + k] = (m < p.M && k < p.K) ? p.x[m * p.ldx + k] : 0.f;
+    const int rows = (int)((p.M - m0 < DENSE_TM) ? (p.M - m0) : DENSE_TM);
+    __syncthreads();   // previous tile fully written out (xs doubles as the staging tile)
+    if (p.vec_x) {
+      for (int i = tid; i < DENSE_TM * kc; i += 256) {
+        const int r = i / kc, c = i - r * kc;
+        const bool ok = r < rows;
+        dense_cp_async16(xs + r * p.XS + c * 4, ok ? p.x + (m0 + r) * p.ldx + c * 4 : p.x, ok ? 16 : 0);
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    } else {
+      for (int i = tid; i < DENSE_TM * p.KP; i += 256) {
+        const int r = i / p.KP, k = i - r * p.KP;
+        xs[r * p.XS + k] = (r < rows && k < p.K) ? p.x[(m0 + r) * p.ldx + k] : 0.f;
+      }
     }
     __syncthreads();
-    for (int item = tid; item < RG * ngd; item += 256) {
-      const int cg = item % ngd, rg = item / ngd;
-      float4 acc[4];
+    if (p.NP >= 16) {
+      // ---- 8 rows x 4 columns per thread; up to two passes over the (row group, column group) items
+      float4 acc[2][8];
+      int n_items = 0;
+      for (int item = tid; item < RG * ngd && n_items < 2; item += 256, ++n_items) {
+        const int cg = item % ngd, rg = item / ngd;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = 0; k < p.KP; k += 4) {
-        const float4 w0 = ld4(Ws + (k + 0) * p.NP + cg * 4);
-        const float4 w1 = ld4(Ws + (k + 1) * p.NP + cg * 4);
-        const float4 w2 = ld4(Ws + (k + 2) * p.NP + cg * 4);
-        const float4 w3 = ld4(Ws + (k + 3) * p.NP + cg * 4);
+        for (int r = 0; r < 8; ++r) acc[n_items][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* arow = xs + rg * p.XS;
+        const float* wcol = Ws + cg * 4;
+#pragma unroll 2
+        for (int k = 0; k < p.KP; k += 4) {
+          const float4 w0 = ld4(wcol + (k + 0) * p.NP);
+          const float4 w1 = ld4(wcol + (k + 1) * p.NP);
+          const float4 w2 = ld4(wcol + (k + 2) * p.NP);
+          const float4 w3 = ld4(wcol + (k + 3) * p.NP);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float4 a = ld4(xs + (rg + r * RG) * p.XS + k);
-          acc[r].x = fmaf(a.x, w0.x, acc[r].x); acc[r].y = fmaf(a.x, w0.y, acc[r].y);
-          acc[r].z = fmaf(a.x, w0.z, acc[r].z); acc[r].w = fmaf(a.x, w0.w, acc[r].w);
-          acc[r].x = fmaf(a.y, w1.x, acc[r].x); acc[r].y = fmaf(a.y, w1.y, acc[r].y);
-          acc[r].z = fmaf(a.y, w1.z, acc[r].z); acc[r].w = fmaf(a.y, w1.w, acc[r].w);
-          acc[r].x = fmaf(a.z, w2.x, acc[r].x); acc[r].y = fmaf(a.z, w2.y, acc[r].y);
-          acc[r].z = fmaf(a.z, w2.z, acc[r].z); acc[r].w = fmaf(a.z, w2.w, acc[r].w);
-          acc[r].x = fmaf(a.w, w3.x, acc[r].x); acc[r].y = fmaf(a.w, w3.y, acc[r].y);
-          acc[r].z = fmaf(a.w, w3.z, acc[r].z); acc[r].w = fmaf(a.w, w3.w, acc[r].w);
-        }
-      }
-      const float4 bias = ld4(bs + cg * 4);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const long long m = m0 + rg + r * RG;
-        if (m >= p.M) continue;
-        float v[4] = {acc[r].x + bias.x, acc[r].y + bias.y, acc[r].z + bias.z, acc[r].w + bias.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = cg * 4 + j;
-          if (c >= p.N) continue;
-          const float val = act_fwd(p.act, v[j]);
-          for (int o = 0; o < p.n_outs; ++o) {
-            const DenseOut& d = p.outs[o];
-            if (c >= d.col_begin && c < d.col_end) {
-              const long long img = m / d.rows_per_img;
-              const int row = (int)(m - img * d.rows_per_img);
-              float* dst = d.ptr + img * d.img_stride + (long long)row * d.row_stride + (c - d.col_begin);
-              if (p.accumulate) *dst += val; else *dst = val;
-            }
+          for (int r = 0; r < 8; ++r) {
+            const float4 a = ld4(arow + r * RG * p.XS + k);
+            float4& c = acc[n_items][r];
+            c.x = fmaf(a.x, w0.x, c.x); c.y = fmaf(a.x, w0.y, c.y); c.z = fmaf(a.x, w0.z, c.z); c.w = fmaf(a.x, w0.w, c.w);
+            c.x = fmaf(a.y, w1.x, c.x); c.y = fmaf(a.y, w1.y, c.y); c.z = fmaf(a.y, w1.z, c.z); c.w = fmaf(a.y, w1.w, c.w);
+            c.x = fmaf(a.z, w2.x, c.x); c.y = fmaf(a.z, w2.y, c.y); c.z = fmaf(a.z, w2.z, c.z); c.w = fmaf(a.z, w2.w, c.w);
+            c.x = fmaf(a.w, w3.x, c.x); c.y = fmaf(a.w, w3.y, c.y); c.z = fmaf(a.w, w3.z, c.z); c.w = fmaf(a.w, w3.w, c.w);
           }
         }
+      }
+      __syncthreads();   // every thread is done reading the x tile: it becomes the staging tile
+      n_items = 0;
+      for (int item = tid; item < RG * ngd && n_items < 2; item += 256, ++n_items) {
+        const int cg = item % ngd, rg = item / ngd;
+        const float4 bias = ld4(bs + cg * 4);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float4 c = acc[n_items][r];
+          float4 o;
+          o.x = act_fwd(p.act, c.x + bias.x); o.y = act_fwd(p.act, c.y + bias.y);
+          o.z = act_fwd(p.act, c.z + bias.z); o.w = act_fwd(p.act, c.w + bias.w);
+          *reinterpret_cast<float4*>(xs + (rg + r * RG) * p.OS + cg * 4) = o;
+        }
+      }
+    } else {
+      // ---- narrow layers (NP = 4, 8, 12): one thread per row
+      float acc[12];
+      if (tid < DENSE_TM) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) acc[c] = 0.f;
+        const float* arow = xs + tid * p.XS;
+        for (int k = 0; k < p.KP; k += 4) {
+          const float4 a = ld4(arow + k);
+          const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int c4 = 0; c4 < 3; ++c4)
+              if (c4 * 4 < p.NP) {
+                const float4 w = ld4(Ws + (k + kk) * p.NP + c4 * 4);
+                acc[c4 * 4 + 0] = fmaf(av[kk], w.x, acc[c4 * 4 + 0]); acc[c4 * 4 + 1] = fmaf(av[kk], w.y, acc[c4 * 4 + 1]);
+                acc[c4 * 4 + 2] = fmaf(av[kk], w.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(av[kk], w.w, acc[c4 * 4 + 3]);
+              }
+        }
+      }
+      __syncthreads();
+      if (tid < DENSE_TM) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c)
+          if (c < p.NP) xs[tid * p.OS + c] = act_fwd(p.act, acc[c] + bs[c]);
+      }
+    }
+    __syncthreads();
+    // ---- coalesced write-out of every output segment
+    for (int o = 0; o < p.n_outs; ++o) {
+      const DenseOut& d = p.outs[o];
+      const int wd = d.col_end - d.col_begin;
+      const int total = rows * wd;
+      for (int j = tid; j < total; j += 256) {
+        const int r = (int)(((unsigned long long)j * p.magic[o]) >> 32);
+        const int c = j - r * wd;
+        const long long m = m0 + r;
+        const long long img = m / d.rows_per_img;
+        const int rin = (int)(m - img * d.rows_per_img);
+        float* dst = d.ptr + img * d.img_stride + (long long)rin * d.row_stride + c;
+        const float val = xs[r * p.OS + d.col_begin + c];
+        if (p.accumulate) *dst += val; else *dst = val;
       }
     }
   }
@@ -139,9 +203,18 @@ int hp_launch_dense(hp_ctx* h, const float* x, int M, int K, int ldx, const floa
   p.transpose_w = transpose_w ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
   p.KP = round_up(K, 4); p.NP = round_up(N, 4);
   p.XS = ((p.KP / 4) & 1) ? p.KP : p.KP + 4;
+  p.OS = ((p.NP / 4) & 1) ? p.NP : p.NP + 4;
+  p.vec_x = (K % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0) ? 1 : 0;
   p.n_outs = n_outs;
-  for (int i = 0; i < n_outs; ++i) p.outs[i] = outs[i];
-  size_t smem = ((size_t)p.KP * p.NP + p.NP + (size_t)DENSE_TM * p.XS) * sizeof(float);
+  for (int i = 0; i < n_outs; ++i) {
+    p.outs[i] = outs[i];
+    const int wd = outs[i].col_end - outs[i].col_begin;
+    HP_REQUIRE(wd >= 1 && outs[i].col_end <= N, HP_ERR_INVALID, "dense: bad output segment [%d, %d)", outs[i].col_begin, outs[i].col_end);
+    p.magic[i] = (unsigned)((0x100000000ull + wd - 1) / wd);
+  }
+  HP_REQUIRE(p.NP >= 16 ? (DENSE_TM / 8) * (p.NP / 4) <= 512 : p.NP <= 12, HP_ERR_UNSUPPORTED, "dense layer with %d outputs too wide", N);
+  const int tile_fl = DENSE_TM * (p.XS > p.OS ? p.XS : p.OS);
+  size_t smem = ((size_t)p.KP * p.NP + p.NP + (size_t)tile_fl) * sizeof(float);
   HP_REQUIRE(smem <= 200 * 1024, HP_ERR_UNSUPPORTED, "dense layer %dx%d too large for the head engine", K, N);
   HP_CUDA(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int n_tiles = ceil_div(M, DENSE_TM);
