@@ -68,11 +68,13 @@ __device__ __forceinline__ void dense_cp_async16(void* smem_dst, const void* gsr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
 }
 
-__global__ void __launch_bounds__(256, 2) dense_kernel(DenseKParams p) {
+template <int NPASS>   // passes over the (row group, column group) items: 1 for NP <= 64, 2 up to NP <= 128
+__global__ void __launch_bounds__(256, NPASS == 1 ? 2 : 1) dense_kernel(DenseKParams p) {
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;                 // [KP][NP]
   float* bs = Ws + p.KP * p.NP;     // [NP]
-  float* xs = bs + p.NP;            // [TM][XS]; reused as the staging tile [TM][OS]
+  long long* rowoff = reinterpret_cast<long long*>(bs + p.NP);   // [2][TM] destination offset of every tile row per segment
+  float* xs = bs + p.NP + 4 * DENSE_TM;   // [TM][XS]; reused as the staging tile [TM][OS]
   const int tid = threadIdx.x;
   for (int i = tid; i < p.KP * p.NP; i += 256) {
     const int k = i / p.NP, n = i - k * p.NP;
@@ -89,6 +91,13 @@ __global__ void __launch_bounds__(256, 2) dense_kernel(DenseKParams p) {
     const long long m0 = (long long)tile * DENSE_TM;
     const int rows = (int)((p.M - m0 < DENSE_TM) ? (p.M - m0) : DENSE_TM);
     __syncthreads();   // previous tile fully written out (xs doubles as the staging tile)
+    for (int i = tid; i < p.n_outs * DENSE_TM; i += 256) {   // one 64-bit division per row and segment, not per element
+      const int o = i / DENSE_TM, r = i - o * DENSE_TM;
+      const DenseOut& d = p.outs[o];
+      const long long m = m0 + r;
+      const long long img = m / d.rows_per_img;
+      rowoff[i] = img * d.img_stride + (m - img * d.rows_per_img) * (long long)d.row_stride;
+    }
     if (p.vec_x) {
       for (int i = tid; i < DENSE_TM * kc; i += 256) {
         const int r = i / kc, c = i - r * kc;
@@ -106,43 +115,49 @@ __global__ void __launch_bounds__(256, 2) dense_kernel(DenseKParams p) {
     __syncthreads();
     if (p.NP >= 16) {
       // ---- 8 rows x 4 columns per thread; up to two passes over the (row group, column group) items
-      float4 acc[2][8];
-      int n_items = 0;
-      for (int item = tid; item < RG * ngd && n_items < 2; item += 256, ++n_items) {
-        const int cg = item % ngd, rg = item / ngd;
+      float4 acc[NPASS][8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[n_items][r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* arow = xs + rg * p.XS;
-        const float* wcol = Ws + cg * 4;
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int item = tid + ps * 256;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[ps][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item < RG * ngd) {
+          const int cg = item % ngd, rg = item / ngd;
+          const float* arow = xs + rg * p.XS;
+          const float* wcol = Ws + cg * 4;
 #pragma unroll 2
-        for (int k = 0; k < p.KP; k += 4) {
-          const float4 w0 = ld4(wcol + (k + 0) * p.NP);
-          const float4 w1 = ld4(wcol + (k + 1) * p.NP);
-          const float4 w2 = ld4(wcol + (k + 2) * p.NP);
-          const float4 w3 = ld4(wcol + (k + 3) * p.NP);
+          for (int k = 0; k < p.KP; k += 4) {
+            const float4 w0 = ld4(wcol + (k + 0) * p.NP);
+            const float4 w1 = ld4(wcol + (k + 1) * p.NP);
+            const float4 w2 = ld4(wcol + (k + 2) * p.NP);
+            const float4 w3 = ld4(wcol + (k + 3) * p.NP);
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const float4 a = ld4(arow + r * RG * p.XS + k);
-            float4& c = acc[n_items][r];
-            c.x = fmaf(a.x, w0.x, c.x); c.y = fmaf(a.x, w0.y, c.y); c.z = fmaf(a.x, w0.z, c.z); c.w = fmaf(a.x, w0.w, c.w);
-            c.x = fmaf(a.y, w1.x, c.x); c.y = fmaf(a.y, w1.y, c.y); c.z = fmaf(a.y, w1.z, c.z); c.w = fmaf(a.y, w1.w, c.w);
-            c.x = fmaf(a.z, w2.x, c.x); c.y = fmaf(a.z, w2.y, c.y); c.z = fmaf(a.z, w2.z, c.z); c.w = fmaf(a.z, w2.w, c.w);
-            c.x = fmaf(a.w, w3.x, c.x); c.y = fmaf(a.w, w3.y, c.y); c.z = fmaf(a.w, w3.z, c.z); c.w = fmaf(a.w, w3.w, c.w);
+            for (int r = 0; r < 8; ++r) {
+              const float4 a = ld4(arow + r * RG * p.XS + k);
+              float4& c = acc[ps][r];
+              c.x = fmaf(a.x, w0.x, c.x); c.y = fmaf(a.x, w0.y, c.y); c.z = fmaf(a.x, w0.z, c.z); c.w = fmaf(a.x, w0.w, c.w);
+              c.x = fmaf(a.y, w1.x, c.x); c.y = fmaf(a.y, w1.y, c.y); c.z = fmaf(a.y, w1.z, c.z); c.w = fmaf(a.y, w1.w, c.w);
+              c.x = fmaf(a.z, w2.x, c.x); c.y = fmaf(a.z, w2.y, c.y); c.z = fmaf(a.z, w2.z, c.z); c.w = fmaf(a.z, w2.w, c.w);
+              c.x = fmaf(a.w, w3.x, c.x); c.y = fmaf(a.w, w3.y, c.y); c.z = fmaf(a.w, w3.z, c.z); c.w = fmaf(a.w, w3.w, c.w);
+            }
           }
         }
       }
       __syncthreads();   // every thread is done reading the x tile: it becomes the staging tile
-      n_items = 0;
-      for (int item = tid; item < RG * ngd && n_items < 2; item += 256, ++n_items) {
-        const int cg = item % ngd, rg = item / ngd;
-        const float4 bias = ld4(bs + cg * 4);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float4 c = acc[n_items][r];
-          float4 o;
-          o.x = act_fwd(p.act, c.x + bias.x); o.y = act_fwd(p.act, c.y + bias.y);
-          o.z = act_fwd(p.act, c.z + bias.z); o.w = act_fwd(p.act, c.w + bias.w);
-          *reinterpret_cast<float4*>(xs + (rg + r * RG) * p.OS + cg * 4) = o;
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int item = tid + ps * 256;
+        if (item < RG * ngd) {
+          const int cg = item % ngd, rg = item / ngd;
+          const float4 bias = ld4(bs + cg * 4);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float4 c = acc[ps][r];
+            float4 o;
+            o.x = act_fwd(p.act, c.x + bias.x); o.y = act_fwd(p.act, c.y + bias.y);
+            o.z = act_fwd(p.act, c.z + bias.z); o.w = act_fwd(p.act, c.w + bias.w);
+            *reinterpret_cast<float4*>(xs + (rg + r * RG) * p.OS + cg * 4) = o;
+          }
         }
       }
     } else {
@@ -182,10 +197,7 @@ __global__ void __launch_bounds__(256, 2) dense_kernel(DenseKParams p) {
       for (int j = tid; j < total; j += 256) {
         const int r = (int)(((unsigned long long)j * p.magic[o]) >> 32);
         const int c = j - r * wd;
-        const long long m = m0 + r;
-        const long long img = m / d.rows_per_img;
-        const int rin = (int)(m - img * d.rows_per_img);
-        float* dst = d.ptr + img * d.img_stride + (long long)rin * d.row_stride + c;
+        float* dst = d.ptr + rowoff[o * DENSE_TM + r] + c;
         const float val = xs[r * p.OS + d.col_begin + c];
         if (p.accumulate) *dst += val; else *dst = val;
       }
@@ -212,18 +224,22 @@ int hp_launch_dense(hp_ctx* h, const float* x, int M, int K, int ldx, const floa
     HP_REQUIRE(wd >= 1 && outs[i].col_end <= N, HP_ERR_INVALID, "dense: bad output segment [%d, %d)", outs[i].col_begin, outs[i].col_end);
     p.magic[i] = (unsigned)((0x100000000ull + wd - 1) / wd);
   }
-  HP_REQUIRE(p.NP >= 16 ? (DENSE_TM / 8) * (p.NP / 4) <= 512 : p.NP <= 12, HP_ERR_UNSUPPORTED, "dense layer with %d outputs too wide", N);
+  const int items = (DENSE_TM / 8) * (p.NP / 4);
+  HP_REQUIRE(p.NP >= 16 ? items <= 512 : p.NP <= 12, HP_ERR_UNSUPPORTED, "dense layer with %d outputs too wide", N);
+  const bool two_pass = p.NP >= 16 && items > 256;
   const int tile_fl = DENSE_TM * (p.XS > p.OS ? p.XS : p.OS);
-  size_t smem = ((size_t)p.KP * p.NP + p.NP + (size_t)tile_fl) * sizeof(float);
+  size_t smem = ((size_t)p.KP * p.NP + p.NP + 4 * DENSE_TM + (size_t)tile_fl) * sizeof(float);   // NP % 4 == 0 keeps rowoff 16-byte aligned
   HP_REQUIRE(smem <= 200 * 1024, HP_ERR_UNSUPPORTED, "dense layer %dx%d too large for the head engine", K, N);
-  HP_CUDA(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  HP_CUDA(cudaFuncSetAttribute(dense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  HP_CUDA(cudaFuncSetAttribute(dense_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int n_tiles = ceil_div(M, DENSE_TM);
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
   long long grid = (long long)h->num_sms * per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  dense_kernel<<<(unsigned)grid, 256, smem, st>>>(p);
+  if (two_pass) dense_kernel<2><<<(unsigned)grid, 256, smem, st>>>(p);
+  else dense_kernel<1><<<(unsigned)grid, 256, smem, st>>>(p);
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;
