@@ -13,7 +13,10 @@ One step = one pass of the unified hot path over one batch of 4096 crops per GPU
            copied host->device every step, pre-processed on the GPU, and counts/boxes/keypoints/scores/poses
            are read back to pinned host memory every step.
 `roofline`: per-kernel CUDA-event timings measured live (hp_backbone_profile) against the measured HBM
-           copy bandwidth in MEASURED_PEAKS.json; algorithmic bytes per SURVEY 8(d) / DESIGN.md.
+           copy bandwidth in MEASURED_PEAKS.json; algorithmic bytes per SURVEY 8(d) / DESIGN.md; `traffic` is the
+           dram__bytes_read + write of the same kernel from the committed ncu --set full capture (profiles/).
+`dtype`  : f32 -- all tensors and accumulators are fp32; the pointwise / stem GEMMs run on the tensor cores as
+           split-precision products (3xTF32, stem: split fp16) with fp32-level error.
 """
 import argparse
 import json
@@ -45,6 +48,25 @@ def layer_table(size):
         rows.append((f"block{i}", (h * h * cin + ho * ho * cout) * 4, 2 * ho * ho * (9 * cin + cin * cout)))
         h = ho
     return rows
+
+
+def ncu_traffic(kernel, batch, size):
+    """DRAM bytes per launch of one backbone kernel from the committed ncu --set full capture (profiles/): None when
+    the capture was taken at another batch / size."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for root, _, files in os.walk(pdir):
+        for f in sorted(files):
+            if f.startswith("ncu_traffic") and f.endswith(".json"):
+                try:
+                    with open(os.path.join(root, f)) as fh:
+                        d = json.load(fh)
+                    e = d.get(kernel)
+                    if e and int(e.get("batch", 0)) == batch and int(e.get("size", 0)) == size:
+                        best = float(e["dram_read_bytes"]) + float(e["dram_write_bytes"])
+                except Exception:
+                    pass
+    return best
 
 
 def measured_peaks():
@@ -297,7 +319,8 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_GBps"], "peak": peak,
-                             "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                             "unit": "GB/s", "frac": dom["frac"], "traffic": ncu_traffic(dom["kernel"], B, S),
+                             "algorithmic_bytes_per_launch": dict((r[0], r[1]) for r in rows)[dom["kernel"]] * B, "peak_source": peak_src,
                              "ms_per_launch": dom["ms"], "share_of_backbone": dom["ms"] / bb_ms},
                 "roofline_backbone": {"bound": "hbm", "achieved": bb_gbs, "peak": peak, "unit": "GB/s", "frac": bb_gbs / peak,
                                       "bytes_per_crop": bb_bytes, "flop_per_crop": bb_flops, "ms": bb_ms,
