@@ -174,6 +174,52 @@ class blazeFaceDetector:
         return [Results(boxes[i, :c].copy(), kps[i, :c].copy(), scores[i, :c].copy(), poses[i, :c].copy())
                 for i, c in enumerate(cnt)]
 
+    def detect_stream(self, host_batches, max_faces=MAX_FACE_NUM, keys=("count", "boxes", "keypoints", "scores", "poses")):
+        """Pipelined serving loop: ``host_batches`` yields pinned (B,H,W,3) uint8 BGR host tensors; for every batch
+        a dict of pinned HOST tensors (``keys``) is yielded, in order.  The host->device copy of batch i+1 and the
+        device->host read of batch i-1 run on their own CUDA streams while batch i computes (two device input
+        buffers, two sets of host result buffers): PCIe time hides behind the kernels instead of adding to them.
+        A yielded dict is reused two batches later: consume (or copy) it before asking for the next-but-one."""
+        import torch
+        dev = self.ctx.torch_device
+        comp = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        d_in, h_out = [None, None], [None, None]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_comp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        pending = []                                      # slots whose results are still on their way to the host
+        n = 0
+        for hb in host_batches:
+            b = n & 1
+            if len(pending) == 2:                          # slot b is reused: hand its results out first
+                q = pending.pop(0)
+                ev_out[q].synchronize()
+                yield h_out[q]
+            if d_in[b] is None or d_in[b].shape != hb.shape:
+                d_in[b] = torch.empty(hb.shape, dtype=hb.dtype, device=dev)
+            with torch.cuda.stream(s_in):
+                if n >= 2:
+                    s_in.wait_event(ev_comp[b])            # the pass that read this input buffer is done
+                d_in[b].copy_(hb, non_blocking=True)
+                ev_in[b].record(s_in)
+            comp.wait_event(ev_in[b])
+            out = self.detect_device(d_in[b], max_faces)
+            ev_comp[b].record(comp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_comp[b])
+                if h_out[b] is None or any(h_out[b][k].shape != out[k].shape for k in keys):
+                    h_out[b] = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in keys}
+                for k in keys:
+                    out[k].record_stream(s_out)
+                    h_out[b][k].copy_(out[k], non_blocking=True)
+                ev_out[b].record(s_out)
+            pending.append(b)
+            n += 1
+        for q in pending:
+            ev_out[q].synchronize()
+            yield h_out[q]
+
     def detect_device(self, images, max_faces=MAX_FACE_NUM, float_input=False):
         import torch
         dev = self.ctx.torch_device

@@ -158,3 +158,33 @@ def test_detect_faces_end_to_end_vs_oracle():
             assert np.abs(batch[i].poses - ref64["poses"]).max() < 0.01      # angles within 0.01 degree
     with pytest.raises(ValueError):
         det.detectFaces(np.zeros((64, 64, 3), np.uint8))
+
+
+def test_detect_stream_matches_detect_device():
+    """The pipelined serving loop (copies overlapped with compute on side streams) returns, batch by batch and in
+    order, exactly what the synchronous path returns."""
+    import torch
+    from hpose_b200 import keras_spec as K, train_88
+    from hpose_b200.attention_model import se_transformer_regr_head
+    from hpose_b200.blazeFaceDetectorH5 import blazeFaceDetector
+    from hpose_b200.unified import UnifiedModel, random_backbone
+    K.reset_names(); K.set_seed(11)
+    head16 = train_88.create_model()
+    K.reset_names()
+    head8 = se_transformer_regr_head(input_channels=96)
+    det = blazeFaceDetector(model=UnifiedModel(random_backbone(seed=4, bias_scale=0.1), head16, head8), inputSize=96)
+    rng = np.random.default_rng(3)
+    host = [torch.from_numpy(rng.integers(0, 256, size=(9, 96, 96, 3), dtype=np.uint8)).pin_memory() for _ in range(5)]
+    want = []
+    for hb in host:
+        out = det.detect_device(hb.cuda())
+        want.append({k: out[k].cpu().numpy().copy() for k in ("count", "boxes", "scores", "poses", "keypoints")})
+    got = []
+    for res in det.detect_stream(iter(host)):
+        got.append({k: res[k].numpy().copy() for k in res})
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert np.array_equal(g["count"], w["count"])
+        for i, c in enumerate(w["count"]):                 # entries beyond count[i] are uninitialised padding
+            for k in ("boxes", "scores", "poses", "keypoints"):
+                assert np.array_equal(g[k][i, :c], w[k][i, :c]), (k, i)
