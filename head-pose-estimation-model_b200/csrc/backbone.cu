@@ -763,10 +763,10 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
     TcCfg tcc;
     const bool v1 = (h->impl == HP_IMPL_CPASYNC);
     bool use_tc = false;
-    if (h->impl == HP_IMPL_FAST && S == 1 && h->tc_override[i][0] >= 0 && hp_tc_choose(i, Ho, Wo, &tcc)) {
-      use_tc = true;
-      const int* tv = h->tc_override[i];   // TR, NSTG, BH, npipe (epilogue sets when nbuf > 0), nsets, nbuf
-      if (tv[0] > 0) {
+    if (h->impl == HP_IMPL_FAST && S == 1 && h->tc_override[i][0] >= 0) {
+      const int* tv = h->tc_override[i];   // TR, NSTG, BH, npipe (epilogue sets when nbuf > 0), nsets, nbuf, unit, issuers
+      if (tv[0] > 0) {                      // explicit geometry (tuning / tests): also on maps the default leaves to the CUDA cores
+        use_tc = true;
         if (tv[5] > 0) {                    // warp-specialised kernel with explicit TR / nsets / esets, rings optional
           HP_REQUIRE(hp_tcd_geometry(i, Ho, Wo, tv[0], tv[4] > 0 ? tv[4] : 2, tv[3] > 0 ? tv[3] : 2, &tcc), HP_ERR_INVALID,
                      "tc override for block %d: TR %d does not fit", i, tv[0]);
@@ -779,13 +779,17 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         } else {                            // pipelined kernel (halo columns, IWB = 7 mod 8)
           tcc.TR = tv[0]; tcc.nbuf = 0; tcc.ni = 1; tcc.unit = 1; tcc.niss = 1;
           tcc.IWB = ((Wo + 2 + 1 + 7) / 8) * 8 - 1;
-          if (tv[1] > 0) tcc.NSTG = tv[1];
-          if (tv[2] > 0) tcc.BH = tv[2];
-          if (tv[3] > 0) tcc.npipe = tv[3];
-          if (tv[4] > 0) tcc.nsets = tv[4];
+          tcc.NSTG = tv[1] > 0 ? tv[1] : 2;
+          tcc.BH = tv[2] > 0 ? tv[2] : tv[0];
+          tcc.npipe = tv[3] > 0 ? tv[3] : 1;
+          tcc.nsets = tv[4] > 0 ? tv[4] : 1;
+          HP_REQUIRE(hp_tc_fits(i, Ho, Wo, tcc), HP_ERR_INVALID, "tc override for block %d does not fit (TR %d NSTG %d BH %d npipe %d nsets %d)", i,
+                     tcc.TR, tcc.NSTG, tcc.BH, tcc.npipe, tcc.nsets);
         }
+      } else {
+        use_tc = hp_tc_choose(i, Ho, Wo, &tcc);
       }
-      if (h->tile_report) {
+      if (use_tc && h->tile_report) {
         int* r = h->tile_report + 8 * i;
         r[0] = tcc.TR; r[1] = tcc.BH; r[2] = tcc.IWB; r[3] = tcc.NSTG; r[4] = tcc.nbuf; r[5] = tcc.npipe; r[6] = tcc.nsets; r[7] = -tcc.ni;
       }

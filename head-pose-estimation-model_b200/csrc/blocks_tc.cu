@@ -905,10 +905,11 @@ bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg*
 
 // Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.
 // Choices measured with tools/tc_sweep.py (profiles/): k-step work units everywhere; 4 rows per lane where two accumulator
-// sets of 4 x N16 columns fit TMEM next to a ring of >= 2 stages (N16 <= 48), else 2; maps narrower than 8 pixels (the
-// 6 x 6 blocks at 96 x 96 input) stay on the CUDA-core kernel, which is faster there.
+// sets of 4 x N16 columns fit TMEM next to a ring of >= 2 stages (N16 <= 48), else 2; maps narrower than 12 pixels (the
+// 6 x 6 / 8 x 8 blocks 12-15) stay on the CUDA-core kernel: with 96 channels only 2-4 images fit a tile and the
+// per-tile latency chain dominates (0.21 ms against 0.12 ms per block at 96 x 96 input, profiles/r01/tc_sweep_96_deep.log).
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
-  if (kBlazeBlocks[blk].stride != 1 || W > 128 || W < 8 || H < 1) return false;
+  if (kBlazeBlocks[blk].stride != 1 || W > 128 || W < 12 || H < 1) return false;
   TcCfg a;
   if (hp_tcd_geometry(blk, H, W, 4, 2, 2, &a)) {
     a.unit = 2; a.niss = 2;
