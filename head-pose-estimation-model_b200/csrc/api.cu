@@ -118,7 +118,7 @@ int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf, 
 }
 int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, int nsets, int nbuf) {
   HP_REQUIRE(h && blk >= 0 && blk < 16, HP_ERR_INVALID, "hp_debug_set_tc: bad arguments");
-  h->tc_override[blk][0] = TR; h->tc_override[blk][1] = NSTG; h->tc_override[blk][2] = BH; h->tc_override[blk][3] = npipe; h->tc_override[blk][4] = nsets; h->tc_override[blk][5] = nbuf % 16; h->tc_override[blk][6] = (nbuf / 16) % 4; h->tc_override[blk][7] = nbuf / 64;
+  h->tc_override[blk][0] = TR; h->tc_override[blk][1] = NSTG; h->tc_override[blk][2] = BH; h->tc_override[blk][3] = npipe; h->tc_override[blk][4] = nsets; h->tc_override[blk][5] = nbuf % 16; h->tc_override[blk][6] = (nbuf / 16) % 4; h->tc_override[blk][7] = (nbuf / 64) % 8; h->tc_override[blk][8] = nbuf / 512;
   return HP_OK;
 }
 int hp_debug_set_stem_tc(hp_handle h, int BH, int nbuf, int nout, int nsets) {

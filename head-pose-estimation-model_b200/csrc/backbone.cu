@@ -774,10 +774,11 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
           if (tv[5] < tcc.nbuf) tcc.nbuf = tv[5];
           if (tv[6] > 0) tcc.unit = tv[6];
           if (tv[7] > 0) tcc.niss = tv[7];
+          tcc.place = tv[8];
           HP_REQUIRE(hp_tc_fits(i, Ho, Wo, tcc), HP_ERR_INVALID, "tc override for block %d does not fit (TR %d NSTG %d nsets %d unit %d nbuf %d)", i,
                      tcc.TR, tcc.NSTG, tcc.nsets, tcc.unit, tcc.nbuf);
         } else {                            // pipelined kernel (halo columns, IWB = 7 mod 8)
-          tcc.TR = tv[0]; tcc.nbuf = 0; tcc.ni = 1; tcc.unit = 1; tcc.niss = 1;
+          tcc.TR = tv[0]; tcc.nbuf = 0; tcc.ni = 1; tcc.unit = 1; tcc.niss = 1; tcc.place = 0;
           tcc.IWB = ((Wo + 2 + 1 + 7) / 8) * 8 - 1;
           tcc.NSTG = tv[1] > 0 ? tv[1] : 2;
           tcc.BH = tv[2] > 0 ? tv[2] : tv[0];

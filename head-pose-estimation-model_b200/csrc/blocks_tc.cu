@@ -61,7 +61,7 @@ __device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0, n = 0;
   long long t0 = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x100;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) break;
     if ((++n & 255u) == 0u) {
@@ -400,8 +400,10 @@ struct TcdParams {
 
 // NISS issuer warps: one thread can only issue a tcgen05.mma every ~46-55 clk whatever its size (tools/mma_rate.cu), the
 // tensor pipe itself needs 128 * N / 256 clk; the accumulator rows are therefore dealt to NISS issuing threads (t % NISS).
-template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS>
-__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 32 * (NISS + 2), 1)
+// PLACE = 1: 4 * NISS helper warps with issuer k at warp W_ISSUE + 4 k + 3, i.e. on SM sub-partition 3, which is idle when at most
+// 96 TMEM lanes are active; the instructions around each tcgen05.mma then do not queue behind the worker warps (stem: 0.49 -> 0.42 ms).
+template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS, int PLACE>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), 1)
 blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcdParams p) {
   using G = TcGeom<CINP, COUTP>;
   constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
@@ -428,8 +430,12 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane_id = tid & 31;
-  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + NISS, W_STORE = W_LOAD + 1;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS;
+  constexpr int W_LOAD = PLACE ? W_ISSUE : W_ISSUE + NISS, W_STORE = W_LOAD + 1;
+  constexpr int W_ALLOC = PLACE ? W_ISSUE + 3 : W_ISSUE;   // the first issuer warp owns the TMEM allocation
   static_assert(NISS >= 1 && NISS <= TR, "issuer warps");
+  const int issuer_of_warp = PLACE ? ((warp >= W_ISSUE && ((warp - W_ISSUE) & 3) == 3) ? (warp - W_ISSUE) >> 2 : -1)
+                                   : ((warp >= W_ISSUE && warp < W_ISSUE + NISS) ? warp - W_ISSUE : -1);
   const int NSTG = p.nstg, NBUF = p.nbuf;
 
   for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
@@ -459,7 +465,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == W_ISSUE) {
+  if (warp == W_ALLOC) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -592,9 +598,9 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       }
     }
   } else if (lane_id == 0) {
-    if (warp >= W_ISSUE && warp < W_ISSUE + NISS) {
+    if (issuer_of_warp >= 0) {
       // =============================================================== MMA issuers (accumulator rows t % NISS == issuer)
-      const int issuer = warp - W_ISSUE;
+      const int issuer = issuer_of_warp;
       const uint32_t idesc = tc_idesc_tf32(N16);
       const uint64_t desc_fixed = tc_bdesc_fixed(N16);
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
@@ -664,7 +670,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == W_ISSUE) {
+  if (warp == W_ALLOC) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
@@ -747,7 +753,7 @@ int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const
   return HP_OK;
 }
 
-template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS>
+template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS, int PLACE>
 int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
   using G = TcGeom<CINP, COUTP>;
   TcdParams p;
@@ -774,11 +780,11 @@ int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, con
   CUtensorMap tin, tout;
   HP_TRY(make_map(&tin, in, B, H, W, CINP, tc.ni, tc.BH + 2, tc.IWB, G::PS));
   HP_TRY(make_map(&tout, out, B, H, W, COUTP, 1, tc.BH, tc.IWB, G::PS));
-  auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSETS, NESETS, UNIT, NISS>;
+  auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSETS, NESETS, UNIT, NISS, PLACE>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + 32 * (NISS + 2), smem, st>>>(tin, tout, p);
+  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), smem, st>>>(tin, tout, p);
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;
@@ -788,15 +794,19 @@ template <int CINP, int COUTP>
 int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc,
                   cudaStream_t st) {
   constexpr int N16 = TcGeom<CINP, COUTP>::N16;
-#define TCD_CASE(TR_, NSETS_, NESETS_, UNIT_, NISS_)                                     \
+#define TCD_CASE(TR_, NSETS_, NESETS_, UNIT_, NISS_, PLACE_)                             \
   if constexpr (2 * TR_ * N16 + 2 * TR_ * 16 <= 512)                                     \
-    if (tc.TR == TR_ && tc.nsets == NSETS_ && tc.npipe == NESETS_ && tc.unit == UNIT_ && tc.niss == NISS_) \
-      return launch_deep<CINP, COUTP, TR_, NSETS_, NESETS_, UNIT_, NISS_>(h, in, out, B, H, W, w, tc, st);
+    if (tc.TR == TR_ && tc.nsets == NSETS_ && tc.npipe == NESETS_ && tc.unit == UNIT_ && tc.niss == NISS_ && tc.place == PLACE_) \
+      return launch_deep<CINP, COUTP, TR_, NSETS_, NESETS_, UNIT_, NISS_, PLACE_>(h, in, out, B, H, W, w, tc, st);
   if (tc.nbuf > 0) {   // warp-specialised kernel: npipe carries the number of epilogue warp sets
-    TCD_CASE(4, 2, 2, 1, 1) TCD_CASE(4, 3, 2, 1, 1) TCD_CASE(2, 2, 2, 1, 1) TCD_CASE(2, 3, 2, 1, 1) TCD_CASE(4, 2, 1, 1, 1) TCD_CASE(2, 3, 1, 1, 1)
-    TCD_CASE(2, 2, 2, 2, 1) TCD_CASE(2, 3, 2, 2, 1) TCD_CASE(2, 4, 1, 2, 1) TCD_CASE(4, 2, 2, 2, 1) TCD_CASE(4, 3, 2, 2, 1)
-    TCD_CASE(4, 2, 2, 2, 2) TCD_CASE(4, 2, 2, 2, 4) TCD_CASE(4, 3, 2, 2, 2) TCD_CASE(2, 3, 2, 2, 2) TCD_CASE(2, 2, 2, 2, 2) TCD_CASE(2, 3, 2, 1, 2)
-    hp_set_error("tc deep block: no kernel for TR %d nsets %d esets %d unit %d issuers %d", tc.TR, tc.nsets, tc.npipe, tc.unit, tc.niss);
+    TCD_CASE(4, 2, 2, 1, 1, 0) TCD_CASE(4, 3, 2, 1, 1, 0) TCD_CASE(2, 2, 2, 1, 1, 0) TCD_CASE(2, 3, 2, 1, 1, 0) TCD_CASE(4, 2, 1, 1, 1, 0)
+    TCD_CASE(2, 3, 1, 1, 1, 0) TCD_CASE(2, 2, 2, 2, 1, 0) TCD_CASE(2, 3, 2, 2, 1, 0) TCD_CASE(2, 4, 1, 2, 1, 0) TCD_CASE(4, 2, 2, 2, 1, 0)
+    TCD_CASE(4, 3, 2, 2, 1, 0) TCD_CASE(4, 2, 2, 2, 2, 0) TCD_CASE(4, 2, 2, 2, 4, 0) TCD_CASE(4, 3, 2, 2, 2, 0) TCD_CASE(2, 3, 2, 2, 2, 0)
+    TCD_CASE(2, 2, 2, 2, 2, 0) TCD_CASE(2, 3, 2, 1, 2, 0)
+    TCD_CASE(4, 2, 1, 2, 2, 1) TCD_CASE(4, 2, 2, 2, 2, 1) TCD_CASE(4, 3, 1, 2, 2, 1) TCD_CASE(2, 3, 1, 2, 2, 1) TCD_CASE(2, 2, 2, 2, 2, 1)
+    TCD_CASE(2, 3, 2, 2, 2, 1)
+    hp_set_error("tc deep block: no kernel for TR %d nsets %d esets %d unit %d issuers %d placement %d", tc.TR, tc.nsets, tc.npipe, tc.unit,
+                 tc.niss, tc.place);
     return HP_ERR_UNSUPPORTED;
   }
 #undef TCD_CASE
@@ -850,7 +860,8 @@ bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc) {
   const int ni = tc.nbuf > 0 ? tc.ni : 1;
   if (tc.TR < 1 || tc.BH < tc.TR || tc.BH % tc.TR || ni < 1 || (tc.BH / tc.TR) * W * ni > 128 || tc.BH + 2 > 256) return false;
   if (tc.nbuf > 0) {
-    if (2 * tc.TR * N16 + tc.NSTG * tc.TR * 16 > 512 || tc.niss < 1 || tc.niss > tc.TR || 128 * tc.nsets + 128 * tc.npipe + 32 * (tc.niss + 2) > 1024 ||
+    if (2 * tc.TR * N16 + tc.NSTG * tc.TR * 16 > 512 || tc.niss < 1 || tc.niss > tc.TR ||
+        128 * tc.nsets + 128 * tc.npipe + (tc.place ? 128 * tc.niss : 32 * (tc.niss + 2)) > 1024 ||
         tc.npipe < 1 || tc.npipe > 2)
       return false;
     if (tc.nbuf < 2 || tc.nbuf > TCD_MAXB || tc.NSTG < 2 || tc.NSTG > TC_MAX_STG || (ni > 1 && tc.BH < H)) return false;
@@ -872,7 +883,7 @@ bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg*
   const int N16 = (coutp + 15) / 16 * 16, K8 = (cinp + 7) / 8 * 8;
   if (kBlazeBlocks[blk].stride != 1 || W > 128 || H < 1 || 2 * TR * N16 + 2 * TR * 16 > 512) return false;
   TcCfg t;
-  t.TR = TR; t.nsets = nsets; t.npipe = esets; t.unit = 1; t.niss = 1;
+  t.TR = TR; t.nsets = nsets; t.npipe = esets; t.unit = 1; t.niss = 1; t.place = 0;
   t.NSTG = (512 - 2 * TR * N16) / (TR * 16);
   if (t.NSTG > TC_MAX_STG) t.NSTG = TC_MAX_STG;
   if (t.NSTG > K8 / 8 && K8 / 8 >= 2) t.NSTG = K8 / 8;
@@ -911,6 +922,11 @@ bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg*
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
   if (kBlazeBlocks[blk].stride != 1 || W > 128 || W < 12 || H < 1) return false;
   TcCfg a;
+  const int n16 = (chan_pad(kBlazeBlocks[blk].cout) + 15) / 16 * 16;
+  if (n16 == 48 && hp_tcd_geometry(blk, H, W, 2, 3, 1, &a)) {   // blocks 3, 4: 2 rows, 3 depthwise sets, issuers on sub-partition 3
+    a.unit = 2; a.niss = 2; a.place = 1;
+    if (hp_tc_fits(blk, H, W, a)) { *tc = a; return true; }
+  }
   if (hp_tcd_geometry(blk, H, W, 4, 2, 2, &a)) {
     a.unit = 2; a.niss = 2;
     if (hp_tc_fits(blk, H, W, a)) { *tc = a; return true; }

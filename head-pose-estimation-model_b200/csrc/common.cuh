@@ -112,7 +112,7 @@ struct hp_ctx {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
   int stem_tc_cfg[4] = {};         // tensor-core stem: band height, input buffers, output stages, gather sets (0 = automatic, [0] = -1: off)
-  int tc_override[16][8] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets, nbuf per block (TR 0 = automatic, -1 = do not use)
+  int tc_override[16][9] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets, nbuf per block (TR 0 = automatic, -1 = do not use)
   int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
   long long* tc_trace = nullptr;   // optional device buffer for per-tile clock stamps of the deep tensor-core kernel
   int tc_trace_tiles = 0;
@@ -152,7 +152,7 @@ int hp_launch_block_tma(hp_ctx* h, int blk, const float* in, float* out, int B, 
 // blocks_tc.cu: third-generation fused BlazeBlock kernel (depthwise on CUDA cores -> TMEM, pointwise as 3xTF32 tcgen05 GEMM)
 struct TcCfg {
   // nbuf > 0 selects the warp-specialised (deep) kernel: nbuf halo buffers, ni images per tile, npipe = epilogue warp sets
-  int TR, NSTG, BH, IWB, npipe, nsets, nbuf, ni, unit, niss;   // niss: MMA issuer warps   // unit: depthwise work unit = 1 chunk (4 channels) or 2 (a k-step)
+  int TR, NSTG, BH, IWB, npipe, nsets, nbuf, ni, unit, niss, place;   // niss: MMA issuer warps; place: issuers on SM sub-partition 3   // unit: depthwise work unit = 1 chunk (4 channels) or 2 (a k-step)
 };
 bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc);
 bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg* tc);

@@ -48,8 +48,11 @@ struct StemTcParams {
   int trace_tiles;
 };
 
-template <int TR, int NSETS, int NESETS, int NISS>
-__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 32 * (NISS + 2), 1)
+// PLACE = 1: 4 * NISS helper warps so that issuer k is warp W_ISSUE + 4 k + 3, i.e. on SM sub-partition 3, which only hosts
+// the (mostly idle) warps of TMEM lane quarter 3 when fewer than 97 lanes are active: the ~15 instructions around every
+// tcgen05.mma then do not queue behind the gather / epilogue warps (133 -> ~60 clk per MMA).
+template <int TR, int NSETS, int NESETS, int NISS, int PLACE>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, StemTcParams p) {
   constexpr uint32_t colA0 = 2 * TR * ST_N16;
   static_assert(colA0 + 2 * TR * 16 <= 512, "TMEM budget");
@@ -73,7 +76,12 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane_id = tid & 31;
-  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + NISS, W_STORE = W_LOAD + 1;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS;
+  constexpr int W_LOAD = PLACE ? W_ISSUE : W_ISSUE + NISS, W_STORE = W_LOAD + 1;
+  // issuer index of this warp (-1: not an issuer)
+  const int issuer_of_warp = PLACE ? ((warp >= W_ISSUE && ((warp - W_ISSUE) & 3) == 3) ? (warp - W_ISSUE) >> 2 : -1)
+                                   : ((warp >= W_ISSUE && warp < W_ISSUE + NISS) ? warp - W_ISSUE : -1);
+  constexpr int W_ALLOC = PLACE ? W_ISSUE + 3 : W_ISSUE;   // the first issuer warp owns the TMEM allocation
   const int NSTG = p.nstg, NBUF = p.nbuf, NOUT = p.nout;
 
   for (int i = tid * 4; i < ST_K8 * ST_N16 / 2; i += nthr * 4) {
@@ -104,7 +112,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == W_ISSUE) {
+  if (warp == W_ALLOC) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -246,10 +254,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       }
     }
   } else if (lane_id == 0) {
-    if (warp >= W_ISSUE && warp < W_ISSUE + NISS) {
+    if (issuer_of_warp >= 0) {
       // =============================================================== MMA issuers: accumulator rows t % NISS == issuer (one thread
       // issues a tcgen05.mma only every ~46-55 clk, the tensor pipe needs 16 clk at N = 32: tools/mma_rate.cu)
-      const int issuer = warp - W_ISSUE;
+      const int issuer = issuer_of_warp;
       // kind::f16: A / B fp16 (format 0), D fp32, K = 16 per instruction; B slice [32 rows][16 k] = 2 core matrices of 8 rows x 16 B
       const uint32_t idesc = (1u << 4) | ((uint32_t)(ST_N16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t desc_fixed = tc_bdesc_fixed(ST_N16);
@@ -317,7 +325,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == W_ISSUE) {
+  if (warp == W_ALLOC) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
@@ -448,23 +456,25 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
     HP_TRY(tc_make_map4(&tout, out, dims, strides, box));
   }
   const int nsets = (cfg && cfg[3] > 0) ? cfg[3] % 16 : 2;
-  const int niss = (cfg && cfg[3] >= 16) ? cfg[3] / 16 : 2;
+  const int niss = (cfg && cfg[3] >= 16) ? (cfg[3] / 16) % 8 : 2;
+  const int place = (cfg && cfg[3] > 0) ? (cfg[3] >= 128 ? 1 : 0) : 1;   // + 128: issuers on SM sub-partition 3 (default)
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
   const size_t smem = total();
-#define STEM_CASE(NSETS_, NESETS_, NISS_)                                                                              \
-  if (nsets == NSETS_ && niss == NISS_) {                                                                              \
-    auto kern = stem_tc_kernel<TR, NSETS_, NESETS_, NISS_>;                                                            \
+#define STEM_CASE(NSETS_, NESETS_, NISS_, PLACE_)                                                                      \
+  if (nsets == NSETS_ && niss == NISS_ && place == PLACE_) {                                                           \
+    auto kern = stem_tc_kernel<TR, NSETS_, NESETS_, NISS_, PLACE_>;                                                    \
     HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                      \
-    kern<<<(unsigned)grid, 128 * NSETS_ + 128 * NESETS_ + 32 * (NISS_ + 2), smem, st>>>(tin, tout, p);                 \
+    kern<<<(unsigned)grid, 128 * NSETS_ + 128 * NESETS_ + (PLACE_ ? 128 * NISS_ : 32 * (NISS_ + 2)), smem, st>>>(tin, tout, p); \
     h->launches++;                                                                                                     \
     HP_CUDA(cudaGetLastError());                                                                                       \
     return HP_OK;                                                                                                      \
   }
   // consecutive units of a gather set are nsets k-steps apart: at most the ring depth (see blaze_block_deep_kernel)
   HP_REQUIRE(nsets <= p.nstg, HP_ERR_INVALID, "stem tc: %d gather sets need a ring of %d stages", nsets, nsets);
-  STEM_CASE(4, 1, 4) STEM_CASE(4, 1, 2) STEM_CASE(3, 1, 4) STEM_CASE(3, 2, 2) STEM_CASE(2, 2, 4) STEM_CASE(2, 2, 2)
+  STEM_CASE(4, 1, 4, 0) STEM_CASE(4, 1, 2, 0) STEM_CASE(3, 1, 4, 0) STEM_CASE(3, 2, 2, 0) STEM_CASE(2, 2, 4, 0) STEM_CASE(2, 2, 2, 0)
+  STEM_CASE(2, 1, 2, 1) STEM_CASE(3, 1, 2, 1) STEM_CASE(2, 2, 2, 1) STEM_CASE(2, 1, 1, 1)
 #undef STEM_CASE
-  hp_set_error("stem tc: no kernel for %d gather sets, %d issuers", nsets, niss);
+  hp_set_error("stem tc: no kernel for %d gather sets, %d issuers, placement %d", nsets, niss, place);
   return HP_ERR_UNSUPPORTED;
 }

@@ -19,13 +19,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 // Blocking wait with a watchdog.  try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware until the
 // phase completes instead of burning issue slots (ncu: un-hinted polling was ~25 % of all issued instructions); the clock
-// is read every 256 wake-ups only.
+// is read every 256 wake-ups only.  The hint is kept at 256 ns: with 16 us, rare runs of some geometries took 1-20 ms
+// instead of 0.2 ms (a completion that lands between the failed test and the sleep is only noticed at the time limit).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, n = 0;
   long long t0 = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x100;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) break;
     if ((++n & 255u) == 0u) {
@@ -41,7 +42,7 @@ __device__ __forceinline__ void mbar_wait_light(uint64_t* bar, uint32_t parity) 
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x100;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}" ::"r"(addr), "r"(parity) : "memory");

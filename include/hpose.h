@@ -211,7 +211,7 @@ int hp_backbone_profile(hp_handle h, const float* x, int B, int H, int W, int it
 int hp_debug_set_tile(hp_handle h, int blk, int TH, int TW, int IMGS, int nbuf, int MT);
 int hp_debug_tile_report(hp_handle h, int* report16x8);
 /* tensor-core BlazeBlock kernel (HP_IMPL_FAST, stride-1 blocks): TR rows per lane, ring depth, band height, pipelines per
- * CTA, warp sets per pipeline, halo buffers of the warp-specialised variant (0 = pipelined variant; + 16 x depthwise work unit (1 or 2) + 64 x MMA issuer warps); TR = 0 restores the defaults, TR = -1 keeps the block on the CUDA-core kernel */
+ * CTA, warp sets per pipeline, halo buffers of the warp-specialised variant (0 = pipelined variant; + 16 x depthwise work unit (1 or 2) + 64 x MMA issuer warps + 512 x issuer placement); TR = 0 restores the defaults, TR = -1 keeps the block on the CUDA-core kernel */
 /* tensor-core stem kernel: band height, input buffers, output stages, gather warp sets (0 = automatic; BH = -1 keeps the
  * stem on the CUDA-core kernel) */
 int hp_debug_set_stem_tc(hp_handle h, int BH, int nbuf, int nout, int nsets);

@@ -10,11 +10,12 @@ _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size,
 B = 4096
 x = torch.rand((B, 96, 96, 3), device="cuda") * 2 - 1
 ms = np.zeros(18, dtype=np.float32)
-for cfg in [(0,0,0,0), (0,4,2,4+64), (0,4,2,4+32), (0,4,2,3+64), (0,4,2,3+32), (0,4,2,2+64), (0,4,2,2+32), (0,2,2,4+64), (0,3,2,4+64), (4,4,3,4+64), (-1,0,0,0)]:
+# cfg[3] = gather sets + 16 x issuers + 128 x (issuers placed on SM sub-partition 3)
+for cfg in [(0,0,0,0), (0,4,2,2+32), (0,4,2,2+32+128), (0,4,2,3+32+128), (0,4,2,2+16+128), (0,4,2,3+32), (-1,0,0,0)]:
     try:
         _lib.check(lib.hp_debug_set_stem_tc(ctx.handle, *cfg))
         for _ in range(2):
             _lib.check(lib.hp_backbone_profile(ctx.handle, x.data_ptr(), B, 96, 96, 5, ms.ctypes.data))
-        print(cfg, "nsets", cfg[3] % 16, "issuers", cfg[3] // 16, f"stem {ms[0]:.4f} ms", flush=True)
+        print(cfg, "nsets", cfg[3] % 16, "issuers", (cfg[3] // 16) % 8, "placed", cfg[3] // 128, f"stem {ms[0]:.4f} ms", flush=True)
     except Exception as e:
         print(cfg, "failed", str(e)[:100])

@@ -28,8 +28,8 @@ ms = np.zeros(18, dtype=np.float32)
 # (TR, NSTG, npipe, nsets, nbuf): nbuf 0 = pipelined kernel; nbuf > 0 = warp-specialised kernel (npipe slot = epilogue warp sets,
 # NSTG 0 = automatic, nbuf % 16 caps the ring of halo buffers, + 16 x work unit + 64 x issuer warps; band height / images per tile
 # are chosen by the library)
-CANDS = [(4, 0, 2, 2, 4 + 32 + 64), (4, 0, 2, 2, 4 + 32 + 128), (4, 0, 2, 2, 4 + 32 + 256), (4, 0, 2, 3, 4 + 32 + 128),
-         (2, 0, 2, 3, 4 + 32 + 64), (2, 0, 2, 3, 4 + 32 + 128), (2, 0, 2, 2, 4 + 32 + 128), (2, 0, 2, 3, 4 + 16 + 128)]
+CANDS = [(4, 0, 2, 2, 4 + 32 + 128), (4, 0, 1, 2, 4 + 32 + 128 + 512), (4, 0, 2, 2, 4 + 32 + 128 + 512), (4, 0, 1, 3, 4 + 32 + 128 + 512),
+         (2, 0, 2, 3, 4 + 32 + 128), (2, 0, 1, 3, 4 + 32 + 128 + 512), (2, 0, 2, 2, 4 + 32 + 128 + 512), (2, 0, 2, 3, 4 + 32 + 128 + 512)]
 TC_BLOCKS = [int(b) for b in os.environ.get("TC_BLOCKS", "0,1,3,4,6,7,8,9,10,12").split(",")]
 HS = {0: size // 2, 1: size // 2, 3: size // 4, 4: size // 4, 6: size // 8, 7: size // 8, 8: size // 8, 9: size // 8, 10: size // 8,
       12: size // 16, 13: size // 16, 14: size // 16, 15: size // 16}
@@ -64,7 +64,7 @@ for b in TC_BLOCKS:
         try:
             t = run()
             res.setdefault(f"block{b}", {})[str(cand)] = float(t[1 + b])
-            print(f"block{b} TR={TR} NSTG={NSTG} BH={BH} npipe={npipe} nsets={nsets} nbuf={nbuf % 16} unit={max(1, (nbuf // 16) % 4)} issuers={max(1, nbuf // 64)}: {t[1 + b]:.4f} ms", flush=True)
+            print(f"block{b} TR={TR} NSTG={NSTG} BH={BH} npipe={npipe} nsets={nsets} nbuf={nbuf % 16} unit={max(1, (nbuf // 16) % 4)} issuers={max(1, (nbuf // 64) % 8)} placed={nbuf // 512}: {t[1 + b]:.4f} ms", flush=True)
         except Exception as e:  # configuration not instantiated / does not fit
             print(f"block{b} {cand} failed: {str(e)[:120]}", flush=True)
     _lib.check(lib.hp_debug_set_tc(ctx.handle, b, -1, 0, 0, 0, 0, 0))
