@@ -449,7 +449,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* Q, const flo
   const int DS = d + 1;
   float* Ks = smem;                  // [T][DS]
   float* Vs = Ks + T * DS;           // [T][DS]
-  float* sc = Vs + T * DS;           // [4][T]
+  float* sc = Vs + T * DS;           // [4][T] probabilities of the row a warp is working on
+  float* qs = sc + 4 * T;            // [4][d] scaled query row of each warp
   const int img = blockIdx.x / heads, hh = blockIdx.x - img * heads;
   const int HD = heads * d;
   const long long base = (long long)img * T * HD + hh * d;
@@ -461,12 +462,17 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* Q, const flo
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* my = sc + warp * T;
+  float* myq = qs + warp * d;
+  // P V: lane = (half, j): output column j (j < d <= 16 uses two halves of the key range, else one pass per 32 columns)
+  const bool split = (d <= 16);
   for (int t = warp; t < T; t += 4) {
-    const float* q = Q + base + (long long)t * HD;
+    for (int j = lane; j < d; j += 32) myq[j] = Q[base + (long long)t * HD + j] * scale;   // the query row is read once
+    __syncwarp();
     float mx = -INFINITY;
     for (int s = lane; s < T; s += 32) {
       float a = 0.f;
-      for (int j = 0; j < d; ++j) a = fmaf(q[j] * scale, Ks[s * DS + j], a);
+      const float* kr = Ks + s * DS;
+      for (int j = 0; j < d; ++j) a = fmaf(myq[j], kr[j], a);
       my[s] = a;
       mx = fmaxf(mx, a);
     }
@@ -484,10 +490,20 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* Q, const flo
       float* pr = Pout + ((long long)blockIdx.x * T + t) * T;
       for (int s = lane; s < T; s += 32) pr[s] = my[s] * inv;
     }
-    for (int j = lane; j < d; j += 32) {
+    if (split) {
+      const int j = lane & 15, half = lane >> 4;
+      const int s0 = half ? (T + 1) / 2 : 0, s1 = half ? T : (T + 1) / 2;
       float a = 0.f;
-      for (int s = 0; s < T; ++s) a = fmaf(my[s], Vs[s * DS + j], a);
-      O[base + (long long)t * HD + j] = a * inv;
+      if (j < d)
+        for (int s = s0; s < s1; ++s) a = fmaf(my[s], Vs[s * DS + j], a);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if (half == 0 && j < d) O[base + (long long)t * HD + j] = a * inv;
+    } else {
+      for (int j = lane; j < d; j += 32) {
+        float a = 0.f;
+        for (int s = 0; s < T; ++s) a = fmaf(my[s], Vs[s * DS + j], a);
+        O[base + (long long)t * HD + j] = a * inv;
+      }
     }
     __syncwarp();
   }
@@ -795,7 +811,7 @@ static int head_plan(hp_head* hd, int n_img, int T, bool training) {
   return HP_OK;
 }
 
-static size_t attn_smem(int T, int d) { return ((size_t)2 * T * (d + 1) + 4 * (size_t)T) * sizeof(float); }
+static size_t attn_smem(int T, int d) { return ((size_t)2 * T * (d + 1) + 4 * (size_t)T + 4 * (size_t)d) * sizeof(float); }
 
 static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, int T, bool training, uint64_t seed,
                         cudaStream_t st) {
