@@ -69,7 +69,7 @@ __device__ __forceinline__ void dense_cp_async16(void* smem_dst, const void* gsr
 }
 
 template <int NPASS>   // passes over the (row group, column group) items: 1 for NP <= 64, 2 up to NP <= 128
-__global__ void __launch_bounds__(256, NPASS == 1 ? 2 : 1) dense_kernel(DenseKParams p) {
+__global__ void __launch_bounds__(256, NPASS == 1 ? 3 : 1) dense_kernel(DenseKParams p) {
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;                 // [KP][NP]
   float* bs = Ws + p.KP * p.NP;     // [NP]
