@@ -55,11 +55,17 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// packed fp32 FMAs (fma.rn.f32x2): same rounding as scalar FMAs, half the FMA issue slots
 __device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
-  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+  const float2 lo = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  const float2 hi = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(c.z, c.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ float4 fma4s(float a, float4 b, float4 c) {
-  return make_float4(fmaf(a, b.x, c.x), fmaf(a, b.y, c.y), fmaf(a, b.z, c.z), fmaf(a, b.w, c.w));
+  const float2 aa = make_float2(a, a);
+  const float2 lo = __ffma2_rn(aa, make_float2(b.x, b.y), make_float2(c.x, c.y));
+  const float2 hi = __ffma2_rn(aa, make_float2(b.z, b.w), make_float2(c.z, c.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
