@@ -63,6 +63,14 @@ struct DenseKParams {
   unsigned magic[2];         // ceil(2^32 / width) of each output segment
 };
 
+// c += a * w with packed fp32 FMAs (fma.rn.f32x2): same rounding as scalar FMAs, half the FMA issue slots
+__device__ __forceinline__ float4 dense_fma4s(float a, float4 w, float4 c) {
+  const float2 aa = make_float2(a, a);
+  const float2 lo = __ffma2_rn(aa, make_float2(w.x, w.y), make_float2(c.x, c.y));
+  const float2 hi = __ffma2_rn(aa, make_float2(w.z, w.w), make_float2(c.z, c.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 __device__ __forceinline__ void dense_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
@@ -136,10 +144,10 @@ __global__ void __launch_bounds__(256, NPASS == 1 ? 3 : 1) dense_kernel(DenseKPa
             for (int r = 0; r < 8; ++r) {
               const float4 a = ld4(arow + r * rstep);
               float4& c = acc[ps][r];
-              c.x = fmaf(a.x, w0.x, c.x); c.y = fmaf(a.x, w0.y, c.y); c.z = fmaf(a.x, w0.z, c.z); c.w = fmaf(a.x, w0.w, c.w);
-              c.x = fmaf(a.y, w1.x, c.x); c.y = fmaf(a.y, w1.y, c.y); c.z = fmaf(a.y, w1.z, c.z); c.w = fmaf(a.y, w1.w, c.w);
-              c.x = fmaf(a.z, w2.x, c.x); c.y = fmaf(a.z, w2.y, c.y); c.z = fmaf(a.z, w2.z, c.z); c.w = fmaf(a.z, w2.w, c.w);
-              c.x = fmaf(a.w, w3.x, c.x); c.y = fmaf(a.w, w3.y, c.y); c.z = fmaf(a.w, w3.z, c.z); c.w = fmaf(a.w, w3.w, c.w);
+              c = dense_fma4s(a.x, w0, c);
+              c = dense_fma4s(a.y, w1, c);
+              c = dense_fma4s(a.z, w2, c);
+              c = dense_fma4s(a.w, w3, c);
             }
           }
         }
