@@ -314,6 +314,21 @@ __global__ void add_kernel(const float* a, const float* b, float* out, long long
     out[i] = va + vb;
   }
 }
+// same-shape fast path of add_kernel: 128-bit accesses, no index arithmetic
+__global__ void add_vec4_kernel(const float4* a, const float4* b, float4* out, long long total4) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total4; i += gridDim.x * 256ll) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+}
+// out[n,t,c] = x[n,t,c] * g[n,c] for C % 4 == 0 and fewer than 2^31 chunks: 128-bit accesses, 32-bit index arithmetic
+__global__ void mulch_vec4_kernel(const float4* x, const float4* g, float4* out, unsigned total4, unsigned C4, unsigned T) {
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gridDim.x * 256u) {
+    const unsigned r = i / C4, c = i - r * C4;
+    const float4 v = x[i], w = g[(r / T) * C4 + c];
+    out[i] = make_float4(v.x * w.x, v.y * w.y, v.z * w.z, v.w * w.w);
+  }
+}
 __global__ void acc_kernel(float* dst, const float* src, long long total) {
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) dst[i] += src[i];
 }
@@ -843,13 +858,24 @@ static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, in
         h->launches++;
         break;
       case HP_OP_ADD:
+        if (!hd->regs[o.in0].per_image == !hd->regs[o.out].per_image && !hd->regs[o.in1].per_image == !hd->regs[o.out].per_image &&
+            total % 4 == 0 && (((uintptr_t)R(o.in0) | (uintptr_t)R(o.in1) | (uintptr_t)RW(o.out)) & 15) == 0) {
+          add_vec4_kernel<<<EW_GRID(total / 4), 256, 0, st>>>((const float4*)R(o.in0), (const float4*)R(o.in1), (float4*)RW(o.out), total / 4);
+          h->launches++;
+          break;
+        }
         add_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), R(o.in1), RW(o.out), rows_out, C, T,
                                                    hd->regs[o.in0].per_image && !hd->regs[o.out].per_image,
                                                    hd->regs[o.in1].per_image && !hd->regs[o.out].per_image);
         h->launches++;
         break;
       case HP_OP_MULCH:
-        mulch_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), R(o.in1), RW(o.out), rows_out, C, T);
+        if (C % 4 == 0 && total / 4 < (1ll << 31) && (((uintptr_t)R(o.in0) | (uintptr_t)R(o.in1) | (uintptr_t)RW(o.out)) & 15) == 0) {
+          mulch_vec4_kernel<<<EW_GRID(total / 4), 256, 0, st>>>((const float4*)R(o.in0), (const float4*)R(o.in1), (float4*)RW(o.out),
+                                                               (unsigned)(total / 4), (unsigned)(C / 4), (unsigned)T);
+        } else {
+          mulch_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), R(o.in1), RW(o.out), rows_out, C, T);
+        }
         h->launches++;
         break;
       case HP_OP_GAP:

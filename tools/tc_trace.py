@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """GPU tool: per-tile timeline (clock64 stamps of CTA 0) of the warp-specialised tensor-core BlazeBlock kernel.
-Usage: tc_trace.py blk TR NSTG nsets nbuf esets [size] [batch]"""
+Usage: tc_trace.py blk TR NSTG nsets nbuf esets [size] [batch]   (TR 0 = the library's default geometry; blk -1 = stem;
+nbuf carries + 16 x work unit + 64 x issuers + 512 x placement as in hp_debug_set_tc)"""
 import os
 import sys
 
@@ -21,9 +22,6 @@ lib = _lib.lib()
 flat = pack_backbone(random_backbone(1234))
 _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
 H = size // 2 if blk < 2 else size // 4 if blk < 5 else size // 8 if blk < 11 else size // 16   # blk -1 = stem
-strips = -(-H // TR)
-bands = -(-strips // max(1, 128 // H))
-BH = -(-strips // bands) * TR
 if blk >= 0:
     _lib.check(lib.hp_debug_set_tc(ctx.handle, blk, TR, NSTG, 0, esets, nsets, nbuf))
 else:
