@@ -55,23 +55,6 @@ struct TcParams {
 
 
 
-// watchdog spin for single-thread roles: try_wait suspends in hardware; the clock is read every 256 polls only
-__device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0, n = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x100;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) break;
-    if ((++n & 255u) == 0u) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();
-    }
-  }
-}
-
 // Depthwise 3x3 (+bias) of one 4-channel chunk for the TR pixels of a lane (sliding window down the column).
 template <int CINP, int TR, int PS>
 __device__ __forceinline__ void tc_dw_compute(const float* win, const float* dww_c, const float* dwb_c, int row_pitch, bool mask_l, bool mask_r,
@@ -348,7 +331,7 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 #pragma unroll 1
       for (int ks = 0; ks < KS; ++ks, ++use) {
         const uint32_t s = use % NSTG;
-        mbar_wait_light(&bar_afull[s], (use / NSTG) & 1);
+        mbar_wait(&bar_afull[s], (use / NSTG) & 1);
         tc_fence_after();
         const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
         const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
