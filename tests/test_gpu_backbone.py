@@ -245,3 +245,44 @@ def test_tensor_core_stem(cfg, size, batch):
     finally:
         _lib.check(lib.hp_debug_set_stem_tc(ctx.handle, 0, 0, 0, 0))
         ctx.set_impl(_lib.HP_IMPL_FAST)
+
+
+def test_full_size_batch_properties():
+    """BASELINE size (4096 crops of 96x96, random-init weights): the tensor-core path agrees with the naive CUDA kernels,
+    is deterministic run to run, and every image is independent of its batch neighbours (a 64-image slice pushed through
+    on its own is bit-identical to the same slice of the full batch): persistent tiles never mix images."""
+    from hpose_b200 import _lib
+    from hpose_b200.unified import pack_backbone, random_backbone
+    ctx = _ctx()
+    lib = _lib.lib()
+    flat = pack_backbone(random_backbone(seed=1234))
+    _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size, 0))
+    B, S = 4096, 96
+    g = torch.Generator(device="cuda").manual_seed(2026)
+    x = torch.rand((B, S, S, 3), generator=g, device="cuda") * 2 - 1
+    A = lib.hp_num_anchors(S, S)
+
+    def run(xx, impl):
+        n = xx.shape[0]
+        ctx.set_impl(impl)
+        f16 = torch.empty((n, 12, 12, 88), device="cuda"); f8 = torch.empty((n, 6, 6, 96), device="cuda")
+        cls = torch.empty((n, A), device="cuda"); loc = torch.empty((n, A, 16), device="cuda")
+        _lib.check(lib.hp_backbone_forward(ctx.handle, xx.data_ptr(), n, S, S, f16.data_ptr(), f8.data_ptr(), cls.data_ptr(),
+                                           loc.data_ptr(), ctx.stream_ptr()))
+        torch.cuda.synchronize()
+        return f16, f8, cls, loc
+
+    try:
+        fast = run(x, _lib.HP_IMPL_FAST)
+        again = run(x, _lib.HP_IMPL_FAST)
+        for a, b in zip(fast, again):
+            assert torch.equal(a, b), "not deterministic"
+        part = run(x[1000:1064].contiguous(), _lib.HP_IMPL_FAST)
+        for a, b in zip(fast, part):
+            assert torch.equal(a[1000:1064], b), "an image depends on its batch neighbours"
+        naive = run(x, _lib.HP_IMPL_NAIVE)
+        for a, b, n in zip(fast, naive, ("feat16", "feat8", "cls", "loc")):
+            err = float((a - b).abs().max() / b.abs().max())
+            assert err < 2e-5, (n, err)
+    finally:
+        ctx.set_impl(_lib.HP_IMPL_FAST)
