@@ -14,7 +14,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhpose.so")
-SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "stem_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
+SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "stem_tc.cu", "dense_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -111,6 +111,7 @@ struct hp_ctx {
   DevBuf scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
+  bool dense_tc = true;            // Dense / 1x1 layers may use the tensor-core kernel (cleared while a training step runs)
   int stem_tc_cfg[4] = {};         // tensor-core stem: band height, input buffers, output stages, gather sets (0 = automatic, [0] = -1: off)
   int tc_override[16][9] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets, nbuf per block (TR 0 = automatic, -1 = do not use)
   int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
@@ -168,3 +169,8 @@ void hp_stem_tc_split_weights(const float* w75x24, float* bhi, float* blo);
 bool hp_stem_tc_supported(int H, int W);
 int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W, const float* bhi, const float* blo, const float* bias,
                       const int* cfg, cudaStream_t st);
+
+// dense_tc.cu: Dense / 1x1-conv layers of the heads as a 3xTF32 tcgen05 GEMM (forward inference)
+bool hp_dense_tc_supported(const float* x, int M, int K, int ldx, int N, bool transpose_w, bool accumulate);
+int hp_launch_dense_tc(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
+                       const DenseOut* outs, int n_outs, cudaStream_t st);

@@ -1,0 +1,336 @@
+// Dense / 1x1-conv layer y = act(x W + b) of the detector and regressor heads as a 3xTF32 GEMM on the tcgen05 tensor cores
+// (forward inference only; training, transposed weights and accumulation stay on dense_kernel in heads.cu).
+//
+// Reference semantics: Conv2D(1x1) / Dense layers of the unified graph's detector heads and of the
+// regressor heads (Model-88/attention_model.py:16-169, Model-88/train_88.py:66-253, Model-96/train_96.py:65-110).
+// north_star (c): "dense and attention contractions on tcgen05 tensor cores only where the GEMM shapes justify it" -- these
+// have M = B * H * W rows (147k-590k at batch 4096) against K, N <= 128; on the CUDA cores they were 1.0 ms of a 5.7 ms step.
+//
+// Same warp-specialised scheme and precision split as blaze_block_deep_kernel (blocks_tc.cu), with one accumulator row
+// per lane (lane <-> token row):
+//   loader   (1 thread): TMA box {KPAD, 128 rows} of x into a ring of buffers; KPAD > K pads the row stride to an odd
+//                        number of 16-byte chunks (conflict-free row access), columns >= K are zero-filled (K padding)
+//   gather sets        : lane copies 16 floats (2 k-steps) of its row, splits them into TF32 hi / lo, tcgen05.st
+//   issuer   (1 thread): 3 tcgen05.mma per k-step (A from TMEM, W_hi / W_lo from smem; W is split in the kernel prologue)
+//   epilogue sets      : tcgen05.ld D + bias -> staging tile -> activation + coalesced scatter to the output segments
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int DT_MAXB = 4, DT_MAXSTG = 4, DT_BAR_FLOATS = 64;
+constexpr int DT_ROWS = 128;
+
+struct DenseTcParams {
+  const float *W, *b;
+  int M, K, N, ldw, act;
+  int K8, KS, N16, KPAD, OS;          // OS: staging row stride (odd number of 16-byte chunks)
+  int n_tiles, nstg, nbuf;
+  uint32_t load_bytes;
+  int off_b, off_bias, off_rowoff, off_stage, off_in, in_floats;
+  int n_outs;
+  DenseOut outs[2];
+  unsigned magic[2];
+};
+
+__device__ __forceinline__ float dt_act(int act, float v) {
+  switch (act) {
+    case HP_ACT_RELU: return fmaxf(v, 0.f);
+    case HP_ACT_TANH: return tanhf(v);
+    case HP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case HP_ACT_SOFTSIGN: return v / (1.f + fabsf(v));
+    default: return v;
+  }
+}
+
+template <int NSETS, int NESETS>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* bar_full = bars;                      // [nbuf]
+  uint64_t* bar_infree = bars + DT_MAXB;          // [nbuf]
+  uint64_t* bar_afull = bars + 2 * DT_MAXB;       // [nstg]
+  uint64_t* bar_aempty = bar_afull + DT_MAXSTG;   // [nstg]
+  uint64_t* bar_dfull = bar_aempty + DT_MAXSTG;   // [2]
+  uint64_t* bar_dempty = bar_dfull + 2;           // [2]
+  static_assert((2 * DT_MAXB + 2 * DT_MAXSTG + 4) * 8 + 4 <= DT_BAR_FLOATS * 4, "barrier block");
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (DT_BAR_FLOATS - 1);
+  float* s_bhi = smem + p.off_b;
+  float* s_blo = s_bhi + p.K8 * p.N16;
+  float* s_bias = smem + p.off_bias;
+  long long* rowoff = reinterpret_cast<long long*>(smem + p.off_rowoff);   // [2][128]
+  float* stage = smem + p.off_stage;                                        // [128][OS]
+  float* in_bufs = smem + p.off_in;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane_id = tid & 31;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1;
+  const int NSTG = p.nstg, NBUF = p.nbuf, KS = p.KS, N16 = p.N16;
+
+  // weights: split into TF32 hi / lo in the UMMA layout [K8/4][N16][4] (k and n padding are zeros)
+  for (int i = tid; i < p.K8 * N16; i += nthr) {
+    const int k = i / N16, n = i - k * N16;
+    const float w = (k < p.K && n < p.N) ? p.W[(long long)k * p.ldw + n] : 0.f;
+    const uint32_t hi = tf32_hi(w);
+    const int idx = ((k >> 2) * N16 + n) * 4 + (k & 3);
+    s_bhi[idx] = __uint_as_float(hi);
+    s_blo[idx] = w - __uint_as_float(hi);
+  }
+  for (int i = tid; i < N16; i += nthr) s_bias[i] = (p.b && i < p.N) ? p.b[i] : 0.f;
+  fence_async_smem();
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&bar_full[b], 1);
+      mbar_init(&bar_infree[b], 128 * NSETS);
+    }
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(&bar_afull[s], 128);
+      mbar_init(&bar_aempty[s], 1);
+    }
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&bar_dfull[d], 1);
+      mbar_init(&bar_dempty[d], 128 * NESETS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  const uint32_t colA0 = 2 * N16;                 // D[0], D[1] (N16 columns each), then the A ring (16 columns per stage)
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp < W_ISSUE) {
+    const int wq = warp & 3;
+    const int lane = wq * 32 + lane_id;           // token row of the tile
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    if (warp < W_EPI) {
+      // =============================================================== gather sets: x tile -> TF32 hi / lo -> TMEM A ring
+      // work unit = one k-step (8 floats of the row); global round-robin over the sets as in blaze_block_deep_kernel
+      const int set = warp >> 2;
+      const uint32_t n_units = (uint32_t)my_tiles * KS;
+      uint64_t* pending = nullptr;
+      int cur_i = -1, cur_b = 0;
+      const float* row = in_bufs;
+#pragma unroll 1
+      for (uint32_t g = set; g < n_units; g += NSETS) {
+        const int i = (int)(g / KS);
+        const int ks = (int)(g - (uint32_t)i * KS);
+        const uint32_t s = g % NSTG;
+        if (i != cur_i) {
+          cur_i = i;
+          cur_b = i % NBUF;
+          row = in_bufs + cur_b * p.in_floats + lane * p.KPAD;
+          mbar_wait(&bar_full[cur_b], (i / NBUF) & 1);
+        }
+        const float4 q0 = ld4(row + 8 * ks), q1 = ld4(row + 8 * ks + 4);
+        const float f[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t v[16];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[e] = tf32_hi(f[e]);
+          v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
+        }
+        if (pending != nullptr) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          mbar_arrive(pending);
+        }
+        if (g >= (uint32_t)NSTG) {
+          mbar_wait(&bar_aempty[s], ((g / NSTG) - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st16(tlane + colA0 + s * 16, v);
+        pending = &bar_afull[s];
+        if (g + NSETS >= n_units || (int)((g + NSETS) / KS) != i) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          mbar_arrive(pending);
+          pending = nullptr;
+          mbar_arrive(&bar_infree[cur_b]);   // this thread reads nothing more from the tile
+        }
+      }
+    } else {
+      // =============================================================== epilogue sets
+      const int eset = (warp - W_EPI) >> 2;
+      const int etid = tid - W_EPI * 32;           // 0 .. 128 * NESETS - 1
+      int tile = blockIdx.x;
+      for (int i = 0; i < my_tiles; ++i, tile += gridDim.x) {
+        const int d = i & 1;
+        const long long m0 = (long long)tile * DT_ROWS;
+        const int rows = (int)((p.M - m0 < DT_ROWS) ? (p.M - m0) : DT_ROWS);
+        // destination offset of every tile row per output segment (one 64-bit division per row, none per element)
+        for (int j = etid; j < p.n_outs * DT_ROWS; j += 128 * NESETS) {
+          const int o = j / DT_ROWS, r = j - o * DT_ROWS;
+          const DenseOut& dd = p.outs[o];
+          const long long m = m0 + r;
+          const long long img = m / dd.rows_per_img;
+          rowoff[j] = img * dd.img_stride + (m - img * dd.rows_per_img) * (long long)dd.row_stride;
+        }
+        mbar_wait(&bar_dfull[d], (i >> 1) & 1);
+        tc_fence_after();
+        // D row + bias -> staging tile; the 32-column groups are dealt to the epilogue sets
+        for (int g = eset; g * 32 < N16; g += NESETS) {
+          uint32_t v[32];
+          if (g * 32 + 32 <= N16) {
+            tmem_ld32(tlane + d * N16 + g * 32, v);
+          } else {
+            uint32_t hlf[16];
+            tmem_ld16(tlane + d * N16 + g * 32, hlf);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = g * 32 + j * 4;
+            if (c < N16) {
+              const float4 bb = ld4(s_bias + c);
+              st4(stage + lane * p.OS + c, make_float4(__uint_as_float(v[j * 4 + 0]) + bb.x, __uint_as_float(v[j * 4 + 1]) + bb.y,
+                                                       __uint_as_float(v[j * 4 + 2]) + bb.z, __uint_as_float(v[j * 4 + 3]) + bb.w));
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bar_dempty[d]);
+        named_bar_sync(1, 128 * NESETS);
+        // activation + coalesced write-out of every output segment
+        for (int o = 0; o < p.n_outs; ++o) {
+          const DenseOut& dd = p.outs[o];
+          const int wd = dd.col_end - dd.col_begin;
+          const int total = rows * wd;
+          for (int j = etid; j < total; j += 128 * NESETS) {
+            const int r = (int)(((unsigned long long)j * p.magic[o]) >> 32);
+            const int c = j - r * wd;
+            dd.ptr[rowoff[o * DT_ROWS + r] + c] = dt_act(p.act, stage[r * p.OS + dd.col_begin + c]);
+          }
+        }
+        named_bar_sync(1, 128 * NESETS);   // the staging tile and rowoff are reused by the next tile
+      }
+    }
+  } else if (lane_id == 0) {
+    if (warp == W_ISSUE) {
+      // =============================================================== MMA issuer
+      const uint32_t idesc = tc_idesc_tf32(N16);
+      const uint64_t desc_fixed = tc_bdesc_fixed(N16);
+      const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
+      uint32_t use = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int d = i & 1;
+        if (i >= 2) {
+          mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ++ks, ++use) {
+          const uint32_t s = use % NSTG;
+          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          tc_fence_after();
+          const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
+          const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
+          const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+          const uint32_t dc = tmem_base + d * N16;
+          const uint32_t a = tmem_base + colA0 + s * 16;
+          mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32_ts(dc, a, dlo, idesc, 1u);
+          mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          tc_commit(&bar_aempty[s]);
+        }
+        tc_commit(&bar_dfull[d]);
+      }
+    } else if (warp == W_LOAD) {
+      // =============================================================== TMA loader
+      int b = 0, i = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        if (i >= NBUF) mbar_wait(&bar_infree[b], ((i / NBUF) - 1) & 1);
+        mbar_expect_tx(&bar_full[b], p.load_bytes);
+        tma_load_4d(in_bufs + b * p.in_floats, &tm_in, &bar_full[b], 0, tile * DT_ROWS, 0, 0);
+        if (++b == NBUF) b = 0;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+}  // namespace
+
+// shared-memory layout (floats); returns the bytes needed with `nbuf` input buffers
+static size_t dense_tc_layout(int K, int N, int nbuf, DenseTcParams* p) {
+  p->K8 = round_up(K, 8); p->KS = p->K8 / 8; p->N16 = round_up(N, 16);
+  p->KPAD = ((p->K8 / 4) | 1) * 4;
+  p->OS = ((p->N16 / 4) | 1) * 4;
+  int off = DT_BAR_FLOATS;
+  p->off_b = off;
+  off += 2 * p->K8 * p->N16;
+  p->off_bias = off;
+  off = tc_align_up(off + p->N16, 4);
+  p->off_rowoff = off;
+  off += 4 * DT_ROWS;                              // 2 x 128 long long
+  p->off_stage = off;
+  off = tc_align_up(off + DT_ROWS * p->OS, 256);
+  p->off_in = off;
+  p->in_floats = tc_align_up(DT_ROWS * p->KPAD, 256);
+  return (size_t)(off + nbuf * p->in_floats) * sizeof(float);
+}
+
+// true when the layer can run on the tensor-core kernel: forward, plain weights, 16-byte aligned rows, at least 3 k-steps
+// (every gather set must own a k-step of every tile), two input buffers next to the split weights in shared memory
+bool hp_dense_tc_supported(const float* x, int M, int K, int ldx, int N, bool transpose_w, bool accumulate) {
+  if (transpose_w || accumulate || M < 4 * DT_ROWS || K % 4 != 0 || K < 20 || K > 128 || N < 1 || N > 128 || ldx % 4 != 0 ||
+      (((uintptr_t)x) & 15) != 0)
+    return false;
+  DenseTcParams p;
+  return dense_tc_layout(K, N, 2, &p) <= 227 * 1024 && 2 * p.N16 + DT_MAXSTG * 16 <= 512;
+}
+
+int hp_launch_dense_tc(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
+                       const DenseOut* outs, int n_outs, cudaStream_t st) {
+  HP_REQUIRE(n_outs >= 1 && n_outs <= 2, HP_ERR_INVALID, "dense tc: 1 or 2 output segments");
+  DenseTcParams p;
+  p.W = W; p.b = b; p.M = M; p.K = K; p.N = N; p.ldw = ldw; p.act = act;
+  p.nbuf = DT_MAXB;
+  while (p.nbuf > 2 && dense_tc_layout(K, N, p.nbuf, &p) > 200 * 1024) --p.nbuf;
+  const size_t smem = dense_tc_layout(K, N, p.nbuf, &p);
+  p.n_tiles = ceil_div(M, DT_ROWS);
+  p.nstg = DT_MAXSTG;
+  HP_REQUIRE(2 * p.N16 + p.nstg * 16 <= 512 && p.KPAD <= 256, HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);
+  p.n_outs = n_outs;
+  for (int i = 0; i < n_outs; ++i) {
+    p.outs[i] = outs[i];
+    const int wd = outs[i].col_end - outs[i].col_begin;
+    HP_REQUIRE(wd >= 1 && outs[i].col_end <= N, HP_ERR_INVALID, "dense tc: bad output segment [%d, %d)", outs[i].col_begin, outs[i].col_end);
+    p.magic[i] = (unsigned)((0x100000000ull + wd - 1) / wd);
+  }
+  p.load_bytes = (uint32_t)((size_t)DT_ROWS * p.KPAD * sizeof(float));
+  HP_REQUIRE(smem <= 227 * 1024, HP_ERR_UNSUPPORTED, "dense tc: %zu bytes of shared memory needed for %dx%d", smem, K, N);
+  CUtensorMap tin;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)M, 1, 1};
+    const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)ldx * 4 * (cuuint64_t)M, (cuuint64_t)ldx * 4 * (cuuint64_t)M};
+    const cuuint32_t box[4] = {(cuuint32_t)p.KPAD, (cuuint32_t)DT_ROWS, 1, 1};
+    HP_TRY(tc_make_map4(&tin, x, dims, strides, box));
+  }
+  long long grid = h->num_sms;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  // narrow layers are bound by the gather (3 sets); wide ones by the epilogue (2 sets)
+  if (p.N16 <= 32) {
+    auto kern = dense_tc_kernel<3, 1>;
+    HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<(unsigned)grid, 128 * 3 + 128 * 1 + 96, smem, st>>>(tin, p);
+  } else {
+    auto kern = dense_tc_kernel<2, 2>;
+    HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<(unsigned)grid, 128 * 2 + 128 * 2 + 96, smem, st>>>(tin, p);
+  }
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}

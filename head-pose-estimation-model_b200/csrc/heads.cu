@@ -218,6 +218,8 @@ int hp_launch_dense(hp_ctx* h, const float* x, int M, int K, int ldx, const floa
                     cudaStream_t st) {
   if (M <= 0) return HP_OK;
   HP_REQUIRE(n_outs >= 1 && n_outs <= 2, HP_ERR_INVALID, "dense: 1 or 2 output segments");
+  if (h->impl == HP_IMPL_FAST && h->dense_tc && hp_dense_tc_supported(x, M, K, ldx, N, transpose_w, accumulate))
+    return hp_launch_dense_tc(h, x, M, K, ldx, W, ldw, b, N, act, outs, n_outs, st);
   DenseKParams p;
   p.x = x; p.W = W; p.b = b; p.M = M; p.K = K; p.ldx = ldx; p.ldw = ldw; p.N = N; p.act = act;
   p.transpose_w = transpose_w ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
@@ -841,6 +843,12 @@ static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, in
   float* A = hd->acts.f();
   auto R = [&](int r) -> const float* { return r == 0 ? feat : A + hd->reg_off[r]; };
   auto RW = [&](int r) -> float* { return A + hd->reg_off[r]; };
+  // a training step keeps plain fp32 FMA accumulation in forward and backward; inference may use the 3xTF32 kernel
+  struct DenseTcScope {
+    hp_ctx* h; bool saved;
+    DenseTcScope(hp_ctx* c, bool on) : h(c), saved(c->dense_tc) { c->dense_tc = saved && on; }
+    ~DenseTcScope() { h->dense_tc = saved; }
+  } dense_tc_scope(h, !training);
   for (size_t i = 0; i < hd->ops.size(); ++i) {
     const hp_head_op& o = hd->ops[i];
     const long long rows_out = reg_rows(hd, o.out, n_img, T);
