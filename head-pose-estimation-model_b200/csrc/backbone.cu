@@ -767,7 +767,13 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
       const int* tv = h->tc_override[i];   // TR, NSTG, BH, npipe (epilogue sets when nbuf > 0), nsets, nbuf, unit, issuers
       if (tv[0] > 0) {                      // explicit geometry (tuning / tests): also on maps the default leaves to the CUDA cores
         use_tc = true;
-        if (tv[5] > 0) {                    // warp-specialised kernel with explicit TR / nsets / esets, rings optional
+        if (tv[5] > 0 && tv[0] == 1) {      // pixel-per-lane kernel (maps of at most 128 pixels)
+          HP_REQUIRE(hp_tcs_geometry(i, Ho, Wo, tv[4] > 0 ? tv[4] : 3, tv[3] > 0 ? tv[3] : 2, &tcc), HP_ERR_INVALID,
+                     "tc override for block %d: the pixel-per-lane kernel does not fit a %dx%d map", i, Ho, Wo);
+          if (tv[5] < tcc.nbuf) tcc.nbuf = tv[5];
+          HP_REQUIRE(hp_tc_fits(i, Ho, Wo, tcc), HP_ERR_INVALID, "tc override for block %d does not fit (pixel-per-lane, nsets %d nbuf %d)", i,
+                     tcc.nsets, tcc.nbuf);
+        } else if (tv[5] > 0) {             // warp-specialised kernel with explicit TR / nsets / esets, rings optional
           HP_REQUIRE(hp_tcd_geometry(i, Ho, Wo, tv[0], tv[4] > 0 ? tv[4] : 2, tv[3] > 0 ? tv[3] : 2, &tcc), HP_ERR_INVALID,
                      "tc override for block %d: TR %d does not fit", i, tv[0]);
           if (tv[1] > 0) tcc.NSTG = tv[1];

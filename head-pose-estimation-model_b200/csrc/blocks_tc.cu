@@ -658,6 +658,259 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   }
 }
 
+
+// ============================================================================ small maps: one pixel per lane
+// Maps of at most 128 pixels (blocks 12-15: 6 x 6 at 88 / 96 input, 8 x 8 at 128; blocks 6-10: 11 x 11 at 88 input).  The
+// band kernel above needs halo rows / padded columns around every image, so only 2-4 images of 96 channels fit a tile
+// and the per-tile latency chain dominates.  Here a tile is NI = 128 / (H W) WHOLE images, stored compactly as
+// [NI H W pixels][PS floats] (one TMA box over the tensor viewed as [B H W][C]), lane <-> pixel, and every lane keeps
+// the shared-memory offsets of its 9 taps: a tap outside the image points at a pixel of zeros behind the tile (SAME
+// padding), so no weight masking and no halo.  Same warp roles and barriers as blaze_block_deep_kernel with one
+// accumulator row per lane (TR = 1); a work unit is a k-step (8 channels: 18 LDS.128 of inputs, 18 of weights).
+// The epilogue sets alternate tiles (set e owns accumulator buffer D[e] when NESETS == 2).
+struct TcsParams {
+  const float *dww, *dwb, *pwb, *bhi, *blo;
+  int W, H, P, NI, rows, n_tiles;            // P = H * W pixels per image, rows = NI * P lanes in use
+  int nstg, nbuf;
+  uint32_t load_bytes;
+  int off_b, off_w, off_pipe, buf_floats;
+  long long* trace;                          // optional clock stamps of CTA 0 (same 12 slots per tile as the band kernel)
+  int trace_tiles;
+};
+
+template <int CINP, int COUTP, int NSETS, int NESETS>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
+blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcsParams p) {
+  using G = TcGeom<CINP, COUTP>;
+  constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
+  constexpr uint32_t colA0 = 2 * N16;                             // TMEM: D[0], D[1], then the A ring (16 columns per stage)
+  static_assert(colA0 + TC_MAX_STG * 16 <= 512, "TMEM budget");
+
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* bar_full = bars;                                       // [nbuf]
+  uint64_t* bar_free = bars + TCD_MAXB;                            // [nbuf]
+  uint64_t* bar_epi = bars + 2 * TCD_MAXB;                         // [nbuf]
+  uint64_t* bar_afull = bars + 3 * TCD_MAXB;                       // [nstg]
+  uint64_t* bar_aempty = bar_afull + TC_MAX_STG;                   // [nstg]
+  uint64_t* bar_dfull = bar_aempty + TC_MAX_STG;                   // [2]
+  uint64_t* bar_dempty = bar_dfull + 2;                            // [2]
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (TC_BAR_FLOATS - 1);
+  float* s_bhi = smem + p.off_b;
+  float* s_blo = s_bhi + K8 * N16;
+  float* s_dww = smem + p.off_w;
+  float* s_dwb = s_dww + 9 * CINP;
+  float* s_pwb = s_dwb + CINP;
+  float* bufs = smem + p.off_pipe;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane_id = tid & 31;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1, W_STORE = W_ISSUE + 2;
+  const int NSTG = p.nstg, NBUF = p.nbuf;
+
+  for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
+    st4(s_bhi + i, ld4(p.bhi + i));
+    st4(s_blo + i, ld4(p.blo + i));
+  }
+  for (int i = tid * 4; i < 9 * CINP; i += nthr * 4) st4(s_dww + i, ld4(p.dww + i));
+  for (int i = tid * 4; i < CINP; i += nthr * 4) st4(s_dwb + i, ld4(p.dwb + i));
+  for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
+  // the pixel of zeros behind every tile (and the alignment padding) is written once; TMA and the epilogue never touch it
+  for (int i = tid * 4; i < NBUF * p.buf_floats; i += nthr * 4) st4(bufs + i, make_float4(0.f, 0.f, 0.f, 0.f));
+  fence_async_smem();
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&bar_full[b], 1);
+      mbar_init(&bar_free[b], 1);
+      mbar_init(&bar_epi[b], 128);
+    }
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(&bar_afull[s], 128);
+      mbar_init(&bar_aempty[s], 1);
+    }
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&bar_dfull[d], 1);
+      mbar_init(&bar_dempty[d], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto stamp = [&](int i, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && i < p.trace_tiles) p.trace[i * 12 + slot] = clock64();
+  };
+
+  if (warp < W_ISSUE) {
+    const int wq = warp & 3;
+    const int lane = wq * 32 + lane_id;                            // pixel of the tile
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const bool active = lane < p.rows;
+    const bool warp_active = wq * 32 < p.rows;
+    if (warp < W_EPI) {
+      // =============================================================== depthwise sets (k-step units, global round-robin)
+      const int set = warp >> 2;
+      int off[9];                                                  // tap offsets in floats; p.rows * PS = the pixel of zeros
+      {
+        const int r = lane % p.P, y = r / p.W, x = r - y * p.W;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          const bool ok = active && y + dy >= 0 && y + dy < p.H && x + dx >= 0 && x + dx < p.W;
+          off[t] = (ok ? lane + dy * p.W + dx : p.rows) * PS;
+        }
+      }
+      const uint32_t n_units = (uint32_t)my_tiles * KS;
+      uint64_t* pending = nullptr;
+      int cur_i = -1;
+      const float* buf = bufs;
+#pragma unroll 1
+      for (uint32_t g = set; g < n_units; g += NSETS) {
+        const int i = (int)(g / KS);
+        const int ks = (int)(g - (uint32_t)i * KS);
+        const uint32_t s = g % NSTG;
+        if (i != cur_i) {                                          // first unit of this set in tile i
+          cur_i = i;
+          const int b = i % NBUF;
+          buf = bufs + b * p.buf_floats;
+          mbar_wait(&bar_full[b], (i / NBUF) & 1);
+          if (tid == 0) stamp(i, 1);
+        }
+        uint32_t v[16];                                            // [hi 8 | lo 8]
+        if (warp_active) {
+          const int c = 8 * ks;
+          const bool two = (2 * ks + 1 < C4);                      // the second 4-channel chunk of the k-step exists
+          float4 a0 = ld4(s_dwb + c), a1 = two ? ld4(s_dwb + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const float* q = buf + off[t] + c;
+            a0 = fma4(ld4(q), ld4(s_dww + t * CINP + c), a0);
+            if (two) a1 = fma4(ld4(q + 4), ld4(s_dww + t * CINP + c + 4), a1);
+          }
+          const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e] = tf32_hi(f[e]);
+            v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
+          }
+        }
+        if (pending != nullptr) {
+          if (warp_active) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
+          mbar_arrive(pending);
+        }
+        if (g >= (uint32_t)NSTG) {
+          mbar_wait(&bar_aempty[s], ((g / NSTG) - 1) & 1);
+          tc_fence_after();
+        }
+        if (warp_active) tmem_st16(tlane + colA0 + s * 16, v);
+        pending = &bar_afull[s];
+        if (g + NSETS >= n_units || (int)((g + NSETS) / KS) != i) {
+          // last unit of this set in tile i: publish now (the next unit may have to wait for a TMA load)
+          if (warp_active) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
+          mbar_arrive(pending);
+          pending = nullptr;
+          if (tid == 0) stamp(i, 2);
+          if (tid == (NSETS - 1) * 128) stamp(i, 8);
+        }
+      }
+    } else {
+      // =============================================================== epilogue sets: tile i belongs to set i % NESETS
+      const int eset = (warp - W_EPI) >> 2;
+      for (int i = eset; i < my_tiles; i += NESETS) {
+        const int d = i & 1, b = i % NBUF;
+        float* buf = bufs + b * p.buf_floats;
+        mbar_wait(&bar_dfull[d], (i >> 1) & 1);
+        tc_fence_after();
+        if ((tid & 127) == 0) stamp(i, 3);
+        if (warp_active) {
+          tc_epilogue_pixel<C4, NG, N16>(buf + lane * PS, tlane + d * N16, s_pwb, active);
+          tc_fence_before();
+          fence_async_smem();
+        }
+        mbar_arrive(&bar_dempty[d]);
+        mbar_arrive(&bar_epi[b]);
+        if ((tid & 127) == 0) stamp(i, 4);
+      }
+    }
+  } else if (lane_id == 0) {
+    if (warp == W_ISSUE) {
+      // =============================================================== MMA issuer
+      const uint32_t idesc = tc_idesc_tf32(N16);
+      const uint64_t desc_fixed = tc_bdesc_fixed(N16);
+      const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
+      uint32_t use = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int d = i & 1;
+        if (i >= 2) {
+          mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        stamp(i, 11);
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ++ks, ++use) {
+          const uint32_t s = use % NSTG;
+          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          tc_fence_after();
+          if (ks == 0) stamp(i, 10);
+          if (ks == KS - 1) stamp(i, 9);
+          const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
+          const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
+          const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+          const uint32_t dc = tmem_base + d * N16;
+          const uint32_t a = tmem_base + colA0 + s * 16;
+          mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32_ts(dc, a, dlo, idesc, 1u);
+          mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          tc_commit(&bar_aempty[s]);
+        }
+        tc_commit(&bar_dfull[d]);
+        stamp(i, 7);
+      }
+    } else if (warp == W_LOAD) {
+      // =============================================================== TMA loader
+      int i = 0, b = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        if (i >= NBUF) mbar_wait(&bar_free[b], ((i / NBUF) - 1) & 1);
+        mbar_expect_tx(&bar_full[b], p.load_bytes);
+        tma_load_4d(bufs + b * p.buf_floats, &tm_in, &bar_full[b], 0, tile * p.rows, 0, 0);
+        stamp(i, 0);
+        if (++b == NBUF) b = 0;
+      }
+    } else if (warp == W_STORE) {
+      // =============================================================== TMA storer
+      int i = 0, b = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        mbar_wait(&bar_epi[b], (i / NBUF) & 1);
+        tma_store_4d(&tm_out, bufs + b * p.buf_floats, 0, tile * p.rows, 0, 0);
+        tma_store_commit();
+        stamp(i, 5);
+        tma_store_wait_read();
+        stamp(i, 6);
+        mbar_arrive(&bar_free[b]);
+        if (++b == NBUF) b = 0;
+      }
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -773,10 +1026,55 @@ int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, con
   return HP_OK;
 }
 
+
+// buffer of the pixel-per-lane kernel: rows pixels + the pixel of zeros, padded to 1 KB
+inline int tcs_buf_floats(int rows, int PS) { return align_up((rows + 1) * PS, 256); }
+
+template <int CINP, int COUTP, int NSETS, int NESETS>
+int launch_small(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
+  using G = TcGeom<CINP, COUTP>;
+  TcsParams p;
+  p.dww = w.dww; p.dwb = w.dwb; p.pwb = w.pwb; p.bhi = w.bhi; p.blo = w.blo;
+  p.W = W; p.H = H; p.P = H * W; p.NI = tc.ni; p.rows = tc.ni * p.P;
+  p.n_tiles = ceil_div(B, tc.ni);
+  p.nstg = tc.NSTG; p.nbuf = tc.nbuf;
+  p.load_bytes = (uint32_t)((size_t)G::PS * p.rows * sizeof(float));
+  p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
+  tc_layout(CINP, COUTP, G::K8, G::N16, &p.off_b, &p.off_w, &p.off_pipe);
+  p.buf_floats = tcs_buf_floats(p.rows, G::PS);
+  const size_t smem = (size_t)(p.off_pipe + tc.nbuf * p.buf_floats) * sizeof(float);
+  HP_REQUIRE(smem <= 227 * 1024, HP_ERR_INVALID, "tc small block <%d,%d>: %zu bytes of shared memory needed", CINP, COUTP, smem);
+  HP_REQUIRE(p.rows >= 1 && p.rows <= 128 && tc.nbuf >= 2 && tc.nbuf <= TCD_MAXB && tc.NSTG >= 2 && tc.NSTG <= TC_MAX_STG &&
+                 tc.nsets <= tc.NSTG && 2 * G::N16 + tc.NSTG * 16 <= 512 && (long long)B * p.P < (1ll << 31),
+             HP_ERR_INVALID, "tc small block <%d,%d>: bad geometry %dx%d NI %d nbuf %d nstg %d", CINP, COUTP, H, W, tc.ni, tc.nbuf, tc.NSTG);
+  // the feature maps as [B H W pixels][C]: one box = the pixels of NI images, PS >= C floats per pixel (zero fill / clipped)
+  CUtensorMap tin, tout;
+  HP_TRY(make_map(&tin, in, 1, 1, B * p.P, CINP, 1, 1, p.rows, G::PS));
+  HP_TRY(make_map(&tout, out, 1, 1, B * p.P, COUTP, 1, 1, p.rows, G::PS));
+  auto kern = blaze_block_small_kernel<CINP, COUTP, NSETS, NESETS>;
+  HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  long long grid = h->num_sms;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + 96, smem, st>>>(tin, tout, p);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}
+
 template <int CINP, int COUTP>
 int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc,
                   cudaStream_t st) {
   constexpr int N16 = TcGeom<CINP, COUTP>::N16;
+  if (tc.TR == 1) {   // pixel-per-lane kernel for maps of at most 128 pixels (npipe = epilogue warp sets)
+    if constexpr (CINP >= 48) {
+      if (tc.nsets == 3 && tc.npipe == 2) return launch_small<CINP, COUTP, 3, 2>(h, in, out, B, H, W, w, tc, st);
+      if (tc.nsets == 3 && tc.npipe == 1) return launch_small<CINP, COUTP, 3, 1>(h, in, out, B, H, W, w, tc, st);
+      if (tc.nsets == 2 && tc.npipe == 1) return launch_small<CINP, COUTP, 2, 1>(h, in, out, B, H, W, w, tc, st);
+      if (tc.nsets == 4 && tc.npipe == 2) return launch_small<CINP, COUTP, 4, 2>(h, in, out, B, H, W, w, tc, st);
+    }
+    hp_set_error("tc small block <%d,%d>: no kernel for nsets %d esets %d", CINP, COUTP, tc.nsets, tc.npipe);
+    return HP_ERR_UNSUPPORTED;
+  }
 #define TCD_CASE(TR_, NSETS_, NESETS_, UNIT_, NISS_, PLACE_)                             \
   if constexpr (2 * TR_ * N16 + 2 * TR_ * 16 <= 512)                                     \
     if (tc.TR == TR_ && tc.nsets == NSETS_ && tc.npipe == NESETS_ && tc.unit == UNIT_ && tc.niss == NISS_ && tc.place == PLACE_) \
@@ -841,6 +1139,14 @@ bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc) {
   const int C4 = cinp / 4, NG = coutp / 4, N16 = (coutp + 15) / 16 * 16, K8 = (cinp + 7) / 8 * 8;
   const int PS = ((C4 > NG ? C4 : NG) | 1) * 4;
   const int ni = tc.nbuf > 0 ? tc.ni : 1;
+  if (tc.TR == 1 && tc.nbuf > 0) {   // pixel-per-lane kernel
+    if (kBlazeBlocks[blk].stride != 1 || cinp < 48 || ni < 1 || ni * H * W > 128 || tc.nbuf < 2 || tc.nbuf > TCD_MAXB || tc.NSTG < 2 ||
+        tc.NSTG > TC_MAX_STG || tc.nsets < 1 || tc.nsets > tc.NSTG || 2 * N16 + tc.NSTG * 16 > 512 || tc.npipe < 1 || tc.npipe > 2)
+      return false;
+    int ob, ow, op;
+    tc_layout(cinp, coutp, K8, N16, &ob, &ow, &op);
+    return (size_t)(op + tc.nbuf * tcs_buf_floats(ni * H * W, PS)) * 4 <= 227 * 1024;
+  }
   if (tc.TR < 1 || tc.BH < tc.TR || tc.BH % tc.TR || ni < 1 || (tc.BH / tc.TR) * W * ni > 128 || tc.BH + 2 > 256) return false;
   if (tc.nbuf > 0) {
     if (2 * tc.TR * N16 + tc.NSTG * tc.TR * 16 > 512 || tc.niss < 1 || tc.niss > tc.TR ||
@@ -897,14 +1203,32 @@ bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg*
   return false;
 }
 
+// Geometry of the pixel-per-lane kernel (maps of at most 128 pixels): whole images per tile, the deepest ring that fits.
+bool hp_tcs_geometry(int blk, int H, int W, int nsets, int esets, TcCfg* tc) {
+  if (H < 1 || W < 1 || H * W > 128) return false;
+  TcCfg t;
+  t.TR = 1; t.nsets = nsets; t.npipe = esets; t.unit = 2; t.niss = 1; t.place = 0;
+  t.NSTG = TC_MAX_STG; t.BH = H; t.IWB = W;
+  t.ni = 128 / (H * W);
+  for (t.nbuf = TCD_MAXB; t.nbuf >= 2; --t.nbuf)
+    if (hp_tc_fits(blk, H, W, t)) {
+      *tc = t;
+      return true;
+    }
+  return false;
+}
+
 // Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.
 // Choices measured with tools/tc_sweep.py (profiles/): k-step work units everywhere; 4 rows per lane where two accumulator
-// sets of 4 x N16 columns fit TMEM next to a ring of >= 2 stages (N16 <= 48), else 2; maps narrower than 12 pixels (the
-// 6 x 6 / 8 x 8 blocks 12-15) stay on the CUDA-core kernel: with 96 channels only 2-4 images fit a tile and the
-// per-tile latency chain dominates (0.21 ms against 0.12 ms per block at 96 x 96 input, profiles/r01/tc_sweep_96_deep.log).
+// sets of 4 x N16 columns fit TMEM next to a ring of >= 2 stages (N16 <= 48), else 2; maps of at most 128 pixels (the
+// 6 x 6 / 8 x 8 blocks 12-15, 11 x 11 at 88 input) use the pixel-per-lane kernel: with halo buffers and 96 channels only 2-4
+// images fit a tile of the band kernel and the per-tile latency chain dominates (0.21 ms against 0.12 ms per block on the
+// CUDA cores at 96 x 96 input, profiles/r01/tc_sweep_96_deep.log).
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
-  if (kBlazeBlocks[blk].stride != 1 || W > 128 || W < 12 || H < 1) return false;
+  if (kBlazeBlocks[blk].stride != 1 || W > 128 || H < 1) return false;
   TcCfg a;
+  if (H * W <= 128) return hp_tcs_geometry(blk, H, W, 3, 2, tc);   // pixel-per-lane kernel (blocks 6-15 on 6 x 6 ... 11 x 11 maps)
+  if (W < 12) return false;
   const int n16 = (chan_pad(kBlazeBlocks[blk].cout) + 15) / 16 * 16;
   if (n16 == 48 && hp_tcd_geometry(blk, H, W, 2, 3, 1, &a)) {   // blocks 3, 4: 2 rows, 3 depthwise sets, issuers on sub-partition 3
     a.unit = 2; a.niss = 2; a.place = 1;

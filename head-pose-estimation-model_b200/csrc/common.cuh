@@ -157,6 +157,7 @@ struct TcCfg {
 };
 bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc);
 bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg* tc);
+bool hp_tcs_geometry(int blk, int H, int W, int nsets, int esets, TcCfg* tc);
 void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, float* blo);
 int hp_tc_weight_floats(int cinp, int coutp);
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc);

@@ -170,7 +170,8 @@ def test_preprocess_matches_reference_arithmetic():
 TC_GEOMETRIES = [(2, 2, 4, 1, 0), (2, 2, 3, 2, 0), (4, 2, 2, 2, 0), (4, 1, 2, 2, 0), (4, 1, 1, 1, 0),
                  (4, 0, 2, 2, 4), (4, 0, 2, 3, 3), (4, 2, 1, 2, 2), (2, 0, 2, 2, 4), (2, 0, 2, 3, 2), (2, 2, 1, 3, 4),
                  (2, 0, 2, 2, 4 + 32), (2, 0, 2, 3, 4 + 32), (2, 0, 1, 4, 3 + 32), (4, 0, 2, 2, 4 + 32), (4, 0, 2, 3, 4 + 32),   # + 32: k-step work units
-                 (4, 0, 2, 2, 4 + 32 + 128), (4, 0, 2, 2, 3 + 32 + 256), (2, 0, 2, 3, 4 + 32 + 128), (2, 0, 2, 3, 4 + 16 + 128)]   # + 64 n: n issuer warps
+                 (4, 0, 2, 2, 4 + 32 + 128), (4, 0, 2, 2, 3 + 32 + 256), (2, 0, 2, 3, 4 + 32 + 128), (2, 0, 2, 3, 4 + 16 + 128),   # + 64 n: n issuer warps
+                 (1, 0, 2, 3, 4), (1, 0, 1, 3, 2), (1, 0, 1, 2, 3), (1, 0, 2, 4, 4)]   # TR 1: pixel-per-lane kernel (maps of <= 128 pixels)
 TC_BLOCK_CHANNELS = {0: 24, 1: 28, 3: 36, 4: 42, 6: 56, 7: 64, 8: 72, 9: 80, 10: 88, 12: 96, 15: 96}
 
 
