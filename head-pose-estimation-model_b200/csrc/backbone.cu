@@ -647,6 +647,17 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
     bb.blk[i].bhi = base + o_bhi[i];
     bb.blk[i].blo = base + o_blo[i];
   }
+  {
+    size_t n = 0, off[16];
+    for (int i = 0; i < 16; ++i) { off[i] = n; n += 10 * (size_t)chan_pad(kBlazeBlocks[i].cin); }
+    bb.host_dw.assign(n, 0.f);
+    for (int i = 0; i < 16; ++i) {
+      const int cinp = chan_pad(kBlazeBlocks[i].cin);
+      memcpy(&bb.host_dw[off[i]], &host[o_dww[i]], 9 * (size_t)cinp * sizeof(float));
+      memcpy(&bb.host_dw[off[i] + 9 * (size_t)cinp], &host[o_dwb[i]], (size_t)cinp * sizeof(float));
+      bb.blk[i].h_dw = &bb.host_dw[off[i]];
+    }
+  }
   bb.det16_w = base + o_d16w;
   bb.det16_b = base + o_d16b;
   bb.det8_w = base + o_d8w;

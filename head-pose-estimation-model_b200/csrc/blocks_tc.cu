@@ -369,6 +369,16 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 // and is IWB >= W pixels wide with IWB * PS * 4 a multiple of 128 bytes, so every row (and the store source, the second
 // row) is 128-byte aligned.  The left neighbour of x = 0 (and the right neighbour of x = W - 1 when IWB == W) is SAME
 // padding: the lane multiplies whatever finite value it reads there by a zeroed depthwise weight.
+// Depthwise weights and bias as kernel-parameter constants: every lane of a warp needs the same 16 bytes, and a broadcast
+// LDS.128 still costs the 4 passes of a full-width one (measured: with the weights in shared memory the depthwise stage of
+// the pixel-per-lane kernel took ~9.5K clk per tile against 3.5K clk of input wavefronts).  From the constant bank they do not touch the
+// shared-memory pipe at all.
+template <int CINP>
+struct DwConst {
+  float w[9 * CINP];
+  float b[CINP];
+};
+
 #define TCD_MAXB 4
 struct TcdParams {
   const float *dww, *dwb, *pwb, *bhi, *blo;
@@ -387,7 +397,8 @@ struct TcdParams {
 // 96 TMEM lanes are active; the instructions around each tcgen05.mma then do not queue behind the worker warps (stem: 0.49 -> 0.42 ms).
 template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS, int PLACE>
 __global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), 1)
-blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcdParams p) {
+blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                        const __grid_constant__ DwConst<CINP> dwc, TcdParams p) {
   using G = TcGeom<CINP, COUTP>;
   constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
   constexpr uint32_t colA0 = 2 * TR * N16;                        // TMEM: D[0], D[1] (TR * N16 columns each), then the A ring
@@ -406,9 +417,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (TC_BAR_FLOATS - 1);
   float* s_bhi = smem + p.off_b;
   float* s_blo = s_bhi + K8 * N16;
-  float* s_dww = smem + p.off_w;
-  float* s_dwb = s_dww + 9 * CINP;
-  float* s_pwb = s_dwb + CINP;
+  float* s_pwb = smem + p.off_w + 10 * CINP;
   float* bufs = smem + p.off_pipe;
 
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -425,8 +434,6 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
     st4(s_bhi + i, ld4(p.bhi + i));
     st4(s_blo + i, ld4(p.blo + i));
   }
-  for (int i = tid * 4; i < 9 * CINP; i += nthr * 4) st4(s_dww + i, ld4(p.dww + i));
-  for (int i = tid * 4; i < CINP; i += nthr * 4) st4(s_dwb + i, ld4(p.dwb + i));
   for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
   // masked taps read (and multiply by zero) floats just outside the rows of a buffer: make every such float finite
   for (int i = p.off_w + 10 * CINP + COUTP + tid * 4; i < p.off_pipe + NBUF * p.buf_floats + 256; i += nthr * 4)
@@ -515,10 +522,10 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
         }
         float4 acc[TR], acc1[TR];
         if (warp_active && c4 < C4)
-          tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4, s_dww + c4 * 4, s_dwb + c4 * 4, row_pitch, mask_l, mask_r, acc);
+          tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4, dwc.w + c4 * 4, dwc.b + c4 * 4, row_pitch, mask_l, mask_r, acc);
         if (UNIT == 2) {
           if (warp_active && c4 + 1 < C4) {
-            tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4 + 4, s_dww + c4 * 4 + 4, s_dwb + c4 * 4 + 4, row_pitch, mask_l, mask_r, acc1);
+            tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4 + 4, dwc.w + c4 * 4 + 4, dwc.b + c4 * 4 + 4, row_pitch, mask_l, mask_r, acc1);
           } else {
 #pragma unroll
             for (int t = 0; t < TR; ++t) acc1[t] = make_float4(0.f, 0.f, 0.f, 0.f);   // K padding
@@ -664,8 +671,8 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
 // band kernel above needs halo rows / padded columns around every image, so only 2-4 images of 96 channels fit a tile
 // and the per-tile latency chain dominates.  Here a tile is NI = 128 / (H W) WHOLE images, stored compactly as
 // [NI H W pixels][PS floats] (one TMA box over the tensor viewed as [B H W][C]), lane <-> pixel, and every lane keeps
-// the shared-memory offsets of its 9 taps: a tap outside the image points at a pixel of zeros behind the tile (SAME
-// padding), so no weight masking and no halo.  Same warp roles and barriers as blaze_block_deep_kernel with one
+// the shared-memory offsets of its 9 taps: a tap outside the image points at zeros behind the tile (SAME padding), so
+// no weight masking and no halo.  Same warp roles and barriers as blaze_block_deep_kernel with one
 // accumulator row per lane (TR = 1); a work unit is a k-step (8 channels: 18 LDS.128 of inputs, 18 of weights).
 // The epilogue sets alternate tiles (set e owns accumulator buffer D[e] when NESETS == 2).
 struct TcsParams {
@@ -680,7 +687,8 @@ struct TcsParams {
 
 template <int CINP, int COUTP, int NSETS, int NESETS>
 __global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
-blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcsParams p) {
+blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                         const __grid_constant__ DwConst<CINP> dwc, TcsParams p) {
   using G = TcGeom<CINP, COUTP>;
   constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
   constexpr uint32_t colA0 = 2 * N16;                             // TMEM: D[0], D[1], then the A ring (16 columns per stage)
@@ -698,12 +706,11 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (TC_BAR_FLOATS - 1);
   float* s_bhi = smem + p.off_b;
   float* s_blo = s_bhi + K8 * N16;
-  float* s_dww = smem + p.off_w;
-  float* s_dwb = s_dww + 9 * CINP;
-  float* s_pwb = s_dwb + CINP;
+  float* s_pwb = smem + p.off_w + 10 * CINP;
   float* bufs = smem + p.off_pipe;
 
   const int tid = threadIdx.x, nthr = blockDim.x;
+  if (tid == 0 && p.trace != nullptr && blockIdx.x == 0 && p.trace_tiles > 0) p.trace[11] = clock64();
   const int warp = tid >> 5, lane_id = tid & 31;
   constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1, W_STORE = W_ISSUE + 2;
   const int NSTG = p.nstg, NBUF = p.nbuf;
@@ -712,11 +719,15 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
     st4(s_bhi + i, ld4(p.bhi + i));
     st4(s_blo + i, ld4(p.blo + i));
   }
-  for (int i = tid * 4; i < 9 * CINP; i += nthr * 4) st4(s_dww + i, ld4(p.dww + i));
-  for (int i = tid * 4; i < CINP; i += nthr * 4) st4(s_dwb + i, ld4(p.dwb + i));
   for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
-  // the pixel of zeros behind every tile (and the alignment padding) is written once; TMA and the epilogue never touch it
-  for (int i = tid * 4; i < NBUF * p.buf_floats; i += nthr * 4) st4(bufs + i, make_float4(0.f, 0.f, 0.f, 0.f));
+  // the zeros behind every tile are written once; TMA and the epilogue never touch them
+  {
+    const int zf = p.buf_floats - p.rows * PS;
+    for (int i = tid * 4; i < NBUF * zf; i += nthr * 4) {
+      const int b = i / zf;
+      st4(bufs + b * p.buf_floats + p.rows * PS + (i - b * zf), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
   fence_async_smem();
   if (tid == 0) {
     for (int b = 0; b < NBUF; ++b) {
@@ -756,14 +767,18 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
     if (warp < W_EPI) {
       // =============================================================== depthwise sets (k-step units, global round-robin)
       const int set = warp >> 2;
-      int off[9];                                                  // tap offsets in floats; p.rows * PS = the pixel of zeros
+      // tap offsets in floats.  A tap outside the image reads zeros behind the tile, at the 16-byte chunk (mod 8) the
+      // in-bounds address would have had: the 8 lanes of a quarter warp then still hit 8 different bank groups (with one
+      // shared pixel of zeros the edge lanes collided with their neighbours: 2 wavefronts per LDS.128 quarter, DW 1.8x slower)
+      int off[9];
       {
         const int r = lane % p.P, y = r / p.W, x = r - y * p.W;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const int dy = t / 3 - 1, dx = t % 3 - 1;
           const bool ok = active && y + dy >= 0 && y + dy < p.H && x + dx >= 0 && x + dx < p.W;
-          off[t] = (ok ? lane + dy * p.W + dx : p.rows) * PS;
+          const int q = lane + dy * p.W + dx;                      // neighbour pixel of the tile (may be < 0 or another image)
+          off[t] = ok ? q * PS : p.rows * PS + ((q * (PS / 4)) & 7) * 4;
         }
       }
       const uint32_t n_units = (uint32_t)my_tiles * KS;
@@ -786,12 +801,12 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
         if (warp_active) {
           const int c = 8 * ks;
           const bool two = (2 * ks + 1 < C4);                      // the second 4-channel chunk of the k-step exists
-          float4 a0 = ld4(s_dwb + c), a1 = two ? ld4(s_dwb + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 a0 = ld4(dwc.b + c), a1 = two ? ld4(dwc.b + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const float* q = buf + off[t] + c;
-            a0 = fma4(ld4(q), ld4(s_dww + t * CINP + c), a0);
-            if (two) a1 = fma4(ld4(q + 4), ld4(s_dww + t * CINP + c + 4), a1);
+            a0 = fma4(ld4(q), ld4(dwc.w + t * CINP + c), a0);
+            if (two) a1 = fma4(ld4(q + 4), ld4(dwc.w + t * CINP + c + 4), a1);
           }
           const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
@@ -857,7 +872,7 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
           mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
           tc_fence_after();
         }
-        stamp(i, 11);
+        if (i > 0) stamp(i, 11);                                     // slot 11 of tile 0: kernel entry
 #pragma unroll 1
         for (int ks = 0; ks < KS; ++ks, ++use) {
           const uint32_t s = use % NSTG;
@@ -1016,19 +1031,22 @@ int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, con
   CUtensorMap tin, tout;
   HP_TRY(make_map(&tin, in, B, H, W, CINP, tc.ni, tc.BH + 2, tc.IWB, G::PS));
   HP_TRY(make_map(&tout, out, B, H, W, COUTP, 1, tc.BH, tc.IWB, G::PS));
+  HP_REQUIRE(w.h_dw != nullptr, HP_ERR_STATE, "tc deep block: host copy of the depthwise weights missing");
+  DwConst<CINP> dwc;
+  memcpy(dwc.w, w.h_dw, sizeof(dwc));
   auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSETS, NESETS, UNIT, NISS, PLACE>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), smem, st>>>(tin, tout, p);
+  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), smem, st>>>(tin, tout, dwc, p);
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;
 }
 
 
-// buffer of the pixel-per-lane kernel: rows pixels + the pixel of zeros, padded to 1 KB
-inline int tcs_buf_floats(int rows, int PS) { return align_up((rows + 1) * PS, 256); }
+// buffer of the pixel-per-lane kernel: rows pixels + zeros for the out-of-image taps (a pixel + 8 chunks), padded to 1 KB
+inline int tcs_buf_floats(int rows, int PS) { return align_up((rows + 1) * PS + 32, 256); }
 
 template <int CINP, int COUTP, int NSETS, int NESETS>
 int launch_small(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
@@ -1051,11 +1069,14 @@ int launch_small(hp_ctx* h, const float* in, float* out, int B, int H, int W, co
   CUtensorMap tin, tout;
   HP_TRY(make_map(&tin, in, 1, 1, B * p.P, CINP, 1, 1, p.rows, G::PS));
   HP_TRY(make_map(&tout, out, 1, 1, B * p.P, COUTP, 1, 1, p.rows, G::PS));
+  HP_REQUIRE(w.h_dw != nullptr, HP_ERR_STATE, "tc small block: host copy of the depthwise weights missing");
+  DwConst<CINP> dwc;
+  memcpy(dwc.w, w.h_dw, sizeof(dwc));
   auto kern = blaze_block_small_kernel<CINP, COUTP, NSETS, NESETS>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + 96, smem, st>>>(tin, tout, p);
+  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + 96, smem, st>>>(tin, tout, dwc, p);
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;

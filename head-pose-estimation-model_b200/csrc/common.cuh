@@ -77,11 +77,13 @@ static inline int chan_pad(int c) { return (c + 3) & ~3; }
 struct BlockWeights {
   const float *dww, *dwb, *pww, *pwb;  // [9][CINP], [CINP], [CINP][COUTP], [COUTP] (zero padded)
   const float *bhi, *blo;              // pointwise weights split into TF32 hi / lo parts, [K8/4][N16][4] (blocks_tc.cu)
+  const float* h_dw;                   // HOST copy of [9][CINP] dww + [CINP] dwb: passed as kernel-parameter constants
 };
 
 struct Backbone {
   bool loaded = false;
   DevBuf arena;
+  std::vector<float> host_dw;     // depthwise weights + bias of the 16 blocks (BlockWeights::h_dw points into it)
   const float* stem_w = nullptr;  // [75][24]
   const float* stem_b = nullptr;
   const float *stem_bhi = nullptr, *stem_blo = nullptr;  // stem kernel split into TF32 hi / lo parts in GEMM layout (stem_tc.cu)

@@ -38,6 +38,10 @@ for rep in range(2):
 _lib.check(lib.hp_debug_tc_trace(ctx.handle, None, 0))
 t = trace.cpu().numpy()
 t0 = t[0, 0]
+if os.environ.get("TC_RAW"):   # absolute stamps of the first tiles relative to slot 11 of tile 0 (kernel entry in the pixel-per-lane kernel)
+    print("tile: slots 0..11 (clk after t[0][11])")
+    for i in range(int(os.environ["TC_RAW"])):
+        print(i, " ".join(f"{int(v - t[0, 11]):7d}" for v in t[i]))
 print("per tile (clk): load = issue->full | dw0/dwL = full->set0/last set done | a_full = last set done->issuer sees last a_full | mma = ->d_full seen by epilogue")
 print("tile   load   dw0   dwL a_full   mma   epi st_wait store | period  issuer: D-free wait (dempty->first a_full)")
 for i in range(8, NT):
