@@ -372,7 +372,8 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 // Depthwise weights and bias as kernel-parameter constants: every lane of a warp needs the same 16 bytes, and a broadcast
 // LDS.128 still costs the 4 passes of a full-width one (measured: with the weights in shared memory the depthwise stage of
 // the pixel-per-lane kernel took ~9.5K clk per tile against 3.5K clk of input wavefronts).  From the constant bank they do not touch the
-// shared-memory pipe at all.
+// shared-memory pipe at all.  (Tried in the band kernel too: there the weights are reused over TR rows and the constant
+// loads cost more than they save -- blocks 0 / 1 went from 0.43 to 0.45 ms -- so it keeps them in shared memory.)
 template <int CINP>
 struct DwConst {
   float w[9 * CINP];
@@ -397,8 +398,7 @@ struct TcdParams {
 // 96 TMEM lanes are active; the instructions around each tcgen05.mma then do not queue behind the worker warps (stem: 0.49 -> 0.42 ms).
 template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS, int PLACE>
 __global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), 1)
-blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
-                        const __grid_constant__ DwConst<CINP> dwc, TcdParams p) {
+blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcdParams p) {
   using G = TcGeom<CINP, COUTP>;
   constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
   constexpr uint32_t colA0 = 2 * TR * N16;                        // TMEM: D[0], D[1] (TR * N16 columns each), then the A ring
@@ -417,7 +417,9 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (TC_BAR_FLOATS - 1);
   float* s_bhi = smem + p.off_b;
   float* s_blo = s_bhi + K8 * N16;
-  float* s_pwb = smem + p.off_w + 10 * CINP;
+  float* s_dww = smem + p.off_w;
+  float* s_dwb = s_dww + 9 * CINP;
+  float* s_pwb = s_dwb + CINP;
   float* bufs = smem + p.off_pipe;
 
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -434,6 +436,8 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
     st4(s_bhi + i, ld4(p.bhi + i));
     st4(s_blo + i, ld4(p.blo + i));
   }
+  for (int i = tid * 4; i < 9 * CINP; i += nthr * 4) st4(s_dww + i, ld4(p.dww + i));
+  for (int i = tid * 4; i < CINP; i += nthr * 4) st4(s_dwb + i, ld4(p.dwb + i));
   for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
   // masked taps read (and multiply by zero) floats just outside the rows of a buffer: make every such float finite
   for (int i = p.off_w + 10 * CINP + COUTP + tid * 4; i < p.off_pipe + NBUF * p.buf_floats + 256; i += nthr * 4)
@@ -522,10 +526,10 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
         }
         float4 acc[TR], acc1[TR];
         if (warp_active && c4 < C4)
-          tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4, dwc.w + c4 * 4, dwc.b + c4 * 4, row_pitch, mask_l, mask_r, acc);
+          tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4, s_dww + c4 * 4, s_dwb + c4 * 4, row_pitch, mask_l, mask_r, acc);
         if (UNIT == 2) {
           if (warp_active && c4 + 1 < C4) {
-            tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4 + 4, dwc.w + c4 * 4 + 4, dwc.b + c4 * 4 + 4, row_pitch, mask_l, mask_r, acc1);
+            tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4 + 4, s_dww + c4 * 4 + 4, s_dwb + c4 * 4 + 4, row_pitch, mask_l, mask_r, acc1);
           } else {
 #pragma unroll
             for (int t = 0; t < TR; ++t) acc1[t] = make_float4(0.f, 0.f, 0.f, 0.f);   // K padding
@@ -1031,14 +1035,11 @@ int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, con
   CUtensorMap tin, tout;
   HP_TRY(make_map(&tin, in, B, H, W, CINP, tc.ni, tc.BH + 2, tc.IWB, G::PS));
   HP_TRY(make_map(&tout, out, B, H, W, COUTP, 1, tc.BH, tc.IWB, G::PS));
-  HP_REQUIRE(w.h_dw != nullptr, HP_ERR_STATE, "tc deep block: host copy of the depthwise weights missing");
-  DwConst<CINP> dwc;
-  memcpy(dwc.w, w.h_dw, sizeof(dwc));
   auto kern = blaze_block_deep_kernel<CINP, COUTP, TR, NSETS, NESETS, UNIT, NISS, PLACE>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), smem, st>>>(tin, tout, dwc, p);
+  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), smem, st>>>(tin, tout, p);
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;

@@ -175,5 +175,13 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
 
 // dense_tc.cu: Dense / 1x1-conv layers of the heads as a 3xTF32 tcgen05 GEMM (forward inference)
 bool hp_dense_tc_supported(const float* x, int M, int K, int ldx, int N, bool transpose_w, bool accumulate);
+struct DenseTail {                 // narrow layer fused behind a dense layer: z = act2(y W2[N][ldw2] + b2), n2 <= 4
+  const float *W2, *b2;
+  int n2, ldw2, act2;
+  DenseOut out;                    // destination of z (col_begin / col_end unused)
+};
+bool hp_dense_tc_tail_supported(const float* x, int M, int K, int ldx, int N, int n2);
+int hp_launch_dense_tc_tail(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
+                            const DenseTail& tail, cudaStream_t st);
 int hp_launch_dense_tc(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
                        const DenseOut* outs, int n_outs, cudaStream_t st);

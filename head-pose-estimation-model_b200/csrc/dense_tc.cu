@@ -13,6 +13,9 @@
 //   gather sets        : lane copies 16 floats (2 k-steps) of its row, splits them into TF32 hi / lo, tcgen05.st
 //   issuer   (1 thread): 3 tcgen05.mma per k-step (A from TMEM, W_hi / W_lo from smem; W is split in the kernel prologue)
 //   epilogue sets      : tcgen05.ld D + bias -> staging tile -> activation + coalesced scatter to the output segments
+// TAIL variant: a following narrow layer z = act2(y W2 + b2) with at most 4 outputs (the 64 -> 3 / 128 -> 3 regressor
+// outputs) is applied to the accumulator row in registers; y is never written (at batch 4096 the 64-channel
+// intermediate of the Model-88 head is 268 MB written and read back).  The epilogue sets then alternate tiles.
 #include "tc_common.cuh"
 
 namespace {
@@ -30,6 +33,10 @@ struct DenseTcParams {
   int n_outs;
   DenseOut outs[2];
   unsigned magic[2];
+  // TAIL variant
+  const float *W2, *b2;               // [N][ldw2], [n2]
+  int n2, ldw2, act2, off_tail;       // off_tail: W2 rows padded to float4, [N16][4]
+  DenseOut out2;
 };
 
 __device__ __forceinline__ float dt_act(int act, float v) {
@@ -42,7 +49,7 @@ __device__ __forceinline__ float dt_act(int act, float v) {
   }
 }
 
-template <int NSETS, int NESETS>
+template <int NSETS, int NESETS, bool TAIL>
 __global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
   extern __shared__ __align__(1024) float smem[];
@@ -77,6 +84,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
     s_blo[idx] = w - __uint_as_float(hi);
   }
   for (int i = tid; i < N16; i += nthr) s_bias[i] = (p.b && i < p.N) ? p.b[i] : 0.f;
+  float* s_tail = smem + p.off_tail;                                        // [N16][4]: W2 row of every hidden channel
+  if (TAIL)
+    for (int i = tid; i < N16 * 4; i += nthr) {
+      const int c = i >> 2, j = i & 3;
+      s_tail[i] = (c < p.N && j < p.n2) ? p.W2[(long long)c * p.ldw2 + j] : 0.f;
+    }
   fence_async_smem();
   if (tid == 0) {
     for (int b = 0; b < NBUF; ++b) {
@@ -89,7 +102,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
     }
     for (int d = 0; d < 2; ++d) {
       mbar_init(&bar_dfull[d], 1);
-      mbar_init(&bar_dempty[d], 128 * NESETS);
+      mbar_init(&bar_dempty[d], TAIL ? 128 : 128 * NESETS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -152,6 +165,57 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
           mbar_arrive(pending);
           pending = nullptr;
           mbar_arrive(&bar_infree[cur_b]);   // this thread reads nothing more from the tile
+        }
+      }
+    } else if (TAIL) {
+      // =============================================================== epilogue sets, fused narrow layer: tile i -> set i % NESETS
+      const int eset = (warp - W_EPI) >> 2;
+      float b2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b2[j] = (p.b2 && j < p.n2) ? p.b2[j] : 0.f;
+      for (int i = eset; i < my_tiles; i += NESETS) {
+        const int d = i & 1;
+        const long long m = ((long long)blockIdx.x + (long long)i * gridDim.x) * DT_ROWS + lane;
+        mbar_wait(&bar_dfull[d], (i >> 1) & 1);
+        tc_fence_after();
+        float4 acc = make_float4(b2[0], b2[1], b2[2], b2[3]);
+        for (int g = 0; g * 32 < N16; ++g) {
+          uint32_t v[32];
+          if (g * 32 + 32 <= N16) {
+            tmem_ld32(tlane + d * N16 + g * 32, v);
+          } else {
+            uint32_t hlf[16];
+            tmem_ld16(tlane + d * N16 + g * 32, hlf);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int cmax = (N16 - g * 32 < 32) ? N16 - g * 32 : 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j * 4 < cmax) {                                   // padded hidden channels (>= N) have zero W2 rows
+              const int c = g * 32 + j * 4;
+              const float4 bb = ld4(s_bias + c);
+              const float y0 = dt_act(p.act, __uint_as_float(v[j * 4 + 0]) + bb.x), y1 = dt_act(p.act, __uint_as_float(v[j * 4 + 1]) + bb.y);
+              const float y2 = dt_act(p.act, __uint_as_float(v[j * 4 + 2]) + bb.z), y3 = dt_act(p.act, __uint_as_float(v[j * 4 + 3]) + bb.w);
+              const float4 w0 = ld4(s_tail + c * 4), w1 = ld4(s_tail + c * 4 + 4), w2 = ld4(s_tail + c * 4 + 8), w3 = ld4(s_tail + c * 4 + 12);
+              acc.x = fmaf(y0, w0.x, acc.x); acc.y = fmaf(y0, w0.y, acc.y); acc.z = fmaf(y0, w0.z, acc.z); acc.w = fmaf(y0, w0.w, acc.w);
+              acc.x = fmaf(y1, w1.x, acc.x); acc.y = fmaf(y1, w1.y, acc.y); acc.z = fmaf(y1, w1.z, acc.z); acc.w = fmaf(y1, w1.w, acc.w);
+              acc.x = fmaf(y2, w2.x, acc.x); acc.y = fmaf(y2, w2.y, acc.y); acc.z = fmaf(y2, w2.z, acc.z); acc.w = fmaf(y2, w2.w, acc.w);
+              acc.x = fmaf(y3, w3.x, acc.x); acc.y = fmaf(y3, w3.y, acc.y); acc.z = fmaf(y3, w3.z, acc.z); acc.w = fmaf(y3, w3.w, acc.w);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bar_dempty[d]);
+        if (m < p.M) {
+          const DenseOut& dd = p.out2;
+          const long long img = m / dd.rows_per_img;
+          float* dst = dd.ptr + img * dd.img_stride + (m - img * dd.rows_per_img) * (long long)dd.row_stride;
+          const float z[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < p.n2) dst[j] = dt_act(p.act2, z[j]);
         }
       }
     } else {
@@ -263,7 +327,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
 }  // namespace
 
 // shared-memory layout (floats); returns the bytes needed with `nbuf` input buffers
-static size_t dense_tc_layout(int K, int N, int nbuf, DenseTcParams* p) {
+static size_t dense_tc_layout(int K, int N, int nbuf, bool tail, DenseTcParams* p) {
   p->K8 = round_up(K, 8); p->KS = p->K8 / 8; p->N16 = round_up(N, 16);
   p->KPAD = ((p->K8 / 4) | 1) * 4;
   p->OS = ((p->N16 / 4) | 1) * 4;
@@ -275,7 +339,8 @@ static size_t dense_tc_layout(int K, int N, int nbuf, DenseTcParams* p) {
   p->off_rowoff = off;
   off += 4 * DT_ROWS;                              // 2 x 128 long long
   p->off_stage = off;
-  off = tc_align_up(off + DT_ROWS * p->OS, 256);
+  p->off_tail = off;
+  off = tc_align_up(off + (tail ? 4 * p->N16 : DT_ROWS * p->OS), 256);   // the fused narrow layer needs no staging tile
   p->off_in = off;
   p->in_floats = tc_align_up(DT_ROWS * p->KPAD, 256);
   return (size_t)(off + nbuf * p->in_floats) * sizeof(float);
@@ -283,22 +348,34 @@ static size_t dense_tc_layout(int K, int N, int nbuf, DenseTcParams* p) {
 
 // true when the layer can run on the tensor-core kernel: forward, plain weights, 16-byte aligned rows, at least 3 k-steps
 // (every gather set must own a k-step of every tile), two input buffers next to the split weights in shared memory
-bool hp_dense_tc_supported(const float* x, int M, int K, int ldx, int N, bool transpose_w, bool accumulate) {
-  if (transpose_w || accumulate || M < 4 * DT_ROWS || K % 4 != 0 || K < 20 || K > 128 || N < 1 || N > 128 || ldx % 4 != 0 ||
+static bool dense_tc_ok(const float* x, int M, int K, int ldx, int N, bool tail) {
+  if (M < 4 * DT_ROWS || K % 4 != 0 || K < 20 || K > 128 || N < 1 || N > 128 || ldx % 4 != 0 ||
       (((uintptr_t)x) & 15) != 0)
     return false;
   DenseTcParams p;
-  return dense_tc_layout(K, N, 2, &p) <= 227 * 1024 && 2 * p.N16 + DT_MAXSTG * 16 <= 512;
+  return dense_tc_layout(K, N, 2, tail, &p) <= 227 * 1024 && 2 * p.N16 + DT_MAXSTG * 16 <= 512;
+}
+bool hp_dense_tc_supported(const float* x, int M, int K, int ldx, int N, bool transpose_w, bool accumulate) {
+  return !transpose_w && !accumulate && dense_tc_ok(x, M, K, ldx, N, false);
+}
+// y = act(x W + b) followed by z = act2(y W2 + b2) with n2 <= 4 outputs, y not stored
+bool hp_dense_tc_tail_supported(const float* x, int M, int K, int ldx, int N, int n2) {
+  return n2 >= 1 && n2 <= 4 && dense_tc_ok(x, M, K, ldx, N, true);
 }
 
-int hp_launch_dense_tc(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
-                       const DenseOut* outs, int n_outs, cudaStream_t st) {
-  HP_REQUIRE(n_outs >= 1 && n_outs <= 2, HP_ERR_INVALID, "dense tc: 1 or 2 output segments");
+static int dense_tc_launch(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
+                           const DenseOut* outs, int n_outs, const DenseTail* tail, cudaStream_t st) {
+  HP_REQUIRE(tail ? n_outs == 0 : (n_outs >= 1 && n_outs <= 2), HP_ERR_INVALID, "dense tc: 1 or 2 output segments");
   DenseTcParams p;
+  p.W2 = nullptr; p.b2 = nullptr; p.n2 = 0; p.ldw2 = 0; p.act2 = 0; p.out2 = DenseOut{};
+  if (tail) {
+    HP_REQUIRE(tail->n2 >= 1 && tail->n2 <= 4 && tail->W2 && tail->out.ptr, HP_ERR_INVALID, "dense tc: fused layer needs 1..4 outputs");
+    p.W2 = tail->W2; p.b2 = tail->b2; p.n2 = tail->n2; p.ldw2 = tail->ldw2; p.act2 = tail->act2; p.out2 = tail->out;
+  }
   p.W = W; p.b = b; p.M = M; p.K = K; p.N = N; p.ldw = ldw; p.act = act;
   p.nbuf = DT_MAXB;
-  while (p.nbuf > 2 && dense_tc_layout(K, N, p.nbuf, &p) > 200 * 1024) --p.nbuf;
-  const size_t smem = dense_tc_layout(K, N, p.nbuf, &p);
+  while (p.nbuf > 2 && dense_tc_layout(K, N, p.nbuf, tail != nullptr, &p) > 200 * 1024) --p.nbuf;
+  const size_t smem = dense_tc_layout(K, N, p.nbuf, tail != nullptr, &p);
   p.n_tiles = ceil_div(M, DT_ROWS);
   p.nstg = DT_MAXSTG;
   HP_REQUIRE(2 * p.N16 + p.nstg * 16 <= 512 && p.KPAD <= 256, HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);
@@ -321,16 +398,30 @@ int hp_launch_dense_tc(hp_ctx* h, const float* x, int M, int K, int ldx, const f
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
   // narrow layers are bound by the gather (3 sets); wide ones by the epilogue (2 sets)
-  if (p.N16 <= 32) {
-    auto kern = dense_tc_kernel<3, 1>;
+  if (tail) {
+    auto kern = dense_tc_kernel<2, 2, true>;
+    HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<(unsigned)grid, 128 * 2 + 128 * 2 + 96, smem, st>>>(tin, p);
+  } else if (p.N16 <= 32) {
+    auto kern = dense_tc_kernel<3, 1, false>;
     HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kern<<<(unsigned)grid, 128 * 3 + 128 * 1 + 96, smem, st>>>(tin, p);
   } else {
-    auto kern = dense_tc_kernel<2, 2>;
+    auto kern = dense_tc_kernel<2, 2, false>;
     HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kern<<<(unsigned)grid, 128 * 2 + 128 * 2 + 96, smem, st>>>(tin, p);
   }
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;
+}
+
+int hp_launch_dense_tc(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
+                       const DenseOut* outs, int n_outs, cudaStream_t st) {
+  return dense_tc_launch(h, x, M, K, ldx, W, ldw, b, N, act, outs, n_outs, nullptr, st);
+}
+
+int hp_launch_dense_tc_tail(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
+                            const DenseTail& tail, cudaStream_t st) {
+  return dense_tc_launch(h, x, M, K, ldx, W, ldw, b, N, act, nullptr, 0, &tail, st);
 }

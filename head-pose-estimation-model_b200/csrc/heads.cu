@@ -699,6 +699,9 @@ struct hp_head {
   std::vector<size_t> reg_off;        // float offsets into acts/gacts (reg 0 unused: external input)
   std::vector<size_t> stat_off;       // per op: layer-norm stats offset in ws
   std::vector<MhaWs> mha;             // per op
+  std::vector<int> nreads;            // per register: ops that read it (+ 1 for the output register)
+  std::vector<int> alias;             // per register: the register that holds its values after the latest forward
+                                      // (inference skips the SpatialDropout2D copies; identity after a training forward)
   uint32_t step = 0;
   bool has_state = false;
   float last_sums[4] = {0, 0, 0, 0};
@@ -717,6 +720,14 @@ int hp_head_create_impl(hp_ctx* h, const hp_head_op* ops, int n_ops, const hp_he
   hd->ops.assign(ops, ops + n_ops);
   hd->regs.assign(regs, regs + n_regs);
   hd->out_reg = out_reg;
+  hd->nreads.assign(n_regs, 0);
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].in0 >= 0 && ops[i].in0 < n_regs) hd->nreads[ops[i].in0]++;
+    if ((ops[i].op == HP_OP_ADD || ops[i].op == HP_OP_MULCH) && ops[i].in1 >= 0 && ops[i].in1 < n_regs) hd->nreads[ops[i].in1]++;
+  }
+  hd->nreads[out_reg]++;
+  hd->alias.resize(n_regs);
+  for (int r = 0; r < n_regs; ++r) hd->alias[r] = r;
   hd->n_params = n_params;
   hd->in_channels = regs[0].channels;
   std::vector<float> l2(n_params, 0.f);
@@ -841,7 +852,8 @@ static size_t attn_smem(int T, int d) { return ((size_t)2 * T * (d + 1) + 4 * (s
 static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, int T, bool training, uint64_t seed,
                         cudaStream_t st) {
   float* A = hd->acts.f();
-  auto R = [&](int r) -> const float* { return r == 0 ? feat : A + hd->reg_off[r]; };
+  for (size_t r = 0; r < hd->alias.size(); ++r) hd->alias[r] = (int)r;
+  auto R = [&](int r) -> const float* { return hd->alias[r] == 0 ? feat : A + hd->reg_off[hd->alias[r]]; };
   auto RW = [&](int r) -> float* { return A + hd->reg_off[r]; };
   // a training step keeps plain fp32 FMA accumulation in forward and backward; inference may use the 3xTF32 kernel
   struct DenseTcScope {
@@ -856,6 +868,23 @@ static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, in
     const long long total = rows_out * C;
     switch (o.op) {
       case HP_OP_DENSE: {
+        if (!training && h->impl == HP_IMPL_FAST && h->dense_tc) {
+          // inference: Dense -> [SpatialDropout2D] -> Dense with at most 4 outputs (the yaw / pitch / roll layer) in one
+          // kernel when nothing else reads the hidden activations; they are then never written (dense_tc.cu, TAIL)
+          size_t k = i + 1;
+          int cur = o.out;
+          while (k < hd->ops.size() && hd->ops[k].op == HP_OP_DROPOUT && hd->ops[k].in0 == cur && hd->nreads[cur] == 1) cur = hd->ops[k++].out;
+          if (k < hd->ops.size() && hd->ops[k].op == HP_OP_DENSE && hd->ops[k].in0 == cur && hd->nreads[cur] == 1 && hd->ops[k].cout <= 4 &&
+              hp_dense_tc_tail_supported(R(o.in0), (int)rows_out, o.cin, o.cin, o.cout, hd->ops[k].cout)) {
+            const hp_head_op& o2 = hd->ops[k];
+            DenseTail tail{hd->params.f() + o2.w_off, hd->params.f() + o2.b_off, o2.cout, o2.cout, o2.act,
+                           DenseOut{RW(o2.out), 0, o2.cout, (int)std::max<long long>(rows_out, 1), 0, o2.cout}};
+            HP_TRY(hp_launch_dense_tc_tail(h, R(o.in0), (int)rows_out, o.cin, o.cin, hd->params.f() + o.w_off, o.cout,
+                                           hd->params.f() + o.b_off, o.cout, o.act, tail, st));
+            i = k;
+            break;
+          }
+        }
         DenseOut d{RW(o.out), 0, o.cout, (int)std::max<long long>(rows_out, 1), 0, o.cout};
         HP_TRY(hp_launch_dense(h, R(o.in0), (int)rows_out, o.cin, o.cin, hd->params.f() + o.w_off, o.cout,
                                hd->params.f() + o.b_off, o.cout, o.act, false, &d, 1, false, st));
@@ -894,6 +923,9 @@ static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, in
         if (training && o.fparam > 0.f) {
           dropout_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), RW(o.out), rows_out, C, T, hd->regs[o.out].per_image,
                                                         o.fparam, seed, hd->step, (uint32_t)o.op_id, 0);
+        } else if (!training) {
+          hd->alias[o.out] = hd->alias[o.in0];   // identity at inference: readers of o.out are pointed at the source, no copy
+          break;
         } else {
           HP_CUDA(cudaMemcpyAsync(RW(o.out), R(o.in0), total * sizeof(float), cudaMemcpyDeviceToDevice, st));
         }
@@ -1091,7 +1123,8 @@ int hp_head_forward_impl(hp_ctx* h, hp_head* hd, const float* feat, int B, int H
   HP_TRY(head_plan(hd, B, T, false));
   HP_TRY(head_forward(h, hd, feat, B, T, false, 0, st));
   const long long total = (long long)B * T * hd->regs[hd->out_reg].channels;
-  HP_CUDA(cudaMemcpyAsync(out, hd->acts.f() + hd->reg_off[hd->out_reg], total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int src = hd->alias[hd->out_reg];
+  HP_CUDA(cudaMemcpyAsync(out, src == 0 ? feat : hd->acts.f() + hd->reg_off[src], total * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return HP_OK;
 }
 
@@ -1109,7 +1142,7 @@ int hp_head_train_step_impl(hp_ctx* h, hp_head* hd, const float* x, const float*
   HP_TRY(head_forward(h, hd, x, n, T, update, seed, st));
   const long long total = (long long)n * T * Cout;
   float* sums = hd->grads.f() + np;
-  const float* pred = hd->acts.f() + hd->reg_off[hd->out_reg];
+  const float* pred = hd->alias[hd->out_reg] == 0 ? x : hd->acts.f() + hd->reg_off[hd->alias[hd->out_reg]];
   if (update) {
     size_t arena = hd->gacts.bytes;
     HP_CUDA(cudaMemsetAsync(hd->gacts.p, 0, arena, st));
