@@ -122,6 +122,8 @@ _PROTOS = {
     "hp_debug_tile_report": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_debug_set_stem_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_debug_tc_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hp_debug_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "hp_debug_set_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_backbone_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }

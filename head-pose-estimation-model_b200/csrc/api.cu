@@ -131,6 +131,20 @@ int hp_debug_tc_trace(hp_handle h, long long* dev_buf, int max_tiles) {
   h->tc_trace = dev_buf; h->tc_trace_tiles = dev_buf ? max_tiles : 0;
   return HP_OK;
 }
+int hp_debug_dense(hp_handle h, const float* x, int M, int K, const float* W, const float* b, int N, int act, float* y,
+                   const float* W2, const float* b2, int n2, int act2, void* stream) {
+  HP_ENTER(h);
+  HP_REQUIRE(x && W && y && M > 0 && K > 0 && N > 0, HP_ERR_INVALID, "hp_debug_dense: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (W2) {   // y receives z = act2(act(x W + b) W2 + b2), [M][n2]
+    HP_REQUIRE(h->impl == HP_IMPL_FAST && hp_dense_tc_tail_supported(x, M, K, K, N, n2), HP_ERR_UNSUPPORTED,
+               "hp_debug_dense: %d x %d -> %d -> %d is not a fused tensor-core shape", M, K, N, n2);
+    DenseTail tail{W2, b2, n2, n2, act2, DenseOut{y, 0, n2, M, 0, n2}};
+    return hp_launch_dense_tc_tail(h, x, M, K, K, W, N, b, N, act, tail, st);
+  }
+  DenseOut d{y, 0, N, M, 0, N};
+  return hp_launch_dense(h, x, M, K, K, W, N, b, N, act, false, &d, 1, false, st);
+}
 int hp_debug_tile_report(hp_handle h, int* report16x8) {
   HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
   h->tile_report = report16x8;

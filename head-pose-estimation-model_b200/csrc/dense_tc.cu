@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int DT_MAXB = 4, DT_MAXSTG = 4, DT_BAR_FLOATS = 64;
+constexpr int DT_MAXB = 4, DT_MAXSTG = 4, DT_BAR_FLOATS = 64, DT_MAXKU = 4;
 constexpr int DT_ROWS = 128;
 
 struct DenseTcParams {
@@ -28,23 +28,65 @@ struct DenseTcParams {
   int M, K, N, ldw, act;
   int K8, KS, N16, KPAD, OS;          // OS: staging row stride (odd number of 16-byte chunks)
   int n_tiles, nstg, nbuf;
+  int ku, upt;                        // k-steps per gather unit (ring stage = 16 ku TMEM columns), units per tile
   uint32_t load_bytes;
   int off_b, off_bias, off_rowoff, off_stage, off_in, in_floats;
   int n_outs;
   DenseOut outs[2];
-  unsigned magic[2];
+  unsigned magic[2], magic4[2];
+  int vec4[2];                        // the segment can be written as float4 (width, offsets and strides multiples of 4)
   // TAIL variant
   const float *W2, *b2;               // [N][ldw2], [n2]
   int n2, ldw2, act2, off_tail;       // off_tail: W2 rows padded to float4, [N16][4]
   DenseOut out2;
+  long long* trace;                   // optional clock64 stamps of CTA 0, 12 slots per tile (tools/dense_trace.py)
+  int trace_tiles;
 };
 
+// compile-time activation for the unrolled epilogue loops (a switch per element became a jump table per element)
+template <int ACT>
+__device__ __forceinline__ float dt_act_c(float v) {
+  if (ACT == HP_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == HP_ACT_TANH) return tanhf(v);
+  if (ACT == HP_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  if (ACT == HP_ACT_SOFTSIGN) return v / (1.f + fabsf(v));
+  return v;
+}
+// hidden channels [c0, c0 + 4 nq) of one row: y = act(D + bias), acc += y W2 (W2 rows as float4 in shared memory)
+template <int ACT>
+__device__ __forceinline__ void dt_tail_group(const uint32_t (&v)[32], int nq, const float* s_bias_c, const float* s_tail_c, float4& acc) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < nq) {
+      const float4 bb = ld4(s_bias_c + j * 4);
+      const float y[4] = {dt_act_c<ACT>(__uint_as_float(v[j * 4 + 0]) + bb.x), dt_act_c<ACT>(__uint_as_float(v[j * 4 + 1]) + bb.y),
+                          dt_act_c<ACT>(__uint_as_float(v[j * 4 + 2]) + bb.z), dt_act_c<ACT>(__uint_as_float(v[j * 4 + 3]) + bb.w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 w = ld4(s_tail_c + (j * 4 + e) * 4);
+        acc.x = fmaf(y[e], w.x, acc.x); acc.y = fmaf(y[e], w.y, acc.y); acc.z = fmaf(y[e], w.z, acc.z); acc.w = fmaf(y[e], w.w, acc.w);
+      }
+    }
+  }
+}
 __device__ __forceinline__ float dt_act(int act, float v) {
   switch (act) {
     case HP_ACT_RELU: return fmaxf(v, 0.f);
     case HP_ACT_TANH: return tanhf(v);
     case HP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     case HP_ACT_SOFTSIGN: return v / (1.f + fabsf(v));
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float4 dt_act4(int act, float4 v) {
+  switch (act) {
+    case HP_ACT_RELU: return make_float4(dt_act_c<HP_ACT_RELU>(v.x), dt_act_c<HP_ACT_RELU>(v.y), dt_act_c<HP_ACT_RELU>(v.z), dt_act_c<HP_ACT_RELU>(v.w));
+    case HP_ACT_TANH: return make_float4(dt_act_c<HP_ACT_TANH>(v.x), dt_act_c<HP_ACT_TANH>(v.y), dt_act_c<HP_ACT_TANH>(v.z), dt_act_c<HP_ACT_TANH>(v.w));
+    case HP_ACT_SIGMOID:
+      return make_float4(dt_act_c<HP_ACT_SIGMOID>(v.x), dt_act_c<HP_ACT_SIGMOID>(v.y), dt_act_c<HP_ACT_SIGMOID>(v.z), dt_act_c<HP_ACT_SIGMOID>(v.w));
+    case HP_ACT_SOFTSIGN:
+      return make_float4(dt_act_c<HP_ACT_SOFTSIGN>(v.x), dt_act_c<HP_ACT_SOFTSIGN>(v.y), dt_act_c<HP_ACT_SOFTSIGN>(v.z), dt_act_c<HP_ACT_SOFTSIGN>(v.w));
     default: return v;
   }
 }
@@ -71,6 +113,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane_id = tid & 31;
+  // slots: 0 load issued, 1 gather sees full, 2 gather set 0 done, 3 epilogue sees d_full, 4 epilogue done with D, 5 epilogue
+  // written out, 7 MMAs issued, 8 last gather set done, 9 / 10 issuer sees last / first a_full, 11 issuer has D (tile 0: entry)
+  if (tid == 0 && p.trace != nullptr && blockIdx.x == 0 && p.trace_tiles > 0) p.trace[11] = clock64();
+  auto stamp = [&](int i, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && i < p.trace_tiles) p.trace[i * 12 + slot] = clock64();
+  };
   constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1;
   const int NSTG = p.nstg, NBUF = p.nbuf, KS = p.KS, N16 = p.N16;
 
@@ -114,7 +162,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
-  const uint32_t colA0 = 2 * N16;                 // D[0], D[1] (N16 columns each), then the A ring (16 columns per stage)
+  const uint32_t colA0 = 2 * N16;                 // D[0], D[1] (N16 columns each), then the A ring (16 ku columns per stage)
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < W_ISSUE) {
@@ -123,48 +171,54 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
     const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
     if (warp < W_EPI) {
       // =============================================================== gather sets: x tile -> TF32 hi / lo -> TMEM A ring
-      // work unit = one k-step (8 floats of the row); global round-robin over the sets as in blaze_block_deep_kernel
+      // work unit = KU k-steps (8 KU floats of the row, one ring stage of 16 KU columns); global round-robin over the sets as
+      // in blaze_block_deep_kernel.  The per-unit protocol (a_empty wait, tcgen05.wait::st, fence, arrive) costs ~1K clk
+      // whatever the unit holds (measured with one k-step per unit: 1.1-1.3K clk per unit, the gather was the bottleneck of
+      // every layer), so a unit carries up to 4 k-steps.
       const int set = warp >> 2;
-      const uint32_t n_units = (uint32_t)my_tiles * KS;
-      uint64_t* pending = nullptr;
+      const int KU = p.ku, UPT = p.upt;
+      const uint32_t n_units = (uint32_t)my_tiles * UPT;
       int cur_i = -1, cur_b = 0;
       const float* row = in_bufs;
 #pragma unroll 1
       for (uint32_t g = set; g < n_units; g += NSETS) {
-        const int i = (int)(g / KS);
-        const int ks = (int)(g - (uint32_t)i * KS);
+        const int i = (int)(g / UPT);
+        const int ks0 = (int)(g - (uint32_t)i * UPT) * KU;
+        const int nk = (KS - ks0 < KU) ? KS - ks0 : KU;
         const uint32_t s = g % NSTG;
         if (i != cur_i) {
           cur_i = i;
           cur_b = i % NBUF;
           row = in_bufs + cur_b * p.in_floats + lane * p.KPAD;
           mbar_wait(&bar_full[cur_b], (i / NBUF) & 1);
-        }
-        const float4 q0 = ld4(row + 8 * ks), q1 = ld4(row + 8 * ks + 4);
-        const float f[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        uint32_t v[16];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          v[e] = tf32_hi(f[e]);
-          v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
-        }
-        if (pending != nullptr) {
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          mbar_arrive(pending);
+          if (tid == 0) stamp(i, 1);
         }
         if (g >= (uint32_t)NSTG) {
           mbar_wait(&bar_aempty[s], ((g / NSTG) - 1) & 1);
           tc_fence_after();
         }
-        tmem_st16(tlane + colA0 + s * 16, v);
-        pending = &bar_afull[s];
-        if (g + NSETS >= n_units || (int)((g + NSETS) / KS) != i) {
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          mbar_arrive(pending);
-          pending = nullptr;
+#pragma unroll
+        for (int kk = 0; kk < DT_MAXKU; ++kk) {
+          if (kk < nk) {
+            const float* q = row + 8 * (ks0 + kk);
+            const float4 q0 = ld4(q), q1 = ld4(q + 4);
+            const float f[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            uint32_t v[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[e] = tf32_hi(f[e]);
+              v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
+            }
+            tmem_st16(tlane + colA0 + s * (16 * KU) + kk * 16, v);
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(&bar_afull[s]);
+        if (g + NSETS >= n_units || (int)((g + NSETS) / UPT) != i) {
           mbar_arrive(&bar_infree[cur_b]);   // this thread reads nothing more from the tile
+          if (tid == 0) stamp(i, 2);
+          if (tid == (NSETS - 1) * 128) stamp(i, 8);
         }
       }
     } else if (TAIL) {
@@ -178,6 +232,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
         const long long m = ((long long)blockIdx.x + (long long)i * gridDim.x) * DT_ROWS + lane;
         mbar_wait(&bar_dfull[d], (i >> 1) & 1);
         tc_fence_after();
+        if ((tid & 127) == 0) stamp(i, 3);
         float4 acc = make_float4(b2[0], b2[1], b2[2], b2[3]);
         for (int g = 0; g * 32 < N16; ++g) {
           uint32_t v[32];
@@ -190,24 +245,20 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
             for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int cmax = (N16 - g * 32 < 32) ? N16 - g * 32 : 32;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j * 4 < cmax) {                                   // padded hidden channels (>= N) have zero W2 rows
-              const int c = g * 32 + j * 4;
-              const float4 bb = ld4(s_bias + c);
-              const float y0 = dt_act(p.act, __uint_as_float(v[j * 4 + 0]) + bb.x), y1 = dt_act(p.act, __uint_as_float(v[j * 4 + 1]) + bb.y);
-              const float y2 = dt_act(p.act, __uint_as_float(v[j * 4 + 2]) + bb.z), y3 = dt_act(p.act, __uint_as_float(v[j * 4 + 3]) + bb.w);
-              const float4 w0 = ld4(s_tail + c * 4), w1 = ld4(s_tail + c * 4 + 4), w2 = ld4(s_tail + c * 4 + 8), w3 = ld4(s_tail + c * 4 + 12);
-              acc.x = fmaf(y0, w0.x, acc.x); acc.y = fmaf(y0, w0.y, acc.y); acc.z = fmaf(y0, w0.z, acc.z); acc.w = fmaf(y0, w0.w, acc.w);
-              acc.x = fmaf(y1, w1.x, acc.x); acc.y = fmaf(y1, w1.y, acc.y); acc.z = fmaf(y1, w1.z, acc.z); acc.w = fmaf(y1, w1.w, acc.w);
-              acc.x = fmaf(y2, w2.x, acc.x); acc.y = fmaf(y2, w2.y, acc.y); acc.z = fmaf(y2, w2.z, acc.z); acc.w = fmaf(y2, w2.w, acc.w);
-              acc.x = fmaf(y3, w3.x, acc.x); acc.y = fmaf(y3, w3.y, acc.y); acc.z = fmaf(y3, w3.z, acc.z); acc.w = fmaf(y3, w3.w, acc.w);
-            }
+          const int nq = (N16 - g * 32 < 32) ? (N16 - g * 32) / 4 : 8;   // padded hidden channels (>= N) have zero W2 rows
+          const float* sb = s_bias + g * 32;
+          const float* stl = s_tail + g * 128;
+          switch (p.act) {
+            case HP_ACT_RELU: dt_tail_group<HP_ACT_RELU>(v, nq, sb, stl, acc); break;
+            case HP_ACT_TANH: dt_tail_group<HP_ACT_TANH>(v, nq, sb, stl, acc); break;
+            case HP_ACT_SIGMOID: dt_tail_group<HP_ACT_SIGMOID>(v, nq, sb, stl, acc); break;
+            case HP_ACT_SOFTSIGN: dt_tail_group<HP_ACT_SOFTSIGN>(v, nq, sb, stl, acc); break;
+            default: dt_tail_group<HP_ACT_LINEAR>(v, nq, sb, stl, acc); break;
           }
         }
         tc_fence_before();
         mbar_arrive(&bar_dempty[d]);
+        if ((tid & 127) == 0) stamp(i, 4);
         if (m < p.M) {
           const DenseOut& dd = p.out2;
           const long long img = m / dd.rows_per_img;
@@ -217,6 +268,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
           for (int j = 0; j < 4; ++j)
             if (j < p.n2) dst[j] = dt_act(p.act2, z[j]);
         }
+        if ((tid & 127) == 0) stamp(i, 5);
       }
     } else {
       // =============================================================== epilogue sets
@@ -237,6 +289,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
         }
         mbar_wait(&bar_dfull[d], (i >> 1) & 1);
         tc_fence_after();
+        if (etid == 0) stamp(i, 3);
         // D row + bias -> staging tile; the 32-column groups are dealt to the epilogue sets
         for (int g = eset; g * 32 < N16; g += NESETS) {
           uint32_t v[32];
@@ -261,18 +314,29 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
         }
         tc_fence_before();
         mbar_arrive(&bar_dempty[d]);
+        if (etid == 0) stamp(i, 4);
         named_bar_sync(1, 128 * NESETS);
         // activation + coalesced write-out of every output segment
         for (int o = 0; o < p.n_outs; ++o) {
           const DenseOut& dd = p.outs[o];
           const int wd = dd.col_end - dd.col_begin;
           const int total = rows * wd;
+          if (p.vec4[o]) {                      // 16-byte aligned segment: one float4 per thread and step
+            const int wq = wd >> 2, total4 = rows * wq;
+            for (int j = etid; j < total4; j += 128 * NESETS) {
+              const int r = (int)(((unsigned long long)j * p.magic4[o]) >> 32);
+              const int c = (j - r * wq) * 4;
+              st4(dd.ptr + rowoff[o * DT_ROWS + r] + c, dt_act4(p.act, ld4(stage + r * p.OS + dd.col_begin + c)));
+            }
+            continue;
+          }
           for (int j = etid; j < total; j += 128 * NESETS) {
             const int r = (int)(((unsigned long long)j * p.magic[o]) >> 32);
             const int c = j - r * wd;
             dd.ptr[rowoff[o * DT_ROWS + r] + c] = dt_act(p.act, stage[r * p.OS + dd.col_begin + c]);
           }
         }
+        if (etid == 0) stamp(i, 5);
         named_bar_sync(1, 128 * NESETS);   // the staging tile and rowoff are reused by the next tile
       }
     }
@@ -289,22 +353,29 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
           mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
           tc_fence_after();
         }
+        if (i > 0) stamp(i, 11);
 #pragma unroll 1
-        for (int ks = 0; ks < KS; ++ks, ++use) {
+        for (int u = 0; u < p.upt; ++u, ++use) {
           const uint32_t s = use % NSTG;
           mbar_wait(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
-          const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
-          const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
-          const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+          if (u == 0) stamp(i, 10);
+          if (u == p.upt - 1) stamp(i, 9);
           const uint32_t dc = tmem_base + d * N16;
-          const uint32_t a = tmem_base + colA0 + s * 16;
-          mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
-          mma_tf32_ts(dc, a, dlo, idesc, 1u);
-          mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          for (int kk = 0; kk < p.ku && u * p.ku + kk < KS; ++kk) {
+            const int ks = u * p.ku + kk;
+            const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
+            const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
+            const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+            const uint32_t a = tmem_base + colA0 + s * (16 * p.ku) + kk * 16;
+            mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+            mma_tf32_ts(dc, a, dlo, idesc, 1u);
+            mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          }
           tc_commit(&bar_aempty[s]);
         }
         tc_commit(&bar_dfull[d]);
+        stamp(i, 7);
       }
     } else if (warp == W_LOAD) {
       // =============================================================== TMA loader
@@ -313,6 +384,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
         if (i >= NBUF) mbar_wait(&bar_infree[b], ((i / NBUF) - 1) & 1);
         mbar_expect_tx(&bar_full[b], p.load_bytes);
         tma_load_4d(in_bufs + b * p.in_floats, &tm_in, &bar_full[b], 0, tile * DT_ROWS, 0, 0);
+        stamp(i, 0);
         if (++b == NBUF) b = 0;
       }
     }
@@ -353,7 +425,7 @@ static bool dense_tc_ok(const float* x, int M, int K, int ldx, int N, bool tail)
       (((uintptr_t)x) & 15) != 0)
     return false;
   DenseTcParams p;
-  return dense_tc_layout(K, N, 2, tail, &p) <= 227 * 1024 && 2 * p.N16 + DT_MAXSTG * 16 <= 512;
+  return dense_tc_layout(K, N, 2, tail, &p) <= 227 * 1024 && 2 * p.N16 + DT_MAXSTG * 16 * DT_MAXKU <= 512;
 }
 bool hp_dense_tc_supported(const float* x, int M, int K, int ldx, int N, bool transpose_w, bool accumulate) {
   return !transpose_w && !accumulate && dense_tc_ok(x, M, K, ldx, N, false);
@@ -377,14 +449,21 @@ static int dense_tc_launch(hp_ctx* h, const float* x, int M, int K, int ldx, con
   while (p.nbuf > 2 && dense_tc_layout(K, N, p.nbuf, tail != nullptr, &p) > 200 * 1024) --p.nbuf;
   const size_t smem = dense_tc_layout(K, N, p.nbuf, tail != nullptr, &p);
   p.n_tiles = ceil_div(M, DT_ROWS);
+  p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
+  // every gather set must own a unit of every tile (it frees the input buffer after its last one): at least 3 units per tile
+  p.ku = DT_MAXKU;
+  while (p.ku > 1 && ceil_div(p.KS, p.ku) < 3) --p.ku;
+  p.upt = ceil_div(p.KS, p.ku);
   p.nstg = DT_MAXSTG;
-  HP_REQUIRE(2 * p.N16 + p.nstg * 16 <= 512 && p.KPAD <= 256, HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);
+  HP_REQUIRE(2 * p.N16 + p.nstg * 16 * p.ku <= 512 && p.upt >= 3 && p.KPAD <= 256, HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);
   p.n_outs = n_outs;
   for (int i = 0; i < n_outs; ++i) {
     p.outs[i] = outs[i];
     const int wd = outs[i].col_end - outs[i].col_begin;
     HP_REQUIRE(wd >= 1 && outs[i].col_end <= N, HP_ERR_INVALID, "dense tc: bad output segment [%d, %d)", outs[i].col_begin, outs[i].col_end);
     p.magic[i] = (unsigned)((0x100000000ull + wd - 1) / wd);
+    p.vec4[i] = ((wd | outs[i].col_begin | outs[i].row_stride) & 3) == 0 && (outs[i].img_stride & 3) == 0 && (((uintptr_t)outs[i].ptr) & 15) == 0;
+    p.magic4[i] = p.vec4[i] ? (unsigned)((0x100000000ull + wd / 4 - 1) / (wd / 4)) : 0u;
   }
   p.load_bytes = (uint32_t)((size_t)DT_ROWS * p.KPAD * sizeof(float));
   HP_REQUIRE(smem <= 227 * 1024, HP_ERR_UNSUPPORTED, "dense tc: %zu bytes of shared memory needed for %dx%d", smem, K, N);

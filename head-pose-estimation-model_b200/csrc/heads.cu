@@ -534,6 +534,108 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* Q, const flo
   }
 }
 
+// Inference variant (no probabilities kept): one CTA per `ipc` images, K and V of all heads staged once in shared memory with
+// coalesced float4 loads, one THREAD per (image, head, query row).  The thread keeps its scaled query row and the output
+// row in registers and walks the keys: K / V rows are warp-broadcast LDS.128, the scores of the row live in a
+// conflict-free shared-memory column ([s][thread]), so there are no shuffles and no per-row warp reductions.  With 36
+// tokens (6 x 6 map) the warp-per-row kernel above used 36 of 64 lane slots in the score loops and 16 of 32 in P V:
+// 0.33 ms at batch 4096 against 0.15 GB of traffic.
+template <int D>
+__global__ void __launch_bounds__(1024) attn_rows_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                                                         const float* __restrict__ V, float* __restrict__ O, int n_img, int T,
+                                                         int heads, float scale, int ipc) {
+  extern __shared__ float4 smem4[];
+  const int HD = heads * D, nthr = blockDim.x, tid = threadIdx.x;
+  float* Ks = reinterpret_cast<float*>(smem4);   // [ipc][T][HD]
+  float* Vs = Ks + ipc * T * HD;                 // [ipc][T][HD]
+  float* sc = Vs + ipc * T * HD;                 // [T][nthr]
+  const int img0 = blockIdx.x * ipc;
+  const int nim = (n_img - img0 < ipc) ? n_img - img0 : ipc;
+  const long long gbase = (long long)img0 * T * HD;
+  {
+    const float4* K4 = reinterpret_cast<const float4*>(K + gbase);
+    const float4* V4 = reinterpret_cast<const float4*>(V + gbase);
+    float4* Ks4 = reinterpret_cast<float4*>(Ks);
+    float4* Vs4 = reinterpret_cast<float4*>(Vs);
+    const int n4 = nim * T * HD / 4;
+    for (int i = tid; i < n4; i += nthr) {
+      Ks4[i] = K4[i];
+      Vs4[i] = V4[i];
+    }
+  }
+  __syncthreads();
+  const int per_img = heads * T, pairs = nim * per_img;
+  for (int p = tid; p < pairs; p += nthr) {
+    const int il = p / per_img, r = p - il * per_img, hh = r / T, t = r - hh * T;
+    const long long row = gbase + (long long)(il * T + t) * HD + hh * D;
+    float q[D], o[D];
+#pragma unroll
+    for (int j = 0; j < D; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(Q + row + j);
+      q[j] = v.x * scale; q[j + 1] = v.y * scale; q[j + 2] = v.z * scale; q[j + 3] = v.w * scale;
+      o[j] = 0.f; o[j + 1] = 0.f; o[j + 2] = 0.f; o[j + 3] = 0.f;
+    }
+    const float* kb = Ks + il * T * HD + hh * D;
+    const float* vb = Vs + il * T * HD + hh * D;
+    float* my = sc + tid;
+    float mx = -INFINITY;
+    for (int s = 0; s < T; ++s) {
+      const float* kr = kb + s * HD;
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; j += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(kr + j);
+        a = fmaf(q[j], kv.x, a); a = fmaf(q[j + 1], kv.y, a); a = fmaf(q[j + 2], kv.z, a); a = fmaf(q[j + 3], kv.w, a);
+      }
+      my[s * nthr] = a;
+      mx = fmaxf(mx, a);
+    }
+    float sum = 0.f;
+    for (int s = 0; s < T; ++s) {
+      const float e = expf(my[s * nthr] - mx);
+      sum += e;
+      const float* vr = vb + s * HD;
+#pragma unroll
+      for (int j = 0; j < D; j += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(vr + j);
+        o[j] = fmaf(e, vv.x, o[j]); o[j + 1] = fmaf(e, vv.y, o[j + 1]); o[j + 2] = fmaf(e, vv.z, o[j + 2]); o[j + 3] = fmaf(e, vv.w, o[j + 3]);
+      }
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < D; j += 4)
+      *reinterpret_cast<float4*>(O + row + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+  }
+}
+
+// images per CTA, threads and shared memory of attn_rows_kernel; false when K, V and one score column per thread do not fit
+static bool attn_rows_plan(int T, int heads, int D, int* ipc, int* threads, size_t* smem) {
+  const int per_img = heads * T;
+  for (int ic = (per_img <= 160 ? 2 : 1); ic >= 1; --ic)
+    for (int th = round_up(ic * per_img < 1024 ? ic * per_img : 1024, 32); th >= 64; th = round_up(th / 2, 32)) {
+      const size_t sm = ((size_t)2 * ic * T * heads * D + (size_t)T * th) * sizeof(float);
+      if (sm <= 200 * 1024) {
+        *ipc = ic; *threads = th; *smem = sm;
+        return true;
+      }
+      if (th == 64) break;
+    }
+  return false;
+}
+
+template <int D>
+static int launch_attn_rows(hp_ctx* h, const float* Q, const float* K, const float* V, float* O, int n_img, int T, int heads,
+                            cudaStream_t st) {
+  int ipc = 1, threads = 64;
+  size_t smem = 0;
+  HP_REQUIRE(attn_rows_plan(T, heads, D, &ipc, &threads, &smem), HP_ERR_UNSUPPORTED, "attention over %d tokens does not fit shared memory", T);
+  HP_CUDA(cudaFuncSetAttribute(attn_rows_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  attn_rows_kernel<D><<<ceil_div(n_img, ipc), threads, smem, st>>>(Q, K, V, O, n_img, T, heads, 1.f / sqrtf((float)D), ipc);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}
+
 // pass A: per query row: dS = P*(dP - sum(P*dP)), dP = dO V^T ; dQ = scale * dS K ; writes dS to global
 __global__ void __launch_bounds__(128) attn_bwd_a_kernel(const float* K, const float* V, const float* dO,
                                                          const float* P, float* dS, float* dQ, int T, int heads, int d,
@@ -951,6 +1053,19 @@ static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, in
         HP_TRY(hp_launch_dense(h, R(o.in0), rows, C, C, Wq, hdm, bq, hdm, HP_ACT_LINEAR, false, &dq, 1, false, st));
         HP_TRY(hp_launch_dense(h, R(o.in0), rows, C, C, Wk, hdm, bk, hdm, HP_ACT_LINEAR, false, &dk, 1, false, st));
         HP_TRY(hp_launch_dense(h, R(o.in0), rows, C, C, Wv, hdm, bv, hdm, HP_ACT_LINEAR, false, &dv, 1, false, st));
+        int rows_ipc, rows_threads;
+        size_t rows_smem;
+        const bool rows_ok = !training && h->impl == HP_IMPL_FAST && (hdm % 4) == 0 &&
+                             ((((uintptr_t)(ws + w.q)) | ((uintptr_t)(ws + w.k)) | ((uintptr_t)(ws + w.v)) | ((uintptr_t)(ws + w.o))) & 15) == 0 &&
+                             attn_rows_plan(T, o.heads, o.key_dim, &rows_ipc, &rows_threads, &rows_smem);
+        if (rows_ok && (o.key_dim == 8 || o.key_dim == 16 || o.key_dim == 32)) {
+          if (o.key_dim == 8) HP_TRY(launch_attn_rows<8>(h, ws + w.q, ws + w.k, ws + w.v, ws + w.o, n_img, T, o.heads, st));
+          else if (o.key_dim == 16) HP_TRY(launch_attn_rows<16>(h, ws + w.q, ws + w.k, ws + w.v, ws + w.o, n_img, T, o.heads, st));
+          else HP_TRY(launch_attn_rows<32>(h, ws + w.q, ws + w.k, ws + w.v, ws + w.o, n_img, T, o.heads, st));
+          DenseOut dout{RW(o.out), 0, C, rows, 0, C};
+          HP_TRY(hp_launch_dense(h, ws + w.o, rows, hdm, hdm, Wo, C, bo, C, HP_ACT_LINEAR, false, &dout, 1, false, st));
+          break;
+        }
         const size_t smem = attn_smem(T, o.key_dim);
         HP_REQUIRE(smem <= 200 * 1024, HP_ERR_UNSUPPORTED, "attention over %d tokens does not fit shared memory", T);
         HP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -46,6 +46,26 @@ __device__ __forceinline__ float iou32(float4 a, float4 b) {
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
 }
 
+// iou32(a, b) > thr without the division in the common cases.  Boxes that do not intersect give exactly 0; otherwise
+// the quotient is only needed when inter is within 1e-6 (relative) of thr * union -- far more than the two roundings
+// involved -- so the decision is bit-identical to comparing the correctly rounded quotient.
+__device__ __forceinline__ bool iou32_gt(float4 a, float4 b, float thr) {
+  const float ymin_i = fminf(a.x, a.z), xmin_i = fminf(a.y, a.w), ymax_i = fmaxf(a.x, a.z), xmax_i = fmaxf(a.y, a.w);
+  const float ymin_j = fminf(b.x, b.z), xmin_j = fminf(b.y, b.w), ymax_j = fmaxf(b.x, b.z), xmax_j = fmaxf(b.y, b.w);
+  const float area_i = __fmul_rn(__fsub_rn(ymax_i, ymin_i), __fsub_rn(xmax_i, xmin_i));
+  const float area_j = __fmul_rn(__fsub_rn(ymax_j, ymin_j), __fsub_rn(xmax_j, xmin_j));
+  if (area_i <= 0.f || area_j <= 0.f) return 0.f > thr;
+  const float iy0 = fmaxf(ymin_i, ymin_j), ix0 = fmaxf(xmin_i, xmin_j);
+  const float iy1 = fminf(ymax_i, ymax_j), ix1 = fminf(xmax_i, xmax_j);
+  const float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.f), fmaxf(__fsub_rn(ix1, ix0), 0.f));
+  const float uni = __fsub_rn(__fadd_rn(area_i, area_j), inter);
+  if (inter <= 0.f || thr < 0.f || !(uni > 0.f)) return __fdiv_rn(inter, uni) > thr;   // exact 0 (or the odd cases): as before
+  const float t = __fmul_rn(thr, uni);
+  if (inter > __fmul_rn(t, 1.000001f)) return true;
+  if (inter < __fmul_rn(t, 0.999999f)) return false;
+  return __fdiv_rn(inter, uni) > thr;
+}
+
 struct NmsParams {
   const float* cls;
   const float* loc;
@@ -93,6 +113,11 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(NmsParams p) {
   __shared__ int s_sel_anchor[HP_MAX_FACES];
   __shared__ float s_sel_score[HP_MAX_FACES];
   __shared__ float4 s_sel_box[HP_MAX_FACES];
+  __shared__ float4 s_cbox[128];          // the chunk of candidates being resolved: box, anchor, score
+  __shared__ int s_canchor[128];
+  __shared__ float s_cscore[128];
+  __shared__ unsigned s_mask[128][4];     // row i: later candidates of the chunk that box i suppresses
+  __shared__ unsigned s_alive[4];         // candidates of the chunk that no earlier selection suppresses
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* cls = p.cls + (long long)b * p.A;
   const float* loc = p.loc + (long long)b * p.A * 16;
@@ -127,45 +152,69 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(NmsParams p) {
       __syncthreads();
     }
   }
-  // ---- greedy selection by warp 0
-  if (tid < 32) {
-    const int lane = tid;
-    int nsel = 0;
-    for (int base = 0; base < n && nsel < p.max_out; base += 32) {
-      const int pos = base + lane;
-      bool alive = pos < n;
-      int a = 0;
-      float sc = 0.f;
+  // ---- greedy selection (tf.image.non_max_suppression order), 128 sorted candidates at a time:
+  //  1. every thread decodes one candidate and tests it against the boxes selected in earlier chunks      (parallel)
+  //  2. every surviving candidate i builds the bit row "candidate j > i of this chunk overlaps me"          (parallel)
+  //  3. warp 0 walks the chunk in order with the removed-bits in lanes 0..3: a surviving candidate is selected and ORs its row
+  //     in -- a few instructions per candidate instead of an IoU loop per candidate on one warp
+  // A candidate is selected iff no earlier SELECTED box overlaps it: the same decisions, IoU arguments (candidate, selected).
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int base = 0; base < n && s_nsel < p.max_out; base += 128) {
+      const int nsel0 = s_nsel;
+      const int pos = base + tid;
+      const int cn = (n - base < 128) ? n - base : 128;          // candidates in this chunk
+      bool alive = tid < cn;
       float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
       if (alive) {
         const unsigned long long key = keys[pos];
-        a = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-        sc = __uint_as_float((unsigned)(key >> 32));
+        const int a = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
         double b4[4];
         decode_box64(p, loc + (long long)a * 16, a, b4);
         bx = make_float4((float)b4[0], (float)b4[1], (float)b4[2], (float)b4[3]);  // tf casts boxes to float32
-        for (int j = 0; j < nsel; ++j) {
-          if (iou32(bx, s_sel_box[j]) > p.iou_thr) { alive = false; break; }
+        s_canchor[tid] = a;
+        s_cscore[tid] = __uint_as_float((unsigned)(key >> 32));
+        for (int j = 0; j < nsel0; ++j)
+          if (iou32_gt(bx, s_sel_box[j], p.iou_thr)) { alive = false; break; }
+      }
+      s_cbox[tid] = bx;
+      const unsigned am = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) s_alive[warp] = am;
+      __syncthreads();
+      {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          unsigned word = 0u;
+          if (alive && w * 32 + 31 > tid) {
+            const unsigned al = s_alive[w];
+            for (int jj = 0; jj < 32; ++jj) {
+              const int j = w * 32 + jj;
+              if (j > tid && j < cn && ((al >> jj) & 1u) && iou32_gt(s_cbox[j], bx, p.iou_thr)) word |= 1u << jj;
+            }
+          }
+          s_mask[tid][w] = word;
         }
       }
-      unsigned mask = __ballot_sync(0xffffffffu, alive);
-      while (mask != 0u && nsel < p.max_out) {
-        const int leader = __ffs(mask) - 1;
-        const float4 lb = make_float4(__shfl_sync(0xffffffffu, bx.x, leader), __shfl_sync(0xffffffffu, bx.y, leader),
-                                      __shfl_sync(0xffffffffu, bx.z, leader), __shfl_sync(0xffffffffu, bx.w, leader));
-        if (lane == leader) {
-          s_sel_anchor[nsel] = a;
-          s_sel_score[nsel] = sc;
-          s_sel_box[nsel] = bx;
-          alive = false;
+      __syncthreads();
+      if (warp == 0) {
+        unsigned rem = lane < 4 ? ~s_alive[lane] : 0xffffffffu;
+        int cnt = nsel0;
+        for (int i = 0; i < cn && cnt < p.max_out; ++i) {
+          const unsigned w = __shfl_sync(0xffffffffu, rem, i >> 5);
+          if (!((w >> (i & 31)) & 1u)) {
+            if (lane == 0) {
+              s_sel_anchor[cnt] = s_canchor[i];
+              s_sel_score[cnt] = s_cscore[i];
+              s_sel_box[cnt] = s_cbox[i];
+            }
+            if (lane < 4) rem |= s_mask[i][lane];
+            ++cnt;
+          }
         }
-        nsel++;
-        if (alive && lane > leader && iou32(bx, lb) > p.iou_thr) alive = false;
-        mask = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_nsel = cnt;
       }
-      __syncwarp();
+      __syncthreads();
     }
-    if (lane == 0) s_nsel = nsel;
   }
   __syncthreads();
   const int nsel = s_nsel;

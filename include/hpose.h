@@ -218,6 +218,12 @@ int hp_debug_set_stem_tc(hp_handle h, int BH, int nbuf, int nout, int nsets);
 /* device buffer of max_tiles x 12 clock64 stamps written by CTA 0 of the warp-specialised tensor-core kernel (NULL = off) */
 int hp_debug_tc_trace(hp_handle h, long long* dev_buf, int max_tiles);
 int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, int nsets, int nbuf);
+/* one Dense / 1x1-conv layer y[M][N] = act(x[M][K] W[K][N] + b) on device pointers, through the same dispatch as the heads
+ * (tensor-core kernel when the shape allows it).  W2 != NULL: the fused pair z[M][n2] = act2(y W2[N][n2] + b2), n2 <= 4, is
+ * written to y instead and the hidden activations are not stored (error if the shape is not supported).  Reference:
+ * Conv2D(1x1) layers of Model-88/train_88.py:30-60 and Model-88/attention_model.py:16-169. */
+int hp_debug_dense(hp_handle h, const float* x, int M, int K, const float* W, const float* b, int N, int act, float* y,
+                   const float* W2, const float* b2, int n2, int act2, void* stream);
 
 #ifdef __cplusplus
 }
