@@ -220,6 +220,29 @@ int hp_launch_dense(hp_ctx* h, const float* x, int M, int K, int ldx, const floa
   HP_REQUIRE(n_outs >= 1 && n_outs <= 2, HP_ERR_INVALID, "dense: 1 or 2 output segments");
   if (h->impl == HP_IMPL_FAST && h->dense_tc && hp_dense_tc_supported(x, M, K, ldx, N, transpose_w, accumulate))
     return hp_launch_dense_tc(h, x, M, K, ldx, W, ldw, b, N, act, outs, n_outs, st);
+  // wide layers whose split weights + staging tile exceed shared memory (the 96 -> 102 detector head of the 8 x 8 map):
+  // two tensor-core launches over column halves (x is read twice, the second time mostly from L2)
+  if (h->impl == HP_IMPL_FAST && h->dense_tc && !transpose_w && !accumulate && N > 64) {
+    const int c_mid = round_up((N + 1) / 2, 4);
+    if (hp_dense_tc_supported(x, M, K, ldx, c_mid, false, false) && hp_dense_tc_supported(x, M, K, ldx, N - c_mid, false, false)) {
+      for (int half = 0; half < 2; ++half) {
+        const int c0 = half ? c_mid : 0, c1 = half ? N : c_mid;
+        DenseOut seg[2];
+        int ns = 0;
+        for (int i = 0; i < n_outs; ++i) {
+          const int cb = outs[i].col_begin > c0 ? outs[i].col_begin : c0, ce = outs[i].col_end < c1 ? outs[i].col_end : c1;
+          if (cb >= ce) continue;
+          seg[ns] = outs[i];
+          seg[ns].ptr = outs[i].ptr + (cb - outs[i].col_begin);
+          seg[ns].col_begin = cb - c0;
+          seg[ns].col_end = ce - c0;
+          ++ns;
+        }
+        if (ns > 0) HP_TRY(hp_launch_dense_tc(h, x, M, K, ldx, W + c0, ldw, b ? b + c0 : nullptr, c1 - c0, act, seg, ns, st));
+      }
+      return HP_OK;
+    }
+  }
   DenseKParams p;
   p.x = x; p.W = W; p.b = b; p.M = M; p.K = K; p.ldx = ldx; p.ldw = ldw; p.N = N; p.act = act;
   p.transpose_w = transpose_w ? 1 : 0; p.accumulate = accumulate ? 1 : 0;

@@ -46,20 +46,23 @@ __device__ __forceinline__ float iou32(float4 a, float4 b) {
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
 }
 
-// iou32(a, b) > thr without the division in the common cases.  Boxes that do not intersect give exactly 0; otherwise
-// the quotient is only needed when inter is within 1e-6 (relative) of thr * union -- far more than the two roundings
-// involved -- so the decision is bit-identical to comparing the correctly rounded quotient.
-__device__ __forceinline__ bool iou32_gt(float4 a, float4 b, float thr) {
-  const float ymin_i = fminf(a.x, a.z), xmin_i = fminf(a.y, a.w), ymax_i = fmaxf(a.x, a.z), xmax_i = fmaxf(a.y, a.w);
-  const float ymin_j = fminf(b.x, b.z), xmin_j = fminf(b.y, b.w), ymax_j = fmaxf(b.x, b.z), xmax_j = fmaxf(b.y, b.w);
-  const float area_i = __fmul_rn(__fsub_rn(ymax_i, ymin_i), __fsub_rn(xmax_i, xmin_i));
-  const float area_j = __fmul_rn(__fsub_rn(ymax_j, ymin_j), __fsub_rn(xmax_j, xmin_j));
-  if (area_i <= 0.f || area_j <= 0.f) return 0.f > thr;
-  const float iy0 = fmaxf(ymin_i, ymin_j), ix0 = fmaxf(xmin_i, xmin_j);
-  const float iy1 = fminf(ymax_i, ymax_j), ix1 = fminf(xmax_i, xmax_j);
+// iou32(a, b) > thr for boxes already normalised to (ymin, xmin, ymax, xmax) with their areas (the same float operations
+// as iou32, hoisted per box), without the division in the common cases: boxes that do not intersect give exactly 0;
+// otherwise the quotient is only needed when inter is within 1e-6 (relative) of thr * union -- far more than the two
+// roundings involved -- so the decision is bit-identical to comparing the correctly rounded quotient.
+__device__ __forceinline__ float4 box_normalise(float4 a, float* area) {
+  const float4 n = make_float4(fminf(a.x, a.z), fminf(a.y, a.w), fmaxf(a.x, a.z), fmaxf(a.y, a.w));
+  *area = __fmul_rn(__fsub_rn(n.z, n.x), __fsub_rn(n.w, n.y));
+  return n;
+}
+__device__ __forceinline__ bool iou32_gt(float4 a, float area_a, float4 b, float area_b, float thr) {
+  if (area_a <= 0.f || area_b <= 0.f) return 0.f > thr;
+  const float iy0 = fmaxf(a.x, b.x), ix0 = fmaxf(a.y, b.y);
+  const float iy1 = fminf(a.z, b.z), ix1 = fminf(a.w, b.w);
   const float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.f), fmaxf(__fsub_rn(ix1, ix0), 0.f));
-  const float uni = __fsub_rn(__fadd_rn(area_i, area_j), inter);
-  if (inter <= 0.f || thr < 0.f || !(uni > 0.f)) return __fdiv_rn(inter, uni) > thr;   // exact 0 (or the odd cases): as before
+  if (inter <= 0.f) return 0.f > thr;                          // 0 / union
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  if (thr < 0.f || !(uni > 0.f)) return __fdiv_rn(inter, uni) > thr;
   const float t = __fmul_rn(thr, uni);
   if (inter > __fmul_rn(t, 1.000001f)) return true;
   if (inter < __fmul_rn(t, 0.999999f)) return false;
@@ -113,7 +116,9 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(NmsParams p) {
   __shared__ int s_sel_anchor[HP_MAX_FACES];
   __shared__ float s_sel_score[HP_MAX_FACES];
   __shared__ float4 s_sel_box[HP_MAX_FACES];
-  __shared__ float4 s_cbox[128];          // the chunk of candidates being resolved: box, anchor, score
+  __shared__ float s_sel_area[HP_MAX_FACES];
+  __shared__ float s_carea[128];
+  __shared__ float4 s_cbox[128];          // the chunk of candidates being resolved: normalised box (+ area), anchor, score
   __shared__ int s_canchor[128];
   __shared__ float s_cscore[128];
   __shared__ unsigned s_mask[128][4];     // row i: later candidates of the chunk that box i suppresses
@@ -166,18 +171,20 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(NmsParams p) {
       const int cn = (n - base < 128) ? n - base : 128;          // candidates in this chunk
       bool alive = tid < cn;
       float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      float area = 0.f;
       if (alive) {
         const unsigned long long key = keys[pos];
         const int a = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
         double b4[4];
         decode_box64(p, loc + (long long)a * 16, a, b4);
-        bx = make_float4((float)b4[0], (float)b4[1], (float)b4[2], (float)b4[3]);  // tf casts boxes to float32
+        bx = box_normalise(make_float4((float)b4[0], (float)b4[1], (float)b4[2], (float)b4[3]), &area);  // tf casts boxes to float32
         s_canchor[tid] = a;
         s_cscore[tid] = __uint_as_float((unsigned)(key >> 32));
         for (int j = 0; j < nsel0; ++j)
-          if (iou32_gt(bx, s_sel_box[j], p.iou_thr)) { alive = false; break; }
+          if (iou32_gt(bx, area, s_sel_box[j], s_sel_area[j], p.iou_thr)) { alive = false; break; }
       }
       s_cbox[tid] = bx;
+      s_carea[tid] = area;
       const unsigned am = __ballot_sync(0xffffffffu, alive);
       if (lane == 0) s_alive[warp] = am;
       __syncthreads();
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(NmsParams p) {
             const unsigned al = s_alive[w];
             for (int jj = 0; jj < 32; ++jj) {
               const int j = w * 32 + jj;
-              if (j > tid && j < cn && ((al >> jj) & 1u) && iou32_gt(s_cbox[j], bx, p.iou_thr)) word |= 1u << jj;
+              if (j > tid && j < cn && ((al >> jj) & 1u) && iou32_gt(s_cbox[j], s_carea[j], bx, area, p.iou_thr)) word |= 1u << jj;
             }
           }
           s_mask[tid][w] = word;
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(NmsParams p) {
               s_sel_anchor[cnt] = s_canchor[i];
               s_sel_score[cnt] = s_cscore[i];
               s_sel_box[cnt] = s_cbox[i];
+              s_sel_area[cnt] = s_carea[i];
             }
             if (lane < 4) rem |= s_mask[i][lane];
             ++cnt;
