@@ -174,19 +174,25 @@ class blazeFaceDetector:
         return [Results(boxes[i, :c].copy(), kps[i, :c].copy(), scores[i, :c].copy(), poses[i, :c].copy())
                 for i, c in enumerate(cnt)]
 
-    def detect_stream(self, host_batches, max_faces=MAX_FACE_NUM, keys=("count", "boxes", "keypoints", "scores", "poses")):
+    def detect_stream(self, host_batches, max_faces=MAX_FACE_NUM, keys=("count", "boxes", "keypoints", "scores", "poses"), chunks=1):
         """Pipelined serving loop: ``host_batches`` yields pinned (B,H,W,3) uint8 BGR host tensors; for every batch
         a dict of pinned HOST tensors (``keys``) is yielded, in order.  The host->device copy of batch i+1 and the
         device->host read of batch i-1 run on their own CUDA streams while batch i computes (two device input
         buffers, two sets of host result buffers): PCIe time hides behind the kernels instead of adding to them.
+        ``chunks`` > 1 splits every batch into that many slices which go through copy / compute / read-back one after
+        the other: the first kernels then wait for 1/chunks of the first copy only and the last read-back is 1/chunks of
+        a batch (shorter pipeline fill and drain; the results are the same).
         A yielded dict is reused two batches later: consume (or copy) it before asking for the next-but-one."""
         import torch
         dev = self.ctx.torch_device
         comp = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        d_in, h_out = [None, None], [None, None]
-        ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_comp = [torch.cuda.Event() for _ in range(2)]
+        chunks = max(1, int(chunks))
+        d_in = [[None] * chunks for _ in range(2)]
+        h_out = [None, None]
+        ev_in = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(2)]
+        ev_comp = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(2)]
+        used = [[False] * chunks for _ in range(2)]
         ev_out = [torch.cuda.Event() for _ in range(2)]
         pending = []                                      # slots whose results are still on their way to the host
         n = 0
@@ -196,24 +202,32 @@ class blazeFaceDetector:
                 q = pending.pop(0)
                 ev_out[q].synchronize()
                 yield h_out[q]
-            if d_in[b] is None or d_in[b].shape != hb.shape:
-                d_in[b] = torch.empty(hb.shape, dtype=hb.dtype, device=dev)
-            with torch.cuda.stream(s_in):
-                if n >= 2:
-                    s_in.wait_event(ev_comp[b])            # the pass that read this input buffer is done
-                d_in[b].copy_(hb, non_blocking=True)
-                ev_in[b].record(s_in)
-            comp.wait_event(ev_in[b])
-            out = self.detect_device(d_in[b], max_faces)
-            ev_comp[b].record(comp)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_comp[b])
-                if h_out[b] is None or any(h_out[b][k].shape != out[k].shape for k in keys):
-                    h_out[b] = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in keys}
-                for k in keys:
-                    out[k].record_stream(s_out)
-                    h_out[b][k].copy_(out[k], non_blocking=True)
-                ev_out[b].record(s_out)
+            B = hb.shape[0]
+            per = -(-B // chunks)
+            for c in range(chunks):
+                c0, c1 = c * per, min(B, (c + 1) * per)
+                if c0 >= c1:
+                    break
+                part = hb[c0:c1]
+                if d_in[b][c] is None or d_in[b][c].shape != part.shape:
+                    d_in[b][c] = torch.empty(part.shape, dtype=part.dtype, device=dev)
+                with torch.cuda.stream(s_in):
+                    if used[b][c]:
+                        s_in.wait_event(ev_comp[b][c])     # the pass that read this input buffer is done
+                    d_in[b][c].copy_(part, non_blocking=True)
+                    ev_in[b][c].record(s_in)
+                comp.wait_event(ev_in[b][c])
+                out = self.detect_device(d_in[b][c], max_faces)
+                ev_comp[b][c].record(comp)
+                used[b][c] = True
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_comp[b][c])
+                    if h_out[b] is None or any(h_out[b][k].shape != (B,) + tuple(out[k].shape[1:]) for k in keys):
+                        h_out[b] = {k: torch.empty((B,) + tuple(out[k].shape[1:]), dtype=out[k].dtype).pin_memory() for k in keys}
+                    for k in keys:
+                        out[k].record_stream(s_out)
+                        h_out[b][k][c0:c1].copy_(out[k], non_blocking=True)
+            ev_out[b].record(s_out)
             pending.append(b)
             n += 1
         for q in pending:

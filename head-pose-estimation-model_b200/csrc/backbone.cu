@@ -773,7 +773,18 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
     Tile2Cfg tc2;
     TcCfg tcc;
     const bool v1 = (h->impl == HP_IMPL_CPASYNC);
-    bool use_tc = false;
+    bool use_tc = false, use_tc_s2 = false;
+    if (h->impl == HP_IMPL_FAST && S == 2 && h->tc_override[i][0] >= 0) {
+      // stride-2 tensor-core kernel; override: TR 1 selects it explicitly with nsets / epilogue sets / buffers / unit
+      const int* tv = h->tc_override[i];
+      // wide outputs: the 96-column epilogue needs registers, 2 depthwise sets leave 96 per thread
+      use_tc_s2 = hp_tcs2_geometry(i, Ho, Wo, tv[0] > 0 && tv[4] > 0 ? tv[4] : (coutp > 64 ? 2 : 3), tv[0] > 0 && tv[3] > 0 ? tv[3] : 2, &tcc);
+      HP_REQUIRE(use_tc_s2 || tv[0] == 0, HP_ERR_INVALID, "tc override for block %d: the stride-2 kernel does not fit a %dx%d map", i, Ho, Wo);
+      if (use_tc_s2 && tv[0] > 0) {
+        if (tv[5] >= 2 && tv[5] < tcc.nbuf) tcc.nbuf = tv[5];
+        if (tv[6] > 0) tcc.unit = tv[6];
+      }
+    }
     if (h->impl == HP_IMPL_FAST && S == 1 && h->tc_override[i][0] >= 0) {
       const int* tv = h->tc_override[i];   // TR, NSTG, BH, npipe (epilogue sets when nbuf > 0), nsets, nbuf, unit, issuers
       if (tv[0] > 0) {                      // explicit geometry (tuning / tests): also on maps the default leaves to the CUDA cores
@@ -812,7 +823,7 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         r[0] = tcc.TR; r[1] = tcc.BH; r[2] = tcc.IWB; r[3] = tcc.NSTG; r[4] = tcc.nbuf; r[5] = tcc.npipe; r[6] = tcc.nsets; r[7] = -tcc.ni;
       }
     }
-    if (!naive && !use_tc) {
+    if (!naive && !use_tc && !use_tc_s2) {
       const int* ov = h->tile_override[i];
       if (v1) {
         if (ov[0] > 0) {
@@ -852,6 +863,8 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         h->launches += 2;
       } else if (use_tc) {
         HP_TRY(hp_launch_block_tc(h, i, cur, out, B, Ho, Wo, bb.blk[i], tcc, st));
+      } else if (use_tc_s2) {
+        HP_TRY(hp_launch_block_tc_s2(h, i, cur, out, B, Hi, Wi, Ho, Wo, pts[i], pls[i], bb.blk[i], tcc, st));
       } else if (!v1) {
         HP_TRY(hp_launch_block_tma(h, i, cur, out, B, Hi, Wi, Ho, Wo, pts[i], pls[i], bb.blk[i], tc2, st));
       } else {

@@ -930,6 +930,294 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
   }
 }
 
+
+// ============================================================================ stride-2 blocks (2, 5, 11): one output pixel per lane
+// out = ReLU(pointwise(depthwise3x3 stride 2 (x)) + channel_pad(maxpool2x2(x))).  A tile is a band of R output rows of one
+// image (R Wo <= 128 lanes, lane <-> output pixel).  The input band -- 2R+1 rows x 2Wo+1 pixels starting at image
+// row 2 y0 - pad_t, column -pad_l -- comes in one TMA box: everything outside the image is zero-filled by the TMA, so the
+// 9 tap offsets of a lane need no boundary logic at all, and the max-pool of the skip path reads 4 of the same pixels
+// (rows / columns + pad_t / + pad_l; the zero fill is harmless there because block inputs are ReLU outputs, >= 0).
+// Depthwise -> TF32 hi / lo -> TMEM A ring (work unit = `ku` k-steps), one accumulator row per lane, epilogue into a
+// separate output staging buffer (the output has different geometry: not in place) -> TMA store.  The input pixel stride is
+// an odd number of 16-byte chunks, but neighbouring lanes are TWO input pixels apart: depthwise LDS.128 are 2-way bank
+// conflicted (accepted: still ~2x faster than the CUDA-core kernel, which is FMA-issue bound).
+struct Tcs2Params {
+  const float *pwb, *bhi, *blo;
+  int Wo, Ho, R, rows, bands_per_img, n_tiles, pad_t, pad_l;
+  int IWB, row_pitch;                        // input box: IWB = 2 Wo + 1 pixels per row, row_pitch = IWB * PSI floats
+  int nstg, nbuf, ku, upt;
+  uint32_t load_bytes;
+  int off_b, off_w, off_out, out_floats, off_in, in_floats;
+  long long* trace;
+  int trace_tiles;
+};
+
+template <int CINP, int COUTP, int NSETS, int NESETS>
+__global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + 96, 1)
+blaze_block_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                      const __grid_constant__ DwConst<CINP> dwc, Tcs2Params p) {
+  using G = TcGeom<CINP, COUTP>;
+  constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16;
+  constexpr int PSI = (C4 | 1) * 4, PSO = (NG | 1) * 4;           // pixel strides of the input band / the output staging tile
+  constexpr uint32_t colA0 = 2 * N16;                             // TMEM: D[0], D[1], then the A ring (16 ku columns per stage)
+
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* bar_full = bars;                                       // [nbuf]  TMA load landed
+  uint64_t* bar_free = bars + TCD_MAXB;                            // [nbuf]  epilogue has read the skip pixels
+  uint64_t* bar_afull = bars + 2 * TCD_MAXB;                       // [nstg]
+  uint64_t* bar_aempty = bar_afull + TC_MAX_STG;                   // [nstg]
+  uint64_t* bar_dfull = bar_aempty + TC_MAX_STG;                   // [2]
+  uint64_t* bar_dempty = bar_dfull + 2;                            // [2]
+  uint64_t* bar_ofull = bar_dempty + 2;                            // [2]     output staging tile written
+  uint64_t* bar_ofree = bar_ofull + 2;                             // [2]     ... and read by the TMA store
+  static_assert((2 * TCD_MAXB + 2 * TC_MAX_STG + 8) * 8 + 4 <= TC_BAR_FLOATS * 4, "barrier block");
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (TC_BAR_FLOATS - 1);
+  float* s_bhi = smem + p.off_b;
+  float* s_blo = s_bhi + K8 * N16;
+  float* s_pwb = smem + p.off_w;
+  float* obufs = smem + p.off_out;
+  float* bufs = smem + p.off_in;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (tid == 0 && p.trace != nullptr && blockIdx.x == 0 && p.trace_tiles > 0) p.trace[11] = clock64();
+  const int warp = tid >> 5, lane_id = tid & 31;
+  constexpr int W_EPI = 4 * NSETS, W_ISSUE = W_EPI + 4 * NESETS, W_LOAD = W_ISSUE + 1, W_STORE = W_ISSUE + 2;
+  const int NSTG = p.nstg, NBUF = p.nbuf;
+
+  for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
+    st4(s_bhi + i, ld4(p.bhi + i));
+    st4(s_blo + i, ld4(p.blo + i));
+  }
+  for (int i = tid * 4; i < COUTP; i += nthr * 4) st4(s_pwb + i, ld4(p.pwb + i));
+  for (int i = tid * 4; i < 2 * p.out_floats; i += nthr * 4) st4(obufs + i, make_float4(0.f, 0.f, 0.f, 0.f));
+  fence_async_smem();
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&bar_full[b], 1);
+      mbar_init(&bar_free[b], 128);
+    }
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(&bar_afull[s], 128);
+      mbar_init(&bar_aempty[s], 1);
+    }
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&bar_dfull[d], 1);
+      mbar_init(&bar_dempty[d], 128);
+      mbar_init(&bar_ofull[d], 128);
+      mbar_init(&bar_ofree[d], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto stamp = [&](int i, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && i < p.trace_tiles) p.trace[i * 12 + slot] = clock64();
+  };
+
+  if (warp < W_ISSUE) {
+    const int wq = warp & 3;
+    const int lane = wq * 32 + lane_id;                            // output pixel of the band: (lane / Wo, lane % Wo)
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const bool active = lane < p.rows;
+    const bool warp_active = wq * 32 < p.rows;
+    const int yl = active ? lane / p.Wo : 0, xl = active ? lane - yl * p.Wo : 0;
+    const int win0 = (2 * yl * p.IWB + 2 * xl) * PSI;             // top-left tap of the 3x3 window in the input band
+    if (warp < W_EPI) {
+      // =============================================================== depthwise sets (units of ku k-steps, global round-robin)
+      const int set = warp >> 2;
+      const int KU = p.ku, UPT = p.upt;
+      const uint32_t n_units = (uint32_t)my_tiles * UPT;
+      int cur_i = -1;
+      const float* buf = bufs;
+#pragma unroll 1
+      for (uint32_t g = set; g < n_units; g += NSETS) {
+        const int i = (int)(g / UPT);
+        const int ks0 = (int)(g - (uint32_t)i * UPT) * KU;
+        const int nk = (KS - ks0 < KU) ? KS - ks0 : KU;
+        const uint32_t s = g % NSTG;
+        if (i != cur_i) {                                          // first unit of this set in tile i
+          cur_i = i;
+          const int b = i % NBUF;
+          buf = bufs + b * p.in_floats + win0;
+          mbar_wait(&bar_full[b], (i / NBUF) & 1);
+          if (tid == 0) stamp(i, 1);
+        }
+        if (g >= (uint32_t)NSTG) {
+          mbar_wait(&bar_aempty[s], ((g / NSTG) - 1) & 1);
+          tc_fence_after();
+        }
+        if (warp_active) {
+#pragma unroll 1
+          for (int kk = 0; kk < nk; ++kk) {
+            const int c = 8 * (ks0 + kk);
+            const bool two = (2 * (ks0 + kk) + 1 < C4);            // the second 4-channel chunk of the k-step exists
+            float4 a0 = ld4(dwc.b + c), a1 = two ? ld4(dwc.b + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const float* q = buf + ((t / 3) * p.IWB + (t % 3)) * PSI + c;
+              a0 = fma4(ld4(q), ld4(dwc.w + t * CINP + c), a0);
+              if (two) a1 = fma4(ld4(q + 4), ld4(dwc.w + t * CINP + c + 4), a1);
+            }
+            const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            uint32_t v[16];                                        // [hi 8 | lo 8]
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[e] = tf32_hi(f[e]);
+              v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
+            }
+            tmem_st16(tlane + colA0 + s * (16 * KU) + kk * 16, v);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        }
+        mbar_arrive(&bar_afull[s]);
+        if (g + NSETS >= n_units || (int)((g + NSETS) / UPT) != i) {
+          if (tid == 0) stamp(i, 2);
+          if (tid == (NSETS - 1) * 128) stamp(i, 8);
+        }
+      }
+    } else {
+      // =============================================================== epilogue sets: tile i belongs to set i % NESETS
+      const int eset = (warp - W_EPI) >> 2;
+      const int skip0 = win0 + (p.pad_t * p.IWB + p.pad_l) * PSI;  // image pixel (2 y, 2 x): the 2x2 max-pool window starts here
+      constexpr int NGRP = (NG + 7) / 8;
+      for (int i = eset; i < my_tiles; i += NESETS) {
+        const int d = i & 1, b = i % NBUF, ob = i & 1;
+        const float* win = bufs + b * p.in_floats + skip0;
+        float* opix = obufs + ob * p.out_floats + lane * PSO;
+        mbar_wait(&bar_dfull[d], (i >> 1) & 1);
+        tc_fence_after();
+        if ((tid & 127) == 0) stamp(i, 3);
+        if (i >= 2) mbar_wait(&bar_ofree[ob], ((i >> 1) - 1) & 1);
+        if (warp_active) {
+          uint32_t v[NGRP][32];
+#pragma unroll
+          for (int g = 0; g < NGRP; ++g) {
+            if (g * 32 + 32 <= N16) {
+              tmem_ld32(tlane + d * N16 + g * 32, v[g]);
+            } else {
+              uint32_t hlf[16];
+              tmem_ld16(tlane + d * N16 + g * 32, hlf);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[g][e] = hlf[e];
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tc_fence_before();
+#pragma unroll
+          for (int g = 0; g < NGRP; ++g) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int j = g * 8 + jj;
+              if (j < NG) {
+                const float4 bb = ld4(s_pwb + j * 4);
+                float4 o = make_float4(__uint_as_float(v[g][jj * 4 + 0]) + bb.x, __uint_as_float(v[g][jj * 4 + 1]) + bb.y,
+                                       __uint_as_float(v[g][jj * 4 + 2]) + bb.z, __uint_as_float(v[g][jj * 4 + 3]) + bb.w);
+                if (j < C4) {
+                  const float4 s0 = ld4(win + j * 4), s1 = ld4(win + PSI + j * 4);
+                  const float4 s2 = ld4(win + p.row_pitch + j * 4), s3 = ld4(win + p.row_pitch + PSI + j * 4);
+                  o.x += fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x)); o.y += fmaxf(fmaxf(s0.y, s1.y), fmaxf(s2.y, s3.y));
+                  o.z += fmaxf(fmaxf(s0.z, s1.z), fmaxf(s2.z, s3.z)); o.w += fmaxf(fmaxf(s0.w, s1.w), fmaxf(s2.w, s3.w));
+                }
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                if (active) st4(opix + j * 4, o);
+              }
+            }
+          }
+          fence_async_smem();
+        }
+        mbar_arrive(&bar_dempty[d]);
+        mbar_arrive(&bar_free[b]);
+        mbar_arrive(&bar_ofull[ob]);
+        if ((tid & 127) == 0) stamp(i, 4);
+      }
+    }
+  } else if (lane_id == 0) {
+    auto tile_coords = [&](int tile, int& img, int& y0) {
+      img = tile / p.bands_per_img;
+      y0 = (tile - img * p.bands_per_img) * p.R;
+    };
+    if (warp == W_ISSUE) {
+      // =============================================================== MMA issuer
+      const uint32_t idesc = tc_idesc_tf32(N16);
+      const uint64_t desc_fixed = tc_bdesc_fixed(N16);
+      const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
+      uint32_t use = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int d = i & 1;
+        if (i >= 2) {
+          mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        if (i > 0) stamp(i, 11);
+#pragma unroll 1
+        for (int u = 0; u < p.upt; ++u, ++use) {
+          const uint32_t s = use % NSTG;
+          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          tc_fence_after();
+          if (u == 0) stamp(i, 10);
+          if (u == p.upt - 1) stamp(i, 9);
+          const uint32_t dc = tmem_base + d * N16;
+          for (int kk = 0; kk < p.ku && u * p.ku + kk < KS; ++kk) {
+            const int ks = u * p.ku + kk;
+            const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
+            const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
+            const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+            const uint32_t a = tmem_base + colA0 + s * (16 * p.ku) + kk * 16;
+            mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+            mma_tf32_ts(dc, a, dlo, idesc, 1u);
+            mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          }
+          tc_commit(&bar_aempty[s]);
+        }
+        tc_commit(&bar_dfull[d]);
+        stamp(i, 7);
+      }
+    } else if (warp == W_LOAD) {
+      // =============================================================== TMA loader
+      int i = 0, b = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        if (i >= NBUF) mbar_wait(&bar_free[b], ((i / NBUF) - 1) & 1);
+        int img, y0;
+        tile_coords(tile, img, y0);
+        mbar_expect_tx(&bar_full[b], p.load_bytes);
+        tma_load_4d(bufs + b * p.in_floats, &tm_in, &bar_full[b], 0, -p.pad_l, 2 * y0 - p.pad_t, img);
+        stamp(i, 0);
+        if (++b == NBUF) b = 0;
+      }
+    } else if (warp == W_STORE) {
+      // =============================================================== TMA storer
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+        const int ob = i & 1;
+        mbar_wait(&bar_ofull[ob], (i >> 1) & 1);
+        int img, y0;
+        tile_coords(tile, img, y0);
+        tma_store_4d(&tm_out, obufs + ob * p.out_floats, 0, 0, y0, img);
+        tma_store_commit();
+        stamp(i, 5);
+        tma_store_wait_read();
+        stamp(i, 6);
+        mbar_arrive(&bar_ofree[ob]);
+      }
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1074,6 +1362,62 @@ int launch_small(hp_ctx* h, const float* in, float* out, int B, int H, int W, co
   DwConst<CINP> dwc;
   memcpy(dwc.w, w.h_dw, sizeof(dwc));
   auto kern = blaze_block_small_kernel<CINP, COUTP, NSETS, NESETS>;
+  HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  long long grid = h->num_sms;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<(unsigned)grid, 128 * NSETS + 128 * NESETS + 96, smem, st>>>(tin, tout, dwc, p);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}
+
+
+// shared-memory layout of the stride-2 kernel (floats); returns the bytes needed
+inline size_t tcs2_layout(int cinp, int coutp, int Wo, int R, int nbuf, Tcs2Params* p) {
+  const int C4 = cinp / 4, NG = coutp / 4, K8 = (cinp + 7) / 8 * 8, N16 = (coutp + 15) / 16 * 16;
+  const int PSI = (C4 | 1) * 4, PSO = (NG | 1) * 4;
+  p->IWB = 2 * Wo + 1;
+  p->row_pitch = p->IWB * PSI;
+  int off = TC_BAR_FLOATS;
+  p->off_b = off;
+  off = align_up(off + 2 * K8 * N16, 32);
+  p->off_w = off;
+  off = align_up(off + coutp, 256);
+  p->off_out = off;
+  p->out_floats = align_up(R * Wo * PSO, 256);
+  off += 2 * p->out_floats;
+  p->off_in = off;
+  p->in_floats = align_up((2 * R + 1) * p->row_pitch, 256);
+  p->load_bytes = (uint32_t)((size_t)(2 * R + 1) * p->row_pitch * sizeof(float));
+  return (size_t)(off + nbuf * p->in_floats) * sizeof(float);
+}
+
+template <int CINP, int COUTP, int NSETS, int NESETS>
+int launch_s2(hp_ctx* h, const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, int pad_t, int pad_l, const BlockWeights& w,
+              const TcCfg& tc, cudaStream_t st) {
+  using G = TcGeom<CINP, COUTP>;
+  constexpr int PSI = (G::C4 | 1) * 4, PSO = (G::NG | 1) * 4;
+  Tcs2Params p;
+  p.pwb = w.pwb; p.bhi = w.bhi; p.blo = w.blo;
+  p.Wo = Wo; p.Ho = Ho; p.R = tc.BH; p.rows = tc.BH * Wo;
+  p.bands_per_img = ceil_div(Ho, tc.BH);
+  p.n_tiles = B * p.bands_per_img;
+  p.pad_t = pad_t; p.pad_l = pad_l;
+  p.nstg = tc.NSTG; p.nbuf = tc.nbuf; p.ku = tc.unit; p.upt = ceil_div(G::KS, tc.unit);
+  p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
+  const size_t smem = tcs2_layout(CINP, COUTP, Wo, tc.BH, tc.nbuf, &p);
+  HP_REQUIRE(smem <= 227 * 1024, HP_ERR_INVALID, "tc stride-2 block <%d,%d>: %zu bytes of shared memory needed", CINP, COUTP, smem);
+  HP_REQUIRE(p.rows >= 1 && p.rows <= 128 && tc.nbuf >= 2 && tc.nbuf <= TCD_MAXB && tc.NSTG >= 2 && tc.NSTG <= TC_MAX_STG &&
+                 tc.unit >= 1 && tc.unit <= 2 && tc.nsets <= tc.NSTG && 2 * G::N16 + tc.NSTG * 16 * tc.unit <= 512 && p.IWB <= 256 &&
+                 2 * tc.BH + 1 <= 256 && pad_t >= 0 && pad_t <= 1 && pad_l >= 0 && pad_l <= 1,
+             HP_ERR_INVALID, "tc stride-2 block <%d,%d>: bad geometry %dx%d R %d nbuf %d nstg %d", CINP, COUTP, Ho, Wo, tc.BH, tc.nbuf, tc.NSTG);
+  HP_REQUIRE(w.h_dw != nullptr, HP_ERR_STATE, "tc stride-2 block: host copy of the depthwise weights missing");
+  CUtensorMap tin, tout;
+  HP_TRY(make_map(&tin, in, B, Hi, Wi, CINP, 1, 2 * tc.BH + 1, p.IWB, PSI));
+  HP_TRY(make_map(&tout, out, B, Ho, Wo, COUTP, 1, tc.BH, Wo, PSO));
+  DwConst<CINP> dwc;
+  memcpy(dwc.w, w.h_dw, sizeof(dwc));
+  auto kern = blaze_block_s2_kernel<CINP, COUTP, NSETS, NESETS>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -1238,6 +1582,53 @@ bool hp_tcs_geometry(int blk, int H, int W, int nsets, int esets, TcCfg* tc) {
       return true;
     }
   return false;
+}
+
+// Geometry of the stride-2 tensor-core kernel: the tallest band of output rows (R Wo <= 128 lanes) whose input band fits
+// shared memory at least twice next to the split weights and two output staging tiles.
+bool hp_tcs2_geometry(int blk, int Ho, int Wo, int nsets, int esets, TcCfg* tc) {
+  const int cinp = chan_pad(kBlazeBlocks[blk].cin), coutp = chan_pad(kBlazeBlocks[blk].cout);
+  const int N16 = (coutp + 15) / 16 * 16;
+  if (kBlazeBlocks[blk].stride != 2 || Wo < 1 || Wo > 127 || Ho < 1) return false;
+  TcCfg t;
+  t.TR = 1; t.nsets = nsets; t.npipe = esets; t.niss = 1; t.place = 0; t.ni = 1; t.IWB = 2 * Wo + 1;
+  t.unit = 2;
+  t.NSTG = TC_MAX_STG;
+  if (2 * N16 + t.NSTG * 16 * t.unit > 512) return false;
+  int R = 128 / Wo;
+  if (R > Ho) R = Ho;
+  for (; R >= 1; --R) {
+    // prefer bands that divide the image evenly among equally tall ones
+    const int bands = ceil_div(Ho, R);
+    const int Rb = ceil_div(Ho, bands);
+    Tcs2Params p;
+    for (t.nbuf = 3; t.nbuf >= 2; --t.nbuf)
+      if (tcs2_layout(cinp, coutp, Wo, Rb, t.nbuf, &p) <= 227 * 1024) {
+        t.BH = Rb;
+        *tc = t;
+        return true;
+      }
+  }
+  return false;
+}
+
+int hp_launch_block_tc_s2(hp_ctx* h, int blk, const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, int pad_t, int pad_l,
+                          const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
+  HP_REQUIRE(w.bhi && w.blo, HP_ERR_STATE, "tc stride-2 block %d: split weights missing", blk);
+#define S2_CASE(CI, CO)                                                                                                            \
+  if (tc.nsets == 3 && tc.npipe == 2) return launch_s2<CI, CO, 3, 2>(h, in, out, B, Hi, Wi, Ho, Wo, pad_t, pad_l, w, tc, st);      \
+  if (tc.nsets == 2 && tc.npipe == 2) return launch_s2<CI, CO, 2, 2>(h, in, out, B, Hi, Wi, Ho, Wo, pad_t, pad_l, w, tc, st);      \
+  if (tc.nsets == 3 && tc.npipe == 1) return launch_s2<CI, CO, 3, 1>(h, in, out, B, Hi, Wi, Ho, Wo, pad_t, pad_l, w, tc, st);      \
+  if (tc.nsets == 4 && tc.npipe == 1) return launch_s2<CI, CO, 4, 1>(h, in, out, B, Hi, Wi, Ho, Wo, pad_t, pad_l, w, tc, st);
+  switch (blk) {
+    case 2: S2_CASE(28, 32) break;
+    case 5: S2_CASE(44, 48) break;
+    case 11: S2_CASE(88, 96) break;
+    default: break;
+  }
+#undef S2_CASE
+  hp_set_error("tc stride-2 block %d: no kernel for nsets %d esets %d", blk, tc.nsets, tc.npipe);
+  return HP_ERR_UNSUPPORTED;
 }
 
 // Default geometry for a stride-1 block with an H x W map; false when the tensor-core kernel does not apply.

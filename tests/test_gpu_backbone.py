@@ -172,14 +172,14 @@ TC_GEOMETRIES = [(2, 2, 4, 1, 0), (2, 2, 3, 2, 0), (4, 2, 2, 2, 0), (4, 1, 2, 2,
                  (2, 0, 2, 2, 4 + 32), (2, 0, 2, 3, 4 + 32), (2, 0, 1, 4, 3 + 32), (4, 0, 2, 2, 4 + 32), (4, 0, 2, 3, 4 + 32),   # + 32: k-step work units
                  (4, 0, 2, 2, 4 + 32 + 128), (4, 0, 2, 2, 3 + 32 + 256), (2, 0, 2, 3, 4 + 32 + 128), (2, 0, 2, 3, 4 + 16 + 128),   # + 64 n: n issuer warps
                  (1, 0, 2, 3, 4), (1, 0, 1, 3, 2), (1, 0, 1, 2, 3), (1, 0, 2, 4, 4)]   # TR 1: pixel-per-lane kernel (maps of <= 128 pixels)
-TC_BLOCK_CHANNELS = {0: 24, 1: 28, 3: 36, 4: 42, 6: 56, 7: 64, 8: 72, 9: 80, 10: 88, 12: 96, 15: 96}
+TC_BLOCK_CHANNELS = {0: 24, 1: 28, 2: 32, 3: 36, 4: 42, 5: 48, 6: 56, 7: 64, 8: 72, 9: 80, 10: 88, 11: 96, 12: 96, 15: 96}
 
 
 @pytest.mark.parametrize("geom", TC_GEOMETRIES)
 @pytest.mark.parametrize("size,batch", [(96, 37), (88, 5), (128, 3)])
 def test_tensor_core_block_geometries(geom, size, batch):
     """Every instantiated geometry of the tensor-core BlazeBlock kernels reproduces the naive CUDA kernels on every
-    stride-1 block (random-init weights; batch 37 gives the persistent CTAs different tile counts and a partial last
+    block (stride-2 blocks: any TR selects the stride-2 kernel with the given warp sets / buffers) (random-init weights; batch 37 gives the persistent CTAs different tile counts and a partial last
     multi-image tile, 88 gives partial bands and odd widths).  Geometries that do not fit a block (TMEM / shared
     memory / not instantiated) must be refused with an error, never run wrong."""
     from hpose_b200 import _lib
@@ -196,7 +196,7 @@ def test_tensor_core_block_geometries(geom, size, batch):
         for blk, c in TC_BLOCK_CHANNELS.items():
             H = -(-size // 2)
             for b in (2, 5, 11):
-                if blk > b:
+                if blk >= b:                     # output map of the block (2, 5, 11 are the stride-2 blocks)
                     H = -(-H // 2)
             shape = (batch, H, H, c)
             ctx.set_impl(_lib.HP_IMPL_NAIVE)

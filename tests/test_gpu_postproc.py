@@ -160,9 +160,10 @@ def test_detect_faces_end_to_end_vs_oracle():
         det.detectFaces(np.zeros((64, 64, 3), np.uint8))
 
 
-def test_detect_stream_matches_detect_device():
-    """The pipelined serving loop (copies overlapped with compute on side streams) returns, batch by batch and in
-    order, exactly what the synchronous path returns."""
+@pytest.mark.parametrize("chunks", [1, 2, 4])
+def test_detect_stream_matches_detect_device(chunks):
+    """The pipelined serving loop (copies overlapped with compute on side streams, every batch optionally cut into
+    slices) returns, batch by batch and in order, exactly what the synchronous path returns."""
     import torch
     from hpose_b200 import keras_spec as K, train_88
     from hpose_b200.attention_model import se_transformer_regr_head
@@ -180,7 +181,7 @@ def test_detect_stream_matches_detect_device():
         out = det.detect_device(hb.cuda())
         want.append({k: out[k].cpu().numpy().copy() for k in ("count", "boxes", "scores", "poses", "keypoints")})
     got = []
-    for res in det.detect_stream(iter(host)):
+    for res in det.detect_stream(iter(host), chunks=chunks):
         got.append({k: res[k].numpy().copy() for k in res})
     assert len(got) == len(want)
     for g, w in zip(got, want):
