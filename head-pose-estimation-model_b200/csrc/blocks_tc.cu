@@ -1595,20 +1595,22 @@ bool hp_tcs2_geometry(int blk, int Ho, int Wo, int nsets, int esets, TcCfg* tc) 
   t.unit = 2;
   t.NSTG = TC_MAX_STG;
   if (2 * N16 + t.NSTG * 16 * t.unit > 512) return false;
-  int R = 128 / Wo;
-  if (R > Ho) R = Ho;
-  for (; R >= 1; --R) {
-    // prefer bands that divide the image evenly among equally tall ones
-    const int bands = ceil_div(Ho, R);
-    const int Rb = ceil_div(Ho, bands);
-    Tcs2Params p;
-    for (t.nbuf = 3; t.nbuf >= 2; --t.nbuf)
-      if (tcs2_layout(cinp, coutp, Wo, Rb, t.nbuf, &p) <= 227 * 1024) {
-        t.BH = Rb;
+  int Rmax = 128 / Wo;
+  if (Rmax > Ho) Rmax = Ho;
+  // three input bands in flight beat taller bands (the band cycle load -> depthwise -> epilogue is latency bound: block 2
+  // went from 5.3K clk per 120-pixel tile with 2 buffers to 3 buffers of 96 pixels), as long as >= 60 % of the rows remain
+  for (int want = 3; want >= 2; --want)
+    for (int R = Rmax; R >= 1; --R) {
+      const int bands = ceil_div(Ho, R);
+      const int Rb = ceil_div(Ho, bands);                       // equally tall bands
+      if (want == 3 && Rb * 10 < Rmax * 6) break;
+      Tcs2Params p;
+      if (tcs2_layout(cinp, coutp, Wo, Rb, want, &p) <= 227 * 1024) {
+        t.BH = Rb; t.nbuf = want;
         *tc = t;
         return true;
       }
-  }
+    }
   return false;
 }
 

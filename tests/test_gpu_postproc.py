@@ -188,4 +188,9 @@ def test_detect_stream_matches_detect_device(chunks):
         assert np.array_equal(g["count"], w["count"])
         for i, c in enumerate(w["count"]):                 # entries beyond count[i] are uninitialised padding
             for k in ("boxes", "scores", "poses", "keypoints"):
-                assert np.array_equal(g[k][i, :c], w[k][i, :c]), (k, i)
+                if chunks == 1:
+                    assert np.array_equal(g[k][i, :c], w[k][i, :c]), (k, i)
+                else:
+                    # a slice of fewer than 512 token rows takes the CUDA-core Dense kernel instead of the 3xTF32 one:
+                    # same values to ~1e-6, not bit for bit
+                    assert np.allclose(g[k][i, :c], w[k][i, :c], rtol=1e-5, atol=2e-5), (k, i)

@@ -30,9 +30,10 @@ ms = np.zeros(18, dtype=np.float32)
 # are chosen by the library)
 CANDS = [(4, 0, 2, 2, 4 + 32 + 128), (4, 0, 1, 2, 4 + 32 + 128 + 512), (4, 0, 2, 2, 4 + 32 + 128 + 512), (4, 0, 1, 3, 4 + 32 + 128 + 512),
          (2, 0, 2, 3, 4 + 32 + 128), (2, 0, 1, 3, 4 + 32 + 128 + 512), (2, 0, 2, 2, 4 + 32 + 128 + 512), (2, 0, 2, 3, 4 + 32 + 128 + 512),
-         (1, 0, 2, 3, 4), (1, 0, 1, 3, 4), (1, 0, 1, 2, 4), (1, 0, 2, 4, 4), (1, 0, 2, 3, 2)]   # TR 1: pixel-per-lane kernel
+         (1, 0, 2, 3, 4), (1, 0, 1, 3, 4), (1, 0, 1, 2, 4), (1, 0, 2, 4, 4), (1, 0, 2, 3, 2), (1, 0, 2, 2, 4), (1, 0, 1, 4, 4),
+         (1, 0, 2, 3, 4 + 16), (1, 0, 2, 2, 4 + 16)]   # TR 1: pixel-per-lane kernel
 TC_BLOCKS = [int(b) for b in os.environ.get("TC_BLOCKS", "0,1,3,4,6,7,8,9,10,12").split(",")]
-HS = {0: size // 2, 1: size // 2, 3: size // 4, 4: size // 4, 6: size // 8, 7: size // 8, 8: size // 8, 9: size // 8, 10: size // 8,
+HS = {0: size // 2, 1: size // 2, 2: size // 4, 5: size // 8, 11: size // 16, 3: size // 4, 4: size // 4, 6: size // 8, 7: size // 8, 8: size // 8, 9: size // 8, 10: size // 8,
       12: size // 16, 13: size // 16, 14: size // 16, 15: size // 16}
 
 
