@@ -270,7 +270,7 @@ def main():
     for _ in range(2):
         step_e2e()
     barrier()
-    e_steps = max(3, min(args.steps, 10))
+    e_steps = max(3, min(args.steps, 50))   # the same K steps as the device-resident measurement (pipeline fill / drain included)
 
     def batches(nb):
         for _ in range(nb):

@@ -796,6 +796,7 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
           HP_REQUIRE(hp_tcs_geometry(i, Ho, Wo, tv[4] > 0 ? tv[4] : 3, tv[3] > 0 ? tv[3] : 2, &tcc), HP_ERR_INVALID,
                      "tc override for block %d: the pixel-per-lane kernel does not fit a %dx%d map", i, Ho, Wo);
           if (tv[5] < tcc.nbuf) tcc.nbuf = tv[5];
+          if (tv[6] > 0) tcc.unit = tv[6];
           HP_REQUIRE(hp_tc_fits(i, Ho, Wo, tcc), HP_ERR_INVALID, "tc override for block %d does not fit (pixel-per-lane, nsets %d nbuf %d)", i,
                      tcc.nsets, tcc.nbuf);
         } else if (tv[5] > 0) {             // warp-specialised kernel with explicit TR / nsets / esets, rings optional

@@ -682,7 +682,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
 struct TcsParams {
   const float *dww, *dwb, *pwb, *bhi, *blo;
   int W, H, P, NI, rows, n_tiles;            // P = H * W pixels per image, rows = NI * P lanes in use
-  int nstg, nbuf;
+  int nstg, nbuf, ku, upt;                   // ku k-steps per depthwise unit (ring stage = 16 ku TMEM columns), units per tile
   uint32_t load_bytes;
   int off_b, off_w, off_pipe, buf_floats;
   long long* trace;                          // optional clock stamps of CTA 0 (same 12 slots per tile as the band kernel)
@@ -696,7 +696,7 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
   using G = TcGeom<CINP, COUTP>;
   constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
   constexpr uint32_t colA0 = 2 * N16;                             // TMEM: D[0], D[1], then the A ring (16 columns per stage)
-  static_assert(colA0 + TC_MAX_STG * 16 <= 512, "TMEM budget");
+  static_assert(colA0 + TC_MAX_STG * 32 <= 512, "TMEM budget");
 
   extern __shared__ __align__(1024) float smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -785,14 +785,16 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
           off[t] = ok ? q * PS : p.rows * PS + ((q * (PS / 4)) & 7) * 4;
         }
       }
-      const uint32_t n_units = (uint32_t)my_tiles * KS;
-      uint64_t* pending = nullptr;
+      // a unit = ku k-steps: the per-unit hand-off (a_empty wait, tcgen05.wait::st, fence, arrive) costs ~1K clk whatever it carries
+      const int KU = p.ku, UPT = p.upt;
+      const uint32_t n_units = (uint32_t)my_tiles * UPT;
       int cur_i = -1;
       const float* buf = bufs;
 #pragma unroll 1
       for (uint32_t g = set; g < n_units; g += NSETS) {
-        const int i = (int)(g / KS);
-        const int ks = (int)(g - (uint32_t)i * KS);
+        const int i = (int)(g / UPT);
+        const int ks0 = (int)(g - (uint32_t)i * UPT) * KU;
+        const int nk = (KS - ks0 < KU) ? KS - ks0 : KU;
         const uint32_t s = g % NSTG;
         if (i != cur_i) {                                          // first unit of this set in tile i
           cur_i = i;
@@ -801,45 +803,36 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
           mbar_wait(&bar_full[b], (i / NBUF) & 1);
           if (tid == 0) stamp(i, 1);
         }
-        uint32_t v[16];                                            // [hi 8 | lo 8]
-        if (warp_active) {
-          const int c = 8 * ks;
-          const bool two = (2 * ks + 1 < C4);                      // the second 4-channel chunk of the k-step exists
-          float4 a0 = ld4(dwc.b + c), a1 = two ? ld4(dwc.b + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const float* q = buf + off[t] + c;
-            a0 = fma4(ld4(q), ld4(dwc.w + t * CINP + c), a0);
-            if (two) a1 = fma4(ld4(q + 4), ld4(dwc.w + t * CINP + c + 4), a1);
-          }
-          const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            v[e] = tf32_hi(f[e]);
-            v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
-          }
-        }
-        if (pending != nullptr) {
-          if (warp_active) {
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-          }
-          mbar_arrive(pending);
-        }
         if (g >= (uint32_t)NSTG) {
           mbar_wait(&bar_aempty[s], ((g / NSTG) - 1) & 1);
           tc_fence_after();
         }
-        if (warp_active) tmem_st16(tlane + colA0 + s * 16, v);
-        pending = &bar_afull[s];
-        if (g + NSETS >= n_units || (int)((g + NSETS) / KS) != i) {
-          // last unit of this set in tile i: publish now (the next unit may have to wait for a TMA load)
-          if (warp_active) {
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
+        if (warp_active) {
+#pragma unroll 1
+          for (int kk = 0; kk < nk; ++kk) {
+            const int c = 8 * (ks0 + kk);
+            const bool two = (2 * (ks0 + kk) + 1 < C4);            // the second 4-channel chunk of the k-step exists
+            float4 a0 = ld4(dwc.b + c), a1 = two ? ld4(dwc.b + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const float* q = buf + off[t] + c;
+              a0 = fma4(ld4(q), ld4(dwc.w + t * CINP + c), a0);
+              if (two) a1 = fma4(ld4(q + 4), ld4(dwc.w + t * CINP + c + 4), a1);
+            }
+            const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            uint32_t v[16];                                        // [hi 8 | lo 8]
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[e] = tf32_hi(f[e]);
+              v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
+            }
+            tmem_st16(tlane + colA0 + s * (16 * KU) + kk * 16, v);
           }
-          mbar_arrive(pending);
-          pending = nullptr;
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        }
+        mbar_arrive(&bar_afull[s]);
+        if (g + NSETS >= n_units || (int)((g + NSETS) / UPT) != i) {
           if (tid == 0) stamp(i, 2);
           if (tid == (NSETS - 1) * 128) stamp(i, 8);
         }
@@ -878,20 +871,23 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
         }
         if (i > 0) stamp(i, 11);                                     // slot 11 of tile 0: kernel entry
 #pragma unroll 1
-        for (int ks = 0; ks < KS; ++ks, ++use) {
+        for (int u = 0; u < p.upt; ++u, ++use) {
           const uint32_t s = use % NSTG;
           mbar_wait(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
-          if (ks == 0) stamp(i, 10);
-          if (ks == KS - 1) stamp(i, 9);
-          const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
-          const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
-          const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+          if (u == 0) stamp(i, 10);
+          if (u == p.upt - 1) stamp(i, 9);
           const uint32_t dc = tmem_base + d * N16;
-          const uint32_t a = tmem_base + colA0 + s * 16;
-          mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
-          mma_tf32_ts(dc, a, dlo, idesc, 1u);
-          mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          for (int kk = 0; kk < p.ku && u * p.ku + kk < KS; ++kk) {
+            const int ks = u * p.ku + kk;
+            const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
+            const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
+            const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+            const uint32_t a = tmem_base + colA0 + s * (16 * p.ku) + kk * 16;
+            mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+            mma_tf32_ts(dc, a, dlo, idesc, 1u);
+            mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+          }
           tc_commit(&bar_aempty[s]);
         }
         tc_commit(&bar_dfull[d]);
@@ -1345,6 +1341,7 @@ int launch_small(hp_ctx* h, const float* in, float* out, int B, int H, int W, co
   p.W = W; p.H = H; p.P = H * W; p.NI = tc.ni; p.rows = tc.ni * p.P;
   p.n_tiles = ceil_div(B, tc.ni);
   p.nstg = tc.NSTG; p.nbuf = tc.nbuf;
+  p.ku = (tc.unit >= 1 && tc.unit <= 2) ? tc.unit : 1; p.upt = ceil_div(G::KS, p.ku);
   p.load_bytes = (uint32_t)((size_t)G::PS * p.rows * sizeof(float));
   p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
   tc_layout(CINP, COUTP, G::K8, G::N16, &p.off_b, &p.off_w, &p.off_pipe);
@@ -1352,7 +1349,7 @@ int launch_small(hp_ctx* h, const float* in, float* out, int B, int H, int W, co
   const size_t smem = (size_t)(p.off_pipe + tc.nbuf * p.buf_floats) * sizeof(float);
   HP_REQUIRE(smem <= 227 * 1024, HP_ERR_INVALID, "tc small block <%d,%d>: %zu bytes of shared memory needed", CINP, COUTP, smem);
   HP_REQUIRE(p.rows >= 1 && p.rows <= 128 && tc.nbuf >= 2 && tc.nbuf <= TCD_MAXB && tc.NSTG >= 2 && tc.NSTG <= TC_MAX_STG &&
-                 tc.nsets <= tc.NSTG && 2 * G::N16 + tc.NSTG * 16 <= 512 && (long long)B * p.P < (1ll << 31),
+                 tc.nsets <= tc.NSTG && 2 * G::N16 + tc.NSTG * 16 * p.ku <= 512 && (long long)B * p.P < (1ll << 31),
              HP_ERR_INVALID, "tc small block <%d,%d>: bad geometry %dx%d NI %d nbuf %d nstg %d", CINP, COUTP, H, W, tc.ni, tc.nbuf, tc.NSTG);
   // the feature maps as [B H W pixels][C]: one box = the pixels of NI images, PS >= C floats per pixel (zero fill / clipped)
   CUtensorMap tin, tout;
@@ -1507,7 +1504,8 @@ bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc) {
   const int ni = tc.nbuf > 0 ? tc.ni : 1;
   if (tc.TR == 1 && tc.nbuf > 0) {   // pixel-per-lane kernel
     if (kBlazeBlocks[blk].stride != 1 || cinp < 48 || ni < 1 || ni * H * W > 128 || tc.nbuf < 2 || tc.nbuf > TCD_MAXB || tc.NSTG < 2 ||
-        tc.NSTG > TC_MAX_STG || tc.nsets < 1 || tc.nsets > tc.NSTG || 2 * N16 + tc.NSTG * 16 > 512 || tc.npipe < 1 || tc.npipe > 2)
+        tc.NSTG > TC_MAX_STG || tc.nsets < 1 || tc.nsets > tc.NSTG || tc.unit < 1 || tc.unit > 2 || 2 * N16 + tc.NSTG * 16 * tc.unit > 512 ||
+        tc.npipe < 1 || tc.npipe > 2)
       return false;
     int ob, ow, op;
     tc_layout(cinp, coutp, K8, N16, &ob, &ow, &op);
