@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Summarise an `ncu --set full` report of tools/profile_target.py: one row per backbone kernel of the LAST forward
+(time, registers, pipes, DRAM bytes, shared-memory wavefronts) + a JSON of DRAM bytes per launch that bench.py reads as
+roofline.traffic.  Usage: ncu_summary.py report.ncu-rep summary.txt traffic.json [batch] [size]"""
+import csv
+import json
+import subprocess
+import sys
+
+rep, out_txt, out_json = sys.argv[1:4]
+batch = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
+size = int(sys.argv[5]) if len(sys.argv) > 5 else 96
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, body = rows[0], rows[1], rows[2:]
+col = {h: i for i, h in enumerate(hdr)}
+
+
+def pick(*names):
+    for n in names:
+        if n in col:
+            return col[n]
+    return None
+
+
+want = [("time us", pick("gpu__time_duration.sum")),
+        ("regs", pick("launch__registers_per_thread")),
+        ("threads", pick("launch__block_size")),
+        ("warps active %", pick("sm__warps_active.avg.pct_of_peak_sustained_active")),
+        ("issue active %", pick("sm__inst_issued.avg.pct_of_peak_sustained_active", "sm__issue_active.avg.pct_of_peak_sustained_active",
+                                "smsp__issue_active.avg.pct_of_peak_sustained_active")),
+        ("fma pipe %", pick("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")),
+        ("tensor pipe %", pick("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                               "sm__pipe_tensor_subpipe_tmem_cycles_active.avg.pct_of_peak_sustained_active",
+                               "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active")),
+        ("dram %", pick("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed")),
+        ("dram read", pick("dram__bytes_read.sum")),
+        ("dram write", pick("dram__bytes_write.sum")),
+        ("smem wavefronts %", pick("l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
+                                   "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")),
+        ("warp instr", pick("smsp__inst_executed.sum", "sm__inst_executed.sum"))]
+kname = col.get("Kernel Name")
+
+
+def to_bytes(v, u):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
+
+
+backbone = [r for r in body if len(r) > kname and ("stem" in r[kname] or "blaze_block" in r[kname])]
+last = backbone[-17:]                      # the last forward: stem + 16 blocks
+names = ["stem"] + [f"block{i}" for i in range(16)]
+traffic = {}
+with open(out_txt, "w") as f:
+    f.write(f"# ncu --set full --clock-control none, tools/profile_target.py {size} {batch}; one row per backbone kernel\n")
+    f.write("kernel | " + " | ".join(n for n, _ in want) + "\n")
+    for nm, r in zip(names, last):
+        vals = []
+        for n, c in want:
+            if c is None:
+                vals.append("n/a")
+            elif n.startswith("dram r") or n.startswith("dram w"):
+                vals.append(f"{to_bytes(r[c], units[c]) / 1e9:.6f} Gbyte")
+            else:
+                vals.append(r[c])
+        f.write(f"{nm} {r[kname][:60]} | " + " | ".join(vals) + "\n")
+        cr, cw = pick("dram__bytes_read.sum"), pick("dram__bytes_write.sum")
+        if cr is not None and cw is not None:
+            traffic[nm] = {"dram_read_bytes": to_bytes(r[cr], units[cr]), "dram_write_bytes": to_bytes(r[cw], units[cw]), "batch": batch, "size": size}
+    missing = [n for n, c in want if c is None]
+    if missing:
+        f.write("# metrics not in this report: " + ", ".join(missing) + "\n")
+json.dump(traffic, open(out_json, "w"), indent=1)
+print(open(out_txt).read())
