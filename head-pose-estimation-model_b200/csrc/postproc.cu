@@ -144,15 +144,15 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(NmsParams p) {
   // ---- bitonic sort, descending
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
+  // one compare-exchange PAIR per thread and step (i = the pair's lower index, partner i | j): no idle half of the threads
   for (int k = 2; k <= n2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < n2; i += 128) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long x = keys[i], y = keys[ixj];
-          const bool desc = ((i & k) == 0);
-          if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[ixj] = x; }
-        }
+      for (int t = tid; t < (n2 >> 1); t += 128) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int ixj = i | j;
+        const unsigned long long x = keys[i], y = keys[ixj];
+        const bool desc = ((i & k) == 0);
+        if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[ixj] = x; }
       }
       __syncthreads();
     }

@@ -163,7 +163,9 @@ def test_detect_faces_end_to_end_vs_oracle():
 @pytest.mark.parametrize("chunks", [1, 2, 4])
 def test_detect_stream_matches_detect_device(chunks):
     """The pipelined serving loop (copies overlapped with compute on side streams, every batch optionally cut into
-    slices) returns, batch by batch and in order, exactly what the synchronous path returns."""
+    slices) returns, batch by batch and in order, exactly what the synchronous path returns.  64 crops per batch keep every
+    slice (16 crops = 576 rows of the 6 x 6 map) on the same Dense kernel as the whole batch: below 512 rows a layer takes the
+    CUDA-core kernel, whose last-bit differences reorder near-tied scores in the NMS of these random-weight detections."""
     import torch
     from hpose_b200 import keras_spec as K, train_88
     from hpose_b200.attention_model import se_transformer_regr_head
@@ -175,7 +177,7 @@ def test_detect_stream_matches_detect_device(chunks):
     head8 = se_transformer_regr_head(input_channels=96)
     det = blazeFaceDetector(model=UnifiedModel(random_backbone(seed=4, bias_scale=0.1), head16, head8), inputSize=96)
     rng = np.random.default_rng(3)
-    host = [torch.from_numpy(rng.integers(0, 256, size=(9, 96, 96, 3), dtype=np.uint8)).pin_memory() for _ in range(5)]
+    host = [torch.from_numpy(rng.integers(0, 256, size=(64, 96, 96, 3), dtype=np.uint8)).pin_memory() for _ in range(4)]
     want = []
     for hb in host:
         out = det.detect_device(hb.cuda())
@@ -188,9 +190,4 @@ def test_detect_stream_matches_detect_device(chunks):
         assert np.array_equal(g["count"], w["count"])
         for i, c in enumerate(w["count"]):                 # entries beyond count[i] are uninitialised padding
             for k in ("boxes", "scores", "poses", "keypoints"):
-                if chunks == 1:
-                    assert np.array_equal(g[k][i, :c], w[k][i, :c]), (k, i)
-                else:
-                    # a slice of fewer than 512 token rows takes the CUDA-core Dense kernel instead of the 3xTF32 one:
-                    # same values to ~1e-6, not bit for bit
-                    assert np.allclose(g[k][i, :c], w[k][i, :c], rtol=1e-5, atol=2e-5), (k, i)
+                assert np.array_equal(g[k][i, :c], w[k][i, :c]), (k, i)
