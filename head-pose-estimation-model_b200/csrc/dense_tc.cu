@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int DT_MAXB = 4, DT_MAXSTG = 4, DT_BAR_FLOATS = 64, DT_MAXKU = 4;
+constexpr int DT_MAXB = 4, DT_MAXSTG = 4, DT_BAR_FLOATS = 64, DT_MAXKU = 4, DT_MAXD = 4;
 constexpr int DT_ROWS = 128;
 
 struct DenseTcParams {
@@ -29,6 +29,7 @@ struct DenseTcParams {
   int K8, KS, N16, KPAD, OS;          // OS: staging row stride (odd number of 16-byte chunks)
   int n_tiles, nstg, nbuf;
   int ku, upt;                        // k-steps per gather unit (ring stage = 16 ku TMEM columns), units per tile
+  int nd;                             // accumulator buffers in TMEM
   uint32_t load_bytes;
   int off_b, off_bias, off_rowoff, off_stage, off_in, in_floats;
   int n_outs;
@@ -100,9 +101,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
   uint64_t* bar_infree = bars + DT_MAXB;          // [nbuf]
   uint64_t* bar_afull = bars + 2 * DT_MAXB;       // [nstg]
   uint64_t* bar_aempty = bar_afull + DT_MAXSTG;   // [nstg]
-  uint64_t* bar_dfull = bar_aempty + DT_MAXSTG;   // [2]
-  uint64_t* bar_dempty = bar_dfull + 2;           // [2]
-  static_assert((2 * DT_MAXB + 2 * DT_MAXSTG + 4) * 8 + 4 <= DT_BAR_FLOATS * 4, "barrier block");
+  uint64_t* bar_dfull = bar_aempty + DT_MAXSTG;   // [nd]
+  uint64_t* bar_dempty = bar_dfull + DT_MAXD;     // [nd]
+  static_assert((2 * DT_MAXB + 2 * DT_MAXSTG + 2 * DT_MAXD) * 8 + 4 <= DT_BAR_FLOATS * 4, "barrier block");
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (DT_BAR_FLOATS - 1);
   float* s_bhi = smem + p.off_b;
   float* s_blo = s_bhi + p.K8 * p.N16;
@@ -148,7 +149,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
       mbar_init(&bar_afull[s], 128);
       mbar_init(&bar_aempty[s], 1);
     }
-    for (int d = 0; d < 2; ++d) {
+    for (int d = 0; d < p.nd; ++d) {
       mbar_init(&bar_dfull[d], 1);
       mbar_init(&bar_dempty[d], TAIL ? 128 : 128 * NESETS);
     }
@@ -162,7 +163,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
-  const uint32_t colA0 = 2 * N16;                 // D[0], D[1] (N16 columns each), then the A ring (16 ku columns per stage)
+  const int ND = p.nd;                            // accumulator buffers: 2, or 4 for the fused narrow layer (its epilogue holds D longest)
+  const uint32_t colA0 = ND * N16;                // D[0 .. nd) (N16 columns each), then the A ring (16 ku columns per stage)
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < W_ISSUE) {
@@ -228,9 +230,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) b2[j] = (p.b2 && j < p.n2) ? p.b2[j] : 0.f;
       for (int i = eset; i < my_tiles; i += NESETS) {
-        const int d = i & 1;
+        const int d = i % ND;
         const long long m = ((long long)blockIdx.x + (long long)i * gridDim.x) * DT_ROWS + lane;
-        mbar_wait(&bar_dfull[d], (i >> 1) & 1);
+        mbar_wait(&bar_dfull[d], (i / ND) & 1);
         tc_fence_after();
         if ((tid & 127) == 0) stamp(i, 3);
         float4 acc = make_float4(b2[0], b2[1], b2[2], b2[3]);
@@ -276,18 +278,18 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
       const int etid = tid - W_EPI * 32;           // 0 .. 128 * NESETS - 1
       int tile = blockIdx.x;
       for (int i = 0; i < my_tiles; ++i, tile += gridDim.x) {
-        const int d = i & 1;
+        const int d = i % ND;
         const long long m0 = (long long)tile * DT_ROWS;
         const int rows = (int)((p.M - m0 < DT_ROWS) ? (p.M - m0) : DT_ROWS);
         // destination offset of every tile row per output segment (one 64-bit division per row, none per element)
         for (int j = etid; j < p.n_outs * DT_ROWS; j += 128 * NESETS) {
           const int o = j / DT_ROWS, r = j - o * DT_ROWS;
           const DenseOut& dd = p.outs[o];
-          const long long m = m0 + r;
-          const long long img = m / dd.rows_per_img;
-          rowoff[j] = img * dd.img_stride + (m - img * dd.rows_per_img) * (long long)dd.row_stride;
+          const unsigned m = (unsigned)(m0 + r);                 // M is an int: 32-bit division
+          const unsigned img = m / (unsigned)dd.rows_per_img;
+          rowoff[j] = (long long)img * dd.img_stride + (long long)(m - img * (unsigned)dd.rows_per_img) * dd.row_stride;
         }
-        mbar_wait(&bar_dfull[d], (i >> 1) & 1);
+        mbar_wait(&bar_dfull[d], (i / ND) & 1);
         tc_fence_after();
         if (etid == 0) stamp(i, 3);
         // D row + bias -> staging tile; the 32-column groups are dealt to the epilogue sets
@@ -348,9 +350,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
       uint32_t use = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int d = i & 1;
-        if (i >= 2) {
-          mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
+        const int d = i % ND;
+        if (i >= ND) {
+          mbar_wait(&bar_dempty[d], ((i / ND) - 1) & 1);
           tc_fence_after();
         }
         if (i > 0) stamp(i, 11);
@@ -454,8 +456,9 @@ static int dense_tc_launch(hp_ctx* h, const float* x, int M, int K, int ldx, con
   p.ku = DT_MAXKU;
   while (p.ku > 1 && ceil_div(p.KS, p.ku) < 3) --p.ku;
   p.upt = ceil_div(p.KS, p.ku);
+  p.nd = (tail && 4 * p.N16 + DT_MAXSTG * 16 * p.ku <= 512) ? 4 : 2;
   p.nstg = DT_MAXSTG;
-  HP_REQUIRE(2 * p.N16 + p.nstg * 16 * p.ku <= 512 && p.upt >= 3 && p.KPAD <= 256, HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);
+  HP_REQUIRE(p.nd * p.N16 + p.nstg * 16 * p.ku <= 512 && p.upt >= 3 && p.KPAD <= 256, HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);
   p.n_outs = n_outs;
   for (int i = 0; i < n_outs; ++i) {
     p.outs[i] = outs[i];
@@ -477,19 +480,24 @@ static int dense_tc_launch(hp_ctx* h, const float* x, int M, int K, int ldx, con
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
   // narrow layers are bound by the gather (3 sets); wide ones by the epilogue (2 sets)
-  if (tail) {
-    auto kern = dense_tc_kernel<2, 2, true>;
-    HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    kern<<<(unsigned)grid, 128 * 2 + 128 * 2 + 96, smem, st>>>(tin, p);
-  } else if (p.N16 <= 32) {
-    auto kern = dense_tc_kernel<3, 1, false>;
-    HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    kern<<<(unsigned)grid, 128 * 3 + 128 * 1 + 96, smem, st>>>(tin, p);
-  } else {
-    auto kern = dense_tc_kernel<2, 2, false>;
-    HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    kern<<<(unsigned)grid, 128 * 2 + 128 * 2 + 96, smem, st>>>(tin, p);
+  // warp sets: gather x epilogue.  Sweeps with tools/dense_trace.py (HP_DENSE_TC_SETS=<gather><epilogue>, e.g. "31", overrides the
+  // defaults for such sweeps only; profiles/r01/dense_sets_sweep.log): the number of gather sets does not matter, 2 epilogue
+  // sets are 20-25 % faster than 1, more than 2 change nothing
+  int ns = (!tail && p.N16 <= 32) ? 3 : 2, ne = (!tail && p.N16 <= 32) ? 1 : 2;
+  {
+    static const char* env = getenv("HP_DENSE_TC_SETS");
+    if (env && env[0] >= '1' && env[0] <= '3' && env[1] >= '1' && env[1] <= '2') { ns = env[0] - '0'; ne = env[1] - '0'; }
   }
+#define DT_LAUNCH(NS_, NE_, TAIL_)                                                                            \
+  if (ns == NS_ && ne == NE_ && (tail != nullptr) == TAIL_) {                                                  \
+    auto kern = dense_tc_kernel<NS_, NE_, TAIL_>;                                                              \
+    HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));              \
+    kern<<<(unsigned)grid, 128 * NS_ + 128 * NE_ + 96, smem, st>>>(tin, p);                                    \
+  }
+  DT_LAUNCH(1, 1, false) DT_LAUNCH(1, 2, false) DT_LAUNCH(2, 1, false) DT_LAUNCH(2, 2, false) DT_LAUNCH(3, 1, false) DT_LAUNCH(3, 2, false)
+  DT_LAUNCH(1, 2, true) DT_LAUNCH(2, 2, true) DT_LAUNCH(3, 2, true)
+  else if (tail && ne != 2) { hp_set_error("dense tc: the fused narrow layer is built with 2 epilogue sets"); return HP_ERR_UNSUPPORTED; }
+#undef DT_LAUNCH
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;
