@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Summarise an `ncu --set full` report of tools/profile_target.py: one row per backbone kernel of the LAST forward
 (time, registers, pipes, DRAM bytes, shared-memory wavefronts) + a JSON of DRAM bytes per launch that bench.py reads as
-roofline.traffic.  Usage: ncu_summary.py report.ncu-rep summary.txt traffic.json [batch] [size]"""
+roofline.traffic.  Usage: ncu_summary.py report.ncu-rep summary.txt traffic.json [batch] [size] [all]
+("all": one row per kernel launch in the report, whatever it is -- used for the head / post-processing kernels of a bench step)"""
 import csv
 import json
 import subprocess
@@ -47,9 +48,13 @@ def to_bytes(v, u):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
 
 
-backbone = [r for r in body if len(r) > kname and ("stem" in r[kname] or "blaze_block" in r[kname])]
-last = backbone[-17:]                      # the last forward: stem + 16 blocks
-names = ["stem"] + [f"block{i}" for i in range(16)]
+if len(sys.argv) > 6 and sys.argv[6] == "all":
+    last = [r for r in body if len(r) > kname]
+    names = [f"#{i}" for i in range(len(last))]
+else:
+    backbone = [r for r in body if len(r) > kname and ("stem" in r[kname] or "blaze_block" in r[kname])]
+    last = backbone[-17:]                      # the last forward: stem + 16 blocks
+    names = ["stem"] + [f"block{i}" for i in range(16)]
 traffic = {}
 with open(out_txt, "w") as f:
     f.write(f"# ncu --set full --clock-control none, tools/profile_target.py {size} {batch}; one row per backbone kernel\n")
@@ -63,7 +68,8 @@ with open(out_txt, "w") as f:
                 vals.append(f"{to_bytes(r[c], units[c]) / 1e9:.6f} Gbyte")
             else:
                 vals.append(r[c])
-        f.write(f"{nm} {r[kname][:60]} | " + " | ".join(vals) + "\n")
+        kn = r[kname].replace("void ", "").replace("<unnamed>::", "")
+        f.write(f"{nm} {kn[:60]} | " + " | ".join(vals) + "\n")
         cr, cw = pick("dram__bytes_read.sum"), pick("dram__bytes_write.sum")
         if cr is not None and cw is not None:
             traffic[nm] = {"dram_read_bytes": to_bytes(r[cr], units[cr]), "dram_write_bytes": to_bytes(r[cw], units[cw]), "batch": batch, "size": size}
