@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int DT_MAXB = 4, DT_MAXSTG = 4, DT_BAR_FLOATS = 64, DT_MAXKU = 4, DT_MAXD = 4;
+constexpr int DT_MAXB = 4, DT_MAXSTG = 4, DT_BAR_FLOATS = 96, DT_MAXKU = 4, DT_MAXD = 4;
 constexpr int DT_ROWS = 128;
 
 struct DenseTcParams {
@@ -30,6 +30,7 @@ struct DenseTcParams {
   int n_tiles, nstg, nbuf;
   int ku, upt;                        // k-steps per gather unit (ring stage = 16 ku TMEM columns), units per tile
   int nd;                             // accumulator buffers in TMEM
+  int niss;                           // issuing threads = A rings (nstg stages each)
   uint32_t load_bytes;
   int off_b, off_bias, off_rowoff, off_stage, off_in, in_floats;
   int n_outs;
@@ -99,11 +100,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint64_t* bar_full = bars;                      // [nbuf]
   uint64_t* bar_infree = bars + DT_MAXB;          // [nbuf]
-  uint64_t* bar_afull = bars + 2 * DT_MAXB;       // [nstg]
-  uint64_t* bar_aempty = bar_afull + DT_MAXSTG;   // [nstg]
-  uint64_t* bar_dfull = bar_aempty + DT_MAXSTG;   // [nd]
+  uint64_t* bar_afull = bars + 2 * DT_MAXB;       // [niss][DT_MAXSTG]: one A ring per issuing thread
+  uint64_t* bar_aempty = bar_afull + 2 * DT_MAXSTG;
+  uint64_t* bar_dfull = bar_aempty + 2 * DT_MAXSTG;   // [nd]
   uint64_t* bar_dempty = bar_dfull + DT_MAXD;     // [nd]
-  static_assert((2 * DT_MAXB + 2 * DT_MAXSTG + 2 * DT_MAXD) * 8 + 4 <= DT_BAR_FLOATS * 4, "barrier block");
+  static_assert((2 * DT_MAXB + 4 * DT_MAXSTG + 2 * DT_MAXD) * 8 + 4 <= DT_BAR_FLOATS * 4, "barrier block");
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (DT_BAR_FLOATS - 1);
   float* s_bhi = smem + p.off_b;
   float* s_blo = s_bhi + p.K8 * p.N16;
@@ -145,10 +146,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
       mbar_init(&bar_full[b], 1);
       mbar_init(&bar_infree[b], 128 * NSETS);
     }
-    for (int s = 0; s < NSTG; ++s) {
-      mbar_init(&bar_afull[s], 128);
-      mbar_init(&bar_aempty[s], 1);
-    }
+    for (int r = 0; r < p.niss; ++r)
+      for (int s = 0; s < NSTG; ++s) {
+        mbar_init(&bar_afull[r * DT_MAXSTG + s], 128);
+        mbar_init(&bar_aempty[r * DT_MAXSTG + s], 1);
+      }
     for (int d = 0; d < p.nd; ++d) {
       mbar_init(&bar_dfull[d], 1);
       mbar_init(&bar_dempty[d], TAIL ? 128 : 128 * NESETS);
@@ -187,7 +189,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
         const int i = (int)(g / UPT);
         const int ks0 = (int)(g - (uint32_t)i * UPT) * KU;
         const int nk = (KS - ks0 < KU) ? KS - ks0 : KU;
-        const uint32_t s = g % NSTG;
+        // two issuing threads (p.niss == 2): tiles alternate between two A rings with their own barriers; q = index of the
+        // unit within its ring
+        const int ring = (p.niss == 2) ? (i & 1) : 0;
+        const uint32_t q = (p.niss == 2) ? (uint32_t)(i >> 1) * UPT + (uint32_t)(ks0 / KU) : g;
+        const uint32_t s = q % NSTG;
+        uint64_t* a_full = &bar_afull[ring * DT_MAXSTG + s];
         if (i != cur_i) {
           cur_i = i;
           cur_b = i % NBUF;
@@ -195,8 +202,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
           mbar_wait(&bar_full[cur_b], (i / NBUF) & 1);
           if (tid == 0) stamp(i, 1);
         }
-        if (g >= (uint32_t)NSTG) {
-          mbar_wait(&bar_aempty[s], ((g / NSTG) - 1) & 1);
+        if (q >= (uint32_t)NSTG) {
+          mbar_wait(&bar_aempty[ring * DT_MAXSTG + s], ((q / NSTG) - 1) & 1);
           tc_fence_after();
         }
 #pragma unroll
@@ -211,12 +218,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
               v[e] = tf32_hi(f[e]);
               v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
             }
-            tmem_st16(tlane + colA0 + s * (16 * KU) + kk * 16, v);
+            tmem_st16(tlane + colA0 + (ring * NSTG + s) * (16 * KU) + kk * 16, v);
           }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        mbar_arrive(&bar_afull[s]);
+        mbar_arrive(a_full);
         if (g + NSETS >= n_units || (int)((g + NSETS) / UPT) != i) {
           mbar_arrive(&bar_infree[cur_b]);   // this thread reads nothing more from the tile
           if (tid == 0) stamp(i, 2);
@@ -343,13 +350,14 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
       }
     }
   } else if (lane_id == 0) {
-    if (warp == W_ISSUE) {
-      // =============================================================== MMA issuer
+    if (warp == W_ISSUE || (warp == W_ISSUE + 2 && p.niss == 2)) {
+      // =============================================================== MMA issuer(s): issuer r owns tiles i = r, r + niss, ... and A ring r
+      const int ring = (warp == W_ISSUE) ? 0 : 1;
       const uint32_t idesc = tc_idesc_tf32(N16);
       const uint64_t desc_fixed = tc_bdesc_fixed(N16);
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
-      uint32_t use = 0;
-      for (int i = 0; i < my_tiles; ++i) {
+      uint32_t use = 0;                                              // index of the unit within this issuer's ring
+      for (int i = ring; i < my_tiles; i += p.niss) {
         const int d = i % ND;
         if (i >= ND) {
           mbar_wait(&bar_dempty[d], ((i / ND) - 1) & 1);
@@ -359,7 +367,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
 #pragma unroll 1
         for (int u = 0; u < p.upt; ++u, ++use) {
           const uint32_t s = use % NSTG;
-          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          mbar_wait(&bar_afull[ring * DT_MAXSTG + s], (use / NSTG) & 1);
           tc_fence_after();
           if (u == 0) stamp(i, 10);
           if (u == p.upt - 1) stamp(i, 9);
@@ -369,12 +377,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
             const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
             const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
             const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
-            const uint32_t a = tmem_base + colA0 + s * (16 * p.ku) + kk * 16;
+            const uint32_t a = tmem_base + colA0 + (ring * NSTG + s) * (16 * p.ku) + kk * 16;
             mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
             mma_tf32_ts(dc, a, dlo, idesc, 1u);
             mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
           }
-          tc_commit(&bar_aempty[s]);
+          tc_commit(&bar_aempty[ring * DT_MAXSTG + s]);
         }
         tc_commit(&bar_dfull[d]);
         stamp(i, 7);
@@ -457,8 +465,8 @@ static int dense_tc_launch(hp_ctx* h, const float* x, int M, int K, int ldx, con
   while (p.ku > 1 && ceil_div(p.KS, p.ku) < 3) --p.ku;
   p.upt = ceil_div(p.KS, p.ku);
   p.nd = (tail && 4 * p.N16 + DT_MAXSTG * 16 * p.ku <= 512) ? 4 : 2;
+  p.niss = 1;
   p.nstg = DT_MAXSTG;
-  HP_REQUIRE(p.nd * p.N16 + p.nstg * 16 * p.ku <= 512 && p.upt >= 3 && p.KPAD <= 256, HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);
   p.n_outs = n_outs;
   for (int i = 0; i < n_outs; ++i) {
     p.outs[i] = outs[i];
@@ -484,10 +492,37 @@ static int dense_tc_launch(hp_ctx* h, const float* x, int M, int K, int ldx, con
   // defaults for such sweeps only; profiles/r01/dense_sets_sweep.log): the number of gather sets does not matter, 2 epilogue
   // sets are 20-25 % faster than 1, more than 2 change nothing
   int ns = (!tail && p.N16 <= 32) ? 3 : 2, ne = (!tail && p.N16 <= 32) ? 1 : 2;
+  // measured (profiles/r01/dense_issuers_sweep.log): 2 issuers 110 -> 90 us on the 88 -> 34 detector head, 37.5 -> 32.5 us on 96 -> 64;
+  // the fused narrow layer prefers 4 accumulator buffers and one issuer (115 vs 127 us)
+  int want_iss = tail ? 1 : 2;
   {
     static const char* env = getenv("HP_DENSE_TC_SETS");
-    if (env && env[0] >= '1' && env[0] <= '3' && env[1] >= '1' && env[1] <= '2') { ns = env[0] - '0'; ne = env[1] - '0'; }
+    if (env && env[0] >= '1' && env[0] <= '3' && env[1] >= '1' && env[1] <= '2') {
+      ns = env[0] - '0'; ne = env[1] - '0';
+      if (env[2] == '1' || env[2] == '2') want_iss = env[2] - '0';
+    }
   }
+  // Two issuing threads: one thread issues a tcgen05.mma only every ~110 clk next to the worker warps and nothing else is
+  // saturated (profiles/r01/ncu_heads_v6_summary.txt).  Each gets its own A ring (tiles alternate) with 2 accumulator buffers;
+  // an mbarrier waiter may be one phase ahead at most, so consecutive units of a gather set within one ring must be at most
+  // nstg ring slots apart: checked by walking the round-robin schedule.
+  if (want_iss == 2) {
+    const int nd2 = 2;
+    int stg = (512 - nd2 * p.N16) / (2 * 16 * p.ku);
+    if (stg > DT_MAXSTG) stg = DT_MAXSTG;
+    bool safe = stg >= 2;
+    for (int x = 0; x < ns && safe; ++x) {
+      long long last[2] = {-1, -1};
+      for (long long g = x; g < 16ll * p.upt; g += ns) {
+        const long long i = g / p.upt, u = g - i * p.upt, r = i & 1, q = (i >> 1) * p.upt + u;
+        if (last[r] >= 0 && q - last[r] > stg) safe = false;
+        last[r] = q;
+      }
+    }
+    if (safe) { p.niss = 2; p.nstg = stg; p.nd = nd2; }
+  }
+  HP_REQUIRE(p.nd * p.N16 + p.niss * p.nstg * 16 * p.ku <= 512 && p.upt >= 3 && p.KPAD <= 256 && ns <= p.nstg * (p.niss == 2 ? 2 : 1),
+             HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);
 #define DT_LAUNCH(NS_, NE_, TAIL_)                                                                            \
   if (ns == NS_ && ne == NE_ && (tail != nullptr) == TAIL_) {                                                  \
     auto kern = dense_tc_kernel<NS_, NE_, TAIL_>;                                                              \
