@@ -65,7 +65,7 @@ def test_trained_weights_128_all_layers(impl):
         ctx.set_impl(_lib.HP_IMPL_FAST)
 
 
-@pytest.mark.parametrize("size,batch", [(128, 2), (96, 5), (88, 3), (64, 1), (120, 2)])
+@pytest.mark.parametrize("size,batch", [(128, 2), (96, 5), (88, 3), (64, 1), (120, 2), (100, 2), (104, 1)])
 def test_unified_outputs_match_oracle(size, batch):
     """All six outputs of the unified graph (trained weights) at several input sizes incl. odd maps (88 -> 11 -> 6)."""
     from hpose_b200 import keras_spec as K
