@@ -189,6 +189,8 @@ class blazeFaceDetector:
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         chunks = max(1, int(chunks))
         d_in = [[None] * chunks for _ in range(2)]
+        d_out = [[None] * chunks for _ in range(2)]       # device result tensors, reused: slot b is idle once its read-back is done
+        ev_read = [[None] * chunks for _ in range(2)]
         h_out = [None, None]
         ev_in = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(2)]
         ev_comp = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(2)]
@@ -217,7 +219,9 @@ class blazeFaceDetector:
                     d_in[b][c].copy_(part, non_blocking=True)
                     ev_in[b][c].record(s_in)
                 comp.wait_event(ev_in[b][c])
-                out = self.detect_device(d_in[b][c], max_faces)
+                if ev_read[b][c] is not None:
+                    comp.wait_event(ev_read[b][c])         # the previous results of this slot have left the device
+                out = d_out[b][c] = self.detect_device(d_in[b][c], max_faces, out=d_out[b][c])
                 ev_comp[b][c].record(comp)
                 used[b][c] = True
                 with torch.cuda.stream(s_out):
@@ -225,8 +229,10 @@ class blazeFaceDetector:
                     if h_out[b] is None or any(h_out[b][k].shape != (B,) + tuple(out[k].shape[1:]) for k in keys):
                         h_out[b] = {k: torch.empty((B,) + tuple(out[k].shape[1:]), dtype=out[k].dtype).pin_memory() for k in keys}
                     for k in keys:
-                        out[k].record_stream(s_out)
                         h_out[b][k][c0:c1].copy_(out[k], non_blocking=True)
+                    if ev_read[b][c] is None:
+                        ev_read[b][c] = torch.cuda.Event()
+                    ev_read[b][c].record(s_out)
             ev_out[b].record(s_out)
             pending.append(b)
             n += 1
@@ -234,7 +240,7 @@ class blazeFaceDetector:
             ev_out[q].synchronize()
             yield h_out[q]
 
-    def detect_device(self, images, max_faces=MAX_FACE_NUM, float_input=False):
+    def detect_device(self, images, max_faces=MAX_FACE_NUM, float_input=False, out=None):
         import torch
         dev = self.ctx.torch_device
         if isinstance(images, np.ndarray):
@@ -245,14 +251,17 @@ class blazeFaceDetector:
         B, H, W, _ = x.shape
         m = self.interpreter
         H16, W16, H8, W8 = -(-H // 8), -(-W // 8), -(-H // 16), -(-W // 16)
-        out = {"count": torch.empty((B,), dtype=torch.int32, device=dev),
-               "anchors": torch.empty((B, max_faces), dtype=torch.int32, device=dev),
-               "boxes": torch.empty((B, max_faces, 4), dtype=torch.float64, device=dev),
-               "keypoints": torch.empty((B, max_faces, KEY_POINT_SIZE, 2), dtype=torch.float64, device=dev),
-               "scores": torch.empty((B, max_faces), dtype=torch.float32, device=dev),
-               "poses": torch.empty((B, max_faces, 3), dtype=torch.float32, device=dev),
-               "pose16": torch.empty((B, H16, W16, 3), dtype=torch.float32, device=dev),
-               "pose8": torch.empty((B, H8, W8, 3), dtype=torch.float32, device=dev)}
+        if out is not None and out["count"].shape[0] == B and out["anchors"].shape[1] == max_faces and out["pose16"].shape[1:3] == (H16, W16):
+            pass                                   # caller-owned result tensors of the right shape (the serving loop reuses them)
+        else:
+            out = {"count": torch.empty((B,), dtype=torch.int32, device=dev),
+                   "anchors": torch.empty((B, max_faces), dtype=torch.int32, device=dev),
+                   "boxes": torch.empty((B, max_faces, 4), dtype=torch.float64, device=dev),
+                   "keypoints": torch.empty((B, max_faces, KEY_POINT_SIZE, 2), dtype=torch.float64, device=dev),
+                   "scores": torch.empty((B, max_faces), dtype=torch.float32, device=dev),
+                   "poses": torch.empty((B, max_faces, 3), dtype=torch.float32, device=dev),
+                   "pose16": torch.empty((B, H16, W16, 3), dtype=torch.float32, device=dev),
+                   "pose8": torch.empty((B, H8, W8, 3), dtype=torch.float32, device=dev)}
         _lib.check(_lib.lib().hp_unified_forward(
             self.ctx.handle, m.head16.head_handle, m.head8.head_handle, x.data_ptr(), B, H, W,
             float(np.float32(self.sigmoidScoreThreshold)), float(np.float32(self.iouThreshold)), int(max_faces),
