@@ -14,7 +14,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhpose.so")
-SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "stem_tc.cu", "dense_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
+SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "blocks_chain.cu", "stem_tc.cu", "dense_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -53,25 +53,50 @@ class hp_opt_config(C.Structure):
                 ("eps", C.c_float)]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"),
+           os.path.join(PKG_DIR, "..", "include", "hpose.h")]
+OBJ_DIR = os.path.join(CSRC, "build")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"),
-                                                       os.path.join(PKG_DIR, "..", "include", "hpose.h")]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def needs_build() -> bool:
+    return _stale(LIB_PATH, [os.path.join(CSRC, s) for s in SOURCES] + HEADERS)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libhpose.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile libhpose.so in-tree for sm_100a (nvcc cross-compiles without a GPU): one object per translation
+    unit (only stale ones are recompiled, in parallel), then one link."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES + ["-ldl"]
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if force or _stale(obj, [os.path.join(CSRC, src)] + HEADERS):
+            cmd = ["nvcc"] + flags + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-ldl"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     return LIB_PATH
 
 
@@ -121,6 +146,8 @@ _PROTOS = {
     "hp_debug_set_tile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_debug_tile_report": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_debug_set_stem_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "hp_debug_set_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "hp_debug_chain_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_debug_tc_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hp_debug_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -126,6 +126,16 @@ int hp_debug_set_stem_tc(hp_handle h, int BH, int nbuf, int nout, int nsets) {
   h->stem_tc_cfg[0] = BH; h->stem_tc_cfg[1] = nbuf; h->stem_tc_cfg[2] = nout; h->stem_tc_cfg[3] = nsets;
   return HP_OK;
 }
+int hp_debug_set_chain(hp_handle h, int mode, int nsets, int niss) {
+  HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
+  h->chain_mode = mode; h->chain_cfg[0] = nsets; h->chain_cfg[1] = niss;
+  return HP_OK;
+}
+int hp_debug_chain_status(hp_handle h, unsigned int* out8_host) {
+  HP_ENTER(h);
+  HP_REQUIRE(out8_host != nullptr, HP_ERR_INVALID, "hp_debug_chain_status: null pointer");
+  return hp_chain_status(out8_host);
+}
 int hp_debug_tc_trace(hp_handle h, long long* dev_buf, int max_tiles) {
   HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
   h->tc_trace = dev_buf; h->tc_trace_tiles = dev_buf ? max_tiles : 0;

@@ -764,6 +764,43 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
   for (int i = 0; i < 16; ++i) {
     const int cin = kBlazeBlocks[i].cin, cout = kBlazeBlocks[i].cout, S = kBlazeBlocks[i].stride;
     const int cinp = chan_pad(cin), coutp = chan_pad(cout);
+    // ---- cross-block fusion: blocks 6-10 (tap 16) and 12-15 (tap 8) as one persistent kernel each (blocks_chain.cu)
+    if (h->impl == HP_IMPL_FAST && h->chain_mode > 0 && (i == 6 || i == 12)) {
+      int last = (i == 6) ? 10 : 15;
+      const int chain_nblk = last - i + 1;
+      if (stop_after_blk >= i && stop_after_blk < last) last = stop_after_blk;
+      bool plain = true;
+      for (int b = i; b <= last; ++b) plain = plain && h->tc_override[b][0] == 0 && h->tile_override[b][0] == 0;
+      ChainCfg ccfg;
+      if (plain && hp_chain_geometry(i, last - i + 1, chain_nblk, hs[i + 1], ws[i + 1], &ccfg)) {
+        if (h->chain_cfg[0] > 0) ccfg.nsets = h->chain_cfg[0];
+        if (h->chain_cfg[1] > 0) ccfg.niss = h->chain_cfg[1];
+        float* cout_buf = (last == 10) ? feat16 : (last == 15) ? feat8 : bb.act[pp ^ 1].f();
+        for (int it = 0; it < iters; ++it) {
+          if (prof && it == 0) HP_CUDA(cudaEventRecord(h->ev[0], st));
+          HP_TRY(hp_launch_chain(h, i, last - i + 1, cur, cout_buf, B, hs[i + 1], ws[i + 1], ccfg, st));
+        }
+        if (prof) {
+          HP_CUDA(cudaEventRecord(h->ev[1], st));
+          HP_CUDA(cudaEventSynchronize(h->ev[1]));
+          float ms = 0;
+          HP_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+          // the chain is one launch: its time is booked on its first block, the others report 0
+          for (int b = i; b <= last; ++b) per_layer_ms[1 + b] = (b == i) ? ms / iters : 0.f;
+        }
+        if (h->tile_report)
+          for (int b = i; b <= last; ++b) {
+            int* r = h->tile_report + 8 * b;
+            r[0] = ccfg.TR; r[1] = ccfg.NI; r[2] = ccfg.PS; r[3] = ccfg.lanes; r[4] = ccfg.nsets; r[5] = (int)ccfg.smem; r[6] = ccfg.niss; r[7] = -100 - i;
+          }
+        cur = cout_buf;
+        if (last != 10 && last != 15) pp ^= 1;
+        if (stop_after_blk == last)
+          return dbg_copy(cur, (long long)B * hs[last + 1] * ws[last + 1], chan_pad(kBlazeBlocks[last].cout), kBlazeBlocks[last].cout);
+        i = last;
+        continue;
+      }
+    }
     float* out;
     if (i == 10) out = feat16;
     else if (i == 15) out = feat8;

@@ -1,0 +1,537 @@
+// Cross-block fusion: a CHAIN of stride-1 BlazeBlocks on one spatial size (blocks 6-10 on the H/8 map, 12-15 on the
+// H/16 map) runs as ONE persistent kernel.  A tile = NI whole images; it is loaded once by TMA, stays resident in
+// shared memory while every block of the chain is applied to it IN PLACE, and is stored once.  HBM traffic drops to
+// "first input + last output" (12x12: 78 KB per image instead of 391 KB), the per-block TMA round trips, launches and
+// weight prologues of the per-block kernels disappear.
+//
+// Reference semantics per block (graph called at BlazePoser/blazeFaceDetectorH5.py:272):
+//   out = ReLU(Conv1x1(DepthwiseConv3x3_SAME(x) + b_dw) + b_pw + channel_pad(x)).
+//
+// Tile layout in shared memory: [NI][H+1][W+1][PS floats] -- one zero row BELOW every image and one zero pixel at the
+// end of every row (TMA zero-fills them: the box is H+1 rows x W+1 pixels from (0, 0); a TMA store must not start at a
+// negative coordinate -- measured: illegal instruction -- so the padding sits on the high side), and a zero row + pixel in
+// front of the first image.  Every 3x3 tap of every pixel is then a plain address, no masks: the left neighbour of x = 0 is
+// the pad pixel of the row above, row -1 is the zero row of the image before (or the lead row), row H the image's own.  PS = odd number of 16-byte chunks >= the widest
+// block of the chain (bank-conflict-free for lanes that own neighbouring columns); the output of a block overwrites its
+// input pixel (C_out >= C_in).
+//
+// Work decomposition (lane <-> TMEM lane <-> pixel column, as in blaze_block_deep_kernel): lane l owns column x of strip
+// yq of image im (l = (im * strips + yq) * W + x) and the TR output pixels (yq*TR + t, x); pixel t of every lane forms
+// M-tile t, so one tile of the chain is TR M-tiles of at most 128 rows.  Per block ("step"):
+//   DW phase : unit = one k-step (8 channels) for all TR M-tiles: sliding 3x3 window down the column -> TF32 hi / lo ->
+//              tcgen05.st into the A stage of the warp set; units are dealt round-robin to NSETS sets of 4 warps.
+//   MMA      : issuer thread(s): 3 tcgen05.mma per M-tile and k-step (a_hi w_hi + a_hi w_lo + a_lo w_hi) into D_t; the
+//              pointwise weights stream through a ring of k-step slices (cp.async.bulk from L2, one slice = W_hi | W_lo
+//              rows of 8 input channels), so nothing but 8 slices of <= 6 KB is resident.
+//   EPI phase: (after all MMAs of the step: every depthwise read of the tile is done, in-place writes are safe) unit =
+//              (M-tile, 32 accumulator columns): tcgen05.ld + bias + skip -> ReLU -> st.shared over the input pixel.
+// The same worker warps run both phases; the next step's DW phase starts when all epilogue units have arrived.
+#include "tc_common.cuh"
+
+namespace {
+
+#define CH_MAXBLK 5
+#define CH_RING 8                 // weight ring: k-step slices in flight
+#define CH_SLOT_FLOATS 1536       // one slice: W_hi | W_lo, each [2][N16 <= 96][4] floats
+#define CH_DSTRIDE 96             // TMEM columns per accumulator D_t
+#define CH_BAR_FLOATS 128
+
+struct ChainBlk {
+  const float *bhi, *blo;         // pointwise weights split hi / lo, each [K8/4][N16][4]
+  const float *dww, *pwb;         // depthwise [9][cin] followed by its bias [cin]; pointwise bias [cout]
+  int cin, cout, ks, n16;         // padded channel counts (cin % 8 == 0), k-steps, MMA N
+  int w_off;                      // float offset of this block's [10 cin | cout] in the shared weight area
+};
+
+struct ChainParams {
+  ChainBlk blk[CH_MAXBLK];
+  int nblk;
+  int H, W, NI, B, n_tiles;
+  int lanes, lpi;                 // TMEM lanes in use, lanes per image (= strips * W)
+  int row_pitch;                  // (W + 1) * PS floats
+  uint32_t load_bytes;
+  int off_w, w_floats, off_ring, off_zero, zero_floats, off_tile;   // shared-memory layout in floats
+  long long* trace;               // optional clock stamps of CTA 0: 8 per step
+  int trace_steps;
+  int dbg;                        // bring-up aid (env HP_CHAIN_DBG): 1 = setup only, 2 = + tile load / store, 3 = + first weight slices
+};
+
+// Watchdog record of the chain kernel: a wait that does not complete within ~0.25 s records {1, barrier id, parity, thread, CTA, step},
+// raises the CTA-wide abort flag (every later wait of the CTA then falls through) and the kernel runs to its end with garbage
+// instead of trapping: the host reads the record (hp_debug_chain_status) and the context stays usable.
+__device__ unsigned int g_chain_timeout[8];
+
+__device__ __forceinline__ void ch_wait(uint64_t* bar, uint32_t parity, int id, volatile uint32_t* s_abort, int step) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, n = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x100;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (*s_abort) break;
+    if ((++n & 63u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 500000000ll) {
+        if (atomicCAS(&g_chain_timeout[0], 0u, 1u) == 0u) {
+          g_chain_timeout[1] = (unsigned)id; g_chain_timeout[2] = parity; g_chain_timeout[3] = threadIdx.x;
+          g_chain_timeout[4] = blockIdx.x; g_chain_timeout[5] = (unsigned)step;
+        }
+        *s_abort = 1u;
+        break;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Thread layout: NSETS * 4 worker warps, then 4 utility warps: +0 tile loader / storer, +1 weight loader, +2 second
+// issuer (NISS == 2), +3 first issuer (owns the TMEM allocation; sub-partition 3 is the least loaded one when fewer than
+// 97 lanes are in use).
+template <int TR, int PS, int NSETS, int NISS>
+__global__ void __launch_bounds__(128 * NSETS + 128, 1)
+blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ ChainParams p) {
+  constexpr uint32_t colA0 = TR * CH_DSTRIDE;          // TMEM: D_0 .. D_{TR-1}, then one A stage of TR * 16 columns per set
+  constexpr uint32_t STAGE = TR * 16;
+  static_assert(colA0 + NSETS * STAGE <= 512, "TMEM budget");
+  static_assert(NISS >= 1 && NISS <= 2 && NISS <= TR, "issuers");
+  constexpr int NWORK = 128 * NSETS;
+
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* bar_tile_full = bars + 0;
+  uint64_t* bar_tile_done = bars + 1;
+  uint64_t* bar_dfull = bars + 2;
+  uint64_t* bar_epi = bars + 3;
+  uint64_t* bar_afull = bars + 4;                        // [NSETS]
+  uint64_t* bar_aempty = bars + 4 + 8;                   // [NSETS]
+  uint64_t* bar_wfull = bars + 4 + 16;                   // [CH_RING]
+  uint64_t* bar_wempty = bars + 4 + 16 + CH_RING;        // [CH_RING]
+  static_assert(NSETS <= 8 && (4 + 16 + 2 * CH_RING) * 8 + 4 <= CH_BAR_FLOATS * 4, "barrier block");
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (CH_BAR_FLOATS - 1);
+  volatile uint32_t* s_abort = reinterpret_cast<uint32_t*>(smem) + (CH_BAR_FLOATS - 2);
+  float* s_w = smem + p.off_w;
+  float* s_ring = smem + p.off_ring;
+  float* tile = smem + p.off_tile;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane_id = tid & 31;
+  constexpr int W_UTIL = 4 * NSETS, W_TLOAD = W_UTIL, W_WLOAD = W_UTIL + 1, W_ISS1 = W_UTIL + 2, W_ISS0 = W_UTIL + 3;
+
+  // depthwise weights + biases of the whole chain, zeros around the tile (pads, lead pixel, trailing rows)
+  for (int b = 0; b < p.nblk; ++b) {
+    const ChainBlk& cb = p.blk[b];
+    float* d = s_w + cb.w_off;
+    for (int i = tid * 4; i < 10 * cb.cin; i += nthr * 4) st4(d + i, ld4(cb.dww + i));
+    for (int i = tid * 4; i < cb.cout; i += nthr * 4) st4(d + 10 * cb.cin + i, ld4(cb.pwb + i));
+  }
+  for (int i = tid * 4; i < p.zero_floats; i += nthr * 4) st4(smem + p.off_zero + i, make_float4(0.f, 0.f, 0.f, 0.f));
+  fence_async_smem();
+  if (tid == 0) {
+    *s_abort = 0u;
+    mbar_init(bar_tile_full, 1);
+    mbar_init(bar_tile_done, NWORK);
+    mbar_init(bar_dfull, NISS);
+    mbar_init(bar_epi, NWORK);
+    for (int s = 0; s < NSETS; ++s) {
+      mbar_init(&bar_afull[s], 128);
+      mbar_init(&bar_aempty[s], NISS);
+    }
+    for (int s = 0; s < CH_RING; ++s) {
+      mbar_init(&bar_wfull[s], 1);
+      mbar_init(&bar_wempty[s], NISS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_ISS0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nblk = p.nblk;
+  auto stamp = [&](int step, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && step < p.trace_steps) p.trace[step * 8 + slot] = clock64();
+  };
+
+  if (p.dbg != 0) {
+    if (p.dbg >= 2 && warp == W_TLOAD && lane_id == 0 && my_tiles > 0) {
+      mbar_expect_tx(bar_tile_full, p.load_bytes);
+      tma_load_4d(tile, &tm_in, bar_tile_full, 0, 0, 0, (int)blockIdx.x * p.NI);
+      ch_wait(bar_tile_full, 0, 1, s_abort, 0);
+      if (p.dbg >= 5 || (p.dbg == 4 && ((int)blockIdx.x + 1) * p.NI <= p.B)) {
+        tma_store_4d(&tm_out, tile, 0, 0, 0, (int)blockIdx.x * p.NI);
+        tma_store_commit();
+        tma_store_wait_all();
+      }
+    }
+    if (p.dbg >= 3 && warp == W_WLOAD && lane_id == 0) {
+      const ChainBlk& cb = p.blk[0];
+      const uint32_t half_bytes = (uint32_t)cb.n16 * 32u;
+      for (int ks = 0; ks < cb.ks && ks < CH_RING; ++ks) {
+        float* dst = s_ring + ks * CH_SLOT_FLOATS;
+        mbar_expect_tx(&bar_wfull[ks], 2u * half_bytes);
+        bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[ks]);
+        bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[ks]);
+        ch_wait(&bar_wfull[ks], 0, 5, s_abort, ks);
+      }
+    }
+  } else if (warp < W_UTIL) {
+    // =============================================================== workers: depthwise units, then epilogue units
+    const int set = warp >> 2, wq = warp & 3;
+    const int lane = wq * 32 + lane_id;
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const bool active = lane < p.lanes;
+    const bool warp_active = wq * 32 < p.lanes;
+    const int l = active ? lane : 0;
+    const int im = l / p.lpi, l2 = l - im * p.lpi;
+    const int yq = l2 / p.W, x = l2 - yq * p.W;
+    const int row_pitch = p.row_pitch;
+    // top-left tap of the window of output row yq*TR: buffer row im*(H+1) + yq*TR - 1 (= image row yq*TR - 1; row -1 of the
+    // buffer is the lead zero row), column x - 1
+    const float* win = tile + ((im * (p.H + 1) + yq * TR - 1) * (p.W + 1) + x - 1) * PS;
+    float* centre0 = const_cast<float*>(win) + row_pitch + PS;
+    uint32_t g0 = 0, e0 = 0;     // global depthwise / epilogue unit counters at the start of the step
+    int step = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      for (int b = 0; b < nblk; ++b, ++step) {
+        const ChainBlk& cb = p.blk[b];
+        const int cin = cb.cin, KS = cb.ks, n16 = cb.n16;
+        const float* s_dww = s_w + cb.w_off;
+        const float* s_pwb = s_dww + 10 * cin;
+        if (b == 0) ch_wait(bar_tile_full, it & 1, 1, s_abort, step);
+        else ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
+        tc_fence_after();
+        if (tid == 0) stamp(step, 0);
+        // ---------------- depthwise units of this set: k-steps ks with (g0 + ks) % NSETS == set
+        int ks = (int)((NSETS + set - (g0 % NSETS)) % NSETS);
+#pragma unroll 1
+        for (; ks < KS; ks += NSETS) {
+          const uint32_t n = (g0 + ks) / NSETS;          // unit index within this set
+          float4 acc[2][TR];
+          if (warp_active) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c = ks * 8 + half * 4;
+              const float* wp = s_dww + c;
+              float4 w[9];
+#pragma unroll
+              for (int k = 0; k < 9; ++k) w[k] = ld4(wp + k * cin);
+              const float4 bias = ld4(wp + 9 * cin);
+#pragma unroll
+              for (int t = 0; t < TR; ++t) acc[half][t] = bias;
+              const float* wc = win + c;
+#pragma unroll
+              for (int r = 0; r < TR + 2; ++r) {
+                const float* row = wc + r * row_pitch;
+                const float4 v0 = ld4(row), v1 = ld4(row + PS), v2 = ld4(row + 2 * PS);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                  const int t = r - ky;
+                  if (t >= 0 && t < TR) {
+                    acc[half][t] = fma4(v0, w[ky * 3 + 0], acc[half][t]);
+                    acc[half][t] = fma4(v1, w[ky * 3 + 1], acc[half][t]);
+                    acc[half][t] = fma4(v2, w[ky * 3 + 2], acc[half][t]);
+                  }
+                }
+              }
+            }
+          }
+          if (n >= 1) {                                   // the MMAs of this set's previous unit have read the stage
+            ch_wait(&bar_aempty[set], (n - 1) & 1, 3, s_abort, step);
+            tc_fence_after();
+          }
+          if (warp_active) {
+            const uint32_t acol = tlane + colA0 + set * STAGE;
+#pragma unroll
+            for (int t = 0; t < TR; ++t) {
+              const float f[8] = {acc[0][t].x, acc[0][t].y, acc[0][t].z, acc[0][t].w, acc[1][t].x, acc[1][t].y, acc[1][t].z, acc[1][t].w};
+              uint32_t v[16];                             // [hi 8 | lo 8]
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                v[e] = tf32_hi(f[e]);
+                v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
+              }
+              tmem_st16(acol + t * 16, v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
+          mbar_arrive(&bar_afull[set]);
+        }
+        g0 += (uint32_t)KS;
+        if (tid == 0) stamp(step, 1);
+        // ---------------- epilogue units (M-tile t, 32 accumulator columns) with (e0 + unit) % NSETS == set
+        ch_wait(bar_dfull, step & 1, 4, s_abort, step);
+        tc_fence_after();
+        if (tid == 0) stamp(step, 2);
+        const int ncg = (n16 + 31) >> 5, n_eu = TR * ncg;
+        const int C4 = cin >> 2, NG = cb.cout >> 2;
+        if (warp_active) {
+          int u = (int)((NSETS + set - (e0 % NSETS)) % NSETS);
+#pragma unroll 1
+          for (; u < n_eu; u += NSETS) {
+            const int t = u / ncg, cg = u - t * ncg;
+            float* cpix = centre0 + t * row_pitch;
+            const bool valid = active && (yq * TR + t < p.H);
+            const uint32_t dcol = tlane + t * CH_DSTRIDE + cg * 32;
+            uint32_t v[32];
+            if (cg * 32 + 32 <= n16) {
+              tmem_ld32(dcol, v);
+            } else {
+              uint32_t hlf[16];
+              tmem_ld16(dcol, hlf);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int j = cg * 8 + jj;
+              if (j < NG) {
+                const float4 bb = ld4(s_pwb + j * 4);
+                float4 o = make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
+                                       __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
+                if (j < C4) {
+                  const float4 sk = ld4(cpix + j * 4);
+                  o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                }
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                if (valid) st4(cpix + j * 4, o);
+              }
+            }
+          }
+          tc_fence_before();
+          if (b == nblk - 1) fence_async_smem();           // the tile leaves through the async proxy (TMA store)
+        }
+        e0 += (uint32_t)n_eu;
+        mbar_arrive(bar_epi);
+        if (b == nblk - 1) mbar_arrive(bar_tile_done);
+        if (tid == 0) stamp(step, 3);
+      }
+    }
+  } else if (lane_id == 0) {
+    if (warp == W_ISS0 || (NISS == 2 && warp == W_ISS1)) {
+      // =============================================================== MMA issuers (M-tiles t % NISS == issuer)
+      const int issuer = (warp == W_ISS0) ? 0 : 1;
+      const uint32_t ring_addr = smem_u32(s_ring);
+      uint32_t g = 0;
+      int step = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int b = 0; b < nblk; ++b, ++step) {
+          const int KS = p.blk[b].ks, n16 = p.blk[b].n16;
+          const uint32_t idesc = tc_idesc_tf32(n16);
+          const uint64_t desc_fixed = tc_bdesc_fixed(n16);
+#pragma unroll 1
+          for (int ks = 0; ks < KS; ++ks, ++g) {
+            const uint32_t set = g % NSETS, n = g / NSETS, slot = g % CH_RING;
+            ch_wait(&bar_wfull[slot], (g / CH_RING) & 1, 5, s_abort, step);
+            ch_wait(&bar_afull[set], n & 1, 6, s_abort, step);
+            tc_fence_after();
+            if (issuer == 0 && ks == 0) stamp(step, 4);
+            const uint32_t hi_addr = ring_addr + slot * (CH_SLOT_FLOATS * 4);
+            const uint32_t lo_addr = hi_addr + (uint32_t)n16 * 32u;
+            const uint64_t dhi = desc_fixed | (uint64_t)((hi_addr >> 4) & 0x3FFF);
+            const uint64_t dlo = desc_fixed | (uint64_t)((lo_addr >> 4) & 0x3FFF);
+#pragma unroll
+            for (int t = 0; t < TR; ++t) {
+              if (t % NISS != issuer) continue;
+              const uint32_t dc = tmem_base + t * CH_DSTRIDE;
+              const uint32_t a = tmem_base + colA0 + set * STAGE + t * 16;
+              mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+              mma_tf32_ts(dc, a, dlo, idesc, 1u);
+              mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+            }
+            tc_commit(&bar_aempty[set]);
+            tc_commit(&bar_wempty[slot]);
+          }
+          tc_commit(bar_dfull);
+          if (issuer == 0) stamp(step, 5);
+        }
+      }
+    } else if (warp == W_WLOAD) {
+      // =============================================================== weight ring loader (one slice per k-step)
+      uint32_t g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int b = 0; b < nblk; ++b) {
+          const ChainBlk& cb = p.blk[b];
+          const uint32_t half_bytes = (uint32_t)cb.n16 * 32u;          // [2][n16][4] floats
+#pragma unroll 1
+          for (int ks = 0; ks < cb.ks; ++ks, ++g) {
+            const uint32_t slot = g % CH_RING;
+            if (g >= CH_RING) ch_wait(&bar_wempty[slot], ((g / CH_RING) - 1) & 1, 7, s_abort, (int)g);
+            float* dst = s_ring + slot * CH_SLOT_FLOATS;
+            mbar_expect_tx(&bar_wfull[slot], 2u * half_bytes);
+            bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[slot]);
+            bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[slot]);
+          }
+        }
+      }
+    } else if (warp == W_TLOAD) {
+      // =============================================================== tile loader / storer
+      int tile_idx = blockIdx.x;
+      if (my_tiles > 0) {
+        mbar_expect_tx(bar_tile_full, p.load_bytes);
+        tma_load_4d(tile, &tm_in, bar_tile_full, 0, 0, 0, tile_idx * p.NI);
+      }
+      for (int it = 0; it < my_tiles; ++it, tile_idx += gridDim.x) {
+        const int next = tile_idx + (int)gridDim.x;
+        if (it + 1 < my_tiles) tma_prefetch_4d(&tm_in, 0, 0, 0, next * p.NI);   // warm L2 while this tile is computed
+        ch_wait(bar_tile_done, it & 1, 8, s_abort, it);
+        tma_store_4d(&tm_out, tile, 0, 0, 0, tile_idx * p.NI);
+        tma_store_commit();
+        stamp(it * nblk + nblk - 1, 6);
+        tma_store_wait_read();
+        stamp(it * nblk + nblk - 1, 7);
+        if (it + 1 < my_tiles) {
+          mbar_expect_tx(bar_tile_full, p.load_bytes);
+          tma_load_4d(tile, &tm_in, bar_tile_full, 0, 0, 0, next * p.NI);
+        }
+      }
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_ISS0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+template <int TR, int PS, int NSETS, int NISS>
+int launch_chain(hp_ctx* h, const CUtensorMap& tin, const CUtensorMap& tout, const ChainParams& p, size_t smem, cudaStream_t st) {
+  auto kern = blaze_chain_kernel<TR, PS, NSETS, NISS>;
+  HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  long long grid = h->num_sms;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<(unsigned)grid, 128 * NSETS + 128, smem, st>>>(tin, tout, p);
+  h->launches++;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}
+
+}  // namespace
+
+// Watchdog record of the last chain kernels (see ch_wait): out[0] != 0 means a wait timed out; clears the record.
+int hp_chain_status(unsigned int out[8]) {
+  HP_CUDA(cudaDeviceSynchronize());
+  HP_CUDA(cudaMemcpyFromSymbol(out, g_chain_timeout, 8 * sizeof(unsigned int)));
+  unsigned int z[8] = {};
+  HP_CUDA(cudaMemcpyToSymbol(g_chain_timeout, z, sizeof(z)));
+  return HP_OK;
+}
+
+// Geometry of the chain kernel for blocks [first, first + nblk) on an H x W map: rows per lane TR, images per tile NI.
+// Returns false when the chain kernel does not apply (the per-block kernels are used instead).
+bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg) {
+  if (nblk < 1 || nblk > CH_MAXBLK || first < 0 || first + nblk > 16 || H < 2 || W < 2 || W > 64) return false;
+  // chain_nblk >= nblk: length of the full chain (a truncated chain, used to read intermediate activations, keeps the geometry
+  // -- pixel stride, rows per lane, images per tile -- of the full one)
+  if (chain_nblk < nblk || first + chain_nblk > 16) return false;
+  int cmax = 0;
+  for (int b = first; b < first + chain_nblk; ++b) {
+    const int cin = chan_pad(kBlazeBlocks[b].cin), cout = chan_pad(kBlazeBlocks[b].cout);
+    if (kBlazeBlocks[b].stride != 1 || cin % 8 != 0 || cout < cin || cout > 96) return false;
+    if (b > first && kBlazeBlocks[b].cin != kBlazeBlocks[b - 1].cout) return false;
+    if (cout > cmax) cmax = cout;
+  }
+  const int PS = ((cmax / 4) | 1) * 4;
+  if (PS != 92 && PS != 100) return false;               // instantiated pixel strides (chains ending at 88 / 96 channels)
+  int w_floats = 0;
+  for (int b = first; b < first + chain_nblk; ++b) w_floats += 10 * chan_pad(kBlazeBlocks[b].cin) + chan_pad(kBlazeBlocks[b].cout);
+  ChainCfg best;
+  double best_cost = 1e30;
+  for (int TR = 2; TR <= 3; ++TR) {
+    const int strips = ceil_div(H, TR), lpi = strips * W;
+    if (lpi > 128) continue;
+    for (int NI = 128 / lpi; NI >= 1; --NI) {
+      ChainCfg c;
+      c.TR = TR; c.NI = NI; c.PS = PS; c.lanes = NI * lpi; c.lpi = lpi;
+      c.nsets = 4; c.niss = 2;
+      const int lead = tc_align_up((W + 2) * PS, 32);     // zero row above the first image + the left neighbour of its first pixel
+      const int rows = NI * (H + 1) + TR;                 // image rows + their zero rows, slack for partial strips
+      int off = CH_BAR_FLOATS;
+      c.off_w = off; off = tc_align_up(off + w_floats, 32);
+      c.off_ring = off; off += CH_RING * CH_SLOT_FLOATS;
+      c.off_zero = off; off += lead;
+      c.off_tile = off;
+      c.tile_floats = rows * (W + 1) * PS;
+      off += c.tile_floats + PS;                          // one more pixel: the right neighbour of the last pad pixel
+      c.zero_floats = off - c.off_zero;
+      c.w_floats = w_floats;
+      c.smem = (size_t)off * sizeof(float);
+      if (c.smem > 227 * 1024) continue;
+      // cost: warp-instructions ~ active warps * M-tiles per image; more images per tile amortise the per-step bubbles
+      const double cost = (double)ceil_div(c.lanes, 32) * TR / NI + 0.05 * TR / NI;
+      if (cost < best_cost) { best_cost = cost; best = c; }
+      break;                                              // the largest NI that fits is the best one for this TR
+    }
+  }
+  if (best_cost >= 1e30) return false;
+  *cfg = best;
+  return true;
+}
+
+int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out, int B, int H, int W, const ChainCfg& cfg,
+                    cudaStream_t st) {
+  const Backbone& bb = h->bb;
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.nblk = nblk;
+  int w_off = 0;
+  for (int b = 0; b < nblk; ++b) {
+    const BlockWeights& w = bb.blk[first + b];
+    HP_REQUIRE(w.bhi && w.blo, HP_ERR_STATE, "chain: split weights of block %d missing", first + b);
+    ChainBlk& cb = p.blk[b];
+    cb.bhi = w.bhi; cb.blo = w.blo; cb.dww = w.dww; cb.pwb = w.pwb;
+    cb.cin = chan_pad(kBlazeBlocks[first + b].cin);
+    cb.cout = chan_pad(kBlazeBlocks[first + b].cout);
+    cb.ks = cb.cin / 8;
+    cb.n16 = (cb.cout + 15) / 16 * 16;
+    cb.w_off = w_off;
+    w_off += 10 * cb.cin + cb.cout;
+    HP_REQUIRE(w.dwb == w.dww + 9 * cb.cin, HP_ERR_STATE, "chain: depthwise bias of block %d does not follow its kernel", first + b);
+  }
+  p.H = H; p.W = W; p.NI = cfg.NI; p.B = B;
+  p.n_tiles = ceil_div(B, cfg.NI);
+  p.lanes = cfg.lanes; p.lpi = cfg.lpi;
+  p.row_pitch = (W + 1) * cfg.PS;
+  p.load_bytes = (uint32_t)((size_t)cfg.NI * (H + 1) * (W + 1) * cfg.PS * sizeof(float));
+  p.off_w = cfg.off_w; p.w_floats = cfg.w_floats; p.off_ring = cfg.off_ring; p.off_zero = cfg.off_zero; p.zero_floats = cfg.zero_floats;
+  p.off_tile = cfg.off_tile;
+  p.trace = h->tc_trace; p.trace_steps = h->tc_trace_tiles;
+  {
+    const char* e = getenv("HP_CHAIN_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  HP_REQUIRE(cfg.smem <= 227 * 1024 && cfg.lanes >= 1 && cfg.lanes <= 128 && (cfg.off_tile * 4) % 128 == 0 && H + 1 <= 256 && W + 1 <= 256 &&
+                 cfg.NI <= 256 && p.load_bytes < (1u << 20),
+             HP_ERR_INVALID, "chain %d..%d: bad geometry TR %d NI %d PS %d on %dx%d", first, first + nblk - 1, cfg.TR, cfg.NI, cfg.PS, H, W);
+  const int cin0 = p.blk[0].cin, coutL = p.blk[nblk - 1].cout;
+  CUtensorMap tin, tout;
+  {
+    const cuuint64_t din[4] = {(cuuint64_t)cin0, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t sin_[3] = {(cuuint64_t)cin0 * 4, (cuuint64_t)W * cin0 * 4, (cuuint64_t)H * W * cin0 * 4};
+    const cuuint64_t dout[4] = {(cuuint64_t)coutL, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t sout[3] = {(cuuint64_t)coutL * 4, (cuuint64_t)W * coutL * 4, (cuuint64_t)H * W * coutL * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)cfg.PS, (cuuint32_t)(W + 1), (cuuint32_t)(H + 1), (cuuint32_t)cfg.NI};
+    HP_TRY(tc_make_map4(&tin, in, din, sin_, box));
+    HP_TRY(tc_make_map4(&tout, out, dout, sout, box));
+  }
+#define CHAIN_CASE(TR_, PS_, NSETS_, NISS_)                                                    \
+  if (cfg.TR == TR_ && cfg.PS == PS_ && cfg.nsets == NSETS_ && cfg.niss == NISS_)                \
+    return launch_chain<TR_, PS_, NSETS_, NISS_>(h, tin, tout, p, cfg.smem, st);
+  CHAIN_CASE(3, 92, 4, 2) CHAIN_CASE(2, 92, 4, 2) CHAIN_CASE(3, 100, 4, 2) CHAIN_CASE(2, 100, 4, 2)
+  CHAIN_CASE(3, 92, 4, 1) CHAIN_CASE(2, 92, 4, 1) CHAIN_CASE(3, 100, 4, 1) CHAIN_CASE(2, 100, 4, 1)
+#undef CHAIN_CASE
+  hp_set_error("chain: no kernel for TR %d PS %d nsets %d issuers %d", cfg.TR, cfg.PS, cfg.nsets, cfg.niss);
+  return HP_ERR_UNSUPPORTED;
+}

@@ -215,6 +215,12 @@ int hp_debug_tile_report(hp_handle h, int* report16x8);
 /* tensor-core stem kernel: band height, input buffers, output stages, gather warp sets (0 = automatic; BH = -1 keeps the
  * stem on the CUDA-core kernel) */
 int hp_debug_set_stem_tc(hp_handle h, int BH, int nbuf, int nout, int nsets);
+/* cross-block fusion (blocks 6-10 and 12-15 as one persistent kernel each): mode 1 = on (default), 0 = one kernel per block;
+ * nsets / niss override the worker warp sets / MMA issuer threads of the chain kernel (0 = default) */
+int hp_debug_set_chain(hp_handle h, int mode, int nsets, int niss);
+/* watchdog record of the chain kernels since the last call: out8_host[0] != 0 -> a barrier wait timed out ({1, barrier id, parity,
+ * thread, CTA, step}); synchronises the device and clears the record */
+int hp_debug_chain_status(hp_handle h, unsigned int* out8_host);
 /* device buffer of max_tiles x 12 clock64 stamps written by CTA 0 of the warp-specialised tensor-core kernel (NULL = off) */
 int hp_debug_tc_trace(hp_handle h, long long* dev_buf, int max_tiles);
 int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, int nsets, int nbuf);
