@@ -13,8 +13,10 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libhpose.so")
-SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "blocks_chain.cu", "stem_tc.cu", "dense_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
+# experiment builds: HPOSE_LIB_SUFFIX=_x selects libhpose_x.so (built with the extra nvcc flags in HPOSE_NVCC_EXTRA)
+_SUFFIX = os.environ.get("HPOSE_LIB_SUFFIX", "")
+LIB_PATH = os.path.join(PKG_DIR, f"libhpose{_SUFFIX}.so")
+SOURCES = ["api.cu", "backbone.cu", "blocks_tma.cu", "blocks_tc.cu", "blocks_chain.cu", "preproc.cu", "detect.cu", "stem_tc.cu", "dense_tc.cu", "heads.cu", "postproc.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -22,6 +24,8 @@ HP_BACKBONE_PARAMS = 101390
 HP_MAX_FACES = 100
 HP_KEYPOINTS = 6
 HP_IMPL_FAST, HP_IMPL_NAIVE, HP_IMPL_CPASYNC, HP_IMPL_TMA = 0, 1, 2, 3
+HP_RESULT_HEADER_INTS = 4
+HP_DETECT_GRAPH = 1
 (HP_OP_DENSE, HP_OP_ACT, HP_OP_ADD, HP_OP_MULCH, HP_OP_GAP, HP_OP_DROPOUT, HP_OP_LAYERNORM,
  HP_OP_MHA) = range(1, 9)
 HP_ACT = {"linear": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3, "softsign": 4}
@@ -55,7 +59,7 @@ class hp_opt_config(C.Structure):
 
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"),
            os.path.join(PKG_DIR, "..", "include", "hpose.h")]
-OBJ_DIR = os.path.join(CSRC, "build")
+OBJ_DIR = os.path.join(CSRC, "build" + _SUFFIX)
 
 
 def _stale(target: str, deps) -> bool:
@@ -76,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(OBJ_DIR, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("HPOSE_NVCC_EXTRA", "").split()
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
@@ -114,6 +118,7 @@ _PROTOS = {
     "hp_backbone_read_activation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "hp_preprocess_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hp_preprocess_resize_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hp_head_create": (C.c_int, [C.c_void_p, C.POINTER(hp_head_op), C.c_int, C.POINTER(hp_head_reg), C.c_int,
                                  C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "hp_head_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -139,6 +144,10 @@ _PROTOS = {
     "hp_unified_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hp_detect_result_faces_offset": (C.c_size_t, [C.c_int]),
+    "hp_detect_result_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "hp_detect_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "hp_comm_unique_id": (C.c_int, [C.c_void_p]),
     "hp_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "hp_comm_destroy": (C.c_int, [C.c_void_p]),

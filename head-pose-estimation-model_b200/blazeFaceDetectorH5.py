@@ -5,8 +5,12 @@ attributes (``anchors``, ``inputHeight``, ``inputWidth``, ``sigmoidScoreThreshol
 (``detectFaces``, ``inference``, ``filterDetections``, ``extractDetections``,
 ``filterWithNonMaxSupression``, ``generateAnchors``).  Every numeric step runs in CUDA through
 libhpose; the extra ``detectFacesBatch`` is the batched form the B200 path is built for.
-The webcam loop, drawing and EMA smoothing of the reference (:16-77,128-219,366-449) are UI and out
-of scope.
+
+``detectFaces(frame)`` is the latency path of the reference's webcam loop (:392-444): ONE host->device copy of the
+uint8 frame (any size: the bicubic resize of :255 runs on the device), ONE CUDA-graph launch of the whole graph
+(``hp_detect_frames``), ONE device->host copy of the packed result.  ``detectFacesStepwise`` walks the reference's five
+methods one after the other (same results; the parity tests compare the two).  ``EMAFilter`` (:16-35) smooths a pose angle
+over frames; drawing and the cv2 window loop (:37-77,128-219,366-449) are UI and stay out of scope.
 """
 import ctypes as C
 import os
@@ -24,6 +28,43 @@ MAX_FACE_NUM = 100
 INPUT_FRONT = 128
 INPUT_BACK = 256
 DEFAULT_MODEL = "UnifiedModels/reg1-stoqa9pt-reg2-hrchr82r-selected.h5"
+
+
+FACE_DTYPE = np.dtype([("box", "<f8", (4,)), ("keypoints", "<f8", (KEY_POINT_SIZE, 2)), ("score", "<f4"), ("pose", "<f4", (3,)),
+                       ("anchor", "<i4"), ("frame", "<i4")])          # hp_face (include/hpose.h), 152 bytes
+assert FACE_DTYPE.itemsize == 152
+
+
+class EMAFilter:
+    """Exponential moving average of one scalar (reference :16-35): the first measurement initialises the state, then
+    ``state = alpha * measurement + (1 - alpha) * state``."""
+
+    def __init__(self, alpha: float, initial_value: float = 0.0):
+        assert 0.0 < alpha <= 1.0, "alpha must be in (0,1]"
+        self.alpha = alpha
+        self.state = initial_value
+        self.initialized = False
+
+    def update(self, measurement: float) -> float:
+        if self.initialized:
+            self.state = self.alpha * measurement + (1.0 - self.alpha) * self.state
+        else:
+            self.state, self.initialized = measurement, True
+        return self.state
+
+
+def unpack_results(raw_u8, B, faces_off):
+    """Packed hp_detect_frames result (host bytes) -> list of ``Results`` (copies: the buffer is reused by the next call)."""
+    hdr = raw_u8[:(_lib.HP_RESULT_HEADER_INTS + B) * 4].view(np.int32)
+    written = int(hdr[1])
+    counts = hdr[_lib.HP_RESULT_HEADER_INTS:_lib.HP_RESULT_HEADER_INTS + B]
+    faces = raw_u8[faces_off:faces_off + written * FACE_DTYPE.itemsize].view(FACE_DTYPE)
+    out, o = [], 0
+    for c in counts:
+        f = faces[o:min(o + int(c), written)]
+        out.append(Results(f["box"].copy(), f["keypoints"].copy(), f["score"].copy(), f["pose"].copy()))
+        o += int(c)
+    return out
 
 
 class Results:
@@ -45,6 +86,7 @@ class blazeFaceDetector:
         self._model_path = modelPath or DEFAULT_MODEL
         self._model = model
         self._input_size = int(inputSize)
+        self._slots = {}
         self.initializeModel()
         self.generateAnchors()
 
@@ -73,8 +115,16 @@ class blazeFaceDetector:
         self.fps = int(1 / (now - self.timeLastPrediction + 0.0001))
         self.timeLastPrediction = now
 
-    # ------------------------------------------------------------------ single image, reference flow
+    # ------------------------------------------------------------------ single image
     def detectFaces(self, image):
+        """One BGR uint8 frame of any size -> ``Results`` (reference :109-126) through the latency path: one pinned
+        host->device copy, one CUDA-graph launch (``hp_detect_frames``), one device->host copy of the packed result."""
+        results = self._detect_packed(np.ascontiguousarray(image)[None], graph=True)[0]
+        self.updateFps()
+        return results
+
+    def detectFacesStepwise(self, image):
+        """The reference's own sequence of calls (:109-126), every step a CUDA call with its own host round trip."""
         input_tensor = self.prepareInputForInference(image)
         loc_concat, cls_concat, pose_front, pose_back = self.inference(input_tensor)
         scores, good = self.filterDetections(cls_concat)
@@ -84,26 +134,78 @@ class blazeFaceDetector:
         return results
 
     def prepareInputForInference(self, image):
-        """BGR uint8 HxWx3 -> (1,H,W,3) float32 in [-1,1] on the GPU (hp_preprocess_u8).  Images must
-        already have the network input size: the bicubic resize of the reference (:255) is a later row."""
+        """BGR uint8 HxWx3 of any size -> (1,inputHeight,inputWidth,3) float32 in [-1,1] (reference :247-269: BGR->RGB,
+        /255, bicubic resize, (x-0.5)/0.5), computed on the GPU (hp_preprocess_resize_u8)."""
         import torch
         image = np.ascontiguousarray(image)
         if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
             raise ValueError("expected a HxWx3 uint8 BGR image")
         self.img_height, self.img_width, self.img_channels = image.shape
-        if (self.img_height, self.img_width) != (self.inputHeight, self.inputWidth):
-            raise ValueError(f"image is {self.img_width}x{self.img_height}; resize to {self.inputWidth}x"
-                             f"{self.inputHeight} first (on-device bicubic resize is not built yet)")
         x = self._preprocess_device(torch.from_numpy(image[None]).to(self.ctx.torch_device))
         return x.cpu().numpy()
 
     def _preprocess_device(self, u8):
         import torch
         B, H, W, _ = u8.shape
-        x = torch.empty((B, H, W, 3), dtype=torch.float32, device=u8.device)
-        _lib.check(_lib.lib().hp_preprocess_u8(self.ctx.handle, u8.data_ptr(), B, H, W, x.data_ptr(),
-                                               self.ctx.stream_ptr()))
+        x = torch.empty((B, self.inputHeight, self.inputWidth, 3), dtype=torch.float32, device=u8.device)
+        _lib.check(_lib.lib().hp_preprocess_resize_u8(self.ctx.handle, u8.data_ptr(), B, H, W, self.inputHeight, self.inputWidth,
+                                                      x.data_ptr(), self.ctx.stream_ptr()))
         return x
+
+    # ------------------------------------------------------------------ packed single-call path (hp_detect_frames)
+    def _latency_slot(self, B, H, W, max_faces):
+        """Persistent buffers of one (batch, frame size): pinned host frame + result, device frame + result, a private
+        non-default stream (graph capture needs one).  Pointers stay fixed, so the captured graph stays valid."""
+        import torch
+        key = (B, H, W, max_faces)
+        slot = self._slots.get(key)
+        if slot is None:
+            if len(self._slots) >= 4:
+                self._slots.clear()
+            dev = self.ctx.torch_device
+            L = _lib.lib()
+            nbytes = int(L.hp_detect_result_bytes(B, B * max_faces))
+            slot = {"h_in": torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory(),
+                    "d_in": torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev),
+                    "d_out": torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev),
+                    "h_out": torch.empty((nbytes + 7) // 8, dtype=torch.int64).pin_memory(),
+                    "faces_off": int(L.hp_detect_result_faces_offset(B)), "nbytes": nbytes,
+                    "stream": torch.cuda.Stream(dev)}
+            self._slots[key] = slot
+        return slot
+
+    def _detect_packed(self, frames, max_faces=MAX_FACE_NUM, graph=False):
+        """frames: (B,H,W,3) uint8 BGR host array -> list of ``Results``.  One H2D, one launch sequence (or graph), one D2H
+        (two for large batches: the header first, then exactly sum(count) face records)."""
+        import torch
+        if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] != 3:
+            raise ValueError("expected (B,H,W,3) uint8 BGR frames")
+        B, H, W, _ = frames.shape
+        self.img_height, self.img_width, self.img_channels = H, W, 3
+        slot = self._latency_slot(B, H, W, max_faces)
+        m = self.interpreter
+        st = slot["stream"]
+        slot["h_in"].numpy()[...] = frames
+        with torch.cuda.stream(st):
+            slot["d_in"].copy_(slot["h_in"], non_blocking=True)
+            _lib.check(_lib.lib().hp_detect_frames(
+                self.ctx.handle, m.head16.head_handle, m.head8.head_handle, slot["d_in"].data_ptr(), B, H, W, self.inputHeight,
+                self.inputWidth, float(np.float32(self.sigmoidScoreThreshold)), float(np.float32(self.iouThreshold)), int(max_faces),
+                slot["d_out"].data_ptr(), slot["nbytes"], _lib.HP_DETECT_GRAPH if graph else 0, C.c_void_p(st.cuda_stream)))
+            h_raw = slot["h_out"].numpy().view(np.uint8)
+            if slot["nbytes"] <= (1 << 20):
+                slot["h_out"].copy_(slot["d_out"], non_blocking=True)
+                st.synchronize()
+            else:
+                n_hdr = (slot["faces_off"] + 7) // 8
+                slot["h_out"][:n_hdr].copy_(slot["d_out"][:n_hdr], non_blocking=True)
+                st.synchronize()
+                written = int(h_raw[:16].view(np.int32)[1])
+                n_all = n_hdr + (written * FACE_DTYPE.itemsize + 7) // 8
+                if written:
+                    slot["h_out"][n_hdr:n_all].copy_(slot["d_out"][n_hdr:n_all], non_blocking=True)
+                    st.synchronize()
+        return unpack_results(h_raw, B, slot["faces_off"])
 
     def inference(self, input_tensor):
         raw = self.interpreter(input_tensor)
@@ -165,8 +267,11 @@ class blazeFaceDetector:
 
     # ------------------------------------------------------------------ batched B200 path
     def detectFacesBatch(self, images, max_faces=MAX_FACE_NUM):
-        """images: (B,H,W,3) uint8 BGR (host array or CUDA tensor) -> list of ``Results``; one fused
-        device pass: preprocess -> backbone -> heads -> decode + NMS + pose lookup."""
+        """images: (B,H,W,3) uint8 BGR frames of any size (host array or CUDA tensor) -> list of ``Results``; one fused
+        device pass: preprocess (+ resize) -> backbone -> heads -> decode + NMS + pose lookup.  Host arrays take the packed
+        single-call path (only sum(count) face records come back)."""
+        if isinstance(images, np.ndarray):
+            return self._detect_packed(np.ascontiguousarray(images), max_faces)
         out = self.detect_device(images, max_faces)
         cnt = out["count"].cpu().numpy()
         boxes, kps = out["boxes"].cpu().numpy(), out["keypoints"].cpu().numpy()
@@ -174,36 +279,64 @@ class blazeFaceDetector:
         return [Results(boxes[i, :c].copy(), kps[i, :c].copy(), scores[i, :c].copy(), poses[i, :c].copy())
                 for i, c in enumerate(cnt)]
 
-    def detect_stream(self, host_batches, max_faces=MAX_FACE_NUM, keys=("count", "boxes", "keypoints", "scores", "poses"), chunks=1):
+    def detect_stream(self, host_batches, max_faces=MAX_FACE_NUM, keys=("count", "boxes", "keypoints", "scores", "poses"), chunks=1,
+                      packed=False):
         """Pipelined serving loop: ``host_batches`` yields pinned (B,H,W,3) uint8 BGR host tensors; for every batch
-        a dict of pinned HOST tensors (``keys``) is yielded, in order.  The host->device copy of batch i+1 and the
-        device->host read of batch i-1 run on their own CUDA streams while batch i computes (two device input
-        buffers, two sets of host result buffers): PCIe time hides behind the kernels instead of adding to them.
-        ``chunks`` > 1 splits every batch into that many slices which go through copy / compute / read-back one after
-        the other: the first kernels then wait for 1/chunks of the first copy only and the last read-back is 1/chunks of
-        a batch (shorter pipeline fill and drain; the results are the same).
-        A yielded dict is reused two batches later: consume (or copy) it before asking for the next-but-one."""
+        a dict of pinned HOST tensors is yielded, in order.  The host->device copy of batch i+1 and the device->host read of
+        batch i-1 run on their own CUDA streams while batch i computes: PCIe time hides behind the kernels instead of
+        adding to them.
+
+        ``packed=False``: the dict holds ``keys`` in the padded [B, max_faces, ...] form of ``hp_unified_forward``.
+        ``chunks`` > 1 splits every batch into that many slices which go through copy / compute / read-back one after the
+        other (shorter pipeline fill and drain; the results are the same).
+        ``packed=True``: ``hp_detect_frames``; the dict holds ``count`` (int32 [B]), ``faces`` (``FACE_DTYPE`` records of
+        all frames, frame-major) and ``total``; only the header and sum(count) records cross PCIe (the padded form moves
+        14.4 KB per frame whatever was found).
+
+        Buffer lifetime: three result slots rotate and at most two batches are in flight, so a yielded dict stays valid
+        until the generator has been advanced TWICE more (the slot being refilled is never the one just handed out)."""
         import torch
         dev = self.ctx.torch_device
         comp = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        chunks = max(1, int(chunks))
-        d_in = [[None] * chunks for _ in range(2)]
-        d_out = [[None] * chunks for _ in range(2)]       # device result tensors, reused: slot b is idle once its read-back is done
-        ev_read = [[None] * chunks for _ in range(2)]
-        h_out = [None, None]
-        ev_in = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(2)]
-        ev_comp = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(2)]
-        used = [[False] * chunks for _ in range(2)]
-        ev_out = [torch.cuda.Event() for _ in range(2)]
+        chunks = 1 if packed else max(1, int(chunks))
+        NS = 3
+        d_in = [[None] * chunks for _ in range(NS)]
+        d_out = [[None] * chunks for _ in range(NS)]      # device result tensors, reused: slot b is idle once its read-back is done
+        ev_read = [[None] * chunks for _ in range(NS)]
+        h_out = [None] * NS
+        ev_in = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(NS)]
+        ev_comp = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(NS)]
+        used = [[False] * chunks for _ in range(NS)]
+        ev_out = [torch.cuda.Event() for _ in range(NS)]
+        meta = [None] * NS
         pending = []                                      # slots whose results are still on their way to the host
+        L = _lib.lib()
+        m = self.interpreter
+
+        def finish(q):
+            ev_out[q].synchronize()
+            if not packed:
+                return h_out[q]
+            B, faces_off, n_hdr = meta[q]
+            raw = h_out[q].numpy().view(np.uint8)
+            hdr = raw[:(_lib.HP_RESULT_HEADER_INTS + B) * 4].view(np.int32)
+            written = int(hdr[1])
+            if written:                                   # second phase: exactly the records that exist
+                n_all = n_hdr + (written * FACE_DTYPE.itemsize + 7) // 8
+                with torch.cuda.stream(s_out):
+                    h_out[q][n_hdr:n_all].copy_(d_out[q][0][n_hdr:n_all], non_blocking=True)
+                    ev_read[q][0].record(s_out)
+                    ev_out[q].record(s_out)
+                ev_out[q].synchronize()
+            return {"total": int(hdr[0]), "count": hdr[_lib.HP_RESULT_HEADER_INTS:_lib.HP_RESULT_HEADER_INTS + B],
+                    "faces": raw[faces_off:faces_off + written * FACE_DTYPE.itemsize].view(FACE_DTYPE)}
+
         n = 0
         for hb in host_batches:
-            b = n & 1
-            if len(pending) == 2:                          # slot b is reused: hand its results out first
-                q = pending.pop(0)
-                ev_out[q].synchronize()
-                yield h_out[q]
+            b = n % NS
+            if len(pending) == 2:                          # keep two batches in flight: hand the oldest out first
+                yield finish(pending.pop(0))
             B = hb.shape[0]
             per = -(-B // chunks)
             for c in range(chunks):
@@ -221,15 +354,34 @@ class blazeFaceDetector:
                 comp.wait_event(ev_in[b][c])
                 if ev_read[b][c] is not None:
                     comp.wait_event(ev_read[b][c])         # the previous results of this slot have left the device
-                out = d_out[b][c] = self.detect_device(d_in[b][c], max_faces, out=d_out[b][c])
+                if packed:
+                    nbytes = int(L.hp_detect_result_bytes(B, B * max_faces))
+                    nwords = (nbytes + 7) // 8
+                    if d_out[b][c] is None or d_out[b][c].numel() != nwords:
+                        d_out[b][c] = torch.empty(nwords, dtype=torch.int64, device=dev)
+                        h_out[b] = torch.empty(nwords, dtype=torch.int64).pin_memory()
+                    _, H, W, _ = part.shape
+                    _lib.check(L.hp_detect_frames(
+                        self.ctx.handle, m.head16.head_handle, m.head8.head_handle, d_in[b][c].data_ptr(), B, H, W, self.inputHeight,
+                        self.inputWidth, float(np.float32(self.sigmoidScoreThreshold)), float(np.float32(self.iouThreshold)),
+                        int(max_faces), d_out[b][c].data_ptr(), nbytes, 0, self.ctx.stream_ptr()))
+                    out = None
+                else:
+                    out = d_out[b][c] = self.detect_device(d_in[b][c], max_faces, out=d_out[b][c])
                 ev_comp[b][c].record(comp)
                 used[b][c] = True
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_comp[b][c])
-                    if h_out[b] is None or any(h_out[b][k].shape != (B,) + tuple(out[k].shape[1:]) for k in keys):
-                        h_out[b] = {k: torch.empty((B,) + tuple(out[k].shape[1:]), dtype=out[k].dtype).pin_memory() for k in keys}
-                    for k in keys:
-                        h_out[b][k][c0:c1].copy_(out[k], non_blocking=True)
+                    if packed:
+                        faces_off = int(L.hp_detect_result_faces_offset(B))
+                        n_hdr = (faces_off + 7) // 8
+                        meta[b] = (B, faces_off, n_hdr)
+                        h_out[b][:n_hdr].copy_(d_out[b][c][:n_hdr], non_blocking=True)
+                    else:
+                        if h_out[b] is None or any(h_out[b][k].shape != (B,) + tuple(out[k].shape[1:]) for k in keys):
+                            h_out[b] = {k: torch.empty((B,) + tuple(out[k].shape[1:]), dtype=out[k].dtype).pin_memory() for k in keys}
+                        for k in keys:
+                            h_out[b][k][c0:c1].copy_(out[k], non_blocking=True)
                     if ev_read[b][c] is None:
                         ev_read[b][c] = torch.cuda.Event()
                     ev_read[b][c].record(s_out)
@@ -237,8 +389,7 @@ class blazeFaceDetector:
             pending.append(b)
             n += 1
         for q in pending:
-            ev_out[q].synchronize()
-            yield h_out[q]
+            yield finish(q)
 
     def detect_device(self, images, max_faces=MAX_FACE_NUM, float_input=False, out=None):
         import torch

@@ -29,6 +29,9 @@ int hp_decode_nms_impl(hp_ctx* h, const float* cls, const float* loc, const floa
                        int H, int W, float logit_thr, float iou_thr, int max_out, int32_t* out_cnt, int32_t* out_anchor,
                        double* boxes, double* kps, float* scores, float* poses, cudaStream_t st);
 int hp_preprocess_u8_impl(hp_ctx* h, const uint8_t* bgr, int B, int H, int W, float* x, cudaStream_t st);
+int hp_preprocess_resize_u8_impl(hp_ctx* h, const uint8_t* bgr, int B, int Hin, int Win, int Hout, int Wout, float* x, cudaStream_t st);
+void hp_resize_plans_free(hp_ctx* h);
+void hp_detect_graphs_free(hp_ctx* h);
 
 #define HP_ENTER(h)                                                                   \
   HP_REQUIRE((h) != nullptr, HP_ERR_INVALID, "null handle");                          \
@@ -64,6 +67,9 @@ int hp_destroy(hp_handle h) {
   if (!h) return HP_OK;
   cudaSetDevice(h->device);
   hp_comm_destroy(h);
+  hp_resize_plans_free(h);
+  hp_detect_graphs_free(h);
+  h->det.release();
   h->bb.arena.release(); h->bb.act[0].release(); h->bb.act[1].release(); h->bb.dwtmp.release();
   h->bb.feat16.release(); h->bb.feat8.release();
   h->pose16.release(); h->pose8.release(); h->cls.release(); h->loc.release(); h->scratch.release();
@@ -164,6 +170,12 @@ int hp_debug_tile_report(hp_handle h, int* report16x8) {
 int hp_preprocess_u8(hp_handle h, const uint8_t* bgr, int B, int H, int W, float* x, void* stream) {
   HP_ENTER(h);
   return hp_preprocess_u8_impl(h, bgr, B, H, W, x, (cudaStream_t)stream);
+}
+
+int hp_preprocess_resize_u8(hp_handle h, const uint8_t* bgr, int B, int Hin, int Win, int Hout, int Wout, float* x, void* stream) {
+  HP_ENTER(h);
+  if (Hin == Hout && Win == Wout) return hp_preprocess_u8_impl(h, bgr, B, Hin, Win, x, (cudaStream_t)stream);   // the resize is the identity there
+  return hp_preprocess_resize_u8_impl(h, bgr, B, Hin, Win, Hout, Wout, x, (cudaStream_t)stream);
 }
 
 int hp_head_create(hp_handle h, const hp_head_op* ops, int n_ops, const hp_head_reg* regs, int n_regs, int out_reg,

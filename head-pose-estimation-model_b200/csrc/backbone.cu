@@ -774,7 +774,7 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
       ChainCfg ccfg;
       if (plain && hp_chain_geometry(i, last - i + 1, chain_nblk, hs[i + 1], ws[i + 1], &ccfg)) {
         if (h->chain_cfg[0] > 0) ccfg.nsets = h->chain_cfg[0];
-        if (h->chain_cfg[1] > 0) ccfg.niss = h->chain_cfg[1];
+        if (h->chain_cfg[1] > 0) ccfg.niss = h->chain_cfg[1] < ccfg.TR ? h->chain_cfg[1] : ccfg.TR;
         float* cout_buf = (last == 10) ? feat16 : (last == 15) ? feat8 : bb.act[pp ^ 1].f();
         for (int it = 0; it < iters; ++it) {
           if (prof && it == 0) HP_CUDA(cudaEventRecord(h->ev[0], st));

@@ -53,6 +53,7 @@ struct ChainParams {
   int off_w, w_floats, off_ring, off_zero, zero_floats, off_tile;   // shared-memory layout in floats
   long long* trace;               // optional clock stamps of CTA 0: 8 per step
   int trace_steps;
+  int exp_;                       // timing experiments (env HP_CHAIN_EXP): 1 = no depthwise loads / math, 2 = no epilogue shared-memory traffic, 4 = no MMAs
   int dbg;                        // bring-up aid (env HP_CHAIN_DBG): 1 = setup only, 2 = + tile load / store, 3 = + first weight slices
 };
 
@@ -66,8 +67,7 @@ __device__ __forceinline__ void ch_wait(uint64_t* bar, uint32_t parity, int id, 
   uint32_t done = 0, n = 0;
   long long t0 = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x100;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    done = mbar_try_wait(addr, parity);
     if (done) break;
     if (*s_abort) break;
     if ((++n & 63u) == 0u) {
@@ -85,6 +85,17 @@ __device__ __forceinline__ void ch_wait(uint64_t* bar, uint32_t parity, int id, 
   }
 }
 
+// Wait of the issuer loops: nothing but the try_wait loop (every instruction of an issuer's k-step is on the critical path: a lone
+// warp retires a dependent instruction every ~5 clk, so the ~25 instructions of the watchdog wait cost more than the MMAs).
+__device__ __forceinline__ void ch_wait_lean(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "CH_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra CH_WAIT_%=;\n\t}"
+      ::"r"(addr), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -94,12 +105,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // issuer (NISS == 2), +3 first issuer (owns the TMEM allocation; sub-partition 3 is the least loaded one when fewer than
 // 97 lanes are in use).
 template <int TR, int PS, int NSETS, int NISS>
-__global__ void __launch_bounds__(128 * NSETS + 128, 1)
+__global__ void __launch_bounds__(128 * NSETS + 64 + 32 * NISS, 1)
 blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ ChainParams p) {
   constexpr uint32_t colA0 = TR * CH_DSTRIDE;          // TMEM: D_0 .. D_{TR-1}, then one A stage of TR * 16 columns per set
   constexpr uint32_t STAGE = TR * 16;
   static_assert(colA0 + NSETS * STAGE <= 512, "TMEM budget");
-  static_assert(NISS >= 1 && NISS <= 2 && NISS <= TR, "issuers");
+  static_assert(NISS >= 1 && NISS <= 3 && NISS <= TR, "issuers");
   constexpr int NWORK = 128 * NSETS;
 
   extern __shared__ __align__(1024) float smem[];
@@ -121,7 +132,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane_id = tid & 31;
-  constexpr int W_UTIL = 4 * NSETS, W_TLOAD = W_UTIL, W_WLOAD = W_UTIL + 1, W_ISS1 = W_UTIL + 2, W_ISS0 = W_UTIL + 3;
+  constexpr int W_UTIL = 4 * NSETS, W_TLOAD = W_UTIL, W_WLOAD = W_UTIL + 1, W_ISS0 = W_UTIL + 2;   // issuer i = warp W_ISS0 + i; issuer 0 owns the TMEM allocation
 
   // depthwise weights + biases of the whole chain, zeros around the tile (pads, lead pixel, trailing rows)
   for (int b = 0; b < p.nblk; ++b) {
@@ -217,7 +228,10 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         for (; ks < KS; ks += NSETS) {
           const uint32_t n = (g0 + ks) / NSETS;          // unit index within this set
           float4 acc[2][TR];
-          if (warp_active) {
+          if (p.exp_ & 1) {
+#pragma unroll
+            for (int t = 0; t < TR; ++t) acc[0][t] = acc[1][t] = make_float4(1.f, 2.f, 3.f, 4.f);
+          } else if (warp_active) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int c = ks * 8 + half * 4;
@@ -245,7 +259,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               }
             }
           }
-          if (n >= 1) {                                   // the MMAs of this set's previous unit have read the stage
+          if (n >= 1 && !(p.exp_ & 16)) {                 // the MMAs of this set's previous unit have read the stage
             ch_wait(&bar_aempty[set], (n - 1) & 1, 3, s_abort, step);
             tc_fence_after();
           }
@@ -296,7 +310,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               const int j = cg * 8 + jj;
-              if (j < NG) {
+              if (j < NG && !(p.exp_ & 2)) {
                 const float4 bb = ld4(s_pwb + j * 4);
                 float4 o = make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
                                        __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
@@ -318,43 +332,58 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         if (tid == 0) stamp(step, 3);
       }
     }
-  } else if (lane_id == 0) {
-    if (warp == W_ISS0 || (NISS == 2 && warp == W_ISS1)) {
+  } else {
+    // utility warps: ALL 32 lanes walk the role loops together (waits included) and one elected lane issues the asynchronous
+    // instructions.  A role written as `if (lane_id == 0) {...}` leaves lanes 1-31 parked at the final barrier as a second
+    // divergent path of the same warp, and the scheduler's switching between the two paths slowed lane 0 by ~5x (measured:
+    // ~1.7K clk per k-step of the issuer loop with nothing to wait for).
+    const bool leader = lane_id == 0;
+    if (warp >= W_ISS0) {
       // =============================================================== MMA issuers (M-tiles t % NISS == issuer)
-      const int issuer = (warp == W_ISS0) ? 0 : 1;
+      const int issuer = warp - W_ISS0;
       const uint32_t ring_addr = smem_u32(s_ring);
+      const uint32_t wfull_addr = smem_u32(bar_wfull), afull_addr = smem_u32(bar_afull);
+      const uint32_t wempty_addr = smem_u32(bar_wempty), aempty_addr = smem_u32(bar_aempty);
       uint32_t g = 0;
       int step = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int b = 0; b < nblk; ++b, ++step) {
           const int KS = p.blk[b].ks, n16 = p.blk[b].n16;
           const uint32_t idesc = tc_idesc_tf32(n16);
-          const uint64_t desc_fixed = tc_bdesc_fixed(n16);
+          const uint64_t desc_hi0 = tc_bdesc_fixed(n16) | (uint64_t)((ring_addr >> 4) & 0x3FFF);
+          const uint32_t lo_off = ((uint32_t)n16 * 32u) >> 4;              // W_lo follows W_hi in the slot (descriptor units of 16 B)
+          const bool traced = p.trace != nullptr && blockIdx.x == 0 && leader && issuer == 0;
+          const bool no_mma = (p.exp_ & 4) != 0;
 #pragma unroll 1
           for (int ks = 0; ks < KS; ++ks, ++g) {
-            const uint32_t set = g % NSETS, n = g / NSETS, slot = g % CH_RING;
-            ch_wait(&bar_wfull[slot], (g / CH_RING) & 1, 5, s_abort, step);
-            ch_wait(&bar_afull[set], n & 1, 6, s_abort, step);
+            const uint32_t set = g % NSETS, slot = g % CH_RING;
+            ch_wait_lean(wfull_addr + slot * 8, (g / CH_RING) & 1);
+            ch_wait_lean(afull_addr + set * 8, (g / NSETS) & 1);
             tc_fence_after();
-            if (issuer == 0 && ks == 0) stamp(step, 4);
-            const uint32_t hi_addr = ring_addr + slot * (CH_SLOT_FLOATS * 4);
-            const uint32_t lo_addr = hi_addr + (uint32_t)n16 * 32u;
-            const uint64_t dhi = desc_fixed | (uint64_t)((hi_addr >> 4) & 0x3FFF);
-            const uint64_t dlo = desc_fixed | (uint64_t)((lo_addr >> 4) & 0x3FFF);
+            if (leader) {
+              if (traced && ks == 0) stamp(step, 4);
+              const uint64_t dhi = desc_hi0 + (uint64_t)(slot * ((CH_SLOT_FLOATS * 4) >> 4));   // the ring stays below 256 KB: no carry into the fixed fields
+              const uint64_t dlo = dhi + lo_off;
+              const uint32_t a0 = tmem_base + colA0 + set * STAGE;
 #pragma unroll
-            for (int t = 0; t < TR; ++t) {
-              if (t % NISS != issuer) continue;
-              const uint32_t dc = tmem_base + t * CH_DSTRIDE;
-              const uint32_t a = tmem_base + colA0 + set * STAGE + t * 16;
-              mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
-              mma_tf32_ts(dc, a, dlo, idesc, 1u);
-              mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+              for (int t = 0; t < TR; ++t) {
+                if (t % NISS != issuer || no_mma) continue;
+                const uint32_t dc = tmem_base + t * CH_DSTRIDE;
+                const uint32_t a = a0 + t * 16;
+                mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+                mma_tf32_ts(dc, a, dlo, idesc, 1u);
+                mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+              }
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(aempty_addr + set * 8) : "memory");
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(wempty_addr + slot * 8) : "memory");
             }
-            tc_commit(&bar_aempty[set]);
-            tc_commit(&bar_wempty[slot]);
+            __syncwarp();
           }
-          tc_commit(bar_dfull);
-          if (issuer == 0) stamp(step, 5);
+          if (leader) {
+            tc_commit(bar_dfull);
+            if (traced) stamp(step, 5);
+          }
+          __syncwarp();
         }
       }
     } else if (warp == W_WLOAD) {
@@ -368,35 +397,42 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           for (int ks = 0; ks < cb.ks; ++ks, ++g) {
             const uint32_t slot = g % CH_RING;
             if (g >= CH_RING) ch_wait(&bar_wempty[slot], ((g / CH_RING) - 1) & 1, 7, s_abort, (int)g);
-            float* dst = s_ring + slot * CH_SLOT_FLOATS;
-            mbar_expect_tx(&bar_wfull[slot], 2u * half_bytes);
-            bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[slot]);
-            bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[slot]);
+            if (leader) {
+              float* dst = s_ring + slot * CH_SLOT_FLOATS;
+              mbar_expect_tx(&bar_wfull[slot], 2u * half_bytes);
+              bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[slot]);
+              bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[slot]);
+            }
+            __syncwarp();
           }
         }
       }
     } else if (warp == W_TLOAD) {
       // =============================================================== tile loader / storer
       int tile_idx = blockIdx.x;
-      if (my_tiles > 0) {
+      if (my_tiles > 0 && leader) {
         mbar_expect_tx(bar_tile_full, p.load_bytes);
         tma_load_4d(tile, &tm_in, bar_tile_full, 0, 0, 0, tile_idx * p.NI);
       }
       for (int it = 0; it < my_tiles; ++it, tile_idx += gridDim.x) {
         const int next = tile_idx + (int)gridDim.x;
-        if (it + 1 < my_tiles) tma_prefetch_4d(&tm_in, 0, 0, 0, next * p.NI);   // warm L2 while this tile is computed
+        if (it + 1 < my_tiles && leader) tma_prefetch_4d(&tm_in, 0, 0, 0, next * p.NI);   // warm L2 while this tile is computed
         ch_wait(bar_tile_done, it & 1, 8, s_abort, it);
-        tma_store_4d(&tm_out, tile, 0, 0, 0, tile_idx * p.NI);
-        tma_store_commit();
-        stamp(it * nblk + nblk - 1, 6);
-        tma_store_wait_read();
-        stamp(it * nblk + nblk - 1, 7);
-        if (it + 1 < my_tiles) {
-          mbar_expect_tx(bar_tile_full, p.load_bytes);
-          tma_load_4d(tile, &tm_in, bar_tile_full, 0, 0, 0, next * p.NI);
+        if (leader) {
+          tma_store_4d(&tm_out, tile, 0, 0, 0, tile_idx * p.NI);
+          tma_store_commit();
+          stamp(it * nblk + nblk - 1, 6);
+          tma_store_wait_read();
+          stamp(it * nblk + nblk - 1, 7);
+          if (it + 1 < my_tiles) {
+            mbar_expect_tx(bar_tile_full, p.load_bytes);
+            tma_load_4d(tile, &tm_in, bar_tile_full, 0, 0, 0, next * p.NI);
+          }
         }
+        __syncwarp();
       }
-      tma_store_wait_all();
+      if (leader) tma_store_wait_all();
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -412,7 +448,7 @@ int launch_chain(hp_ctx* h, const CUtensorMap& tin, const CUtensorMap& tout, con
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, 128 * NSETS + 128, smem, st>>>(tin, tout, p);
+  kern<<<(unsigned)grid, 128 * NSETS + 64 + 32 * NISS, smem, st>>>(tin, tout, p);
   h->launches++;
   HP_CUDA(cudaGetLastError());
   return HP_OK;
@@ -509,8 +545,15 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
   p.off_tile = cfg.off_tile;
   p.trace = h->tc_trace; p.trace_steps = h->tc_trace_tiles;
   {
-    const char* e = getenv("HP_CHAIN_DBG");
-    p.dbg = e ? atoi(e) : 0;
+    static int dbg_env = -1, exp_env = -1;             // read once: bring-up / timing-experiment switches
+    if (dbg_env < 0) {
+      const char* e = getenv("HP_CHAIN_DBG");
+      dbg_env = e ? atoi(e) : 0;
+      e = getenv("HP_CHAIN_EXP");
+      exp_env = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg_env;
+    p.exp_ = exp_env;
   }
   HP_REQUIRE(cfg.smem <= 227 * 1024 && cfg.lanes >= 1 && cfg.lanes <= 128 && (cfg.off_tile * 4) % 128 == 0 && H + 1 <= 256 && W + 1 <= 256 &&
                  cfg.NI <= 256 && p.load_bytes < (1u << 20),
@@ -531,6 +574,7 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
     return launch_chain<TR_, PS_, NSETS_, NISS_>(h, tin, tout, p, cfg.smem, st);
   CHAIN_CASE(3, 92, 4, 2) CHAIN_CASE(2, 92, 4, 2) CHAIN_CASE(3, 100, 4, 2) CHAIN_CASE(2, 100, 4, 2)
   CHAIN_CASE(3, 92, 4, 1) CHAIN_CASE(2, 92, 4, 1) CHAIN_CASE(3, 100, 4, 1) CHAIN_CASE(2, 100, 4, 1)
+  CHAIN_CASE(3, 92, 4, 3) CHAIN_CASE(3, 100, 4, 3)
 #undef CHAIN_CASE
   hp_set_error("chain: no kernel for TR %d PS %d nsets %d issuers %d", cfg.TR, cfg.PS, cfg.nsets, cfg.niss);
   return HP_ERR_UNSUPPORTED;

@@ -610,7 +610,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
 #pragma unroll 1
         for (int ks = 0; ks < KS; ++ks, ++use) {
           const uint32_t s = use % NSTG;
-          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          mbar_wait_lean(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
           if (issuer == 0 && ks == 0) stamp(i, 10);
           if (issuer == 0 && ks == KS - 1) stamp(i, 9);
@@ -873,7 +873,7 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
 #pragma unroll 1
         for (int u = 0; u < p.upt; ++u, ++use) {
           const uint32_t s = use % NSTG;
-          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          mbar_wait_lean(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
           if (u == 0) stamp(i, 10);
           if (u == p.upt - 1) stamp(i, 9);
@@ -1157,7 +1157,7 @@ blaze_block_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 #pragma unroll 1
         for (int u = 0; u < p.upt; ++u, ++use) {
           const uint32_t s = use % NSTG;
-          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          mbar_wait_lean(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
           if (u == 0) stamp(i, 10);
           if (u == p.upt - 1) stamp(i, 9);

@@ -35,11 +35,14 @@ void hp_set_error(const char* fmt, ...);
   } while (0)
 
 // Growable device buffer owned by a handle.
+extern long long g_devbuf_epoch;   // detect.cu: counts reallocations (captured CUDA graphs hold raw pointers)
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   int ensure(size_t n) {
     if (n <= bytes) return HP_OK;
+    ++g_devbuf_epoch;
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
@@ -102,6 +105,31 @@ struct Comm {
 
 struct hp_head;  // heads.cu
 
+// preproc.cu: tap tables of one (input size -> output size) bicubic resize, on the device: [Hout + Wout][4] indices, then weights
+struct ResizePlan {
+  int hin = 0, win = 0, hout = 0, wout = 0;
+  void* dev = nullptr;
+};
+
+// detect.cu: internals of hp_detect_frames (padded decode / NMS outputs before packing) and its captured graphs
+struct DetectBufs {
+  DevBuf x, cnt, offsets, anchor, boxes, kps, scores, poses;
+  void release() { x.release(); cnt.release(); offsets.release(); anchor.release(); boxes.release(); kps.release(); scores.release(); poses.release(); }
+};
+struct DetectGraph {
+  const void *head16 = nullptr, *head8 = nullptr, *frames = nullptr, *result = nullptr;
+  int B = 0, Hin = 0, Win = 0, H = 0, W = 0, max_out = 0, cap = 0, impl = 0, chain_mode = 0;
+  float logit_thr = 0.f, iou_thr = 0.f;
+  long long epoch = 0;
+  int launches = 0;
+  cudaGraphExec_t exec = nullptr;
+  bool same_key(const DetectGraph& o) const {
+    return head16 == o.head16 && head8 == o.head8 && frames == o.frames && result == o.result && B == o.B && Hin == o.Hin && Win == o.Win &&
+           H == o.H && W == o.W && max_out == o.max_out && cap == o.cap && impl == o.impl && chain_mode == o.chain_mode &&
+           logit_thr == o.logit_thr && iou_thr == o.iou_thr;
+  }
+};
+
 struct hp_ctx {
   int device = 0;
   int num_sms = 148;
@@ -111,6 +139,9 @@ struct hp_ctx {
   Comm comm;
   DevBuf pose16, pose8, cls, loc;  // unified-path internals
   DevBuf scratch;
+  std::vector<ResizePlan> resize_plans;
+  DetectBufs det;
+  std::vector<DetectGraph> det_graphs;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
   bool dense_tc = true;            // Dense / 1x1 layers may use the tensor-core kernel (cleared while a training step runs)

@@ -367,7 +367,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
 #pragma unroll 1
         for (int u = 0; u < p.upt; ++u, ++use) {
           const uint32_t s = use % NSTG;
-          mbar_wait(&bar_afull[ring * DT_MAXSTG + s], (use / NSTG) & 1);
+          mbar_wait_lean(&bar_afull[ring * DT_MAXSTG + s], (use / NSTG) & 1);
           tc_fence_after();
           if (u == 0) stamp(i, 10);
           if (u == p.upt - 1) stamp(i, 9);
@@ -431,7 +431,9 @@ static size_t dense_tc_layout(int K, int N, int nbuf, bool tail, DenseTcParams* 
 // true when the layer can run on the tensor-core kernel: forward, plain weights, 16-byte aligned rows, at least 3 k-steps
 // (every gather set must own a k-step of every tile), two input buffers next to the split weights in shared memory
 static bool dense_tc_ok(const float* x, int M, int K, int ldx, int N, bool tail) {
-  if (M < 4 * DT_ROWS || K % 4 != 0 || K < 20 || K > 128 || N < 1 || N > 128 || ldx % 4 != 0 ||
+  // no lower bound on M: a layer takes the same kernel (same arithmetic, row by row) whatever the batch size, so results do
+  // not depend on how a caller batches its crops
+  if (M < 1 || K % 4 != 0 || K < 20 || K > 128 || N < 1 || N > 128 || ldx % 4 != 0 ||
       (((uintptr_t)x) & 15) != 0)
     return false;
   DenseTcParams p;

@@ -272,7 +272,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll 1
         for (int ks = 0; ks < ST_KS; ++ks, ++use) {
           const uint32_t s = use % NSTG;
-          mbar_wait(&bar_afull[s], (use / NSTG) & 1);
+          mbar_wait_lean(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
           if (issuer == 0 && ks == 0) stamp(i, 10);
           if (issuer == 0 && ks == ST_KS - 1) stamp(i, 9);

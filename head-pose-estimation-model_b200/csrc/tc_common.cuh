@@ -21,13 +21,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // phase completes instead of burning issue slots (ncu: un-hinted polling was ~25 % of all issued instructions); the clock
 // is read every 256 wake-ups only.  The hint is kept at 256 ns: with 16 us, rare runs of some geometries took 1-20 ms
 // instead of 0.2 ms (a completion that lands between the failed test and the sleep is only noticed at the time limit).
+#ifndef HP_WAIT_HINT
+#define HP_WAIT_HINT 0x100
+#endif
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+#if HP_WAIT_HINT > 0
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(addr), "r"(parity), "n"(HP_WAIT_HINT) : "memory");
+#else
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+#endif
+  return done;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, n = 0;
   long long t0 = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x100;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    done = mbar_try_wait(addr, parity);
     if (done) break;
     if ((++n & 255u) == 0u) {
       const long long now = clock64();
@@ -35,6 +48,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       else if (now - t0 > 4000000000ll) __trap();   // ~2 s: never hang the device on a lost signal
     }
   }
+}
+// Wait for the MMA-issuing threads: nothing but the try_wait loop.  An issuer is a lone thread whose dependent instructions
+// retire every ~5 clk, so the ~25 instructions of mbar_wait (watchdog) on every k-step cost more than the MMAs they guard
+// (measured in the chain kernel: 1.1-1.7K clk per k-step with nothing to wait for, tools/chain_check.py).
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MBAR_LEAN_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra MBAR_LEAN_%=;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(

@@ -84,6 +84,12 @@ int hp_backbone_read_activation(hp_handle h, const float* x, int B, int H, int W
  * Replaces prepareInputForInference (blazeFaceDetectorH5.py:247-269) for images that already
  * have the network input size: BGR uint8 [B,H,W,3] -> RGB float32 ((v/255)-0.5)/0.5. */
 int hp_preprocess_u8(hp_handle h, const uint8_t* bgr, int B, int H, int W, float* x, void* stream);
+/* The whole of prepareInputForInference (blazeFaceDetectorH5.py:247-269) for frames of any size: BGR uint8 [B,Hin,Win,3] ->
+ * RGB, /255.0, tf.image.resize(method='bicubic') to Hout x Wout (TensorFlow's ResizeBicubic with half-pixel centres: Keys
+ * cubic A = -0.5 from its 1025-entry table, border taps dropped and renormalised, rows then columns, float32), (t-0.5)/0.5
+ * -> float32 [B,Hout,Wout,3].  Equal sizes take the hp_preprocess_u8 path (the resize is the identity there). */
+int hp_preprocess_resize_u8(hp_handle h, const uint8_t* bgr, int B, int Hin, int Win, int Hout, int Wout, float* x,
+                            void* stream);
 
 /* ---------------------------------------------------------------- regressor heads (a4-a6)
  * A head is a small program over per-token tensors ("registers"); the Python layer compiles the
@@ -180,6 +186,35 @@ int hp_extract_detections(hp_handle h, const float* loc, const int32_t* idx, int
                           double* boxes, double* kps, void* stream);
 int hp_nms(hp_handle h, const double* boxes, const float* scores, int n, float iou_thr, int max_out,
            int32_t* out_sel, int32_t* out_cnt, void* stream);
+
+/* ---------------------------------------------------------------- frames -> faces in one call
+ * Replaces blazeFaceDetector.detectFaces (blazeFaceDetectorH5.py:109-126) end to end for B uint8 BGR frames [B,Hin,Win,3]
+ * (device pointer): prepareInputForInference with the bicubic resize to H x W, the unified graph, filterDetections,
+ * extractDetections, filterWithNonMaxSupression and the pose lookup.  The kept faces of all frames are PACKED into
+ * `result` (device pointer, 8-byte aligned):
+ *     int32 header[HP_RESULT_HEADER_INTS] = { total = sum(count), written = min(total, capacity), B, capacity }
+ *     int32 count[B]                         faces kept per frame, frame order
+ *     (padding to 8 bytes: hp_detect_result_faces_offset(B))
+ *     hp_face faces[written]                 frame-major, score-descending within a frame (the reference's order)
+ * so that the caller moves one buffer each way.  capacity = (result_bytes - offset) / sizeof(hp_face), at most B * max_out.
+ * flags & HP_DETECT_GRAPH: the launch sequence is captured on the second call with the same arguments (pointers and
+ * thresholds included) and replayed as ONE CUDA-graph launch from then on -- the per-frame latency path of the
+ * reference's webcam loop (:392-444).  Needs a non-default stream. */
+typedef struct hp_face {
+  double box[4];          /* x1, y1, x2, y2, normalised (extractDetections :284-317, float64 like the reference) */
+  double keypoints[12];   /* 6 x (x, y) */
+  float score;            /* sigmoid(cls), float32 (:319-327) */
+  float pose[3];          /* yaw, pitch, roll of the anchor's cell (:342-356) */
+  int32_t anchor;         /* kept anchor id */
+  int32_t frame;          /* index of the frame in the batch */
+} hp_face;
+#define HP_RESULT_HEADER_INTS 4
+#define HP_DETECT_GRAPH 1
+size_t hp_detect_result_faces_offset(int B);
+size_t hp_detect_result_bytes(int B, int capacity);
+int hp_detect_frames(hp_handle h, hp_head_t head16, hp_head_t head8, const uint8_t* frames_bgr, int B, int Hin, int Win,
+                     int H, int W, float logit_thr, float iou_thr, int max_out, void* result, size_t result_bytes,
+                     int flags, void* stream);
 
 /* ---------------------------------------------------------------- unified path (config 5)
  * backbone + detector heads + two pose heads (JoinModels.py:5-90 output order) + decode + NMS.

@@ -156,8 +156,7 @@ def test_detect_faces_end_to_end_vs_oracle():
         ref64 = opp.detect_postprocess(cls, loc, o64[4][i].numpy(), o64[5][i].numpy(), anchors)
         if len(ref64["poses"]):
             assert np.abs(batch[i].poses - ref64["poses"]).max() < 0.01      # angles within 0.01 degree
-    with pytest.raises(ValueError):
-        det.detectFaces(np.zeros((64, 64, 3), np.uint8))
+    assert det.detectFaces(np.zeros((64, 64, 3), np.uint8)).boxes.shape[1:] == (4,)   # any frame size (bicubic resize on the device)
 
 
 @pytest.mark.parametrize("chunks", [1, 2, 4])
