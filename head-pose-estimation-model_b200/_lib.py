@@ -26,6 +26,7 @@ HP_KEYPOINTS = 6
 HP_IMPL_FAST, HP_IMPL_NAIVE, HP_IMPL_CPASYNC, HP_IMPL_TMA = 0, 1, 2, 3
 HP_RESULT_HEADER_INTS = 4
 HP_DETECT_GRAPH = 1
+HP_TRAIN_GRAPH = 1
 (HP_OP_DENSE, HP_OP_ACT, HP_OP_ADD, HP_OP_MULCH, HP_OP_GAP, HP_OP_DROPOUT, HP_OP_LAYERNORM,
  HP_OP_MHA) = range(1, 9)
 HP_ACT = {"linear": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3, "softsign": 4}
@@ -129,6 +130,9 @@ _PROTOS = {
                                   C.c_void_p]),
     "hp_head_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.POINTER(hp_opt_config), C.c_uint64, C.c_void_p, C.c_void_p]),
+    "hp_head_train_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(hp_opt_config), C.c_uint64, C.c_int,
+                                    C.c_void_p, C.c_void_p]),
     "hp_head_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p]),
     "hp_dropout_hash": (C.c_uint32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),

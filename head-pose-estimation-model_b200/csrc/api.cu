@@ -25,6 +25,9 @@ int hp_head_out_channels(hp_head* hd);
 int hp_head_forward_impl(hp_ctx* h, hp_head* hd, const float* feat, int B, int H, int W, float* out, cudaStream_t st);
 int hp_head_train_step_impl(hp_ctx* h, hp_head* hd, const float* x, const float* y, int n, int H, int W, int n_global,
                             const hp_opt_config* opt, uint64_t seed, float* loss_mae_host, bool update, cudaStream_t st);
+int hp_head_train_run_impl(hp_ctx* h, hp_head* hd, const float* x_all, const float* y_all, const int32_t* idx, long long n_items,
+                           long long first_item, int batch_global, int n_steps, int rank, int world, int H, int W,
+                           const hp_opt_config* opt, uint64_t seed, int flags, double* sums_host, cudaStream_t st);
 int hp_decode_nms_impl(hp_ctx* h, const float* cls, const float* loc, const float* pose16, const float* pose8, int B,
                        int H, int W, float logit_thr, float iou_thr, int max_out, int32_t* out_cnt, int32_t* out_anchor,
                        double* boxes, double* kps, float* scores, float* poses, cudaStream_t st);
@@ -208,6 +211,13 @@ int hp_head_train_step(hp_handle h, hp_head_t head, const float* x, const float*
                        const hp_opt_config* opt, uint64_t seed, float* loss_mae_host, void* stream) {
   HP_ENTER(h);
   return hp_head_train_step_impl(h, head, x, y, n, H, W, n_global, opt, seed, loss_mae_host, true, (cudaStream_t)stream);
+}
+int hp_head_train_run(hp_handle h, hp_head_t head, const float* x_all, const float* y_all, const int32_t* idx, long long n_items,
+                      long long first_item, int batch_global, int n_steps, int rank, int world, int H, int W,
+                      const hp_opt_config* opt, uint64_t seed, int flags, double* sums_host, void* stream) {
+  HP_ENTER(h);
+  return hp_head_train_run_impl(h, head, x_all, y_all, idx, n_items, first_item, batch_global, n_steps, rank, world, H, W, opt, seed,
+                                flags, sums_host, (cudaStream_t)stream);
 }
 int hp_head_evaluate(hp_handle h, hp_head_t head, const float* x, const float* y, int n, int H, int W,
                      float* mse_mae_host, void* stream) {

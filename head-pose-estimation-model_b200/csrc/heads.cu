@@ -418,8 +418,11 @@ __host__ __device__ inline bool dropout_keep(uint32_t u, float rate) {
   return (float)(u >> 8) * (1.0f / 16777216.0f) >= rate;
 }
 // mode 0: out = x*m ; mode 1: gx += gy*m  (m = keep/(1-rate), mask over (image, channel))
+// step_dev != nullptr: the step index is *step_dev - 1 (device-resident counter of hp_head_train_run, already advanced for
+// this step), so that a captured step can be replayed
 __global__ void dropout_kernel(const float* in, float* out, long long rows, int C, int T, int per_image, float rate,
-                               uint64_t seed, uint32_t step, uint32_t op_id, int mode) {
+                               uint64_t seed, uint32_t step, uint32_t op_id, int mode, const uint32_t* step_dev = nullptr) {
+  if (step_dev) step = *step_dev - 1u;
   const long long total = rows * C;
   const float scale = 1.f / (1.f - rate);
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
@@ -854,8 +857,15 @@ __global__ void l2_penalty_kernel(const float* w, const float* l2, int n, float*
   }
 }
 // Keras 2.13 update rules.  g_total = g + 2*l2*w
+struct TrainState {            // device-resident state of hp_head_train_run
+  uint32_t t;                  // optimizer steps taken, this one included (must stay the first member: dropout reads it)
+  uint32_t k;                  // steps done in this call
+  float alpha_t, lr_t;         // Adam / Adamax step sizes of step t
+  float acc[2];                // sum over the call's steps of loss * n_global, mae * n_global
+};
 __global__ void optimizer_kernel(float* w, const float* g, const float* l2, float* m, float* v, int n, int kind,
-                                 float lr, float b1, float b2, float eps, float alpha_t, float lr_t) {
+                                 float lr, float b1, float b2, float eps, float alpha_t, float lr_t, const TrainState* ts = nullptr) {
+  if (ts) { alpha_t = ts->alpha_t; lr_t = ts->lr_t; }
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const float wi = w[i];
     const float gi = g[i] + 2.f * l2[i] * wi;
@@ -896,6 +906,20 @@ struct hp_head {
   uint32_t step = 0;
   bool has_state = false;
   float last_sums[4] = {0, 0, 0, 0};
+  // hp_head_train_run: device-resident step state, staging batch, captured step graphs
+  DevBuf tstate, xs, ys;
+  const uint32_t* step_dev = nullptr;   // set while a train_run step is being issued: dropout reads the step from tstate
+  struct RunGraph {
+    const void *x = nullptr, *y = nullptr, *idx = nullptr;
+    long long first = 0, epoch = 0;
+    int batch_global = 0, n_local = 0, rank = 0, world = 0, H = 0, W = 0, impl = 0;
+    hp_opt_config opt{};
+    uint64_t seed = 0;
+    void* comm = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+  };
+  std::vector<RunGraph> run_graphs;
 };
 
 static long long reg_rows(const hp_head* hd, int r, int n_img, int T) {
@@ -994,10 +1018,13 @@ int hp_head_create_impl(hp_ctx* h, const hp_head_op* ops, int n_ops, const hp_he
   return HP_OK;
 }
 
+void hp_head_run_graphs_free(hp_head* hd);
 void hp_head_free_impl(hp_head* hd) {
+  if (hd) hp_head_run_graphs_free(hd);
   if (!hd) return;
   hd->params.release(); hd->grads.release(); hd->m.release(); hd->v.release(); hd->l2coef.release();
   hd->acts.release(); hd->gacts.release(); hd->ws.release();
+  hd->tstate.release(); hd->xs.release(); hd->ys.release();
   delete hd;
 }
 
@@ -1125,7 +1152,7 @@ static int head_forward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, in
       case HP_OP_DROPOUT:
         if (training && o.fparam > 0.f) {
           dropout_kernel<<<EW_GRID(total), 256, 0, st>>>(R(o.in0), RW(o.out), rows_out, C, T, hd->regs[o.out].per_image,
-                                                        o.fparam, seed, hd->step, (uint32_t)o.op_id, 0);
+                                                        o.fparam, seed, hd->step, (uint32_t)o.op_id, 0, hd->step_dev);
         } else if (!training) {
           hd->alias[o.out] = hd->alias[o.in0];   // identity at inference: readers of o.out are pointed at the source, no copy
           break;
@@ -1264,7 +1291,7 @@ static int head_backward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, i
         if (GR(o.in0)) {
           if (o.fparam > 0.f)
             dropout_kernel<<<EW_GRID(total), 256, 0, st>>>(gy, GR(o.in0), rows_out, C, T, hd->regs[o.out].per_image,
-                                                          o.fparam, seed, hd->step, (uint32_t)o.op_id, 1);
+                                                          o.fparam, seed, hd->step, (uint32_t)o.op_id, 1, hd->step_dev);
           else
             acc_kernel<<<EW_GRID(total), 256, 0, st>>>(GR(o.in0), gy, total);
           h->launches++;
@@ -1407,6 +1434,173 @@ int hp_head_train_step_impl(hp_ctx* h, hp_head* hd, const float* x, const float*
     loss_mae_host[0] = hd->last_sums[0] / cnt + (update ? hd->last_sums[3] : 0.f);
     loss_mae_host[1] = hd->last_sums[1] / cnt;
     if (!update) loss_mae_host[2] = hd->last_sums[3];
+  }
+  return HP_OK;
+}
+
+// ============================================================================ hp_head_train_run: many steps, no host round trips
+// Step prologue: advance the device-resident counters and derive the step sizes of optimizer step t (Keras 2.13: alpha_t =
+// lr sqrt(1 - b2^t) / (1 - b1^t) for Adam, lr / (1 - b1^t) for Adamax, in double like the host path).
+__global__ void train_begin_kernel(TrainState* ts, float lr, float b1, float b2) {
+  if (threadIdx.x == 0) {
+    const uint32_t t = ts->t + 1u;
+    ts->t = t;
+    const double td = (double)t, d1 = 1.0 - pow((double)b1, td);
+    ts->alpha_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, td)) / d1);
+    ts->lr_t = (float)((double)lr / d1);
+  }
+}
+// This rank's rows of global batch k: items idx[first + k * batch_global + rank + j * world], j < n_local (idx == nullptr:
+// identity).  One CTA per row.
+__global__ void __launch_bounds__(128) train_gather_kernel(const TrainState* ts, const float* __restrict__ x_all, const float* __restrict__ y_all,
+                                                          const int32_t* __restrict__ idx, long long first, int batch_global, int rank, int world,
+                                                          int xrow, int yrow, float* __restrict__ xs, float* __restrict__ ys) {
+  const int j = blockIdx.x;
+  const long long pos = first + (long long)ts->k * batch_global + rank + (long long)j * world;
+  const long long item = idx ? (long long)idx[pos] : pos;
+  const float* xr = x_all + item * xrow;
+  const float* yr = y_all + item * yrow;
+  for (int i = threadIdx.x; i < xrow; i += blockDim.x) xs[(long long)j * xrow + i] = xr[i];
+  for (int i = threadIdx.x; i < yrow; i += blockDim.x) ys[(long long)j * yrow + i] = yr[i];
+}
+// Step epilogue: loss (mse of the GLOBAL batch + L2 of the pre-update weights) and mae into the call's accumulators.
+__global__ void train_end_kernel(TrainState* ts, const float* sums, float count, float n_global) {
+  if (threadIdx.x == 0) {
+    ts->acc[0] += (sums[0] / count + sums[3]) * n_global;
+    ts->acc[1] += (sums[1] / count) * n_global;
+    ts->k += 1u;
+  }
+}
+
+static int train_run_one_step(hp_ctx* h, hp_head* hd, const float* x_all, const float* y_all, const int32_t* idx, long long first,
+                              int batch_global, int n_local, int rank, int world, int H, int W, const hp_opt_config* opt, uint64_t seed,
+                              cudaStream_t st) {
+  const int T = H * W, Cin = hd->in_channels, Cout = hd->regs[hd->out_reg].channels, np = hd->n_params;
+  TrainState* ts = (TrainState*)hd->tstate.p;
+  float* sums = hd->grads.f() + np;
+  train_begin_kernel<<<1, 32, 0, st>>>(ts, opt->lr, opt->beta1, opt->beta2);
+  h->launches++;
+  HP_CUDA(cudaMemsetAsync(hd->grads.p, 0, (size_t)(np + 4) * sizeof(float), st));
+  if (n_local > 0) {
+    train_gather_kernel<<<n_local, 128, 0, st>>>(ts, x_all, y_all, idx, first, batch_global, rank, world, T * Cin, T * Cout, hd->xs.f(), hd->ys.f());
+    h->launches++;
+    hd->step_dev = &ts->t;
+    int rc = head_forward(h, hd, hd->xs.f(), n_local, T, true, seed, st);
+    if (rc == HP_OK) {
+      const long long total = (long long)n_local * T * Cout;
+      const float* pred = hd->alias[hd->out_reg] == 0 ? hd->xs.f() : hd->acts.f() + hd->reg_off[hd->alias[hd->out_reg]];
+      rc = cudaMemsetAsync(hd->gacts.p, 0, hd->gacts.bytes, st) == cudaSuccess ? HP_OK : HP_ERR_CUDA;
+      const float inv_count = 1.f / ((float)batch_global * (float)T * (float)Cout);
+      mse_loss_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 1024), 256, 0, st>>>(pred, hd->ys.f(), hd->gacts.f() + hd->reg_off[hd->out_reg],
+                                                                                             total, inv_count, sums);
+      h->launches++;
+      if (rc == HP_OK) rc = head_backward(h, hd, hd->xs.f(), n_local, T, seed, st);
+    }
+    hd->step_dev = nullptr;
+    HP_TRY(rc);
+  }
+  if (world > 1) HP_TRY(hp_comm_allreduce_sum(h, hd->grads.f(), (size_t)np + 3, st));   // a single-rank run never touches a communicator the context may hold
+  l2_penalty_kernel<<<1, 256, 0, st>>>(hd->params.f(), hd->l2coef.f(), np, sums + 3);
+  optimizer_kernel<<<ceil_div(np, 256), 256, 0, st>>>(hd->params.f(), hd->grads.f(), hd->l2coef.f(), hd->m.f(), hd->v.f(), np, opt->kind, opt->lr,
+                                                     opt->beta1, opt->beta2, opt->eps, 0.f, 0.f, ts);
+  train_end_kernel<<<1, 32, 0, st>>>(ts, sums, (float)batch_global * T * Cout, (float)batch_global);
+  h->launches += 3;
+  HP_CUDA(cudaGetLastError());
+  return HP_OK;
+}
+
+void hp_head_run_graphs_free(hp_head* hd) {
+  for (auto& g : hd->run_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  hd->run_graphs.clear();
+}
+
+int hp_head_train_run_impl(hp_ctx* h, hp_head* hd, const float* x_all, const float* y_all, const int32_t* idx, long long n_items,
+                           long long first_item, int batch_global, int n_steps, int rank, int world, int H, int W,
+                           const hp_opt_config* opt, uint64_t seed, int flags, double* sums_host, cudaStream_t st) {
+  HP_REQUIRE(hd && x_all && y_all && opt && H > 0 && W > 0, HP_ERR_INVALID, "hp_head_train_run: bad arguments");
+  HP_REQUIRE(world >= 1 && rank >= 0 && rank < world && batch_global >= 1 && n_steps >= 1, HP_ERR_INVALID, "hp_head_train_run: bad batch / rank arguments");
+  HP_REQUIRE(first_item >= 0 && first_item + (long long)n_steps * batch_global <= n_items, HP_ERR_INVALID,
+             "hp_head_train_run: %d steps of %d items from item %lld exceed the %lld items of the data set", n_steps, batch_global, first_item, n_items);
+  HP_REQUIRE(world == 1 || (h->comm.comm && h->comm.nranks == world && h->comm.rank == rank), HP_ERR_STATE,
+             "hp_head_train_run: %d ranks but the gradient communicator is not initialised for them (hp_comm_init)", world);
+  const int n_local = batch_global > rank ? (batch_global - rank + world - 1) / world : 0;     // rows rank, rank + world, ... of the batch
+  const int T = H * W, Cin = hd->in_channels, Cout = hd->regs[hd->out_reg].channels, np = hd->n_params;
+  const int n_plan = n_local > 0 ? n_local : 1;
+  HP_TRY(head_plan(hd, n_plan, T, true));
+  HP_TRY(hd->xs.ensure((size_t)n_plan * T * Cin * sizeof(float)));
+  HP_TRY(hd->ys.ensure((size_t)n_plan * T * Cout * sizeof(float)));
+  HP_TRY(hd->tstate.ensure(sizeof(TrainState)));
+  if (!hd->has_state) {        // SGD keeps no moments, but one code path: the optimizer kernel is handed valid pointers either way
+    HP_TRY(hd->m.ensure((size_t)np * sizeof(float)));
+    HP_TRY(hd->v.ensure((size_t)np * sizeof(float)));
+    HP_CUDA(cudaMemsetAsync(hd->m.p, 0, (size_t)np * sizeof(float), st));
+    HP_CUDA(cudaMemsetAsync(hd->v.p, 0, (size_t)np * sizeof(float), st));
+    hd->has_state = true;
+  }
+  TrainState init;
+  memset(&init, 0, sizeof(init));
+  init.t = hd->step;
+  HP_CUDA(cudaMemcpyAsync(hd->tstate.p, &init, sizeof(init), cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
+
+  int done = 0;
+  if ((flags & HP_TRAIN_GRAPH) && st != nullptr) {
+    hp_head::RunGraph key;
+    key.x = x_all; key.y = y_all; key.idx = idx; key.first = first_item; key.batch_global = batch_global; key.n_local = n_local;
+    key.rank = rank; key.world = world; key.H = H; key.W = W; key.impl = h->impl; key.opt = *opt; key.seed = seed; key.comm = h->comm.comm;
+    hp_head::RunGraph* hit = nullptr;
+    for (auto& g : hd->run_graphs)
+      if (g.x == key.x && g.y == key.y && g.idx == key.idx && g.first == key.first && g.batch_global == key.batch_global && g.n_local == key.n_local &&
+          g.rank == key.rank && g.world == key.world && g.H == key.H && g.W == key.W && g.impl == key.impl && g.seed == key.seed && g.comm == key.comm &&
+          memcmp(&g.opt, &key.opt, sizeof(hp_opt_config)) == 0)
+        hit = &g;
+    if (hit && hit->epoch != g_devbuf_epoch) {
+      hp_head_run_graphs_free(hd);
+      hit = nullptr;
+    }
+    if (!hit) {
+      // first step of a new key runs as plain launches (kernel attributes, lazily sized scratch), the next one is captured
+      HP_TRY(train_run_one_step(h, hd, x_all, y_all, idx, first_item, batch_global, n_local, rank, world, H, W, opt, seed, st));
+      done = 1;
+      if (hd->run_graphs.size() >= 8) hp_head_run_graphs_free(hd);
+      key.epoch = g_devbuf_epoch;
+      hd->run_graphs.push_back(key);
+      hit = &hd->run_graphs.back();
+    }
+    if (done < n_steps && !hit->exec) {
+      const int64_t before = h->launches;
+      HP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int rc = train_run_one_step(h, hd, x_all, y_all, idx, first_item, batch_global, n_local, rank, world, H, W, opt, seed, st);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc != HP_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      HP_REQUIRE(ce == cudaSuccess && graph, HP_ERR_CUDA, "hp_head_train_run: stream capture failed: %s", cudaGetErrorString(ce));
+      HP_REQUIRE(hit->epoch == g_devbuf_epoch, HP_ERR_STATE, "hp_head_train_run: a buffer was reallocated during capture");
+      cudaGraphExec_t exec = nullptr;
+      const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      HP_REQUIRE(ie == cudaSuccess, HP_ERR_CUDA, "hp_head_train_run: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+      hit->exec = exec;
+      hit->launches = (int)(h->launches - before);
+      h->launches = before;
+    }
+    for (; done < n_steps; ++done) {
+      HP_CUDA(cudaGraphLaunch(hit->exec, st));
+      h->launches += hit->launches;
+    }
+  }
+  for (; done < n_steps; ++done)
+    HP_TRY(train_run_one_step(h, hd, x_all, y_all, idx, first_item, batch_global, n_local, rank, world, H, W, opt, seed, st));
+  hd->step += (uint32_t)n_steps;
+  if (sums_host) {
+    TrainState fin;
+    HP_CUDA(cudaMemcpyAsync(&fin, hd->tstate.p, sizeof(fin), cudaMemcpyDeviceToHost, st));
+    HP_CUDA(cudaStreamSynchronize(st));
+    sums_host[0] = fin.acc[0];
+    sums_host[1] = fin.acc[1];
   }
   return HP_OK;
 }

@@ -21,6 +21,7 @@ Nothing in here touches the GPU.
 from __future__ import annotations
 
 import json
+import os
 import struct
 from typing import Dict, Iterator, List, Optional, Tuple
 
@@ -443,5 +444,7 @@ def write_h5(path: str, weights: Dict[str, np.ndarray], model_config: dict,
     w.align()
     w.patch(56 + 8, struct.pack("<Q", root_addr))
     w.patch(24 + 16, struct.pack("<Q", len(w.buf)))
-    with open(path, "wb") as f:
+    tmp = f"{path}.tmp.{os.getpid()}"                     # a reader (or a crash) never sees a half-written checkpoint
+    with open(tmp, "wb") as f:
         f.write(bytes(w.buf))
+    os.replace(tmp, path)

@@ -589,6 +589,8 @@ class ModelCheckpoint(Callback):
             if cur is None or not cur < self.best:
                 return
             self.best = cur
+        if getattr(self.model, "_fit_rank", 0) != 0:
+            return                                     # data-parallel fit: the weights are identical on every rank, rank 0 writes
         self.model.save(self.filepath.format(epoch=epoch + 1, **(logs or {})))
 
 
@@ -821,18 +823,45 @@ class Model:
             print(f"loss: {loss:.4f} - mae: {mae:.4f}")
         return [loss, mae]
 
-    def fit(self, x, y, epochs=1, batch_size=32, validation_data=None, callbacks=None, verbose=1, shuffle=True,
-            seed=42, distributed=None, **_):
-        """model.fit: shuffled mini-batches (final partial batch included), per-epoch validation, callbacks.
+    def train_run_device(self, x_all, y_all, idx, first_item, batch_global, n_steps, rank=0, world=1, seed=0, graph=True,
+                         want_sums=True):
+        """``n_steps`` optimizer steps on a device-resident data set (``hp_head_train_run``): step s uses the global batch
+        ``idx[first_item + s * batch_global ...]`` (``idx``: CUDA int32 tensor or None), of which this rank takes rows
+        rank, rank + world, ...  Returns (sum of loss * batch_global, sum of mae * batch_global) or None."""
+        if self.optimizer is None:
+            raise RuntimeError("call compile() before training")
+        self.to_device()
+        ctx, head = self._device
+        n_items, H, W, _ = x_all.shape
+        sums = (C.c_double * 2)()
+        opt = self.optimizer.c_config()
+        _lib.check(_lib.lib().hp_head_train_run(
+            ctx.handle, head, x_all.data_ptr(), y_all.data_ptr(), idx.data_ptr() if idx is not None else None, int(n_items),
+            int(first_item), int(batch_global), int(n_steps), int(rank), int(world), H, W, C.byref(opt), C.c_uint64(seed),
+            _lib.HP_TRAIN_GRAPH if graph else 0, C.cast(sums, C.c_void_p) if want_sums else None, ctx.stream_ptr()))
+        self._train_steps += int(n_steps)
+        return (float(sums[0]), float(sums[1])) if want_sums else None
 
-        With ``distributed`` (a ``parallel.DataParallel`` object) every global batch is split across the
-        ranks and the gradients are all-reduced inside ``hp_head_train_step``."""
+    def fit(self, x, y, epochs=1, batch_size=32, validation_data=None, callbacks=None, verbose=1, shuffle=True,
+            seed=42, distributed=None, graph=True, **_):
+        """model.fit (train_96.py:175-183): shuffled mini-batches (final partial batch included), per-epoch validation,
+        callbacks.  The data set stays on the device; an epoch is one ``hp_head_train_run`` call for the full batches (each
+        step one CUDA-graph launch, no host round trip: loss and mae are accumulated on the device and read once per epoch)
+        plus one for the partial batch.
+
+        With ``distributed`` (a ``parallel.DataParallel`` object) every global batch is split across the ranks (rank r takes
+        rows r, r + world, ... of it; a rank left without rows in a short final batch contributes zeros) and the gradients
+        are all-reduced inside the step; the weights stay identical on all ranks."""
         import torch
         from .device import default_context
         if self.optimizer is None:
             raise RuntimeError("call compile() before fit()")
         ctx = default_context()
         dev = ctx.torch_device
+        rank, world = (distributed.rank, distributed.world_size) if distributed else (0, 1)
+        if world > 1 and not distributed._comm_ready:
+            distributed.init_gradient_comm()               # collective: every rank reaches fit() (ADVICE r1: never train un-reduced)
+        self._fit_rank = rank
         xt = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dev)
         yt = torch.from_numpy(np.ascontiguousarray(y, np.float32)).to(dev)
         val = None
@@ -846,35 +875,34 @@ class Model:
             cb.on_train_begin()
         self.stop_training = False
         n = xt.shape[0]
+        batch_size = int(batch_size)
+        n_full, tail = divmod(n, batch_size)
         rng = np.random.default_rng(seed)
-        rank, world = (distributed.rank, distributed.world_size) if distributed else (0, 1)
+        perm_t = torch.empty(n, dtype=torch.int32, device=dev)            # one buffer for all epochs: the captured step reads it
+        side = torch.cuda.Stream(dev)                                      # graph capture needs a non-default stream
+        side.wait_stream(torch.cuda.current_stream(dev))
         for epoch in range(int(epochs)):
             perm = rng.permutation(n) if shuffle else np.arange(n)
-            perm_t = torch.from_numpy(perm).to(dev)
-            tot_loss = tot_mae = 0.0
-            seen = 0
-            for i in range(0, n, batch_size):
-                idx = perm_t[i:i + batch_size]
-                n_global = int(idx.numel())
-                if world > 1:
-                    idx = idx[rank::world]
-                if idx.numel() == 0:
-                    raise RuntimeError("global batch smaller than the number of ranks")
-                loss, mae = self.train_on_device(xt.index_select(0, idx), yt.index_select(0, idx), n_global=n_global,
-                                                 seed=seed)
-                tot_loss += loss * n_global
-                tot_mae += mae * n_global
-                seen += n_global
-            logs = {"loss": tot_loss / seen, "mae": tot_mae / seen}
-            if val is not None:
-                vl, vm = self.evaluate_device(val[0], val[1])
-                logs.update(val_loss=vl, val_mae=vm)
+            with torch.cuda.stream(side):
+                perm_t.copy_(torch.from_numpy(perm.astype(np.int32)))
+                tot_loss = tot_mae = 0.0
+                if n_full:
+                    a, b = self.train_run_device(xt, yt, perm_t, 0, batch_size, n_full, rank, world, seed, graph)
+                    tot_loss, tot_mae = tot_loss + a, tot_mae + b
+                if tail:
+                    a, b = self.train_run_device(xt, yt, perm_t, n_full * batch_size, tail, 1, rank, world, seed, graph)
+                    tot_loss, tot_mae = tot_loss + a, tot_mae + b
+                logs = {"loss": tot_loss / n, "mae": tot_mae / n}
+                if val is not None:
+                    vl, vm = self.evaluate_device(val[0], val[1])
+                    logs.update(val_loss=vl, val_mae=vm)
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
             for cb in cbs:
                 cb.on_epoch_end(epoch, logs)
             if self.stop_training:
                 break
+        torch.cuda.current_stream(dev).wait_stream(side)
         for cb in cbs:
             cb.on_train_end()
         self.history = hist

@@ -150,6 +150,19 @@ typedef struct hp_opt_config {
 int hp_head_train_step(hp_handle h, hp_head_t head, const float* x, const float* y, int n, int H, int W,
                        int n_global, const hp_opt_config* opt, uint64_t seed, float* loss_mae_host,
                        void* stream);
+/* Many steps without host round trips: the body of one epoch of model.fit (train_96.py:175-183) on a DEVICE-RESIDENT data
+ * set x_all[n_items,H,W,Cin], y_all[n_items,H,W,3].  Step s (0 <= s < n_steps) trains on the global batch of items
+ * idx[first_item + s * batch_global ...] (idx: device int32 permutation of the epoch, NULL = identity); this rank gathers
+ * rows rank, rank + world, ... of it (a rank may get none: it then contributes zeros to the all-reduce), runs forward,
+ * loss, backward, the gradient all-reduce and the optimizer exactly as hp_head_train_step does.  The step counter, the
+ * Adam / Adamax step sizes and the loss / mae accumulators live in device memory, so with HP_TRAIN_GRAPH one step is
+ * captured once and every further step is ONE CUDA-graph launch (needs a non-default stream).
+ * sums_host (may be NULL: fully asynchronous) receives {sum over steps of loss * batch_global, of mae * batch_global}
+ * after one stream synchronisation at the end of the call. */
+#define HP_TRAIN_GRAPH 1
+int hp_head_train_run(hp_handle h, hp_head_t head, const float* x_all, const float* y_all, const int32_t* idx,
+                      long long n_items, long long first_item, int batch_global, int n_steps, int rank, int world, int H,
+                      int W, const hp_opt_config* opt, uint64_t seed, int flags, double* sums_host, void* stream);
 /* gradients of the last train step (after allreduce, before L2), for parity tests */
 int hp_head_get_grads(hp_handle h, hp_head_t head, float* grads_host, int n_params);
 /* model.evaluate (train_96.py:186): mse_mae_host[3] = {mse, mae, l2 penalty}; Keras reports

@@ -240,3 +240,77 @@ def test_dense_layer_matches_fp64(M, K, N, n2, act):
     # north_star asks for 1e-4 on feature maps
     err = float((y.double() - want).abs().max() / want.abs().max())
     assert err < 1e-5, (M, K, N, n2, act, err)
+
+
+# ------------------------------------------------------------------------------ hp_head_train_run (many steps, CUDA graph)
+def _make_train96(seed, rate=0.25, opt="adam"):
+    from hpose_b200 import keras_spec as K, train_96
+    train_96.config.update(num_filters=64, dropout_rate=rate, regularizer_rate=1e-5, optimizer=opt)
+    K.reset_names(); K.set_seed(seed)
+    m = train_96.create_model()
+    m.optimizer.learning_rate = 2.8e-4
+    return m
+
+
+@pytest.mark.parametrize("optname,graph", [("adam", True), ("adam", False), ("adamax", True), ("sgd", True)])
+def test_train_run_equals_single_steps(optname, graph):
+    """hp_head_train_run (device-resident data set, on-device gather of idx[...], step counter / Adam step sizes / loss
+    accumulators in device memory, one CUDA-graph launch per step) takes the same steps as hp_head_train_step called once
+    per batch from the host -- dropout masks included (they are keyed by the step index, read from device memory here)."""
+    n, bs, steps = 128 * 7 + 40, 128, 7
+    x = synthetic_features(n, 96, seed=2, sigma=0.55, p=0.31).reshape(n, 1, 1, 96)
+    y = synthetic_poses(n, seed=3).reshape(n, 1, 1, 3)
+    perm = np.random.default_rng(5).permutation(n).astype(np.int32)
+    xt, yt, pt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(perm).cuda()
+    a, b = _make_train96(1, opt=optname), _make_train96(1, opt=optname)
+    want_loss = want_mae = 0.0
+    for s in range(steps):
+        idx = torch.from_numpy(perm[s * bs:(s + 1) * bs].astype(np.int64)).cuda()
+        loss, mae = a.train_on_device(xt.index_select(0, idx), yt.index_select(0, idx), seed=77)
+        want_loss, want_mae = want_loss + loss * bs, want_mae + mae * bs
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        got_loss, got_mae = b.train_run_device(xt, yt, pt, 0, bs, steps, seed=77, graph=graph)
+        tail = b.train_run_device(xt, yt, pt, steps * bs, 40, 1, seed=77, graph=graph)      # the partial batch of an epoch
+    side.synchronize()
+    idx = torch.from_numpy(perm[steps * bs:].astype(np.int64)).cuda()
+    tl, tm = a.train_on_device(xt.index_select(0, idx), yt.index_select(0, idx), seed=77)
+    wa, wb = a.get_weights_dict(), b.get_weights_dict()
+    for k in wa:
+        assert np.abs(wa[k] - wb[k]).max() <= 1e-7 * max(1.0, float(np.abs(wa[k]).max())), k
+    assert abs(got_loss - want_loss) <= 1e-5 * abs(want_loss) and abs(got_mae - want_mae) <= 1e-5 * abs(want_mae)
+    assert abs(tail[0] - tl * 40) <= 1e-5 * abs(tl * 40) and abs(tail[1] - tm * 40) <= 1e-5 * abs(tm * 40)
+
+
+def test_train_run_attention_head_graph_and_errors():
+    """The attention head (LayerNorm / MHA backward, T = 4 tokens) through the captured step; argument checks."""
+    from hpose_b200 import _lib, keras_spec as K
+    from hpose_b200.attention_model import se_transformer_regr_head
+
+    def make():
+        K.reset_names(); K.set_seed(4)
+        m = se_transformer_regr_head(input_channels=88, reduction=8, num_heads=2, key_dim=8, ff_dim=16, hidden_channels=16)
+        m.compile(optimizer=K.Adam(1e-3), loss="mse", metrics=["mae"])
+        return m
+    n, bs = 96, 32
+    x = synthetic_features(n * 4, 88, seed=8).reshape(n, 2, 2, 88)
+    y = np.repeat(synthetic_poses(n, seed=9).reshape(n, 1, 1, 3), 2, axis=1).repeat(2, axis=2).copy()
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    a, b = make(), make()
+    for s in range(3):
+        a.train_on_device(xt[s * bs:(s + 1) * bs].contiguous(), yt[s * bs:(s + 1) * bs].contiguous(), seed=5)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        b.train_run_device(xt, yt, None, 0, bs, 3, seed=5, graph=True)          # idx = None: identity order
+        with pytest.raises(_lib.HposeError):
+            b.train_run_device(xt, yt, None, 64, bs, 2, seed=5)                 # runs past the end of the data set
+        with pytest.raises(_lib.HposeError):
+            b.train_run_device(xt, yt, None, 0, bs, 1, rank=0, world=2, seed=5)  # two ranks without a communicator
+    side.synchronize()
+    wa, wb = a.get_weights_dict(), b.get_weights_dict()
+    for k in wa:
+        # the attention backward accumulates with atomics (order varies run to run) and Adam normalises the ~1e-9 gradient of
+        # the key bias (zero in exact arithmetic: softmax is shift-invariant) to +-lr: compare on the scale of one Adam step
+        assert np.abs(wa[k] - wb[k]).max() <= 3e-3 * 1e-3 * 3, k
