@@ -299,6 +299,7 @@ class blazeFaceDetector:
         dev = self.ctx.torch_device
         comp = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_rec = torch.cuda.Stream(dev)                    # second-phase record copies: must not queue behind the NEXT batch's read-back
         chunks = 1 if packed else max(1, int(chunks))
         NS = 3
         d_in = [[None] * chunks for _ in range(NS)]
@@ -324,10 +325,10 @@ class blazeFaceDetector:
             written = int(hdr[1])
             if written:                                   # second phase: exactly the records that exist
                 n_all = n_hdr + (written * FACE_DTYPE.itemsize + 7) // 8
-                with torch.cuda.stream(s_out):
+                with torch.cuda.stream(s_rec):
                     h_out[q][n_hdr:n_all].copy_(d_out[q][0][n_hdr:n_all], non_blocking=True)
-                    ev_read[q][0].record(s_out)
-                    ev_out[q].record(s_out)
+                    ev_read[q][0].record(s_rec)
+                    ev_out[q].record(s_rec)
                 ev_out[q].synchronize()
             return {"total": int(hdr[0]), "count": hdr[_lib.HP_RESULT_HEADER_INTS:_lib.HP_RESULT_HEADER_INTS + B],
                     "faces": raw[faces_off:faces_off + written * FACE_DTYPE.itemsize].view(FACE_DTYPE)}
