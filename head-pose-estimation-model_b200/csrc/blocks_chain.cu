@@ -119,11 +119,14 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   uint64_t* bar_tile_done = bars + 1;
   uint64_t* bar_dfull = bars + 2;
   uint64_t* bar_epi = bars + 3;
-  uint64_t* bar_afull = bars + 4;                        // [NSETS]
-  uint64_t* bar_aempty = bars + 4 + 8;                   // [NSETS]
-  uint64_t* bar_wfull = bars + 4 + 16;                   // [CH_RING]
-  uint64_t* bar_wempty = bars + 4 + 16 + CH_RING;        // [CH_RING]
-  static_assert(NSETS <= 8 && (4 + 16 + 2 * CH_RING) * 8 + 4 <= CH_BAR_FLOATS * 4, "barrier block");
+  // hand-offs between workers, issuers and the weight loader happen once per ROUND (= one k-step per warp set): the sets
+  // work on NSETS k-steps at the same time and finish together anyway, and every mbarrier / tcgen05.commit round trip costs
+  // several hundred cycles of latency whatever it carries (measured: tools/chain_check.py with HP_CHAIN_EXP)
+  uint64_t* bar_afull = bars + 4;                        // all worker threads: the A stages of round R are written
+  uint64_t* bar_aempty = bars + 5;                       // issuers (commit): the MMAs of round R have read them
+  uint64_t* bar_wfull = bars + 6;                        // [2] weight slices of round R (ring half R & 1) have landed
+  uint64_t* bar_wempty = bars + 8;                       // [2] issuers (commit): ring half R & 1 may be overwritten
+  static_assert(2 * NSETS <= CH_RING && 10 * 8 + 8 <= CH_BAR_FLOATS * 4, "weight ring / barrier block");
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (CH_BAR_FLOATS - 1);
   volatile uint32_t* s_abort = reinterpret_cast<uint32_t*>(smem) + (CH_BAR_FLOATS - 2);
   float* s_w = smem + p.off_w;
@@ -149,11 +152,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     mbar_init(bar_tile_done, NWORK);
     mbar_init(bar_dfull, NISS);
     mbar_init(bar_epi, NWORK);
-    for (int s = 0; s < NSETS; ++s) {
-      mbar_init(&bar_afull[s], 128);
-      mbar_init(&bar_aempty[s], NISS);
-    }
-    for (int s = 0; s < CH_RING; ++s) {
+    mbar_init(bar_afull, NWORK);
+    mbar_init(bar_aempty, NISS);
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_wfull[s], 1);
       mbar_init(&bar_wempty[s], NISS);
     }
@@ -187,13 +188,14 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     if (p.dbg >= 3 && warp == W_WLOAD && lane_id == 0) {
       const ChainBlk& cb = p.blk[0];
       const uint32_t half_bytes = (uint32_t)cb.n16 * 32u;
-      for (int ks = 0; ks < cb.ks && ks < CH_RING; ++ks) {
+      const int nk = cb.ks < NSETS ? cb.ks : NSETS;
+      mbar_expect_tx(&bar_wfull[0], (uint32_t)nk * 2u * half_bytes);
+      for (int ks = 0; ks < nk; ++ks) {
         float* dst = s_ring + ks * CH_SLOT_FLOATS;
-        mbar_expect_tx(&bar_wfull[ks], 2u * half_bytes);
-        bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[ks]);
-        bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[ks]);
-        ch_wait(&bar_wfull[ks], 0, 5, s_abort, ks);
+        bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[0]);
+        bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[0]);
       }
+      ch_wait(&bar_wfull[0], 0, 5, s_abort, 0);
     }
   } else if (warp < W_UTIL) {
     // =============================================================== workers: depthwise units, then epilogue units
@@ -210,7 +212,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     // buffer is the lead zero row), column x - 1
     const float* win = tile + ((im * (p.H + 1) + yq * TR - 1) * (p.W + 1) + x - 1) * PS;
     float* centre0 = const_cast<float*>(win) + row_pitch + PS;
-    uint32_t g0 = 0, e0 = 0;     // global depthwise / epilogue unit counters at the start of the step
+    uint32_t g0 = 0, e0 = 0;     // global round counter / epilogue unit counter
     int step = 0;
     for (int it = 0; it < my_tiles; ++it) {
       for (int b = 0; b < nblk; ++b, ++step) {
@@ -222,16 +224,17 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         else ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
         tc_fence_after();
         if (tid == 0) stamp(step, 0);
-        // ---------------- depthwise units of this set: k-steps ks with (g0 + ks) % NSETS == set
-        int ks = (int)((NSETS + set - (g0 % NSETS)) % NSETS);
+        // ---------------- depthwise rounds: in round r this set computes k-step r * NSETS + set (if the block has it)
+        const int rounds = (KS + NSETS - 1) / NSETS;
 #pragma unroll 1
-        for (; ks < KS; ks += NSETS) {
-          const uint32_t n = (g0 + ks) / NSETS;          // unit index within this set
+        for (int r = 0; r < rounds; ++r, ++g0) {
+          const int ks = r * NSETS + set;
+          const bool has = ks < KS && warp_active;
           float4 acc[2][TR];
           if (p.exp_ & 1) {
 #pragma unroll
             for (int t = 0; t < TR; ++t) acc[0][t] = acc[1][t] = make_float4(1.f, 2.f, 3.f, 4.f);
-          } else if (warp_active) {
+          } else if (has) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int c = ks * 8 + half * 4;
@@ -244,12 +247,12 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               for (int t = 0; t < TR; ++t) acc[half][t] = bias;
               const float* wc = win + c;
 #pragma unroll
-              for (int r = 0; r < TR + 2; ++r) {
-                const float* row = wc + r * row_pitch;
+              for (int rr = 0; rr < TR + 2; ++rr) {
+                const float* row = wc + rr * row_pitch;
                 const float4 v0 = ld4(row), v1 = ld4(row + PS), v2 = ld4(row + 2 * PS);
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
-                  const int t = r - ky;
+                  const int t = rr - ky;
                   if (t >= 0 && t < TR) {
                     acc[half][t] = fma4(v0, w[ky * 3 + 0], acc[half][t]);
                     acc[half][t] = fma4(v1, w[ky * 3 + 1], acc[half][t]);
@@ -259,11 +262,11 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               }
             }
           }
-          if (n >= 1 && !(p.exp_ & 16)) {                 // the MMAs of this set's previous unit have read the stage
-            ch_wait(&bar_aempty[set], (n - 1) & 1, 3, s_abort, step);
+          if (g0 >= 1) {                                  // the MMAs of the previous round have read the A stages
+            ch_wait(bar_aempty, (g0 - 1) & 1, 3, s_abort, step);
             tc_fence_after();
           }
-          if (warp_active) {
+          if (has) {
             const uint32_t acol = tlane + colA0 + set * STAGE;
 #pragma unroll
             for (int t = 0; t < TR; ++t) {
@@ -279,9 +282,8 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
           }
-          mbar_arrive(&bar_afull[set]);
+          mbar_arrive(bar_afull);
         }
-        g0 += (uint32_t)KS;
         if (tid == 0) stamp(step, 1);
         // ---------------- epilogue units (M-tile t, 32 accumulator columns) with (e0 + unit) % NSETS == set
         ch_wait(bar_dfull, step & 1, 4, s_abort, step);
@@ -333,10 +335,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       }
     }
   } else {
-    // utility warps: ALL 32 lanes walk the role loops together (waits included) and one elected lane issues the asynchronous
-    // instructions.  A role written as `if (lane_id == 0) {...}` leaves lanes 1-31 parked at the final barrier as a second
-    // divergent path of the same warp, and the scheduler's switching between the two paths slowed lane 0 by ~5x (measured:
-    // ~1.7K clk per k-step of the issuer loop with nothing to wait for).
+    // utility warps: all 32 lanes walk the role loops together (waits included), lane 0 issues the asynchronous instructions.
+    // (Keeping the warp converged measured the same as `if (lane_id == 0) {...}` with lanes 1-31 parked at the final barrier;
+    // what costs is the instruction count of the issuing lane: a lone warp retires a dependent instruction every ~5 clk.)
     const bool leader = lane_id == 0;
     if (warp >= W_ISS0) {
       // =============================================================== MMA issuers (M-tiles t % NISS == issuer)
@@ -344,7 +345,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       const uint32_t ring_addr = smem_u32(s_ring);
       const uint32_t wfull_addr = smem_u32(bar_wfull), afull_addr = smem_u32(bar_afull);
       const uint32_t wempty_addr = smem_u32(bar_wempty), aempty_addr = smem_u32(bar_aempty);
-      uint32_t g = 0;
+      uint32_t R = 0;                                                     // global round counter
       int step = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int b = 0; b < nblk; ++b, ++step) {
@@ -354,28 +355,34 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           const uint32_t lo_off = ((uint32_t)n16 * 32u) >> 4;              // W_lo follows W_hi in the slot (descriptor units of 16 B)
           const bool traced = p.trace != nullptr && blockIdx.x == 0 && leader && issuer == 0;
           const bool no_mma = (p.exp_ & 4) != 0;
+          const int rounds = (KS + NSETS - 1) / NSETS;
 #pragma unroll 1
-          for (int ks = 0; ks < KS; ++ks, ++g) {
-            const uint32_t set = g % NSETS, slot = g % CH_RING;
-            ch_wait_lean(wfull_addr + slot * 8, (g / CH_RING) & 1);
-            ch_wait_lean(afull_addr + set * 8, (g / NSETS) & 1);
+          for (int r = 0; r < rounds; ++r, ++R) {
+            const uint32_t half = R & 1u;
+            ch_wait_lean(wfull_addr + half * 8, (R >> 1) & 1);
+            ch_wait_lean(afull_addr, R & 1);
             tc_fence_after();
             if (leader) {
-              if (traced && ks == 0) stamp(step, 4);
-              const uint64_t dhi = desc_hi0 + (uint64_t)(slot * ((CH_SLOT_FLOATS * 4) >> 4));   // the ring stays below 256 KB: no carry into the fixed fields
-              const uint64_t dlo = dhi + lo_off;
-              const uint32_t a0 = tmem_base + colA0 + set * STAGE;
+              if (traced && r == 0) stamp(step, 4);
+              const int nk = KS - r * NSETS < NSETS ? KS - r * NSETS : NSETS;
+              uint64_t dhi = desc_hi0 + (uint64_t)(half * NSETS * ((CH_SLOT_FLOATS * 4) >> 4));   // the ring stays below 256 KB: no carry
+              uint32_t a0 = tmem_base + colA0;
+#pragma unroll 1
+              for (int j = 0; j < nk; ++j, dhi += (CH_SLOT_FLOATS * 4) >> 4, a0 += STAGE) {
+                const uint64_t dlo = dhi + lo_off;
+                const uint32_t acc_flag = (r | j) ? 1u : 0u;
 #pragma unroll
-              for (int t = 0; t < TR; ++t) {
-                if (t % NISS != issuer || no_mma) continue;
-                const uint32_t dc = tmem_base + t * CH_DSTRIDE;
-                const uint32_t a = a0 + t * 16;
-                mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
-                mma_tf32_ts(dc, a, dlo, idesc, 1u);
-                mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+                for (int t = 0; t < TR; ++t) {
+                  if (t % NISS != issuer || no_mma) continue;
+                  const uint32_t dc = tmem_base + t * CH_DSTRIDE;
+                  const uint32_t a = a0 + t * 16;
+                  mma_tf32_ts(dc, a, dhi, idesc, acc_flag);
+                  mma_tf32_ts(dc, a, dlo, idesc, 1u);
+                  mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+                }
               }
-              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(aempty_addr + set * 8) : "memory");
-              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(wempty_addr + slot * 8) : "memory");
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(aempty_addr) : "memory");
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(wempty_addr + half * 8) : "memory");
             }
             __syncwarp();
           }
@@ -387,21 +394,26 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         }
       }
     } else if (warp == W_WLOAD) {
-      // =============================================================== weight ring loader (one slice per k-step)
-      uint32_t g = 0;
+      // =============================================================== weight ring loader (the slices of one round per barrier)
+      uint32_t R = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int b = 0; b < nblk; ++b) {
           const ChainBlk& cb = p.blk[b];
           const uint32_t half_bytes = (uint32_t)cb.n16 * 32u;          // [2][n16][4] floats
+          const int rounds = (cb.ks + NSETS - 1) / NSETS;
 #pragma unroll 1
-          for (int ks = 0; ks < cb.ks; ++ks, ++g) {
-            const uint32_t slot = g % CH_RING;
-            if (g >= CH_RING) ch_wait(&bar_wempty[slot], ((g / CH_RING) - 1) & 1, 7, s_abort, (int)g);
+          for (int r = 0; r < rounds; ++r, ++R) {
+            const uint32_t half = R & 1u;
+            if (R >= 2) ch_wait(&bar_wempty[half], ((R >> 1) - 1) & 1, 7, s_abort, (int)R);
             if (leader) {
-              float* dst = s_ring + slot * CH_SLOT_FLOATS;
-              mbar_expect_tx(&bar_wfull[slot], 2u * half_bytes);
-              bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[slot]);
-              bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[slot]);
+              const int nk = cb.ks - r * NSETS < NSETS ? cb.ks - r * NSETS : NSETS;
+              mbar_expect_tx(&bar_wfull[half], (uint32_t)nk * 2u * half_bytes);
+              for (int j = 0; j < nk; ++j) {
+                const int ks = r * NSETS + j;
+                float* dst = s_ring + (half * NSETS + j) * CH_SLOT_FLOATS;
+                bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[half]);
+                bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[half]);
+              }
             }
             __syncwarp();
           }
@@ -491,7 +503,7 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
     for (int NI = 128 / lpi; NI >= 1; --NI) {
       ChainCfg c;
       c.TR = TR; c.NI = NI; c.PS = PS; c.lanes = NI * lpi; c.lpi = lpi;
-      c.nsets = 4; c.niss = 2;
+      c.nsets = 4; c.niss = 1;   // measured at 96 x 96, batch 4096: 1 issuer 0.589 ms, 2 issuers 0.609, 3 issuers 0.659 (every extra issuer adds its commits to each round)
       const int lead = tc_align_up((W + 2) * PS, 32);     // zero row above the first image + the left neighbour of its first pixel
       const int rows = NI * (H + 1) + TR;                 // image rows + their zero rows, slack for partial strips
       int off = CH_BAR_FLOATS;
