@@ -29,7 +29,8 @@ HP_DETECT_GRAPH = 1
 HP_TRAIN_GRAPH = 1
 (HP_OP_DENSE, HP_OP_ACT, HP_OP_ADD, HP_OP_MULCH, HP_OP_GAP, HP_OP_DROPOUT, HP_OP_LAYERNORM,
  HP_OP_MHA) = range(1, 9)
-HP_ACT = {"linear": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3, "softsign": 4}
+HP_ACT = {"linear": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3, "softsign": 4, "elu": 5, "selu": 6, "softplus": 7, "swish": 8,
+          "leaky_relu": 9}
 HP_OPT = {"sgd": 0, "adam": 1, "adamax": 2}
 
 

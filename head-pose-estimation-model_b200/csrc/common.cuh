@@ -233,3 +233,36 @@ int hp_launch_dense_tc_tail(hp_ctx* h, const float* x, int M, int K, int ldx, co
                             const DenseTail& tail, cudaStream_t st);
 int hp_launch_dense_tc(hp_ctx* h, const float* x, int M, int K, int ldx, const float* W, int ldw, const float* b, int N, int act,
                        const DenseOut* outs, int n_outs, cudaStream_t st);
+
+// ---------------------------------------------------------------------------- activations (enum hp_act), shared by heads.cu / dense_tc.cu
+#ifdef __CUDACC__
+#define HP_SELU_ALPHA 1.6732632423543772f
+#define HP_SELU_SCALE 1.0507009873554805f
+template <int ACT>
+__device__ __forceinline__ float hp_act_c(float v) {
+  if (ACT == HP_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == HP_ACT_TANH) return tanhf(v);
+  if (ACT == HP_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  if (ACT == HP_ACT_SOFTSIGN) return v / (1.f + fabsf(v));
+  if (ACT == HP_ACT_ELU) return v > 0.f ? v : expm1f(v);
+  if (ACT == HP_ACT_SELU) return HP_SELU_SCALE * (v > 0.f ? v : HP_SELU_ALPHA * expm1f(v));
+  if (ACT == HP_ACT_SOFTPLUS) return fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));
+  if (ACT == HP_ACT_SWISH) return v / (1.f + expf(-v));
+  if (ACT == HP_ACT_LEAKY_RELU) return v > 0.f ? v : 0.2f * v;
+  return v;
+}
+__device__ __forceinline__ float hp_act_rt(int act, float v) {
+  switch (act) {
+    case HP_ACT_RELU: return hp_act_c<HP_ACT_RELU>(v);
+    case HP_ACT_TANH: return hp_act_c<HP_ACT_TANH>(v);
+    case HP_ACT_SIGMOID: return hp_act_c<HP_ACT_SIGMOID>(v);
+    case HP_ACT_SOFTSIGN: return hp_act_c<HP_ACT_SOFTSIGN>(v);
+    case HP_ACT_ELU: return hp_act_c<HP_ACT_ELU>(v);
+    case HP_ACT_SELU: return hp_act_c<HP_ACT_SELU>(v);
+    case HP_ACT_SOFTPLUS: return hp_act_c<HP_ACT_SOFTPLUS>(v);
+    case HP_ACT_SWISH: return hp_act_c<HP_ACT_SWISH>(v);
+    case HP_ACT_LEAKY_RELU: return hp_act_c<HP_ACT_LEAKY_RELU>(v);
+    default: return v;
+  }
+}
+#endif

@@ -47,13 +47,7 @@ struct DenseTcParams {
 
 // compile-time activation for the unrolled epilogue loops (a switch per element became a jump table per element)
 template <int ACT>
-__device__ __forceinline__ float dt_act_c(float v) {
-  if (ACT == HP_ACT_RELU) return fmaxf(v, 0.f);
-  if (ACT == HP_ACT_TANH) return tanhf(v);
-  if (ACT == HP_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
-  if (ACT == HP_ACT_SOFTSIGN) return v / (1.f + fabsf(v));
-  return v;
-}
+__device__ __forceinline__ float dt_act_c(float v) { return hp_act_c<ACT>(v); }
 // hidden channels [c0, c0 + 4 nq) of one row: y = act(D + bias), acc += y W2 (W2 rows as float4 in shared memory)
 template <int ACT>
 __device__ __forceinline__ void dt_tail_group(const uint32_t (&v)[32], int nq, const float* s_bias_c, const float* s_tail_c, float4& acc) {
@@ -71,24 +65,21 @@ __device__ __forceinline__ void dt_tail_group(const uint32_t (&v)[32], int nq, c
     }
   }
 }
-__device__ __forceinline__ float dt_act(int act, float v) {
-  switch (act) {
-    case HP_ACT_RELU: return fmaxf(v, 0.f);
-    case HP_ACT_TANH: return tanhf(v);
-    case HP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-    case HP_ACT_SOFTSIGN: return v / (1.f + fabsf(v));
-    default: return v;
-  }
-}
+__device__ __forceinline__ float dt_act(int act, float v) { return hp_act_rt(act, v); }
 
+template <int ACT>
+__device__ __forceinline__ float4 dt_act4_c(float4 v) { return make_float4(hp_act_c<ACT>(v.x), hp_act_c<ACT>(v.y), hp_act_c<ACT>(v.z), hp_act_c<ACT>(v.w)); }
 __device__ __forceinline__ float4 dt_act4(int act, float4 v) {
   switch (act) {
-    case HP_ACT_RELU: return make_float4(dt_act_c<HP_ACT_RELU>(v.x), dt_act_c<HP_ACT_RELU>(v.y), dt_act_c<HP_ACT_RELU>(v.z), dt_act_c<HP_ACT_RELU>(v.w));
-    case HP_ACT_TANH: return make_float4(dt_act_c<HP_ACT_TANH>(v.x), dt_act_c<HP_ACT_TANH>(v.y), dt_act_c<HP_ACT_TANH>(v.z), dt_act_c<HP_ACT_TANH>(v.w));
-    case HP_ACT_SIGMOID:
-      return make_float4(dt_act_c<HP_ACT_SIGMOID>(v.x), dt_act_c<HP_ACT_SIGMOID>(v.y), dt_act_c<HP_ACT_SIGMOID>(v.z), dt_act_c<HP_ACT_SIGMOID>(v.w));
-    case HP_ACT_SOFTSIGN:
-      return make_float4(dt_act_c<HP_ACT_SOFTSIGN>(v.x), dt_act_c<HP_ACT_SOFTSIGN>(v.y), dt_act_c<HP_ACT_SOFTSIGN>(v.z), dt_act_c<HP_ACT_SOFTSIGN>(v.w));
+    case HP_ACT_RELU: return dt_act4_c<HP_ACT_RELU>(v);
+    case HP_ACT_TANH: return dt_act4_c<HP_ACT_TANH>(v);
+    case HP_ACT_SIGMOID: return dt_act4_c<HP_ACT_SIGMOID>(v);
+    case HP_ACT_SOFTSIGN: return dt_act4_c<HP_ACT_SOFTSIGN>(v);
+    case HP_ACT_ELU: return dt_act4_c<HP_ACT_ELU>(v);
+    case HP_ACT_SELU: return dt_act4_c<HP_ACT_SELU>(v);
+    case HP_ACT_SOFTPLUS: return dt_act4_c<HP_ACT_SOFTPLUS>(v);
+    case HP_ACT_SWISH: return dt_act4_c<HP_ACT_SWISH>(v);
+    case HP_ACT_LEAKY_RELU: return dt_act4_c<HP_ACT_LEAKY_RELU>(v);
     default: return v;
   }
 }
@@ -262,6 +253,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
             case HP_ACT_TANH: dt_tail_group<HP_ACT_TANH>(v, nq, sb, stl, acc); break;
             case HP_ACT_SIGMOID: dt_tail_group<HP_ACT_SIGMOID>(v, nq, sb, stl, acc); break;
             case HP_ACT_SOFTSIGN: dt_tail_group<HP_ACT_SOFTSIGN>(v, nq, sb, stl, acc); break;
+            case HP_ACT_ELU: dt_tail_group<HP_ACT_ELU>(v, nq, sb, stl, acc); break;
+            case HP_ACT_SELU: dt_tail_group<HP_ACT_SELU>(v, nq, sb, stl, acc); break;
+            case HP_ACT_SOFTPLUS: dt_tail_group<HP_ACT_SOFTPLUS>(v, nq, sb, stl, acc); break;
+            case HP_ACT_SWISH: dt_tail_group<HP_ACT_SWISH>(v, nq, sb, stl, acc); break;
+            case HP_ACT_LEAKY_RELU: dt_tail_group<HP_ACT_LEAKY_RELU>(v, nq, sb, stl, acc); break;
             default: dt_tail_group<HP_ACT_LINEAR>(v, nq, sb, stl, acc); break;
           }
         }

@@ -18,16 +18,8 @@
 #include "common.cuh"
 
 // ============================================================================ activations
-__device__ __forceinline__ float act_fwd(int act, float v) {
-  switch (act) {
-    case HP_ACT_RELU: return fmaxf(v, 0.f);
-    case HP_ACT_TANH: return tanhf(v);
-    case HP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-    case HP_ACT_SOFTSIGN: return v / (1.f + fabsf(v));
-    default: return v;
-  }
-}
-// derivative expressed with the OUTPUT y of the activation
+__device__ __forceinline__ float act_fwd(int act, float v) { return hp_act_rt(act, v); }
+// derivative expressed with the OUTPUT y of the activation (swish has none: rejected when a training program is planned)
 __device__ __forceinline__ float act_bwd(int act, float y) {
   switch (act) {
     case HP_ACT_RELU: return y > 0.f ? 1.f : 0.f;
@@ -37,6 +29,10 @@ __device__ __forceinline__ float act_bwd(int act, float y) {
       float t = 1.f - fabsf(y);
       return t * t;
     }
+    case HP_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
+    case HP_ACT_SELU: return y > 0.f ? HP_SELU_SCALE : y + HP_SELU_SCALE * HP_SELU_ALPHA;
+    case HP_ACT_SOFTPLUS: return 1.f - expf(-y);                  // sigmoid(x) with y = log(1 + e^x)
+    case HP_ACT_LEAKY_RELU: return y > 0.f ? 1.f : 0.2f;
     default: return 1.f;
   }
 }
@@ -1244,6 +1240,10 @@ static int head_backward(hp_ctx* h, hp_head* hd, const float* feat, int n_img, i
     const int C = hd->regs[o.out].channels;
     const long long total = rows_out * C;
     float* gy = GR(o.out);
+    if ((o.op == HP_OP_DENSE || o.op == HP_OP_ACT) && o.act == HP_ACT_SWISH) {
+      hp_set_error("training through a swish activation is not supported (its derivative is not a function of its output)");
+      return HP_ERR_UNSUPPORTED;
+    }
     switch (o.op) {
       case HP_OP_DENSE: {
         if (o.act != HP_ACT_LINEAR) {

@@ -107,7 +107,10 @@ enum hp_head_opcode {
   HP_OP_MHA = 8        /* self-attention over tokens: params at w_off in the order
                           Wq[C][h*d] bq[h*d] Wk bk Wv bv Wo[h*d][C] bo[C]                        */
 };
-enum hp_act { HP_ACT_LINEAR = 0, HP_ACT_RELU = 1, HP_ACT_TANH = 2, HP_ACT_SIGMOID = 3, HP_ACT_SOFTSIGN = 4 };
+/* Keras activation names; elu has alpha = 1, leaky_relu the slope 0.2 of tf.nn.leaky_relu, selu the Keras constants.  swish
+ * (x sigmoid(x)) is forward-only: its derivative is not a function of its output, which is all a training step keeps. */
+enum hp_act { HP_ACT_LINEAR = 0, HP_ACT_RELU = 1, HP_ACT_TANH = 2, HP_ACT_SIGMOID = 3, HP_ACT_SOFTSIGN = 4,
+              HP_ACT_ELU = 5, HP_ACT_SELU = 6, HP_ACT_SOFTPLUS = 7, HP_ACT_SWISH = 8, HP_ACT_LEAKY_RELU = 9 };
 
 typedef struct hp_head_op {
   int32_t op, in0, in1, out;

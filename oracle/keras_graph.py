@@ -55,6 +55,16 @@ def activation(name: str, x: torch.Tensor) -> torch.Tensor:
         return torch.sigmoid(x)
     if name == "softsign":
         return x / (1.0 + x.abs())
+    if name == "elu":                                   # keras.activations.elu, alpha = 1
+        return torch.where(x > 0, x, torch.expm1(x))
+    if name == "selu":                                  # keras.activations.selu: scale * elu(x, alpha)
+        return 1.0507009873554805 * torch.where(x > 0, x, 1.6732632423543772 * torch.expm1(x))
+    if name == "softplus":
+        return torch.nn.functional.softplus(x)
+    if name == "swish":
+        return x * torch.sigmoid(x)
+    if name == "leaky_relu":                            # tf.nn.leaky_relu, alpha = 0.2 (how the name gets into a Keras 2.13 config)
+        return torch.where(x > 0, x, 0.2 * x)
     raise NotImplementedError(f"activation {name}")
 
 

@@ -314,3 +314,30 @@ def test_train_run_attention_head_graph_and_errors():
         # the attention backward accumulates with atomics (order varies run to run) and Adam normalises the ~1e-9 gradient of
         # the key bias (zero in exact arithmetic: softmax is shift-invariant) to +-lr: compare on the scale of one Adam step
         assert np.abs(wa[k] - wb[k]).max() <= 3e-3 * 1e-3 * 3, k
+
+
+@pytest.mark.parametrize("act", ["elu", "selu", "softplus", "leaky_relu", "swish"])
+def test_new_activations_forward_and_training(act):
+    """The activations of the 17 zoo checkpoints round 1 refused: inference (tensor-core Dense kernel with the activation in
+    its epilogue and in the fused narrow layer) against the float64 oracle, and a training step (swish: inference only)."""
+    from hpose_b200 import _lib, keras_spec as K
+    K.reset_names(); K.set_seed(21)
+    x_in = K.Input((None, None, 88))
+    h = K.Conv2D(32, 1, activation=act)(x_in)
+    h = K.Conv2D(16, 1, activation=act)(h)
+    m = K.Model(x_in, K.Conv2D(3, 1)(h))
+    x = synthetic_features(600 * 4, 88, seed=5).reshape(600, 2, 2, 88) - 0.3          # both signs reach the activation
+    g, _ = head_oracle(m)
+    with torch.no_grad():
+        want = g(torch.tensor(x, dtype=torch.float64)).numpy()
+    got = m.predict(x)
+    assert rel_err(got, want) < 2e-5
+    small = m.predict(x[:3])                                                          # same kernel, same bits, whatever the batch
+    assert np.array_equal(small, got[:3])
+    y = synthetic_poses(600, seed=6).reshape(600, 1, 1, 3).repeat(2, 1).repeat(2, 2).copy()
+    if act == "swish":
+        m.compile(optimizer=K.SGD(1e-4), loss="mse", metrics=["mae"])
+        with pytest.raises(_lib.HposeError):
+            m.train_on_device(torch.from_numpy(x[:64]).cuda(), torch.from_numpy(y[:64]).cuda())
+    else:
+        _train_parity(m, K.Adam(1e-3), x[:64], y[:64], steps=2)

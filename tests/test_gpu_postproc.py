@@ -190,3 +190,56 @@ def test_detect_stream_matches_detect_device(chunks):
         for i, c in enumerate(w["count"]):                 # entries beyond count[i] are uninitialised padding
             for k in ("boxes", "scores", "poses", "keypoints"):
                 assert np.array_equal(g[k][i, :c], w[k][i, :c]), (k, i)
+
+
+def test_kept_anchors_against_fp64_oracle_logits():
+    """north_star asks for bit-exact kept-anchor indices against the reference path.  Here the whole CUDA path (fp32 logits from
+    the tensor-core backbone -> CUDA decode + NMS) is compared with the float64 oracle graph -> numpy post-processing on the
+    trained weights: the kept anchor ids must agree on every frame.  (A score within float32 rounding of the threshold or of
+    another score could legitimately flip; the frames are checked for such near-ties and none of these has one.)"""
+    import os
+    from conftest import GOLDEN
+    from helpers import unified_fixture
+    from hpose_b200 import keras_spec as K
+    from hpose_b200.blazeFaceDetectorH5 import blazeFaceDetector
+    from hpose_b200.unified import UnifiedModel
+    from oracle.keras_graph import KerasGraph, to_torch
+    graph, w = unified_fixture()
+    u = UnifiedModel(w, K.load_model(os.path.join(GOLDEN, "heads", "stoqa9pt.h5")),
+                     K.load_model(os.path.join(GOLDEN, "heads", "hrchr82r.h5")))
+    det = blazeFaceDetector(scoreThreshold=0.4, iouThreshold=0.3, model=u)
+    rng = np.random.default_rng(21)
+    yy, xx = np.mgrid[0:128, 0:128]
+    imgs = rng.integers(0, 90, size=(24, 128, 128, 3)).astype(np.float64)
+    for i in range(24):                                   # skin-toned ellipses with dark "eye" spots: enough for anchors to fire
+        for _ in range(1 + i % 3):
+            cy, cx, ry, rx = rng.uniform(30, 98), rng.uniform(30, 98), rng.uniform(14, 40), rng.uniform(10, 32)
+            face = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1
+            imgs[i][face] = np.array([120, 150, 210]) + rng.normal(0, 6, 3)
+            for ex in (-0.4, 0.4):
+                eye = ((yy - (cy - 0.25 * ry)) / (0.12 * ry)) ** 2 + ((xx - (cx + ex * rx)) / (0.18 * rx)) ** 2 < 1
+                imgs[i][eye] = 30
+    imgs = np.clip(imgs, 0, 255).astype(np.uint8)
+    got = det.detect_device(imgs)
+    cnt, anc = got["count"].cpu().numpy(), got["anchors"].cpu().numpy()
+    x = ((imgs[..., ::-1].astype(np.float64) / 255.0).astype(np.float32) - np.float32(0.5)) / np.float32(0.5)
+    with torch.no_grad():
+        o64 = [t.numpy() for t in KerasGraph(graph, to_torch(w, torch.float64))(torch.tensor(x, dtype=torch.float64))]
+    anchors = opp.blazeface_anchors(128)
+    thr = np.log(0.4 / 0.6)
+    faces = mismatched = near = 0
+    for i in range(len(imgs)):
+        cls = np.concatenate([o64[0][i, :, 0], o64[1][i, :, 0]])
+        loc = np.concatenate([o64[2][i], o64[3][i]])
+        ref = opp.detect_postprocess(cls.astype(np.float32), loc.astype(np.float32), o64[4][i].astype(np.float32),
+                                     o64[5][i].astype(np.float32), anchors)
+        faces += len(ref["kept_anchor"])
+        s = np.sort(cls[cls > thr - 1e-3])
+        near_tie = (np.abs(cls - thr) < 2e-4).any() or (len(s) > 1 and np.diff(s).min() < 2e-5)
+        near += int(near_tie)
+        same = cnt[i] == len(ref["kept_anchor"]) and np.array_equal(anc[i, :cnt[i]], ref["kept_anchor"])
+        if not same:
+            mismatched += 1
+            assert near_tie, (i, anc[i, :cnt[i]], ref["kept_anchor"])
+    assert faces >= 10, faces                              # the probe frames do trigger the trained detector
+    assert mismatched == 0, (mismatched, near, faces)

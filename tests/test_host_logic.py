@@ -165,9 +165,10 @@ def test_spec_compiler_rejects_unsupported_graphs():
     x = K.Input((None, None, 8))
     with pytest.raises(ValueError):
         K.MultiHeadAttention(2, 4, value_dim=8)
-    y = K.Conv2D(3, 1, activation="selu")(x)
+    y = K.Conv2D(3, 1, activation="gelu")(x)                # outside the reference's zoo (relu, tanh, softsign, elu, selu, ...)
     with pytest.raises(ValueError):
         K.Model(x, y)
+    assert K.Model(x, K.Conv2D(3, 1, activation="selu")(x)).count_params() == 27
 
 
 def test_callbacks_follow_keras_rules():
@@ -221,3 +222,66 @@ def test_shard_bounds_cover_everything():
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_join_models_happy_path(tmp_path):
+    """join_models (reference JoinModels.py:5-90): detector .h5 + two regressor .h5 -> unified model with the six outputs in
+    the reference order, saved as a Keras-format .h5 that loads back bit-identically and carries the shipped unified graph."""
+    from hpose_b200 import h5lite
+    from hpose_b200.JoinModels import join_models
+    from hpose_b200.unified import UnifiedModel, backbone_weight_specs
+    graph, w = unified_fixture()
+    det_path = str(tmp_path / "face_detector.h5")
+    det_w = {}
+    for key, _ in backbone_weight_specs():
+        layer, var = key.split("/", 1)
+        det_w[f"{layer}/{layer}/{var}:0"] = w[key]
+    det_cfg = {"class_name": "Functional", "config": {"name": "blazeface_front", "layers": [], "input_layers": [], "output_layers": []}}
+    h5lite.write_h5(det_path, det_w, det_cfg)
+    r1 = os.path.join(GOLDEN, "heads", "stoqa9pt.h5")
+    r2 = os.path.join(GOLDEN, "heads", "hrchr82r.h5")
+    out = str(tmp_path / "reg1-stoqa9pt-reg2-hrchr82r.h5")
+    u = join_models(det_path, r1, r2, "re_lu_10", "re_lu_15", out, metadata={"note": "test"})
+    assert u._metadata == {"note": "test"} and os.path.exists(out) and not os.path.exists(out + ".tmp")
+    assert u.count_params() == 110964                                 # SURVEY App. A: the shipped unified model
+    back = UnifiedModel.load(out)
+    assert np.array_equal(back.backbone_flat, u.backbone_flat)
+    assert np.array_equal(back.head16.get_flat_weights(), u.head16.get_flat_weights())
+    assert np.array_equal(back.head8.get_flat_weights(), u.head8.get_flat_weights())
+    cfg = h5lite.H5File(out).model_config()
+    assert [o[0] for o in cfg["config"]["output_layers"]] == [
+        "tf_op_layer_classificators_1", "tf_op_layer_classificators_2", "tf_op_layer_regressors_1", "tf_op_layer_regressors_2",
+        "model", "model_10"]                                          # JoinModels.py:152-158 / blazeFaceDetectorH5.py:273-278
+    # the joined graph evaluates, in the oracle, to what the reference's own unified graph gives on the same weights
+    x = torch.tensor(np.load(os.path.join(GOLDEN, "unified_kat.npz"))["x"][:1], dtype=torch.float64)
+    wj = {}
+    for k, v in h5lite.H5File(out).weights().items():
+        parts = k.split("/")
+        parts[-1] = parts[-1].split(":")[0]
+        if len(parts) >= 3 and parts[0] == parts[1]:
+            parts = parts[1:]
+        wj["/".join(parts)] = v
+    with torch.no_grad():
+        a = KerasGraph(graph, to_torch(w, torch.float64))(x)
+        b = KerasGraph(cfg, to_torch(wj, torch.float64))(x)
+    for s, t in zip(a, b):
+        assert torch.equal(s, t)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only exists in the build container")
+def test_real_unified_h5_files_load():
+    """Every unified .h5 the reference ships loads through h5lite + UnifiedModel.load; the selected one equals the fixture."""
+    import glob
+    from hpose_b200.unified import UnifiedModel, pack_backbone
+    _, w = unified_fixture()
+    files = sorted(glob.glob("/root/reference/BlazePoser/UnifiedModels/*.h5"))
+    assert len(files) == 4
+    for f in files:
+        u = UnifiedModel.load(f)
+        assert u.backbone_flat.size == 101390 and u.head16.program.in_channels == 88 and u.head8.program.in_channels == 96
+        assert np.array_equal(u.backbone_flat, pack_backbone(w))      # one detector, four head pairs
+        if f.endswith("reg1-stoqa9pt-reg2-hrchr82r-selected.h5"):
+            for k, v in u.head16.get_weights_dict().items():
+                assert np.array_equal(v, w[f"model/{k}"])
+            for k, v in u.head8.get_weights_dict().items():
+                assert np.array_equal(v, w[f"model_10/{k}"])

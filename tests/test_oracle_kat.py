@@ -162,3 +162,89 @@ def test_oracle_conv_matches_direct_numpy_loops():
                                         acc += (x[n, iy, ix, :] * ker[ky, kx, :, co]).sum()
                         want[n, oy, ox, co] = acc
         assert np.abs(got - want).max() < 1e-12
+
+
+def _synthetic_probe_images(n=48, size=128, seed=0):
+    """Noise, gratings, flat fields, blobs, blocks: a spread of inputs, none of them a face."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:size, 0:size] / (size - 1.0)
+    imgs = []
+    for i in range(n):
+        k = i % 6
+        if k == 0:
+            im = rng.uniform(-1, 1, (size, size, 3))
+        elif k == 1:
+            im = np.stack([np.sin(xx * rng.uniform(1, 20) + rng.uniform(0, 6)), np.cos(yy * rng.uniform(1, 20)), xx * yy * 2 - 1], -1)
+        elif k == 2:
+            im = np.full((size, size, 3), rng.uniform(-1, 1)) + rng.normal(0, 0.05, (size, size, 3))
+        elif k == 3:
+            im = rng.uniform(-1, 0, (size, size, 3))
+            cy, cx, r = rng.uniform(.3, .7), rng.uniform(.3, .7), rng.uniform(.1, .4)
+            im += np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * r * r))[..., None] * rng.uniform(0.5, 2, 3)
+        elif k == 4:
+            im = rng.uniform(-1, 1, (8, 8, 3)).repeat(size // 8, 0).repeat(size // 8, 1)
+        else:
+            im = np.clip(rng.normal(0, 1, (size, size, 3)), -1, 1)
+        imgs.append(np.clip(im, -1, 1))
+    return np.stack(imgs).astype(np.float32)
+
+
+def test_backbone_oracle_reproduces_the_channel_usage_of_the_shipped_feature_maps():
+    """A pin for the BACKBONE restatement (the reference ships no backbone test and TensorFlow cannot run): the shipped npz
+    data sets are real re_lu_15 outputs of the reference's trained backbone.  Channels that never fire in any
+    of them (17 of 96) must be nearly silent in the oracle's re_lu_15 on the same trained weights, channels that fire often
+    there must fire often here, and the per-channel firing rates must correlate -- a mis-ordered channel, a wrong padding
+    rule or a wrong skip connection in the restatement destroys all three.  (The inputs differ -- synthetic probes, not
+    face crops -- so the comparison is statistical; measured: Spearman 0.62, 0.12 against 0.78 mean firing rate.)"""
+    from scipy.stats import spearmanr
+    with open(os.path.join(GOLDEN, "tap_channel_stats.json")) as f:
+        stats = json.load(f)
+    fd = np.array(stats["96"]["nonzero_fraction"])
+    dead, alive = np.where(fd == 0)[0], np.where(fd > 0.3)[0]
+    assert len(dead) == 17 and len(alive) >= 30
+    for e in stats["96"]["files"]:                       # SURVEY App. E: 23-29 dead channels in each 96-channel set
+        assert 23 <= len(e["dead"]) <= 29 and set(dead) <= set(e["dead"])
+    for e in stats["88"]["files"]:                       # ... and 2-3 in each 88-channel set
+        assert 2 <= len(e["dead"]) <= 3
+    graph, w = unified_fixture()
+    g = KerasGraph(graph, to_torch(w, torch.float32))
+    taps = {}
+    with torch.no_grad():
+        g(torch.from_numpy(_synthetic_probe_images()), taps=taps)
+    t8 = taps["re_lu_15"].numpy()
+    assert t8.shape[1:] == (8, 8, 96) and taps["re_lu_10"].shape[1:] == (16, 16, 88) and t8.min() >= 0
+    fo = (t8 > 0).reshape(-1, 96).mean(0)
+    assert fo[dead].mean() < 0.2 and fo[alive].mean() > 0.65, (fo[dead].mean(), fo[alive].mean())
+    assert spearmanr(fd, fo).correlation > 0.5
+    # channels silent in the data and in the oracle
+    assert set(np.where(fo == 0)[0]) <= set(np.where(fd < 0.02)[0])
+
+
+def test_new_activations_match_their_definitions():
+    from oracle.keras_graph import activation
+    x = torch.tensor([-3.0, -0.5, 0.0, 0.25, 2.0], dtype=torch.float64)
+    a, s = 1.6732632423543772, 1.0507009873554805
+    np.testing.assert_allclose(activation("elu", x).numpy(), [np.expm1(-3), np.expm1(-0.5), 0, 0.25, 2.0])
+    np.testing.assert_allclose(activation("selu", x).numpy(), [s * a * np.expm1(-3), s * a * np.expm1(-0.5), 0, s * 0.25, s * 2.0])
+    np.testing.assert_allclose(activation("softplus", x).numpy(), np.log1p(np.exp(x.numpy())))
+    np.testing.assert_allclose(activation("swish", x).numpy(), x.numpy() / (1 + np.exp(-x.numpy())))
+    np.testing.assert_allclose(activation("leaky_relu", x).numpy(), [-0.6, -0.1, 0, 0.25, 2.0])
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout only exists in the build container")
+def test_zoo_checkpoints_with_new_activations_load_and_evaluate():
+    """The 17 zoo checkpoints round 1 refused for their activation (elu, selu, softplus, swish, leaky_relu) now compile;
+    every regressor checkpoint of the reference either loads or is refused for a layer class outside SURVEY 8a."""
+    import glob
+    from hpose_b200 import keras_spec as K
+    files = sorted(f for f in glob.glob(f"{REFERENCE}/Model-*/**/*.h5", recursive=True))
+    assert len(files) >= 600
+    loaded, refused = 0, {}
+    for f in files:
+        try:
+            m = K.load_model(f)
+            loaded += 1
+        except ValueError as e:
+            refused[f] = str(e)
+    assert not [v for v in refused.values() if "activation" in v and "unsupported" in v], refused
+    assert loaded >= 665 and all(("layer class" in v or "1x1" in v or "per-pixel" in v) for v in refused.values()), (loaded, set(refused.values()))
