@@ -109,14 +109,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
 _PROTOS = {
     "hp_last_error": (C.c_char_p, []),
     "hp_version": (C.c_int, []),
+    "hp_build_features": (C.c_int, []),
     "hp_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "hp_destroy": (C.c_int, [C.c_void_p]),
     "hp_set_impl": (C.c_int, [C.c_void_p, C.c_int]),
     "hp_launch_count": (C.c_int64, [C.c_void_p]),
     "hp_backbone_load_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "hp_backbone_generation": (C.c_longlong, [C.c_void_p]),
     "hp_num_anchors": (C.c_int, [C.c_int, C.c_int]),
     "hp_backbone_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hp_backbone_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hp_backbone_read_activation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "hp_preprocess_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -183,7 +183,7 @@ class blazeFaceDetector:
         B, H, W, _ = frames.shape
         self.img_height, self.img_width, self.img_channels = H, W, 3
         slot = self._latency_slot(B, H, W, max_faces)
-        m = self.interpreter
+        m = self.interpreter.to_device(self.ctx)
         st = slot["stream"]
         slot["h_in"].numpy()[...] = frames
         with torch.cuda.stream(st):
@@ -313,7 +313,7 @@ class blazeFaceDetector:
         meta = [None] * NS
         pending = []                                      # slots whose results are still on their way to the host
         L = _lib.lib()
-        m = self.interpreter
+        m = self.interpreter.to_device(self.ctx)
 
         def finish(q):
             ev_out[q].synchronize()
@@ -401,7 +401,7 @@ class blazeFaceDetector:
             raise ValueError("expected (B,H,W,3) images")
         x = images.float().contiguous() if float_input else self._preprocess_device(images.contiguous())
         B, H, W, _ = x.shape
-        m = self.interpreter
+        m = self.interpreter.to_device(self.ctx)
         H16, W16, H8, W8 = -(-H // 8), -(-W // 8), -(-H // 16), -(-W // 16)
         if out is not None and out["count"].shape[0] == B and out["anchors"].shape[1] == max_faces and out["pose16"].shape[1:3] == (H16, W16):
             pass                                   # caller-owned result tensors of the right shape (the serving loop reuses them)

@@ -44,6 +44,13 @@ extern "C" {
 
 const char* hp_last_error(void) { return g_err; }
 int hp_version(void) { return 100; }
+int hp_build_features(void) {
+#ifdef HP_LEGACY_KERNELS
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 int hp_create(int device, hp_handle* out) {
   HP_REQUIRE(out != nullptr, HP_ERR_INVALID, "hp_create: null out pointer");
@@ -62,6 +69,11 @@ int hp_create(int device, hp_handle* out) {
   hp_ctx* h = new hp_ctx();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  if (h->status.ensure(sizeof(unsigned int)) != HP_OK || cudaMemset(h->status.p, 0, sizeof(unsigned int)) != cudaSuccess) {
+    delete h;
+    hp_set_error("hp_create: cannot allocate the status word");
+    return HP_ERR_CUDA;
+  }
   *out = h;
   return HP_OK;
 }
@@ -75,7 +87,7 @@ int hp_destroy(hp_handle h) {
   h->det.release();
   h->bb.arena.release(); h->bb.act[0].release(); h->bb.act[1].release(); h->bb.dwtmp.release();
   h->bb.feat16.release(); h->bb.feat8.release();
-  h->pose16.release(); h->pose8.release(); h->cls.release(); h->loc.release(); h->scratch.release();
+  h->pose16.release(); h->pose8.release(); h->cls.release(); h->loc.release(); h->scratch.release(); h->status.release();
   if (h->ev[0]) cudaEventDestroy(h->ev[0]);
   if (h->ev[1]) cudaEventDestroy(h->ev[1]);
   delete h;
@@ -91,8 +103,11 @@ int64_t hp_launch_count(hp_handle h) { return h ? h->launches : 0; }
 
 int hp_backbone_load_weights(hp_handle h, const float* packed_host, size_t n_floats, int layout_id) {
   HP_ENTER(h);
-  return hp_backbone_load_weights_impl(h, packed_host, n_floats, layout_id);
+  const int rc = hp_backbone_load_weights_impl(h, packed_host, n_floats, layout_id);
+  if (rc == HP_OK) h->bb_generation++;
+  return rc;
 }
+long long hp_backbone_generation(hp_handle h) { return h ? h->bb_generation : -1; }
 
 int hp_num_anchors(int H, int W) { return ceil_div(H, 8) * ceil_div(W, 8) * 2 + ceil_div(H, 16) * ceil_div(W, 16) * 6; }
 
@@ -167,6 +182,16 @@ int hp_debug_dense(hp_handle h, const float* x, int M, int K, const float* W, co
 int hp_debug_tile_report(hp_handle h, int* report16x8) {
   HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
   h->tile_report = report16x8;
+  return HP_OK;
+}
+
+int hp_backbone_status(hp_handle h, unsigned int* flags_host, void* stream) {
+  HP_ENTER(h);
+  HP_REQUIRE(flags_host != nullptr, HP_ERR_INVALID, "hp_backbone_status: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  HP_CUDA(cudaMemcpyAsync(flags_host, h->status.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  HP_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(unsigned int), st));
+  HP_CUDA(cudaStreamSynchronize(st));
   return HP_OK;
 }
 

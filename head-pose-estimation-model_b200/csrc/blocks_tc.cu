@@ -163,6 +163,7 @@ __device__ __forceinline__ void tc_dw_store2(const float4 (&a0)[TR], const float
   }
 }
 
+#ifdef HP_LEGACY_KERNELS   // first tensor-core generation (pipelines instead of warp roles): test-only builds, see _lib.build
 // NSETS warp sets (4 warps each) share one pipeline: the 4-channel chunks of a tile are dealt round-robin to the sets
 // (chunk c -> set c % NSETS), the accumulator rows of the epilogue likewise (row t -> set t % NSETS).  More warps per tile
 // without more TMEM or shared memory: the kernel is latency bound with one warp per SM sub-partition.
@@ -355,6 +356,8 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
+
+#endif  // HP_LEGACY_KERNELS
 
 // ---------------------------------------------------------------------------- deep (warp-specialised) variant
 // One pipeline per CTA, every stage of a tile in its own warps so that load, depthwise + MMA, epilogue and store of
@@ -668,6 +671,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
+
 
 
 // ============================================================================ small maps: one pixel per lane
@@ -1257,6 +1261,7 @@ inline void tc_layout(int cinp, int coutp, int K8, int N16, int* off_b, int* off
   *off_pipe = off;
 }
 
+#ifdef HP_LEGACY_KERNELS
 template <int CINP, int COUTP, int TR, int NSTG, int NPIPE, int NSETS>
 int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
   using G = TcGeom<CINP, COUTP>;
@@ -1291,6 +1296,8 @@ int launch_tc(hp_ctx* h, const float* in, float* out, int B, int H, int W, const
   HP_CUDA(cudaGetLastError());
   return HP_OK;
 }
+
+#endif  // HP_LEGACY_KERNELS
 
 template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS, int PLACE>
 int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
@@ -1454,6 +1461,7 @@ int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, c
     return HP_ERR_UNSUPPORTED;
   }
 #undef TCD_CASE
+#ifdef HP_LEGACY_KERNELS
 #define TC_CASE(TR_, NSTG_, NPIPE_, NSETS_)                                              \
   if constexpr (NPIPE_ * TR_ * (N16 + 16 * NSTG_) <= 512)                                \
     if (tc.TR == TR_ && tc.NSTG == NSTG_ && tc.npipe == NPIPE_ && tc.nsets == NSETS_)    \
@@ -1462,6 +1470,12 @@ int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, c
     TC_CASE(4, 2, 2, 2) TC_CASE(4, 1, 2, 2) TC_CASE(4, 1, 1, 1) TC_CASE(2, 2, 3, 2) TC_CASE(2, 2, 4, 1) TC_CASE(2, 1, 4, 1)
   }
 #undef TC_CASE
+#else
+  if (tc.nbuf == 0) {
+    hp_set_error("the pipelined tensor-core block kernel is not part of this build (test-only: rebuild with -DHP_LEGACY_KERNELS)");
+    return HP_ERR_UNSUPPORTED;
+  }
+#endif
   hp_set_error("tc block: no kernel for TR %d NSTG %d npipe %d nsets %d", tc.TR, tc.NSTG, tc.npipe, tc.nsets);
   return HP_ERR_UNSUPPORTED;
 }

@@ -135,10 +135,12 @@ struct hp_ctx {
   int num_sms = 148;
   int impl = HP_IMPL_FAST;
   int64_t launches = 0;
+  long long bb_generation = 0;     // successful hp_backbone_load_weights calls: lets a host model detect that another one replaced its weights
   Backbone bb;
   Comm comm;
   DevBuf pose16, pose8, cls, loc;  // unified-path internals
   DevBuf scratch;
+  DevBuf status;                   // one device word of sticky flags (HP_STATUS_*), read and cleared by hp_backbone_status
   std::vector<ResizePlan> resize_plans;
   DetectBufs det;
   std::vector<DetectGraph> det_graphs;

@@ -279,6 +279,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
       // =============================================================== epilogue sets
       const int eset = (warp - W_EPI) >> 2;
       const int etid = tid - W_EPI * 32;           // 0 .. 128 * NESETS - 1
+      const bool linear_act = p.act == HP_ACT_LINEAR;
       int tile = blockIdx.x;
       for (int i = 0; i < my_tiles; ++i, tile += gridDim.x) {
         const int d = i % ND;
@@ -331,14 +332,20 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
             for (int j = etid; j < total4; j += 128 * NESETS) {
               const int r = (int)(((unsigned long long)j * p.magic4[o]) >> 32);
               const int c = (j - r * wq) * 4;
-              st4(dd.ptr + rowoff[o * DT_ROWS + r] + c, dt_act4(p.act, ld4(stage + r * p.OS + dd.col_begin + c)));
+              {
+                const float4 sv = ld4(stage + r * p.OS + dd.col_begin + c);
+                st4(dd.ptr + rowoff[o * DT_ROWS + r] + c, linear_act ? sv : dt_act4(p.act, sv));   // most layers (all detector heads) are linear
+              }
             }
             continue;
           }
           for (int j = etid; j < total; j += 128 * NESETS) {
             const int r = (int)(((unsigned long long)j * p.magic[o]) >> 32);
             const int c = j - r * wd;
-            dd.ptr[rowoff[o * DT_ROWS + r] + c] = dt_act(p.act, stage[r * p.OS + dd.col_begin + c]);
+            {
+              const float sv = stage[r * p.OS + dd.col_begin + c];
+              dd.ptr[rowoff[o * DT_ROWS + r] + c] = linear_act ? sv : dt_act(p.act, sv);
+            }
           }
         }
         if (etid == 0) stamp(i, 5);

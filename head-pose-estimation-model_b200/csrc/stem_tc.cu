@@ -46,6 +46,7 @@ struct StemTcParams {
   int off_b, off_bias, off_in, in_floats, off_out, out_floats;
   long long* trace;                // optional per-tile clock64 stamps of CTA 0 (12 per tile, same slots as the block kernel)
   int trace_tiles;
+  unsigned int* status;            // device word of the context: bit 0 is set when an input does not fit fp16 (|x| > 65504, inf, NaN)
 };
 
 // PLACE = 1: 4 * NISS helper warps so that issuer k is warp W_ISSUE + 4 k + 3, i.e. on SM sub-partition 3, which only hosts
@@ -152,6 +153,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       uint64_t* pending = nullptr;
       int cur_i = -1, cur_b = 0;
       const float* buf = in_bufs;
+      __half2 amax = __floats2half2_rn(0.f, 0.f);   // running NaN-propagating max of |hi|: inf / NaN <=> an input that does not fit fp16
 #pragma unroll 1
       for (uint32_t g = set; g < n_units; g += NSETS) {
         const int i = (int)(g / UPT);
@@ -181,6 +183,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
               const float2 back = __half22float2(hi);
               const __half2 lo = __floats2half2_rn(q.x - back.x, q.y - back.y);
               v[t][e] = *reinterpret_cast<const uint32_t*>(&hi);
+              amax = __hmax2_nan(amax, __habs2(hi));                        // one HMNMX2 per pair (three integer ops per pair cost 0.06 ms)
               v[t][8 + e] = *reinterpret_cast<const uint32_t*>(&lo);
             }
           }
@@ -214,6 +217,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           if (tid == 0) stamp(i, 2);
           if (tid == (NSETS - 1) * 128) stamp(i, 8);
         }
+      }
+      {
+        const uint32_t ab = *reinterpret_cast<const uint32_t*>(&amax);
+        if ((((ab & 0x7C007C00u) + 0x04000400u) & 0x80008000u) && p.status) atomicOr(p.status, 1u);   // an all-ones fp16 exponent
       }
     } else {
       // =============================================================== epilogue warps
@@ -406,6 +413,7 @@ int hp_launch_stem_tc(hp_ctx* h, const float* x, float* out, int B, int H, int W
   StemTcParams p;
   p.bhi = bhi; p.blo = blo; p.bias = bias;
   p.trace = h->tc_trace; p.trace_tiles = h->tc_trace_tiles;
+  p.status = (unsigned int*)h->status.p;
   p.W = W; p.H = H; p.Wo = Wo; p.Ho = Ho;
   const int strips = ceil_div(Ho, TR);
   const int max_strips = 128 / Wo;

@@ -177,6 +177,7 @@ class UnifiedModel:
         self.head16, self.head8 = head16, head8
         self.head16_name, self.head8_name = head16_name, head8_name
         self._ctx = None
+        self._generation = -1             # hp_backbone_generation right after this model's own load
 
     # ---- persistence
     @classmethod
@@ -216,14 +217,19 @@ class UnifiedModel:
 
     # ---- device
     def to_device(self, ctx=None):
+        """Make this model's weights the ones on the device.  The backbone weights live in the per-GPU context, which several
+        models may share: the context remembers whose weights it holds and a model that finds another owner reloads its own
+        (a second model on the same context used to leave the first one running on the wrong backbone)."""
         from .device import default_context
         ctx = ctx or default_context()
         if self._ctx is not ctx:
-            _lib.check(_lib.lib().hp_backbone_load_weights(ctx.handle, self.backbone_flat.ctypes.data,
-                                                           self.backbone_flat.size, 0))
             self.head16.to_device(ctx)
             self.head8.to_device(ctx)
             self._ctx = ctx
+        L = _lib.lib()
+        if self._generation != L.hp_backbone_generation(ctx.handle):
+            _lib.check(L.hp_backbone_load_weights(ctx.handle, self.backbone_flat.ctypes.data, self.backbone_flat.size, 0))
+            self._generation = L.hp_backbone_generation(ctx.handle)
         return self
 
     def forward_device(self, x):
@@ -255,6 +261,15 @@ class UnifiedModel:
         if xt.dim() != 4 or xt.shape[-1] != 3:
             raise ValueError(f"expected input (B,H,W,3), got {tuple(xt.shape)}")
         o = self.forward_device(xt)
+        flags = C.c_uint(0)
+        _lib.check(_lib.lib().hp_backbone_status(ctx.handle, C.byref(flags), ctx.stream_ptr()))
+        if flags.value & 1:
+            # an input outside the fp16 range of the tensor-core stem (|x| > 65504, inf, NaN): redo the batch with the fp32 stem
+            _lib.check(_lib.lib().hp_debug_set_stem_tc(ctx.handle, -1, 0, 0, 0))
+            try:
+                o = self.forward_device(xt)
+            finally:
+                _lib.check(_lib.lib().hp_debug_set_stem_tc(ctx.handle, 0, 0, 0, 0))
         B = xt.shape[0]
         A16 = o["feat16"].shape[1] * o["feat16"].shape[2] * 2
         cls, loc = o["cls"].cpu().numpy(), o["loc"].cpu().numpy()

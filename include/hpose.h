@@ -46,6 +46,9 @@ enum hp_impl { HP_IMPL_FAST = 0, HP_IMPL_NAIVE = 1, HP_IMPL_CPASYNC = 2, HP_IMPL
 
 const char* hp_last_error(void);
 int hp_version(void);
+/* bit 0: built with -DHP_LEGACY_KERNELS (the first-generation pipelined tensor-core block kernel, kept for the geometry tests
+ * and sweeps only; the default build does not carry it) */
+int hp_build_features(void);
 
 int hp_create(int device, hp_handle* out);
 int hp_destroy(hp_handle h);
@@ -64,6 +67,9 @@ int64_t hp_launch_count(hp_handle h);
  *   loc16 kernel[88][32], bias[32], loc8 kernel[96][96], bias[96]          (HP_BACKBONE_PARAMS floats)
  */
 int hp_backbone_load_weights(hp_handle h, const float* packed_host, size_t n_floats, int layout_id);
+/* number of successful hp_backbone_load_weights calls on this context: the backbone weights belong to the context, so a host
+ * object that shares it compares this counter with the value it saw after its own load to learn whether to reload */
+long long hp_backbone_generation(hp_handle h);
 
 /* anchors for an HxW input: A = ceil(H/8)*ceil(W/8)*2 + ceil(H/16)*ceil(W/16)*6 */
 int hp_num_anchors(int H, int W);
@@ -74,6 +80,15 @@ int hp_num_anchors(int H, int W);
  * Any of the four outputs may be NULL (feature maps are then kept in internal buffers). */
 int hp_backbone_forward(hp_handle h, const float* x, int B, int H, int W,
                         float* feat16, float* feat8, float* cls, float* loc, void* stream);
+
+/* Input range of the float entry points (hp_backbone_forward, hp_unified_forward): the tensor-core stem splits x into two
+ * fp16 parts, exact to fp32 level for |x| <= 65504 -- the reference feeds normalised pixels in [-1, 1]
+ * (blazeFaceDetectorH5.py:262).  A value outside that range (or inf / NaN) cannot be represented: the stem kernel then sets
+ * HP_STATUS_STEM_RANGE in a sticky per-context status word instead of failing silently.  hp_backbone_status synchronises
+ * `stream`, returns the word and clears it; hp_debug_set_stem_tc(h, -1, 0, 0, 0) selects the fp32 CUDA-core stem, which has
+ * no such limit (the Python layer re-runs a flagged batch that way).  The uint8 entry points cannot trigger it. */
+#define HP_STATUS_STEM_RANGE 1u
+int hp_backbone_status(hp_handle h, unsigned int* flags_host, void* stream);
 
 /* debugging / parity hook: run the backbone on x up to BlazeBlock `blk` (0..15; -1 = stem only) and
  * copy that activation into dst (real channel count, NHWC). */
