@@ -772,24 +772,32 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
       bool plain = true;
       for (int b = i; b <= last; ++b) plain = plain && h->tc_override[b][0] == 0 && h->tile_override[b][0] == 0;
       ChainCfg ccfg;
-      if (plain && hp_chain_geometry(i, last - i + 1, chain_nblk, hs[i + 1], ws[i + 1], &ccfg)) {
+      // block 11 (stride 2, 12x12x88 -> 6x6x96 at 96x96 input) rides on the chain 6-10: it is computed from the resident tile
+      // while the tile's TMA store is in flight (chain_mode 2 = default; 1 = chains without the tail)
+      int tail_blk = -1;
+      if (i == 6 && last == 10 && h->chain_mode >= 2 && (stop_after_blk < 0 || stop_after_blk > 10) && h->tc_override[11][0] == 0 &&
+          h->tile_override[11][0] == 0 && plain && hp_chain_geometry(i, chain_nblk, chain_nblk, hs[i + 1], ws[i + 1], &ccfg, 11))
+        tail_blk = 11;
+      if (plain && (tail_blk >= 0 || hp_chain_geometry(i, last - i + 1, chain_nblk, hs[i + 1], ws[i + 1], &ccfg))) {
         if (h->chain_cfg[0] > 0) ccfg.nsets = h->chain_cfg[0];
         if (h->chain_cfg[1] > 0) ccfg.niss = h->chain_cfg[1] < ccfg.TR ? h->chain_cfg[1] : ccfg.TR;
         float* cout_buf = (last == 10) ? feat16 : (last == 15) ? feat8 : bb.act[pp ^ 1].f();
+        float* tail_buf = tail_blk >= 0 ? bb.act[pp ^ 1].f() : nullptr;
         for (int it = 0; it < iters; ++it) {
           if (prof && it == 0) HP_CUDA(cudaEventRecord(h->ev[0], st));
-          HP_TRY(hp_launch_chain(h, i, last - i + 1, cur, cout_buf, B, hs[i + 1], ws[i + 1], ccfg, st));
+          HP_TRY(hp_launch_chain(h, i, last - i + 1, cur, cout_buf, B, hs[i + 1], ws[i + 1], ccfg, st, tail_blk, tail_buf));
         }
+        const int last_done = tail_blk >= 0 ? tail_blk : last;
         if (prof) {
           HP_CUDA(cudaEventRecord(h->ev[1], st));
           HP_CUDA(cudaEventSynchronize(h->ev[1]));
           float ms = 0;
           HP_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
           // the chain is one launch: its time is booked on its first block, the others report 0
-          for (int b = i; b <= last; ++b) per_layer_ms[1 + b] = (b == i) ? ms / iters : 0.f;
+          for (int b = i; b <= last_done; ++b) per_layer_ms[1 + b] = (b == i) ? ms / iters : 0.f;
         }
         if (h->tile_report)
-          for (int b = i; b <= last; ++b) {
+          for (int b = i; b <= last_done; ++b) {
             int* r = h->tile_report + 8 * b;
             r[0] = ccfg.TR; r[1] = ccfg.NI; r[2] = ccfg.PS; r[3] = ccfg.lanes; r[4] = ccfg.nsets; r[5] = (int)ccfg.smem; r[6] = ccfg.niss; r[7] = -100 - i;
           }
@@ -797,6 +805,13 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
         if (last != 10 && last != 15) pp ^= 1;
         if (stop_after_blk == last)
           return dbg_copy(cur, (long long)B * hs[last + 1] * ws[last + 1], chan_pad(kBlazeBlocks[last].cout), kBlazeBlocks[last].cout);
+        if (tail_blk >= 0) {
+          cur = tail_buf;
+          pp ^= 1;
+          if (stop_after_blk == tail_blk)
+            return dbg_copy(cur, (long long)B * hs[tail_blk + 1] * ws[tail_blk + 1], chan_pad(kBlazeBlocks[tail_blk].cout), kBlazeBlocks[tail_blk].cout);
+          last = tail_blk;
+        }
         i = last;
         continue;
       }

@@ -46,6 +46,12 @@ struct ChainBlk {
 struct ChainParams {
   ChainBlk blk[CH_MAXBLK];
   int nblk;
+  // optional stride-2 TAIL block (block 11 behind the chain 6-10): computed from the resident tile right after the last
+  // chain block, while the TMA store of the tile (the 88-channel tap) is in flight; its output goes straight to global memory
+  int tail;                       // 0 / 1
+  ChainBlk tblk;
+  float* tail_out;                // [B][Ho][Wo][tblk.cout]
+  int Ho, Wo, tail_lpi, tail_lanes, pad_t, pad_l;   // output map, lanes per image / in use, SAME padding of the depthwise conv
   int H, W, NI, B, n_tiles;
   int lanes, lpi;                 // TMEM lanes in use, lanes per image (= strips * W)
   int row_pitch;                  // (W + 1) * PS floats
@@ -126,7 +132,8 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   uint64_t* bar_aempty = bars + 5;                       // issuers (commit): the MMAs of round R have read them
   uint64_t* bar_wfull = bars + 6;                        // [2] weight slices of round R (ring half R & 1) have landed
   uint64_t* bar_wempty = bars + 8;                       // [2] issuers (commit): ring half R & 1 may be overwritten
-  static_assert(2 * NSETS <= CH_RING && 10 * 8 + 8 <= CH_BAR_FLOATS * 4, "weight ring / barrier block");
+  uint64_t* bar_tail_done = bars + 10;                   // all worker threads: the tail block has read the tile for the last time
+  static_assert(2 * NSETS <= CH_RING && 11 * 8 + 8 <= CH_BAR_FLOATS * 4, "weight ring / barrier block");
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (CH_BAR_FLOATS - 1);
   volatile uint32_t* s_abort = reinterpret_cast<uint32_t*>(smem) + (CH_BAR_FLOATS - 2);
   float* s_w = smem + p.off_w;
@@ -144,6 +151,11 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     for (int i = tid * 4; i < 10 * cb.cin; i += nthr * 4) st4(d + i, ld4(cb.dww + i));
     for (int i = tid * 4; i < cb.cout; i += nthr * 4) st4(d + 10 * cb.cin + i, ld4(cb.pwb + i));
   }
+  if (p.tail) {
+    float* d = s_w + p.tblk.w_off;
+    for (int i = tid * 4; i < 10 * p.tblk.cin; i += nthr * 4) st4(d + i, ld4(p.tblk.dww + i));
+    for (int i = tid * 4; i < p.tblk.cout; i += nthr * 4) st4(d + 10 * p.tblk.cin + i, ld4(p.tblk.pwb + i));
+  }
   for (int i = tid * 4; i < p.zero_floats; i += nthr * 4) st4(smem + p.off_zero + i, make_float4(0.f, 0.f, 0.f, 0.f));
   fence_async_smem();
   if (tid == 0) {
@@ -152,6 +164,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     mbar_init(bar_tile_done, NWORK);
     mbar_init(bar_dfull, NISS);
     mbar_init(bar_epi, NWORK);
+    mbar_init(bar_tail_done, NWORK);
     mbar_init(bar_afull, NWORK);
     mbar_init(bar_aempty, NISS);
     for (int s = 0; s < 2; ++s) {
@@ -333,6 +346,115 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         if (b == nblk - 1) mbar_arrive(bar_tile_done);
         if (tid == 0) stamp(step, 3);
       }
+      if (p.tail) {
+        // ------------------------------------------------------------ stride-2 tail block on the finished tile (read only)
+        // lane <-> OUTPUT pixel (im2, oy, ox): one M-tile.  out = ReLU(PW(DW3x3_s2(x) + b_dw) + b_pw + pad_c(maxpool2x2(x)));
+        // SAME padding: the depthwise window of output y starts at input row 2 y - pad_t (TensorFlow puts the odd padding
+        // pixel after), the pool window at row 2 y; everything outside the image reads the zeros around it (inputs are
+        // ReLU outputs, so a zero is neutral for the max).
+        const ChainBlk& cb = p.tblk;
+        const int cin = cb.cin, KS = cb.ks, n16 = cb.n16;
+        const float* s_dww = s_w + cb.w_off;
+        const float* s_pwb = s_dww + 10 * cin;
+        const bool active2 = lane < p.tail_lanes;
+        const bool warp_active2 = wq * 32 < p.tail_lanes;
+        const int l3 = active2 ? lane : 0;
+        const int im2 = l3 / p.tail_lpi, r2 = l3 - im2 * p.tail_lpi;
+        const int oy = r2 / p.Wo, ox = r2 - oy * p.Wo;
+        const float* win2 = tile + ((im2 * (p.H + 1) + 2 * oy - p.pad_t) * (p.W + 1) + 2 * ox - p.pad_l) * PS;
+        const float* pool = tile + ((im2 * (p.H + 1) + 2 * oy) * (p.W + 1) + 2 * ox) * PS;
+        ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
+        tc_fence_after();
+        if (tid == 0) stamp(step, 0);
+        const int rounds = (KS + NSETS - 1) / NSETS;
+#pragma unroll 1
+        for (int r = 0; r < rounds; ++r, ++g0) {
+          const int ks = r * NSETS + set;
+          const bool has = ks < KS && warp_active2;
+          float4 acc[2];
+          if (has) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c = ks * 8 + half * 4;
+              const float* wp = s_dww + c;
+              float4 a = ld4(wp + 9 * cin);
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) a = fma4(ld4(win2 + ky * row_pitch + kx * PS + c), ld4(wp + (ky * 3 + kx) * cin), a);
+              acc[half] = a;
+            }
+          }
+          if (g0 >= 1) {
+            ch_wait(bar_aempty, (g0 - 1) & 1, 3, s_abort, step);
+            tc_fence_after();
+          }
+          if (has) {
+            const float f[8] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w, acc[1].x, acc[1].y, acc[1].z, acc[1].w};
+            uint32_t v[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[e] = tf32_hi(f[e]);
+              v[8 + e] = __float_as_uint(f[e] - __uint_as_float(v[e]));
+            }
+            tmem_st16(tlane + colA0 + set * STAGE, v);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
+          mbar_arrive(bar_afull);
+        }
+        if (tid == 0) stamp(step, 1);
+        ch_wait(bar_dfull, step & 1, 4, s_abort, step);
+        tc_fence_after();
+        if (tid == 0) stamp(step, 2);
+        const int ncg = (n16 + 31) >> 5;
+        const int C4 = cin >> 2, NG = cb.cout >> 2;
+        const long long img = (long long)(blockIdx.x + (long long)it * gridDim.x) * p.NI + im2;
+        const bool valid2 = active2 && img < p.B;
+        float* dst = p.tail_out + ((img * p.Ho + oy) * p.Wo + ox) * (long long)cb.cout;
+        if (warp_active2) {
+          int u = (int)((NSETS + set - (e0 % NSETS)) % NSETS);
+#pragma unroll 1
+          for (; u < ncg; u += NSETS) {
+            const uint32_t dcol = tlane + u * 32;
+            uint32_t v[32];
+            if (u * 32 + 32 <= n16) {
+              tmem_ld32(dcol, v);
+            } else {
+              uint32_t hlf[16];
+              tmem_ld16(dcol, hlf);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int j = u * 8 + jj;
+              if (j < NG) {
+                const float4 bb = ld4(s_pwb + j * 4);
+                float4 o = make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
+                                       __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
+                if (j < C4) {
+                  const float4 p00 = ld4(pool + j * 4), p01 = ld4(pool + PS + j * 4);
+                  const float4 p10 = ld4(pool + row_pitch + j * 4), p11 = ld4(pool + row_pitch + PS + j * 4);
+                  o.x += fmaxf(fmaxf(p00.x, p01.x), fmaxf(p10.x, p11.x));
+                  o.y += fmaxf(fmaxf(p00.y, p01.y), fmaxf(p10.y, p11.y));
+                  o.z += fmaxf(fmaxf(p00.z, p01.z), fmaxf(p10.z, p11.z));
+                  o.w += fmaxf(fmaxf(p00.w, p01.w), fmaxf(p10.w, p11.w));
+                }
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                if (valid2) *reinterpret_cast<float4*>(dst + j * 4) = o;
+              }
+            }
+          }
+          tc_fence_before();
+        }
+        e0 += (uint32_t)ncg;
+        mbar_arrive(bar_epi);
+        mbar_arrive(bar_tail_done);
+        if (tid == 0) stamp(step, 3);
+        ++step;
+      }
     }
   } else {
     // utility warps: all 32 lanes walk the role loops together (waits included), lane 0 issues the asynchronous instructions.
@@ -348,8 +470,10 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       uint32_t R = 0;                                                     // global round counter
       int step = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        for (int b = 0; b < nblk; ++b, ++step) {
-          const int KS = p.blk[b].ks, n16 = p.blk[b].n16;
+        for (int b = 0; b < nblk + p.tail; ++b, ++step) {
+          const ChainBlk& cbi = b < nblk ? p.blk[b] : p.tblk;
+          const int KS = cbi.ks, n16 = cbi.n16;
+          const int trn = b < nblk ? TR : 1;                               // the tail block has one M-tile
           const uint32_t idesc = tc_idesc_tf32(n16);
           const uint64_t desc_hi0 = tc_bdesc_fixed(n16) | (uint64_t)((ring_addr >> 4) & 0x3FFF);
           const uint32_t lo_off = ((uint32_t)n16 * 32u) >> 4;              // W_lo follows W_hi in the slot (descriptor units of 16 B)
@@ -373,7 +497,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                 const uint32_t acc_flag = (r | j) ? 1u : 0u;
 #pragma unroll
                 for (int t = 0; t < TR; ++t) {
-                  if (t % NISS != issuer || no_mma) continue;
+                  if (t % NISS != issuer || no_mma || t >= trn) continue;
                   const uint32_t dc = tmem_base + t * CH_DSTRIDE;
                   const uint32_t a = a0 + t * 16;
                   mma_tf32_ts(dc, a, dhi, idesc, acc_flag);
@@ -397,8 +521,8 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       // =============================================================== weight ring loader (the slices of one round per barrier)
       uint32_t R = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        for (int b = 0; b < nblk; ++b) {
-          const ChainBlk& cb = p.blk[b];
+        for (int b = 0; b < nblk + p.tail; ++b) {
+          const ChainBlk& cb = b < nblk ? p.blk[b] : p.tblk;
           const uint32_t half_bytes = (uint32_t)cb.n16 * 32u;          // [2][n16][4] floats
           const int rounds = (cb.ks + NSETS - 1) / NSETS;
 #pragma unroll 1
@@ -433,9 +557,12 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         if (leader) {
           tma_store_4d(&tm_out, tile, 0, 0, 0, tile_idx * p.NI);
           tma_store_commit();
-          stamp(it * nblk + nblk - 1, 6);
+          stamp(it * (nblk + p.tail) + nblk - 1, 6);
+        }
+        if (p.tail) ch_wait(bar_tail_done, it & 1, 9, s_abort, it);          // the tail block reads the tile while the store is in flight
+        if (leader) {
           tma_store_wait_read();
-          stamp(it * nblk + nblk - 1, 7);
+          stamp(it * (nblk + p.tail) + nblk - 1, 7);
           if (it + 1 < my_tiles) {
             mbar_expect_tx(bar_tile_full, p.load_bytes);
             tma_load_4d(tile, &tm_in, bar_tile_full, 0, 0, 0, next * p.NI);
@@ -479,7 +606,7 @@ int hp_chain_status(unsigned int out[8]) {
 
 // Geometry of the chain kernel for blocks [first, first + nblk) on an H x W map: rows per lane TR, images per tile NI.
 // Returns false when the chain kernel does not apply (the per-block kernels are used instead).
-bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg) {
+bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg, int tail_blk) {
   if (nblk < 1 || nblk > CH_MAXBLK || first < 0 || first + nblk > 16 || H < 2 || W < 2 || W > 64) return false;
   // chain_nblk >= nblk: length of the full chain (a truncated chain, used to read intermediate activations, keeps the geometry
   // -- pixel stride, rows per lane, images per tile -- of the full one)
@@ -495,6 +622,13 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
   if (PS != 92 && PS != 100) return false;               // instantiated pixel strides (chains ending at 88 / 96 channels)
   int w_floats = 0;
   for (int b = first; b < first + chain_nblk; ++b) w_floats += 10 * chan_pad(kBlazeBlocks[b].cin) + chan_pad(kBlazeBlocks[b].cout);
+  if (tail_blk >= 0) {
+    // a stride-2 block behind the chain: same input channels as the chain's output, at most 96 outputs, one M-tile of output pixels
+    if (tail_blk != first + chain_nblk || tail_blk > 15 || kBlazeBlocks[tail_blk].stride != 2 || kBlazeBlocks[tail_blk].cin != kBlazeBlocks[tail_blk - 1].cout ||
+        chan_pad(kBlazeBlocks[tail_blk].cin) % 8 != 0 || chan_pad(kBlazeBlocks[tail_blk].cout) > 96 || nblk != chain_nblk)
+      return false;
+    w_floats += 10 * chan_pad(kBlazeBlocks[tail_blk].cin) + chan_pad(kBlazeBlocks[tail_blk].cout);
+  }
   ChainCfg best;
   double best_cost = 1e30;
   for (int TR = 2; TR <= 3; ++TR) {
@@ -517,6 +651,7 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
       c.w_floats = w_floats;
       c.smem = (size_t)off * sizeof(float);
       if (c.smem > 227 * 1024) continue;
+      if (tail_blk >= 0 && NI * ceil_div(H, 2) * ceil_div(W, 2) > 128) continue;
       // cost: warp-instructions ~ active warps * M-tiles per image; more images per tile amortise the per-step bubbles
       const double cost = (double)ceil_div(c.lanes, 32) * TR / NI + 0.05 * TR / NI;
       if (cost < best_cost) { best_cost = cost; best = c; }
@@ -529,7 +664,7 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
 }
 
 int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out, int B, int H, int W, const ChainCfg& cfg,
-                    cudaStream_t st) {
+                    cudaStream_t st, int tail_blk, float* tail_out) {
   const Backbone& bb = h->bb;
   ChainParams p;
   memset(&p, 0, sizeof(p));
@@ -548,6 +683,29 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
     w_off += 10 * cb.cin + cb.cout;
     HP_REQUIRE(w.dwb == w.dww + 9 * cb.cin, HP_ERR_STATE, "chain: depthwise bias of block %d does not follow its kernel", first + b);
   }
+  if (tail_blk >= 0) {
+    const BlockWeights& w = bb.blk[tail_blk];
+    HP_REQUIRE(w.bhi && w.blo && tail_out, HP_ERR_STATE, "chain: tail block %d needs split weights and an output buffer", tail_blk);
+    ChainBlk& cb = p.tblk;
+    cb.bhi = w.bhi; cb.blo = w.blo; cb.dww = w.dww; cb.pwb = w.pwb;
+    cb.cin = chan_pad(kBlazeBlocks[tail_blk].cin);
+    cb.cout = chan_pad(kBlazeBlocks[tail_blk].cout);
+    cb.ks = cb.cin / 8;
+    cb.n16 = (cb.cout + 15) / 16 * 16;
+    cb.w_off = w_off;
+    w_off += 10 * cb.cin + cb.cout;
+    HP_REQUIRE(w.dwb == w.dww + 9 * cb.cin, HP_ERR_STATE, "chain: depthwise bias of block %d does not follow its kernel", tail_blk);
+    p.tail = 1;
+    p.tail_out = tail_out;
+    p.Ho = ceil_div(H, 2); p.Wo = ceil_div(W, 2);
+    p.tail_lpi = p.Ho * p.Wo;
+    p.tail_lanes = cfg.NI * p.tail_lpi;
+    int o_, pb;
+    same_pad(H, 3, 2, &o_, &pb); p.pad_t = pb;
+    same_pad(W, 3, 2, &o_, &pb); p.pad_l = pb;
+    HP_REQUIRE(p.tail_lanes <= 128 && p.pad_t <= 1 && p.pad_l <= 1, HP_ERR_INVALID, "chain: tail block on %dx%d does not fit one M-tile", H, W);
+  }
+  HP_REQUIRE(w_off <= cfg.w_floats, HP_ERR_STATE, "chain: weight area too small (%d > %d floats)", w_off, cfg.w_floats);
   p.H = H; p.W = W; p.NI = cfg.NI; p.B = B;
   p.n_tiles = ceil_div(B, cfg.NI);
   p.lanes = cfg.lanes; p.lpi = cfg.lpi;

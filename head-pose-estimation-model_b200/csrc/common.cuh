@@ -149,7 +149,7 @@ struct hp_ctx {
   bool dense_tc = true;            // Dense / 1x1 layers may use the tensor-core kernel (cleared while a training step runs)
   int stem_tc_cfg[4] = {};         // tensor-core stem: band height, input buffers, output stages, gather sets (0 = automatic, [0] = -1: off)
   int tc_override[16][9] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets, nbuf per block (TR 0 = automatic, -1 = do not use)
-  int chain_mode = 1;              // 1: blocks 6-10 / 12-15 run as fused chain kernels when the geometry allows (0: one kernel per block)
+  int chain_mode = 2;              // >= 1: blocks 6-10 / 12-15 run as fused chain kernels when the geometry allows; 2: block 11 rides on the first chain (0: one kernel per block)
   int chain_cfg[2] = {};           // chain kernel overrides: worker warp sets, MMA issuer threads (0 = default)
   int* tile_report = nullptr;      // optional int[16][8] filled by the forward pass
   long long* tc_trace = nullptr;   // optional device buffer for per-tile clock stamps of the deep tensor-core kernel
@@ -211,10 +211,10 @@ struct ChainCfg {
   int off_w, w_floats, off_ring, off_zero, zero_floats, off_tile, tile_floats;   // shared-memory layout (floats)
   size_t smem;
 };
-bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg);
+bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg, int tail_blk = -1);
 int hp_chain_status(unsigned int out[8]);
 int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out, int B, int H, int W, const ChainCfg& cfg,
-                    cudaStream_t st);
+                    cudaStream_t st, int tail_blk = -1, float* tail_out = nullptr);
 
 // stem_tc.cu: stem conv as an implicit 3xTF32 GEMM (tcgen05), warp-specialised
 int hp_stem_tc_weight_floats();

@@ -59,7 +59,7 @@ def parity(ctx, S, B):
         ctx.set_impl(_lib.HP_IMPL_NAIVE)
         nv = read_act(ctx, x, blk, (B, h, h, c))
         ctx.set_impl(_lib.HP_IMPL_FAST)
-        _lib.check(L.hp_debug_set_chain(ctx.handle, 1, 0, 0))
+        _lib.check(L.hp_debug_set_chain(ctx.handle, 2, 0, 0))
         got = read_act(ctx, x, blk, (B, h, h, c))
         if chain_status(ctx, f"block {blk}"):
             return 1.0
@@ -78,14 +78,14 @@ def timing(ctx, S, B, iters=5):
     L = _lib.lib()
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand((B, S, S, 3), generator=g, device="cuda") * 2 - 1
-    for mode, nsets, niss in ((0, 0, 0), (1, 0, 0), (1, 4, 1), (1, 4, 3)):
+    for mode, nsets, niss in ((0, 0, 0), (1, 0, 0), (2, 0, 0), (2, 4, 2)):
         _lib.check(L.hp_debug_set_chain(ctx.handle, mode, nsets, niss))
         per = np.zeros(18, np.float32)
         for _ in range(2):
             _lib.check(L.hp_backbone_profile(ctx.handle, x.data_ptr(), B, S, S, iters, per.ctypes.data))
         print(f"size {S} B {B} chain mode {mode} nsets {nsets} niss {niss}: backbone {per[:17].sum():.3f} ms | blocks 6-10 {per[7:12].sum():.3f} | "
               f"block 11 {per[12]:.3f} | blocks 12-15 {per[13:17].sum():.3f} | stem {per[0]:.3f} | 0-5 {per[1:7].sum():.3f}", flush=True)
-    _lib.check(L.hp_debug_set_chain(ctx.handle, 1, 0, 0))
+    _lib.check(L.hp_debug_set_chain(ctx.handle, 2, 0, 0))
 
 
 def trace(ctx, S, B, steps=40):
@@ -95,7 +95,7 @@ def trace(ctx, S, B, steps=40):
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand((B, S, S, 3), generator=g, device="cuda") * 2 - 1
     sz = sizes(S)
-    for blk_last, name, nblk in ((10, "chain 6-10", 5), (15, "chain 12-15", 4)):
+    for blk_last, name, nblk in ((10, "chain 6-10", 5), (11, "chain 6-10 + tail block 11", 6), (15, "chain 12-15", 4)):
         buf = torch.zeros(steps * 8, dtype=torch.int64, device="cuda")
         h, c = sz[blk_last]
         read_act(ctx, x, blk_last, (B, h, h, c))
