@@ -342,7 +342,7 @@ def latency_run(args, ctx):
     return out
 
 
-def trained_e2e(args, ctx, steps):
+def trained_e2e(args, ctx, steps, world=1):
     """End to end with the TRAINED detector + shipped pose heads (tests/golden, the reference's own weights) on synthetic
     frames: few anchors fire, so the packed result is a few bytes per crop instead of the 14.4 KB of the padded form."""
     import torch
@@ -367,6 +367,9 @@ def trained_e2e(args, ctx, steps):
     for r in det.detect_stream(batches(3), args.max_faces, packed=True):
         total = r["total"]
     torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for r in det.detect_stream(batches(steps), args.max_faces, packed=True):
@@ -374,8 +377,13 @@ def trained_e2e(args, ctx, steps):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=ctx.torch_device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     hdr = (4 + B) * 4
-    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(host.numel()),
+    return {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "h2d_bytes_per_step": int(host.numel()),
             "d2h_bytes_per_step": int(hdr + total * 152), "faces_per_step": int(total),
             "weights": "trained BlazeFace-front detector + shipped stoqa9pt / hrchr82r heads (tests/golden)", "api": "detect_stream(packed=True)"}
 
@@ -398,9 +406,13 @@ def train_leg(args, ctx, rank, world):
     if world > 1:
         dp = DataParallel()
         dp.init_gradient_comm()
+        out_p2p = bool(dp.p2p)
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     out = {"model": "train_96.create_model(num_filters=64, dropout 0, l2 1e-5), Adam lr 2.8e-4", "items": N, "world": world}
+    if world > 1:
+        out["gradient_exchange"] = ("fused all-reduce + optimizer kernel over NVLink peer memory (CUDA IPC inboxes, rank-ordered sums)"
+                                    if out_p2p else "ncclAllReduce + optimizer kernel (peer memory not available)")
 
     def make():
         train_96.config.update(num_filters=64, dropout_rate=0.0, regularizer_rate=1e-5, optimizer="adam")
@@ -459,6 +471,25 @@ def train_leg(args, ctx, rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             r["us_per_step_without_allreduce"] = 1e3 * float(t.item()) / steps
             r["allreduce_us"] = r["us_per_step"] - r["us_per_step_without_allreduce"]
+            if out_p2p:
+                # the same steps with ncclAllReduce + a separate optimizer kernel (the library baseline of the fused exchange)
+                from hpose_b200 import _lib
+                _lib.check(_lib.lib().hp_debug_set_p2p(ctx.handle, 0))
+                mn = make()
+                with torch.cuda.stream(side):
+                    mn.train_run_device(xt, yt, None, 0, gb, 20, rank, world, seed=1, graph=True)
+                    side.synchronize()
+                    dist.barrier()
+                    e0.record(side)
+                    mn.train_run_device(xt, yt, None, 0, gb, steps, rank, world, seed=1, graph=True)
+                    e1.record(side)
+                    side.synchronize()
+                _lib.check(_lib.lib().hp_debug_set_p2p(ctx.handle, 1))
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                r["us_per_step_nccl"] = 1e3 * float(t.item()) / steps
+                r["allreduce_us_nccl"] = r["us_per_step_nccl"] - r["us_per_step_without_allreduce"]
+                r["max_rel_dev_p2p_vs_nccl"] = float(np.abs(flat(m) - flat(mn)).max() / max(1.0, np.abs(flat(mn)).max()))
         else:
             # host-driven baseline of round 1: one hp_head_train_step call per step, loss read back every step
             m2 = make()
@@ -642,15 +673,16 @@ def main():
                                               "unavailable): torch-CPU fp32 graph + numpy decode/NMS"}
         if world == 1 and not args.no_extras:
             line["sustained"] = sustained_run(args, det, x)
-            line["e2e_trained_weights"] = trained_e2e(args, ctx, e_steps)
             line["latency"] = latency_run(args, ctx)
             line["configs"] = extra_configs(args, ctx, peak)
-    train = None
+    train = e2e_tr = None
     if not args.no_extras:
         del x, u8, out
         torch.cuda.empty_cache()
-        train = train_leg(args, ctx, rank, world)          # every rank takes part (gradient all-reduce)
+        e2e_tr = trained_e2e(args, ctx, e_steps, world)    # every rank: host <-> device copies of all GPUs at the same time
+        train = train_leg(args, ctx, rank, world)          # every rank takes part (gradient exchange)
     if rank == 0:
+        line["e2e_trained_weights"] = e2e_tr
         line["train"] = train
         print(json.dumps(line, default=float))
     if world > 1:

@@ -159,6 +159,10 @@ _PROTOS = {
     "hp_comm_unique_id": (C.c_int, [C.c_void_p]),
     "hp_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "hp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "hp_p2p_alloc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "hp_p2p_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "hp_p2p_close": (C.c_int, [C.c_void_p]),
+    "hp_debug_set_p2p": (C.c_int, [C.c_void_p, C.c_int]),
     "hp_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "hp_debug_set_tile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_debug_tile_report": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -150,6 +150,11 @@ int hp_debug_set_stem_tc(hp_handle h, int BH, int nbuf, int nout, int nsets) {
   h->stem_tc_cfg[0] = BH; h->stem_tc_cfg[1] = nbuf; h->stem_tc_cfg[2] = nout; h->stem_tc_cfg[3] = nsets;
   return HP_OK;
 }
+int hp_debug_set_p2p(hp_handle h, int on) {
+  HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
+  h->p2p_off = !on;
+  return HP_OK;
+}
 int hp_debug_set_chain(hp_handle h, int mode, int nsets, int niss) {
   HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
   h->chain_mode = mode; h->chain_cfg[0] = nsets; h->chain_cfg[1] = niss;

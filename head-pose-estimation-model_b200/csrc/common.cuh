@@ -97,10 +97,21 @@ struct Backbone {
 };
 
 // ---------------------------------------------------------------------------- comm (NCCL via dlsym)
+#define HP_P2P_MAX_RANKS 8
+#define HP_P2P_SLICES 16          // CTAs of the fused all-reduce + optimizer kernel: each owns one slice of the flat gradient buffer
 struct Comm {
   void* lib = nullptr;
   void* comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer-memory exchange (comm.cu): this rank's INBOX (cudaMalloc, exported through CUDA IPC) holds, per source rank and step
+  // parity, a copy of that rank's flat gradient buffer plus one arrival flag per slice; peers[] are the inboxes of all ranks
+  // mapped into this process (NVLink / NVSwitch peer access)
+  void* inbox = nullptr;
+  void* peers[HP_P2P_MAX_RANKS] = {};
+  void** peers_dev = nullptr;     // device copy of peers[]
+  unsigned int* p2p_seq = nullptr; // device counter of exchanges on this context: the tag of a step's slices and flags (the same on all ranks)
+  int p2p_cap = 0;                // floats per slot
+  bool p2p_ready = false;
 };
 
 struct hp_head;  // heads.cu
@@ -146,6 +157,7 @@ struct hp_ctx {
   std::vector<DetectGraph> det_graphs;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tile_override[16][5] = {};   // TH, TW, IMGS, nbuf, MT per block (0 = automatic)
+  bool p2p_off = false;            // hp_debug_set_p2p: keep the NCCL all-reduce although the peer-memory exchange is set up (comparison runs)
   bool dense_tc = true;            // Dense / 1x1 layers may use the tensor-core kernel (cleared while a training step runs)
   int stem_tc_cfg[4] = {};         // tensor-core stem: band height, input buffers, output stages, gather sets (0 = automatic, [0] = -1: off)
   int tc_override[16][9] = {};     // tensor-core kernel: TR, NSTG, BH, npipe, nsets, nbuf per block (TR 0 = automatic, -1 = do not use)

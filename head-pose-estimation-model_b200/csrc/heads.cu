@@ -912,6 +912,7 @@ struct hp_head {
     hp_opt_config opt{};
     uint64_t seed = 0;
     void* comm = nullptr;
+    int p2p = 0;
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
   };
@@ -1441,8 +1442,9 @@ int hp_head_train_step_impl(hp_ctx* h, hp_head* hd, const float* x, const float*
 // ============================================================================ hp_head_train_run: many steps, no host round trips
 // Step prologue: advance the device-resident counters and derive the step sizes of optimizer step t (Keras 2.13: alpha_t =
 // lr sqrt(1 - b2^t) / (1 - b1^t) for Adam, lr / (1 - b1^t) for Adamax, in double like the host path).
-__global__ void train_begin_kernel(TrainState* ts, float lr, float b1, float b2) {
+__global__ void train_begin_kernel(TrainState* ts, float lr, float b1, float b2, unsigned int* exchange_seq) {
   if (threadIdx.x == 0) {
+    if (exchange_seq) *exchange_seq += 1u;          // tag of this step's peer-memory exchange (context-wide, the same on all ranks)
     const uint32_t t = ts->t + 1u;
     ts->t = t;
     const double td = (double)t, d1 = 1.0 - pow((double)b1, td);
@@ -1472,13 +1474,91 @@ __global__ void train_end_kernel(TrainState* ts, const float* sums, float count,
   }
 }
 
+// Fused gradient all-reduce + optimizer over NVLink peer memory (one CTA per slice of the flat buffer [grads..., sum err^2,
+// sum |err|, count]; see comm.cu for the inbox layout).  CTA c of rank r at step t:
+//   1. pushes slice c of its buffer into slot [t & 1][r] of EVERY rank's inbox (its own included) with 128-bit stores,
+//      __threadfence_system(), then stores t into flag c of that slot (the release of the slice),
+//   2. spins until flag c of slots [t & 1][0 .. world) of its OWN inbox holds t (acquire),
+//   3. sums the world's copies of the slice in rank order -- the same order on every rank, so the sums, hence the weights, are
+//      bit-identical everywhere -- writes the sums back to the buffer (loss epilogue, hp_head_get_grads) and applies the
+//      optimizer to the parameters of the slice.
+// Two parities suffice: a rank cannot start step t + 2 before every peer has pushed step t + 1, i.e. finished reading step t.
+// A wait that lasts ~2 s (a peer that died) raises HP_STATUS_P2P_TIMEOUT and goes on, so a lost rank cannot hang the GPU.
+__global__ void __launch_bounds__(256) p2p_allreduce_optimizer_kernel(float* buf, int n_total, int np, void* const* peers, int rank, int world,
+                                                                       int cap, const TrainState* ts, const unsigned int* seq, float* w,
+                                                                       const float* l2, float* m,
+                                                                       float* v, int kind, float lr, float b1, float b2, float eps,
+                                                                       unsigned int* status) {
+  const int c = blockIdx.x;
+  const uint32_t t = *seq;                                    // exchange tag, advanced for this step by train_begin_kernel
+  const size_t slot_floats = (size_t)cap + HP_P2P_SLICES;
+  const int per = (((n_total + HP_P2P_SLICES - 1) / HP_P2P_SLICES) + 3) & ~3;     // floats per slice, a multiple of 4
+  const int lo = c * per, hi = min(n_total, lo + per);
+  const size_t slot_off = ((size_t)(t & 1u) * world + rank) * slot_floats;
+  // ---- 1. push
+  for (int r = 0; r < world; ++r) {
+    float* dst = (float*)peers[r] + slot_off;
+    for (int i = lo + 4 * threadIdx.x; i < hi; i += 4 * blockDim.x) {
+      if (i + 4 <= hi) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(buf + i);
+      else for (int j = i; j < hi; ++j) dst[j] = buf[j];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    volatile uint32_t* flag = (volatile uint32_t*)((float*)peers[threadIdx.x] + slot_off + cap) + c;
+    *flag = t;
+  }
+  // ---- 2. wait for the world's slices
+  float* mine = (float*)peers[rank];
+  if (threadIdx.x < world) {
+    volatile uint32_t* flag = (volatile uint32_t*)(mine + ((size_t)(t & 1u) * world + threadIdx.x) * slot_floats + cap) + c;
+    const long long t0 = clock64();
+    while (*flag != t) {
+      if (clock64() - t0 > 4000000000ll) {
+        if (status) atomicOr(status, HP_STATUS_P2P_TIMEOUT);
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  // ---- 3. rank-ordered sum + optimizer
+  const float alpha_t = ts->alpha_t, lr_t = ts->lr_t;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float g = 0.f;
+    for (int r = 0; r < world; ++r) g += __ldcv(mine + ((size_t)(t & 1u) * world + r) * slot_floats + i);
+    buf[i] = g;
+    if (i < np) {
+      const float wi = w[i];
+      const float gi = g + 2.f * l2[i] * wi;
+      if (kind == HP_OPT_SGD) {
+        w[i] = wi - lr * gi;
+      } else if (kind == HP_OPT_ADAM) {
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+        m[i] = mi;
+        v[i] = vi;
+        w[i] = wi - (mi * alpha_t) / (sqrtf(vi) + eps);
+      } else {
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        const float ui = fmaxf(b2 * v[i], fabsf(gi));
+        m[i] = mi;
+        v[i] = ui;
+        w[i] = wi - (lr_t * mi) / (ui + eps);
+      }
+    }
+  }
+}
+
 static int train_run_one_step(hp_ctx* h, hp_head* hd, const float* x_all, const float* y_all, const int32_t* idx, long long first,
                               int batch_global, int n_local, int rank, int world, int H, int W, const hp_opt_config* opt, uint64_t seed,
                               cudaStream_t st) {
   const int T = H * W, Cin = hd->in_channels, Cout = hd->regs[hd->out_reg].channels, np = hd->n_params;
   TrainState* ts = (TrainState*)hd->tstate.p;
   float* sums = hd->grads.f() + np;
-  train_begin_kernel<<<1, 32, 0, st>>>(ts, opt->lr, opt->beta1, opt->beta2);
+  const bool use_p2p = world > 1 && h->comm.p2p_ready && np + 3 <= h->comm.p2p_cap && !h->p2p_off;
+  train_begin_kernel<<<1, 32, 0, st>>>(ts, opt->lr, opt->beta1, opt->beta2, use_p2p ? h->comm.p2p_seq : nullptr);
   h->launches++;
   HP_CUDA(cudaMemsetAsync(hd->grads.p, 0, (size_t)(np + 4) * sizeof(float), st));
   if (n_local > 0) {
@@ -1499,10 +1579,17 @@ static int train_run_one_step(hp_ctx* h, hp_head* hd, const float* x_all, const 
     hd->step_dev = nullptr;
     HP_TRY(rc);
   }
-  if (world > 1) HP_TRY(hp_comm_allreduce_sum(h, hd->grads.f(), (size_t)np + 3, st));   // a single-rank run never touches a communicator the context may hold
-  l2_penalty_kernel<<<1, 256, 0, st>>>(hd->params.f(), hd->l2coef.f(), np, sums + 3);
-  optimizer_kernel<<<ceil_div(np, 256), 256, 0, st>>>(hd->params.f(), hd->grads.f(), hd->l2coef.f(), hd->m.f(), hd->v.f(), np, opt->kind, opt->lr,
-                                                     opt->beta1, opt->beta2, opt->eps, 0.f, 0.f, ts);
+  l2_penalty_kernel<<<1, 256, 0, st>>>(hd->params.f(), hd->l2coef.f(), np, sums + 3);      // of the pre-update weights (Keras reports loss before the step)
+  if (use_p2p) {
+    // gradient exchange and optimizer in ONE kernel over NVLink peer memory
+    p2p_allreduce_optimizer_kernel<<<HP_P2P_SLICES, 256, 0, st>>>(hd->grads.f(), np + 3, np, h->comm.peers_dev, rank, world, h->comm.p2p_cap, ts,
+                                                                 h->comm.p2p_seq, hd->params.f(), hd->l2coef.f(), hd->m.f(), hd->v.f(), opt->kind, opt->lr, opt->beta1,
+                                                                 opt->beta2, opt->eps, (unsigned int*)h->status.p);
+  } else {
+    if (world > 1) HP_TRY(hp_comm_allreduce_sum(h, hd->grads.f(), (size_t)np + 3, st));   // a single-rank run never touches a communicator the context may hold
+    optimizer_kernel<<<ceil_div(np, 256), 256, 0, st>>>(hd->params.f(), hd->grads.f(), hd->l2coef.f(), hd->m.f(), hd->v.f(), np, opt->kind, opt->lr,
+                                                       opt->beta1, opt->beta2, opt->eps, 0.f, 0.f, ts);
+  }
   train_end_kernel<<<1, 32, 0, st>>>(ts, sums, (float)batch_global * T * Cout, (float)batch_global);
   h->launches += 3;
   HP_CUDA(cudaGetLastError());
@@ -1522,8 +1609,8 @@ int hp_head_train_run_impl(hp_ctx* h, hp_head* hd, const float* x_all, const flo
   HP_REQUIRE(world >= 1 && rank >= 0 && rank < world && batch_global >= 1 && n_steps >= 1, HP_ERR_INVALID, "hp_head_train_run: bad batch / rank arguments");
   HP_REQUIRE(first_item >= 0 && first_item + (long long)n_steps * batch_global <= n_items, HP_ERR_INVALID,
              "hp_head_train_run: %d steps of %d items from item %lld exceed the %lld items of the data set", n_steps, batch_global, first_item, n_items);
-  HP_REQUIRE(world == 1 || (h->comm.comm && h->comm.nranks == world && h->comm.rank == rank), HP_ERR_STATE,
-             "hp_head_train_run: %d ranks but the gradient communicator is not initialised for them (hp_comm_init)", world);
+  HP_REQUIRE(world == 1 || ((h->comm.comm || h->comm.p2p_ready) && h->comm.nranks == world && h->comm.rank == rank), HP_ERR_STATE,
+             "hp_head_train_run: %d ranks but the gradient exchange is not initialised for them (hp_comm_init / hp_p2p_open)", world);
   const int n_local = batch_global > rank ? (batch_global - rank + world - 1) / world : 0;     // rows rank, rank + world, ... of the batch
   const int T = H * W, Cin = hd->in_channels, Cout = hd->regs[hd->out_reg].channels, np = hd->n_params;
   const int n_plan = n_local > 0 ? n_local : 1;
@@ -1547,11 +1634,11 @@ int hp_head_train_run_impl(hp_ctx* h, hp_head* hd, const float* x_all, const flo
   if ((flags & HP_TRAIN_GRAPH) && st != nullptr) {
     hp_head::RunGraph key;
     key.x = x_all; key.y = y_all; key.idx = idx; key.first = first_item; key.batch_global = batch_global; key.n_local = n_local;
-    key.rank = rank; key.world = world; key.H = H; key.W = W; key.impl = h->impl; key.opt = *opt; key.seed = seed; key.comm = h->comm.comm;
+    key.rank = rank; key.world = world; key.H = H; key.W = W; key.impl = h->impl; key.opt = *opt; key.seed = seed; key.comm = h->comm.comm; key.p2p = (h->comm.p2p_ready && !h->p2p_off) ? 1 : 0;
     hp_head::RunGraph* hit = nullptr;
     for (auto& g : hd->run_graphs)
       if (g.x == key.x && g.y == key.y && g.idx == key.idx && g.first == key.first && g.batch_global == key.batch_global && g.n_local == key.n_local &&
-          g.rank == key.rank && g.world == key.world && g.H == key.H && g.W == key.W && g.impl == key.impl && g.seed == key.seed && g.comm == key.comm &&
+          g.rank == key.rank && g.world == key.world && g.H == key.H && g.W == key.W && g.impl == key.impl && g.seed == key.seed && g.comm == key.comm && g.p2p == key.p2p &&
           memcmp(&g.opt, &key.opt, sizeof(hp_opt_config)) == 0)
         hit = &g;
     if (hit && hit->epoch != g_devbuf_epoch) {

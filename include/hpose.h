@@ -88,6 +88,7 @@ int hp_backbone_forward(hp_handle h, const float* x, int B, int H, int W,
  * `stream`, returns the word and clears it; hp_debug_set_stem_tc(h, -1, 0, 0, 0) selects the fp32 CUDA-core stem, which has
  * no such limit (the Python layer re-runs a flagged batch that way).  The uint8 entry points cannot trigger it. */
 #define HP_STATUS_STEM_RANGE 1u
+#define HP_STATUS_P2P_TIMEOUT 2u    /* a rank of the peer-memory gradient exchange waited ~2 s for a peer (see hp_p2p_open) */
 int hp_backbone_status(hp_handle h, unsigned int* flags_host, void* stream);
 
 /* debugging / parity hook: run the backbone on x up to BlazeBlock `blk` (0..15; -1 = stem only) and
@@ -262,6 +263,18 @@ int hp_unified_forward(hp_handle h, hp_head_t head16, hp_head_t head8, const flo
 int hp_comm_unique_id(void* id128_host);
 int hp_comm_init(hp_handle h, const void* nccl_unique_id_host, int rank, int nranks);
 int hp_comm_destroy(hp_handle h);
+/* Peer-memory gradient exchange (the default of hp_head_train_run when it is set up): instead of ncclAllReduce followed by an
+ * optimizer kernel, ONE kernel pushes every rank's gradient slices into every peer's inbox over NVLink / NVSwitch, waits for the
+ * world's slices, sums them in rank order (bit-identical on all ranks) and applies the optimizer.
+ *   hp_p2p_alloc : allocate this rank's inbox for buffers of up to cap_floats floats and return its 64-byte CUDA IPC handle
+ *   hp_p2p_open  : all_handles_host = the nranks handles in rank order (exchanged by the caller); maps the peers' inboxes
+ *   hp_p2p_close : unmap / free (also done by hp_comm_destroy / hp_destroy)
+ * Needs peer access between the GPUs (one process per GPU on one node, at most 8 ranks); when it is not set up, or a head has
+ * more than cap_floats - 3 parameters, the step falls back to hp_comm_init's NCCL all-reduce. */
+int hp_p2p_alloc(hp_handle h, int cap_floats, int nranks, void* ipc_handle64_host);
+int hp_p2p_open(hp_handle h, const void* all_handles_host, int rank, int nranks);
+int hp_p2p_close(hp_handle h);
+int hp_debug_set_p2p(hp_handle h, int on);
 
 /* ---------------------------------------------------------------- measurement helpers
  * fp32 FMA micro-benchmark (SURVEY 8d asks for the measured CUDA-core peak): returns TFLOP/s.

@@ -32,4 +32,5 @@ def test_data_parallel_fit_two_ranks_nccl():
     line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["world"] == 2 and out["adam"]["ranks_identical"] and out["sgd"]["ranks_identical"] and out["dropout_ranks_identical"]
+    assert out["p2p"] and out["adam_nccl"]["ranks_identical"] and out["adam_nccl"]["max_rel_dev_vs_single_gpu"] <= 2e-5 and out["status_flags"] == 0
     assert out["sgd"]["max_rel_dev_vs_single_gpu"] <= 2e-5 and out["adam_one_step_max_rel_dev"] <= 2e-5

@@ -41,15 +41,20 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from helpers import synthetic_features, synthetic_poses
     from hpose_b200.parallel import DataParallel
+    from hpose_b200 import _lib
+    from hpose_b200.device import default_context
     dp = DataParallel()
-    out = {"world": world}
+    dp.init_gradient_comm()                              # NCCL communicator + peer-memory exchange (fused all-reduce + optimizer)
+    out = {"world": world, "p2p": bool(dp.p2p)}
+    ctx = default_context()
     # n = 128 * 6 + world - 1: the final batch has fewer rows than ranks when world > 1 (the last rank gets none)
     n = 128 * 6 + max(1, world - 1)
     x = synthetic_features(n, 96, seed=1, sigma=0.55, p=0.31).reshape(n, 1, 1, 96)
     y = synthetic_poses(n, seed=2).reshape(n, 1, 1, 3)
-    for opt in ("adam", "sgd"):
+    for opt, p2p in (("adam", 1), ("sgd", 1), ("adam", 0)):
+        _lib.check(_lib.lib().hp_debug_set_p2p(ctx.handle, p2p))          # 0: ncclAllReduce + optimizer kernel (comparison path)
         m = make_model(opt)
-        hist = m.fit(x, y, epochs=3, batch_size=128, verbose=0, seed=9, distributed=dp)      # init_gradient_comm happens inside
+        hist = m.fit(x, y, epochs=3, batch_size=128, verbose=0, seed=9, distributed=dp)
         w = torch.from_numpy(flat(m)).cuda()
         gathered = [torch.empty_like(w) for _ in range(world)]
         dist.all_gather(gathered, w)
@@ -58,11 +63,12 @@ def main():
         h1 = single.fit(x, y, epochs=3, batch_size=128, verbose=0, seed=9)                   # one GPU, the same global batches
         ref = flat(single)
         dev = float(np.abs(flat(m) - ref).max() / max(1.0, np.abs(ref).max()))
-        out[opt] = {"ranks_identical": bool(identical), "max_rel_dev_vs_single_gpu": dev,
+        out[opt if p2p else opt + "_nccl"] = {"ranks_identical": bool(identical), "max_rel_dev_vs_single_gpu": dev,
                     "loss_dp": hist.history["loss"], "loss_single": h1.history["loss"]}
         assert identical, "ranks diverged"
         assert dev <= 2e-5, (opt, dev)                     # measured on 2 B200: 1.1e-7 (Adam, 21 steps), 3e-8 (SGD)
         assert np.allclose(hist.history["loss"], h1.history["loss"], rtol=1e-4), (opt, hist.history["loss"], h1.history["loss"])
+    _lib.check(_lib.lib().hp_debug_set_p2p(ctx.handle, 1))
     # one global-batch Adam step: data-parallel vs single GPU
     m, single = make_model("adam"), make_model("adam")
     m.fit(x[:128], y[:128], epochs=1, batch_size=128, verbose=0, seed=9, shuffle=False, distributed=dp)
@@ -78,6 +84,10 @@ def main():
     dist.all_gather(gathered, w)
     out["dropout_ranks_identical"] = bool(all(torch.equal(gathered[0], g) for g in gathered[1:]))
     assert out["dropout_ranks_identical"]
+    flags = __import__("ctypes").c_uint(0)
+    _lib.check(_lib.lib().hp_backbone_status(ctx.handle, __import__("ctypes").byref(flags), ctx.stream_ptr()))
+    out["status_flags"] = int(flags.value)               # bit 1 = a peer-memory wait timed out
+    assert flags.value == 0
     dist.barrier()
     if rank == 0:
         print(json.dumps(out))
