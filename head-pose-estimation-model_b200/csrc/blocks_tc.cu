@@ -610,16 +610,16 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
           tc_fence_after();
         }
         if (issuer == 0) stamp(i, 11);
+        uint64_t dhi = desc_fixed | (uint64_t)((bhi_addr >> 4) & 0x3FFF), dlo = desc_fixed | (uint64_t)((blo_addr >> 4) & 0x3FFF);
 #pragma unroll 1
-        for (int ks = 0; ks < KS; ++ks, ++use) {
+        for (int ks = 0; ks < KS; ++ks, ++use, dhi += (2u * N16 * 16u) >> 4, dlo += (2u * N16 * 16u) >> 4) {
           const uint32_t s = use % NSTG;
           mbar_wait_lean(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
-          if (issuer == 0 && ks == 0) stamp(i, 10);
-          if (issuer == 0 && ks == KS - 1) stamp(i, 9);
-          const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
-          const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
-          const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+          if (issuer == 0 && p.trace != nullptr) {            // off the critical path of an untraced run: one predictable branch
+            if (ks == 0) stamp(i, 10);
+            if (ks == KS - 1) stamp(i, 9);
+          }
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
             if (t % NISS != issuer) continue;

@@ -270,22 +270,27 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const uint64_t desc_fixed = tc_bdesc_fixed(ST_N16);
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
       uint32_t use = 0;
+      // every instruction of this loop is on the critical path (a lone warp retires a dependent instruction every ~5 clk):
+      // descriptors advance by additions, the trace test is hoisted, the wait is the bare try_wait loop
+      const bool traced = issuer == 0 && p.trace != nullptr && blockIdx.x == 0;
+      const uint64_t dhi0 = desc_fixed | (uint64_t)((bhi_addr >> 4) & 0x3FFF), dlo0 = desc_fixed | (uint64_t)((blo_addr >> 4) & 0x3FFF);
+      constexpr uint32_t KSTEP_DESC = (2u * ST_N16 * 16u) >> 4;       // one k-step of B in descriptor units (16 B); no carry out of the address field
       for (int i = 0; i < my_tiles; ++i) {
         const int d = i & 1;
         if (i >= 2) {
-          mbar_wait(&bar_dempty[d], ((i >> 1) - 1) & 1);
+          mbar_wait_lean(&bar_dempty[d], ((i >> 1) - 1) & 1);
           tc_fence_after();
         }
+        uint64_t dhi = dhi0, dlo = dlo0;
 #pragma unroll 1
-        for (int ks = 0; ks < ST_KS; ++ks, ++use) {
+        for (int ks = 0; ks < ST_KS; ++ks, ++use, dhi += KSTEP_DESC, dlo += KSTEP_DESC) {
           const uint32_t s = use % NSTG;
           mbar_wait_lean(&bar_afull[s], (use / NSTG) & 1);
           tc_fence_after();
-          if (issuer == 0 && ks == 0) stamp(i, 10);
-          if (issuer == 0 && ks == ST_KS - 1) stamp(i, 9);
-          const uint32_t koff = (uint32_t)ks * 2u * ST_N16 * 16u;
-          const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
-          const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
+          if (traced) {
+            if (ks == 0) stamp(i, 10);
+            if (ks == ST_KS - 1) stamp(i, 9);
+          }
 #pragma unroll
           for (int t = 0; t < TR; ++t) {
             if (t % NISS != issuer) continue;
@@ -298,7 +303,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           tc_commit(&bar_aempty[s]);
         }
         tc_commit(&bar_dfull[d]);
-        if (issuer == 0) stamp(i, 7);
+        if (traced) stamp(i, 7);
       }
     } else if (warp == W_LOAD) {
       // =============================================================== TMA loader
