@@ -52,9 +52,20 @@ if len(sys.argv) > 6 and sys.argv[6] == "all":
     last = [r for r in body if len(r) > kname]
     names = [f"#{i}" for i in range(len(last))]
 else:
-    backbone = [r for r in body if len(r) > kname and ("stem" in r[kname] or "blaze_block" in r[kname])]
-    last = backbone[-17:]                      # the last forward: stem + 16 blocks
-    names = ["stem"] + [f"block{i}" for i in range(16)]
+    backbone = [r for r in body if len(r) > kname and ("stem" in r[kname] or "blaze_block" in r[kname] or "blaze_chain" in r[kname])]
+    # the last forward: stem, blocks 0-5, then either one kernel per block or the two chain kernels (6-10 + tail 11, 12-15);
+    # names follow bench.py's merged rows
+    n_chain = sum(1 for r in backbone if "blaze_chain" in r[kname])
+    if n_chain:
+        last = backbone[-9:]
+        tail = any("blaze_block" in r[kname] for r in last[8:9]) is False and len([r for r in last if "blaze_chain" in r[kname]]) == 2
+        names = ["stem"] + [f"block{i}" for i in range(6)] + ["blocks6-11", "blocks12-15"]
+        if sum(1 for r in backbone[-10:] if "blaze_chain" in r[kname]) == 2 and "blaze_chain" not in backbone[-2][kname]:
+            last = backbone[-10:]             # chains without the tail: block 11 is its own kernel between them
+            names = ["stem"] + [f"block{i}" for i in range(6)] + ["blocks6-10", "block11", "blocks12-15"]
+    else:
+        last = backbone[-17:]
+        names = ["stem"] + [f"block{i}" for i in range(16)]
 traffic = {}
 with open(out_txt, "w") as f:
     f.write(f"# ncu --set full --clock-control none, tools/profile_target.py {size} {batch}; one row per backbone kernel\n")
