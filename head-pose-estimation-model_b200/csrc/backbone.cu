@@ -580,7 +580,8 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
     std::vector<float> sw(host.begin() + o_stem_w, host.begin() + o_stem_w + 75 * 24);
     hp_stem_tc_split_weights(sw.data(), &host[o_stem_bhi], &host[o_stem_blo]);
   }
-  size_t o_dww[16], o_dwb[16], o_pww[16], o_pwb[16], o_bhi[16], o_blo[16];
+  size_t o_dww[16], o_dwb[16], o_pww[16], o_pwb[16], o_bhi[16], o_blo[16], o_hhi[16], o_hlo[16];
+  float h_unscale[16];
   for (int i = 0; i < 16; ++i) {
     const int cin = kBlazeBlocks[i].cin, cout = kBlazeBlocks[i].cout;
     const int cinp = chan_pad(cin), coutp = chan_pad(cout);
@@ -604,6 +605,10 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
     {
       std::vector<float> pw(host.begin() + o_pww[i], host.begin() + o_pww[i] + (size_t)cinp * coutp);
       hp_tc_split_weights(pw.data(), cinp, coutp, &host[o_bhi[i]], &host[o_blo[i]]);
+      const int nh = hp_tc_weight_floats_f16(cinp, coutp);
+      o_hhi[i] = reserve(nh);
+      o_hlo[i] = reserve(nh);
+      h_unscale[i] = hp_tc_split_weights_f16(pw.data(), cinp, coutp, &host[o_hhi[i]], &host[o_hlo[i]]);
     }
   }
   // detector heads: concatenate cls|loc per tap
@@ -646,6 +651,9 @@ int hp_backbone_load_weights_impl(hp_ctx* h, const float* src, size_t n_floats, 
     bb.blk[i].pwb = base + o_pwb[i];
     bb.blk[i].bhi = base + o_bhi[i];
     bb.blk[i].blo = base + o_blo[i];
+    bb.blk[i].hhi = base + o_hhi[i];
+    bb.blk[i].hlo = base + o_hlo[i];
+    bb.blk[i].h_unscale = h_unscale[i];
   }
   {
     size_t n = 0, off[16];
@@ -765,7 +773,7 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
     const int cin = kBlazeBlocks[i].cin, cout = kBlazeBlocks[i].cout, S = kBlazeBlocks[i].stride;
     const int cinp = chan_pad(cin), coutp = chan_pad(cout);
     // ---- cross-block fusion: blocks 6-10 (tap 16) and 12-15 (tap 8) as one persistent kernel each (blocks_chain.cu)
-    if (h->impl == HP_IMPL_FAST && h->chain_mode > 0 && (i == 6 || i == 12)) {
+    if (h->impl == HP_IMPL_FAST && (h->chain_mode & 3) > 0 && (i == 6 || i == 12)) {
       int last = (i == 6) ? 10 : 15;
       const int chain_nblk = last - i + 1;
       if (stop_after_blk >= i && stop_after_blk < last) last = stop_after_blk;
@@ -775,7 +783,7 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
       // block 11 (stride 2, 12x12x88 -> 6x6x96 at 96x96 input) rides on the chain 6-10: it is computed from the resident tile
       // while the tile's TMA store is in flight (chain_mode 2 = default; 1 = chains without the tail)
       int tail_blk = -1;
-      if (i == 6 && last == 10 && h->chain_mode >= 2 && (stop_after_blk < 0 || stop_after_blk > 10) && h->tc_override[11][0] == 0 &&
+      if (i == 6 && last == 10 && (h->chain_mode & 3) >= 2 && (stop_after_blk < 0 || stop_after_blk > 10) && h->tc_override[11][0] == 0 &&
           h->tile_override[11][0] == 0 && plain && hp_chain_geometry(i, chain_nblk, chain_nblk, hs[i + 1], ws[i + 1], &ccfg, 11))
         tail_blk = 11;
       if (plain && (tail_blk >= 0 || hp_chain_geometry(i, last - i + 1, chain_nblk, hs[i + 1], ws[i + 1], &ccfg))) {

@@ -26,6 +26,8 @@
 //   EPI phase: (after all MMAs of the step: every depthwise read of the tile is done, in-place writes are safe) unit =
 //              (M-tile, 32 accumulator columns): tcgen05.ld + bias + skip -> ReLU -> st.shared over the input pixel.
 // The same worker warps run both phases; the next step's DW phase starts when all epilogue units have arrived.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -37,7 +39,8 @@ namespace {
 #define CH_BAR_FLOATS 128
 
 struct ChainBlk {
-  const float *bhi, *blo;         // pointwise weights split hi / lo, each [K8/4][N16][4]
+  const float *bhi, *blo;         // pointwise weights split hi / lo: TF32 [K8/4][N16][4] floats, or (F16 kernels) fp16 [K16/8][N16][8] halves
+  float unscale;                  // F16: the weights carry a power-of-two scale, the epilogue multiplies the accumulator by its inverse
   const float *dww, *pwb;         // depthwise [9][cin] followed by its bias [cin]; pointwise bias [cout]
   int cin, cout, ks, n16;         // padded channel counts (cin % 8 == 0), k-steps, MMA N
   int w_off;                      // float offset of this block's [10 cin | cout] in the shared weight area
@@ -59,6 +62,7 @@ struct ChainParams {
   int off_w, w_floats, off_ring, off_zero, zero_floats, off_tile;   // shared-memory layout in floats
   long long* trace;               // optional clock stamps of CTA 0: 8 per step
   int trace_steps;
+  unsigned int* status;           // sticky status word of the context: HP_STATUS_CHAIN_RANGE when a depthwise output does not fit fp16
   int exp_;                       // timing experiments (env HP_CHAIN_EXP): 1 = no depthwise loads / math, 2 = no epilogue shared-memory traffic, 4 = no MMAs
   int dbg;                        // bring-up aid (env HP_CHAIN_DBG): 1 = setup only, 2 = + tile load / store, 3 = + first weight slices
 };
@@ -110,13 +114,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // Thread layout: NSETS * 4 worker warps, then 4 utility warps: +0 tile loader / storer, +1 weight loader, +2 second
 // issuer (NISS == 2), +3 first issuer (owns the TMEM allocation; sub-partition 3 is the least loaded one when fewer than
 // 97 lanes are in use).
-template <int TR, int PS, int NSETS, int NISS>
+// F16 = 1: the pointwise conv runs as split-fp16 MMAs (kind::f16, K = 16 per instruction) instead of 3xTF32 (K = 8): the MMA count
+// -- one thread issues ~110 clk per MMA next to the depthwise warps, 360 MMAs per tile of the chain 6-10 were on the critical
+// path of every block -- and the B-operand shared-memory traffic halve.  x = hi + lo with both parts fp16 (22 significant bits,
+// lo may be subnormal: absolute error <= 2^-25), weights pre-scaled by a power of two so that their lo parts stay normal.  Two
+// worker sets (8 channels each) fill one A stage of 16 channels.  A depthwise output beyond the fp16 range (|a| >= 65520) gives an
+// inf / NaN accumulator row, which the epilogue reports in the status word (the host re-runs the batch with the TF32 kernels).
+template <int TR, int PS, int NSETS, int NISS, int F16>
 __global__ void __launch_bounds__(128 * NSETS + 64 + 32 * NISS, 1)
 blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ ChainParams p) {
   constexpr uint32_t colA0 = TR * CH_DSTRIDE;          // TMEM: D_0 .. D_{TR-1}, then one A stage of TR * 16 columns per set
   constexpr uint32_t STAGE = TR * 16;
   static_assert(colA0 + NSETS * STAGE <= 512, "TMEM budget");
   static_assert(NISS >= 1 && NISS <= 3 && NISS <= TR, "issuers");
+  static_assert(!F16 || NSETS % 2 == 0, "two worker sets share an A stage of 16 channels");
   constexpr int NWORK = 128 * NSETS;
 
   extern __shared__ __align__(1024) float smem[];
@@ -226,6 +237,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     const float* win = tile + ((im * (p.H + 1) + yq * TR - 1) * (p.W + 1) + x - 1) * PS;
     float* centre0 = const_cast<float*>(win) + row_pitch + PS;
     uint32_t g0 = 0, e0 = 0;     // global round counter / epilogue unit counter
+    uint32_t guard = 0u;         // F16: set when an accumulator of this lane is inf / NaN
     int step = 0;
     for (int it = 0; it < my_tiles; ++it) {
       for (int b = 0; b < nblk; ++b, ++step) {
@@ -279,7 +291,38 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             ch_wait(bar_aempty, (g0 - 1) & 1, 3, s_abort, step);
             tc_fence_after();
           }
-          if (has) {
+          if (F16) {
+            // stage set / 2 holds 16 channels: columns [0, 8) fp16 pairs hi, [8, 16) lo; this set's 8 channels are pairs half * 4 ...
+            const uint32_t acol = tlane + colA0 + (set >> 1) * STAGE + (set & 1) * 4;
+            if (has) {
+#pragma unroll
+              for (int t = 0; t < TR; ++t) {
+                const float f[8] = {acc[0][t].x, acc[0][t].y, acc[0][t].z, acc[0][t].w, acc[1][t].x, acc[1][t].y, acc[1][t].z, acc[1][t].w};
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 h2 = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                  const float2 back = __half22float2(h2);
+                  const __half2 l2 = __floats2half2_rn(f[2 * e] - back.x, f[2 * e + 1] - back.y);
+                  hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                  lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                tmem_st4(acol + t * 16, hi[0], hi[1], hi[2], hi[3]);
+                tmem_st4(acol + t * 16 + 8, lo[0], lo[1], lo[2], lo[3]);
+              }
+            } else if (warp_active && ks >= KS && (ks ^ 1) < KS) {
+              // the block ends in the middle of this stage's 16 channels: the other half multiplies zero weights, keep it finite
+#pragma unroll
+              for (int t = 0; t < TR; ++t) {
+                tmem_st4(acol + t * 16, 0u, 0u, 0u, 0u);
+                tmem_st4(acol + t * 16 + 8, 0u, 0u, 0u, 0u);
+              }
+            }
+            if (warp_active) {
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              tc_fence_before();
+            }
+          } else if (has) {
             const uint32_t acol = tlane + colA0 + set * STAGE;
 #pragma unroll
             for (int t = 0; t < TR; ++t) {
@@ -322,13 +365,18 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // an fp16 infinity among the A operands of this pixel makes every accumulator column inf or NaN: test one
+            if (F16 && cg == 0 && valid && (v[0] & 0x7F800000u) == 0x7F800000u) guard = 1u;
+            const float us = cb.unscale;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               const int j = cg * 8 + jj;
               if (j < NG && !(p.exp_ & 2)) {
                 const float4 bb = ld4(s_pwb + j * 4);
-                float4 o = make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
-                                       __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
+                float4 o = F16 ? make_float4(fmaf(__uint_as_float(v[jj * 4 + 0]), us, bb.x), fmaf(__uint_as_float(v[jj * 4 + 1]), us, bb.y),
+                                             fmaf(__uint_as_float(v[jj * 4 + 2]), us, bb.z), fmaf(__uint_as_float(v[jj * 4 + 3]), us, bb.w))
+                               : make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
+                                             __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
                 if (j < C4) {
                   const float4 sk = ld4(cpix + j * 4);
                   o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
@@ -389,7 +437,30 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             ch_wait(bar_aempty, (g0 - 1) & 1, 3, s_abort, step);
             tc_fence_after();
           }
-          if (has) {
+          if (F16) {
+            const uint32_t acol = tlane + colA0 + (set >> 1) * STAGE + (set & 1) * 4;
+            if (has) {
+              const float f[8] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w, acc[1].x, acc[1].y, acc[1].z, acc[1].w};
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 h2 = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                const float2 back = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(f[2 * e] - back.x, f[2 * e + 1] - back.y);
+                hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              tmem_st4(acol, hi[0], hi[1], hi[2], hi[3]);
+              tmem_st4(acol + 8, lo[0], lo[1], lo[2], lo[3]);
+            } else if (warp_active2 && ks >= KS && (ks ^ 1) < KS) {
+              tmem_st4(acol, 0u, 0u, 0u, 0u);
+              tmem_st4(acol + 8, 0u, 0u, 0u, 0u);
+            }
+            if (warp_active2) {
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              tc_fence_before();
+            }
+          } else if (has) {
             const float f[8] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w, acc[1].x, acc[1].y, acc[1].z, acc[1].w};
             uint32_t v[16];
 #pragma unroll
@@ -427,13 +498,17 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (F16 && u == 0 && valid2 && (v[0] & 0x7F800000u) == 0x7F800000u) guard = 1u;
+            const float us = cb.unscale;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               const int j = u * 8 + jj;
               if (j < NG) {
                 const float4 bb = ld4(s_pwb + j * 4);
-                float4 o = make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
-                                       __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
+                float4 o = F16 ? make_float4(fmaf(__uint_as_float(v[jj * 4 + 0]), us, bb.x), fmaf(__uint_as_float(v[jj * 4 + 1]), us, bb.y),
+                                             fmaf(__uint_as_float(v[jj * 4 + 2]), us, bb.z), fmaf(__uint_as_float(v[jj * 4 + 3]), us, bb.w))
+                               : make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
+                                             __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
                 if (j < C4) {
                   const float4 p00 = ld4(pool + j * 4), p01 = ld4(pool + PS + j * 4);
                   const float4 p10 = ld4(pool + row_pitch + j * 4), p11 = ld4(pool + row_pitch + PS + j * 4);
@@ -456,6 +531,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         ++step;
       }
     }
+    if (F16 && guard && p.status) atomicOr(p.status, 4u);
   } else {
     // utility warps: all 32 lanes walk the role loops together (waits included), lane 0 issues the asynchronous instructions.
     // (Keeping the warp converged measured the same as `if (lane_id == 0) {...}` with lanes 1-31 parked at the final barrier;
@@ -474,7 +550,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           const ChainBlk& cbi = b < nblk ? p.blk[b] : p.tblk;
           const int KS = cbi.ks, n16 = cbi.n16;
           const int trn = b < nblk ? TR : 1;                               // the tail block has one M-tile
-          const uint32_t idesc = tc_idesc_tf32(n16);
+          const uint32_t idesc = F16 ? ((1u << 4) | ((uint32_t)(n16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : tc_idesc_tf32(n16);
           const uint64_t desc_hi0 = tc_bdesc_fixed(n16) | (uint64_t)((ring_addr >> 4) & 0x3FFF);
           const uint32_t lo_off = ((uint32_t)n16 * 32u) >> 4;              // W_lo follows W_hi in the slot (descriptor units of 16 B)
           const bool traced = p.trace != nullptr && blockIdx.x == 0 && leader && issuer == 0;
@@ -488,7 +564,8 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             tc_fence_after();
             if (leader) {
               if (traced && r == 0) stamp(step, 4);
-              const int nk = KS - r * NSETS < NSETS ? KS - r * NSETS : NSETS;
+              const int nk8 = KS - r * NSETS < NSETS ? KS - r * NSETS : NSETS;
+              const int nk = F16 ? (nk8 + 1) >> 1 : nk8;                     // MMA k-steps (A stages, weight slices) of this round
               uint64_t dhi = desc_hi0 + (uint64_t)(half * NSETS * ((CH_SLOT_FLOATS * 4) >> 4));   // the ring stays below 256 KB: no carry
               uint32_t a0 = tmem_base + colA0;
 #pragma unroll 1
@@ -500,9 +577,15 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                   if (t % NISS != issuer || no_mma || t >= trn) continue;
                   const uint32_t dc = tmem_base + t * CH_DSTRIDE;
                   const uint32_t a = a0 + t * 16;
-                  mma_tf32_ts(dc, a, dhi, idesc, acc_flag);
-                  mma_tf32_ts(dc, a, dlo, idesc, 1u);
-                  mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+                  if (F16) {
+                    mma_f16_ts(dc, a, dhi, idesc, acc_flag);
+                    mma_f16_ts(dc, a, dlo, idesc, 1u);
+                    mma_f16_ts(dc, a + 8, dhi, idesc, 1u);
+                  } else {
+                    mma_tf32_ts(dc, a, dhi, idesc, acc_flag);
+                    mma_tf32_ts(dc, a, dlo, idesc, 1u);
+                    mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+                  }
                 }
               }
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(aempty_addr) : "memory");
@@ -530,10 +613,11 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             const uint32_t half = R & 1u;
             if (R >= 2) ch_wait(&bar_wempty[half], ((R >> 1) - 1) & 1, 7, s_abort, (int)R);
             if (leader) {
-              const int nk = cb.ks - r * NSETS < NSETS ? cb.ks - r * NSETS : NSETS;
+              const int nk8 = cb.ks - r * NSETS < NSETS ? cb.ks - r * NSETS : NSETS;
+              const int nk = F16 ? (nk8 + 1) >> 1 : nk8;
               mbar_expect_tx(&bar_wfull[half], (uint32_t)nk * 2u * half_bytes);
               for (int j = 0; j < nk; ++j) {
-                const int ks = r * NSETS + j;
+                const int ks = (F16 ? (r * NSETS) >> 1 : r * NSETS) + j;
                 float* dst = s_ring + (half * NSETS + j) * CH_SLOT_FLOATS;
                 bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[half]);
                 bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[half]);
@@ -581,9 +665,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   }
 }
 
-template <int TR, int PS, int NSETS, int NISS>
+template <int TR, int PS, int NSETS, int NISS, int F16>
 int launch_chain(hp_ctx* h, const CUtensorMap& tin, const CUtensorMap& tout, const ChainParams& p, size_t smem, cudaStream_t st) {
-  auto kern = blaze_chain_kernel<TR, PS, NSETS, NISS>;
+  auto kern = blaze_chain_kernel<TR, PS, NSETS, NISS, F16>;
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = h->num_sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -668,13 +752,16 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
   const Backbone& bb = h->bb;
   ChainParams p;
   memset(&p, 0, sizeof(p));
+  const bool f16 = !(h->chain_mode & 4) && cfg.nsets % 2 == 0 && cfg.niss <= 2;   // chain_mode + 4: 3xTF32 products
+  p.status = (unsigned int*)h->status.p;
   p.nblk = nblk;
   int w_off = 0;
   for (int b = 0; b < nblk; ++b) {
     const BlockWeights& w = bb.blk[first + b];
     HP_REQUIRE(w.bhi && w.blo, HP_ERR_STATE, "chain: split weights of block %d missing", first + b);
     ChainBlk& cb = p.blk[b];
-    cb.bhi = w.bhi; cb.blo = w.blo; cb.dww = w.dww; cb.pwb = w.pwb;
+    cb.bhi = f16 ? w.hhi : w.bhi; cb.blo = f16 ? w.hlo : w.blo; cb.dww = w.dww; cb.pwb = w.pwb;
+    cb.unscale = f16 ? w.h_unscale : 1.f;
     cb.cin = chan_pad(kBlazeBlocks[first + b].cin);
     cb.cout = chan_pad(kBlazeBlocks[first + b].cout);
     cb.ks = cb.cin / 8;
@@ -687,7 +774,8 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
     const BlockWeights& w = bb.blk[tail_blk];
     HP_REQUIRE(w.bhi && w.blo && tail_out, HP_ERR_STATE, "chain: tail block %d needs split weights and an output buffer", tail_blk);
     ChainBlk& cb = p.tblk;
-    cb.bhi = w.bhi; cb.blo = w.blo; cb.dww = w.dww; cb.pwb = w.pwb;
+    cb.bhi = f16 ? w.hhi : w.bhi; cb.blo = f16 ? w.hlo : w.blo; cb.dww = w.dww; cb.pwb = w.pwb;
+    cb.unscale = f16 ? w.h_unscale : 1.f;
     cb.cin = chan_pad(kBlazeBlocks[tail_blk].cin);
     cb.cout = chan_pad(kBlazeBlocks[tail_blk].cout);
     cb.ks = cb.cin / 8;
@@ -739,12 +827,14 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
     HP_TRY(tc_make_map4(&tin, in, din, sin_, box));
     HP_TRY(tc_make_map4(&tout, out, dout, sout, box));
   }
-#define CHAIN_CASE(TR_, PS_, NSETS_, NISS_)                                                    \
-  if (cfg.TR == TR_ && cfg.PS == PS_ && cfg.nsets == NSETS_ && cfg.niss == NISS_)                \
-    return launch_chain<TR_, PS_, NSETS_, NISS_>(h, tin, tout, p, cfg.smem, st);
-  CHAIN_CASE(3, 92, 4, 2) CHAIN_CASE(2, 92, 4, 2) CHAIN_CASE(3, 100, 4, 2) CHAIN_CASE(2, 100, 4, 2)
-  CHAIN_CASE(3, 92, 4, 1) CHAIN_CASE(2, 92, 4, 1) CHAIN_CASE(3, 100, 4, 1) CHAIN_CASE(2, 100, 4, 1)
-  CHAIN_CASE(3, 92, 4, 3) CHAIN_CASE(3, 100, 4, 3)
+#define CHAIN_CASE(TR_, PS_, NSETS_, NISS_, F16_)                                                             \
+  if (cfg.TR == TR_ && cfg.PS == PS_ && cfg.nsets == NSETS_ && cfg.niss == NISS_ && (int)f16 == F16_)           \
+    return launch_chain<TR_, PS_, NSETS_, NISS_, F16_>(h, tin, tout, p, cfg.smem, st);
+  CHAIN_CASE(3, 92, 4, 1, 1) CHAIN_CASE(2, 92, 4, 1, 1) CHAIN_CASE(3, 100, 4, 1, 1) CHAIN_CASE(2, 100, 4, 1, 1)
+  CHAIN_CASE(3, 92, 4, 2, 1) CHAIN_CASE(2, 92, 4, 2, 1) CHAIN_CASE(3, 100, 4, 2, 1) CHAIN_CASE(2, 100, 4, 2, 1)
+  CHAIN_CASE(3, 92, 4, 2, 0) CHAIN_CASE(2, 92, 4, 2, 0) CHAIN_CASE(3, 100, 4, 2, 0) CHAIN_CASE(2, 100, 4, 2, 0)
+  CHAIN_CASE(3, 92, 4, 1, 0) CHAIN_CASE(2, 92, 4, 1, 0) CHAIN_CASE(3, 100, 4, 1, 0) CHAIN_CASE(2, 100, 4, 1, 0)
+  CHAIN_CASE(3, 92, 4, 3, 0) CHAIN_CASE(3, 100, 4, 3, 0)
 #undef CHAIN_CASE
   hp_set_error("chain: no kernel for TR %d PS %d nsets %d issuers %d", cfg.TR, cfg.PS, cfg.nsets, cfg.niss);
   return HP_ERR_UNSUPPORTED;

@@ -22,6 +22,8 @@
 //
 // Reference semantics: BlazeBlock = DepthwiseConv2D(3x3, SAME) -> Conv2D(1x1) -> Add(skip / channel-padded skip) -> ReLU
 // (graph called at BlazePoser/blazeFaceDetectorH5.py:272).  Stride-1 blocks only.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -112,8 +114,11 @@ __device__ __forceinline__ void tc_zero_chunk(uint32_t acol) {   // K padding (o
 }
 // Epilogue of one pixel: accumulator row (N16 columns at dcol) + bias + skip -> ReLU -> in place over the centre pixel.
 // All column groups are requested before the single tcgen05.wait::ld (the TMEM load latency is paid once per pixel).
-template <int C4, int NG, int N16>
-__device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, const float* s_pwb, bool active) {
+// F16: the accumulator carries the power-of-two scale of the fp16 weights (multiplied out here) and, when a depthwise output did
+// not fit fp16, inf / NaN in every column: column 0 is tested (guard).
+template <int C4, int NG, int N16, int F16 = 0>
+__device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, const float* s_pwb, bool active, float us = 1.f,
+                                                  uint32_t* guard = nullptr) {
   constexpr int NGRP = (NG + 7) / 8;   // 32-column groups that hold real output channels
   uint32_t v[NGRP][32];
 #pragma unroll
@@ -128,6 +133,7 @@ __device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, co
     }
   }
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (F16 && active && (v[0][0] & 0x7F800000u) == 0x7F800000u) *guard = 1u;
 #pragma unroll
   for (int g = 0; g < NGRP; ++g) {
 #pragma unroll
@@ -135,8 +141,10 @@ __device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, co
       const int j = g * 8 + jj;
       if (j < NG) {
         const float4 bb = ld4(s_pwb + j * 4);
-        float4 o = make_float4(__uint_as_float(v[g][jj * 4 + 0]) + bb.x, __uint_as_float(v[g][jj * 4 + 1]) + bb.y,
-                               __uint_as_float(v[g][jj * 4 + 2]) + bb.z, __uint_as_float(v[g][jj * 4 + 3]) + bb.w);
+        float4 o = F16 ? make_float4(fmaf(__uint_as_float(v[g][jj * 4 + 0]), us, bb.x), fmaf(__uint_as_float(v[g][jj * 4 + 1]), us, bb.y),
+                                     fmaf(__uint_as_float(v[g][jj * 4 + 2]), us, bb.z), fmaf(__uint_as_float(v[g][jj * 4 + 3]), us, bb.w))
+                       : make_float4(__uint_as_float(v[g][jj * 4 + 0]) + bb.x, __uint_as_float(v[g][jj * 4 + 1]) + bb.y,
+                                     __uint_as_float(v[g][jj * 4 + 2]) + bb.z, __uint_as_float(v[g][jj * 4 + 3]) + bb.w);
         if (j < C4) {
           const float4 sk = ld4(cpix + j * 4);
           o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
@@ -393,8 +401,12 @@ struct TcdParams {
   int off_b, off_w, off_pipe, buf_floats;
   long long* trace;
   int trace_tiles;
+  float unscale;                   // UNIT 4 (split-fp16 MMAs): inverse of the power-of-two scale of the weights
+  unsigned int* status;            // sticky status word of the context (HP_STATUS_CHAIN_RANGE)
 };
 
+// UNIT 4: a work unit is 16 channels = one kind::f16 MMA k-step (split fp16 instead of 3xTF32: half the MMAs, half the hand-offs
+// between depthwise sets and issuers per tile, half the B-operand traffic; same scheme as the chain kernel, blocks_chain.cu).
 // NISS issuer warps: one thread can only issue a tcgen05.mma every ~46-55 clk whatever its size (tools/mma_rate.cu), the
 // tensor pipe itself needs 128 * N / 256 clk; the accumulator rows are therefore dealt to NISS issuing threads (t % NISS).
 // PLACE = 1: 4 * NISS helper warps with issuer k at warp W_ISSUE + 4 k + 3, i.e. on SM sub-partition 3, which is idle when at most
@@ -403,9 +415,13 @@ template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS
 __global__ void __launch_bounds__(128 * NSETS + 128 * NESETS + (PLACE ? 128 * NISS : 32 * (NISS + 2)), 1)
 blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, TcdParams p) {
   using G = TcGeom<CINP, COUTP>;
-  constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, KS = G::KS, N16 = G::N16, PS = G::PS;
+  constexpr int C4 = G::C4, NG = G::NG, K8 = G::K8, N16 = G::N16, PS = G::PS;
+  constexpr bool F16 = UNIT == 4;
+  constexpr int KS = F16 ? (CINP + 15) / 16 : G::KS;              // MMA k-steps per tile
+  constexpr int BFLOATS = F16 ? KS * 16 * N16 / 2 : K8 * N16;     // floats of one weight part (hi or lo)
   constexpr uint32_t colA0 = 2 * TR * N16;                        // TMEM: D[0], D[1] (TR * N16 columns each), then the A ring
   static_assert(colA0 + 2 * TR * 16 <= 512, "TMEM budget");
+  static_assert(BFLOATS <= K8 * N16, "weight area");
 
   extern __shared__ __align__(1024) float smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -435,7 +451,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
                                    : ((warp >= W_ISSUE && warp < W_ISSUE + NISS) ? warp - W_ISSUE : -1);
   const int NSTG = p.nstg, NBUF = p.nbuf;
 
-  for (int i = tid * 4; i < K8 * N16; i += nthr * 4) {
+  for (int i = tid * 4; i < BFLOATS; i += nthr * 4) {
     st4(s_bhi + i, ld4(p.bhi + i));
     st4(s_blo + i, ld4(p.blo + i));
   }
@@ -453,7 +469,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       mbar_init(&bar_epi[b], 128 * NESETS);
     }
     for (int s = 0; s < NSTG; ++s) {
-      mbar_init(&bar_afull[s], UNIT == 2 ? 128 : 256);   // one set per k-step (UNIT 2) or one set per 4-channel half
+      mbar_init(&bar_afull[s], UNIT >= 2 ? 128 : 256);   // one set per k-step (UNIT 2, 4) or one set per 4-channel half
       mbar_init(&bar_aempty[s], NISS);                   // one tcgen05.commit per issuer
     }
     for (int d = 0; d < 2; ++d) {
@@ -506,7 +522,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       // host checks that consecutive units of a set are at most NSTG k-steps apart).  The TMEM stores of a unit are waited for, and the unit published, only after
       // the next unit has been computed: tcgen05.st latency and the a_empty round trip hide behind the LDS / FFMA work.
       const int set = warp >> 2;
-      constexpr int UPT = (UNIT == 2) ? KS : 2 * KS;                       // units per tile
+      constexpr int UPT = (UNIT >= 2) ? KS : 2 * KS;                       // units per tile
       const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const uint32_t n_units = (uint32_t)my_tiles * UPT;
       uint64_t* pending = nullptr;
@@ -516,8 +532,8 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       for (uint32_t g = set; g < n_units; g += NSETS) {
         const int i = (int)(g / UPT);
         const int u = (int)(g - (uint32_t)i * UPT);
-        const int ks = (UNIT == 2) ? u : (u >> 1), half = (UNIT == 2) ? 0 : (u & 1);
-        const int c4 = (UNIT == 2) ? 2 * u : u;
+        const int ks = (UNIT >= 2) ? u : (u >> 1), half = (UNIT >= 2) ? 0 : (u & 1);
+        const int c4 = F16 ? 4 * u : (UNIT == 2) ? 2 * u : u;
         const uint32_t use = (uint32_t)i * KS + ks;
         const uint32_t s = use % NSTG;
         if (i != cur_i) {                                                    // first unit of this set in tile i
@@ -528,7 +544,30 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
           if (tid == 0) stamp(i, 1);
         }
         float4 acc[TR], acc1[TR];
-        if (warp_active && c4 < C4)
+        uint32_t hv[F16 ? TR : 1][16];                                       // F16: the 16 columns of every stage row
+        if (F16) {
+          if (warp_active) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (c4 + q < C4) {
+                tc_dw_compute<CINP, TR, PS>(buf + my_off + (c4 + q) * 4, s_dww + (c4 + q) * 4, s_dwb + (c4 + q) * 4, row_pitch, mask_l, mask_r, acc);
+#pragma unroll
+                for (int t = 0; t < TR; ++t) {
+                  const __half2 h0 = __floats2half2_rn(acc[t].x, acc[t].y), h1 = __floats2half2_rn(acc[t].z, acc[t].w);
+                  const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+                  const __half2 l0 = __floats2half2_rn(acc[t].x - b0.x, acc[t].y - b0.y), l1 = __floats2half2_rn(acc[t].z - b1.x, acc[t].w - b1.y);
+                  hv[F16 ? t : 0][2 * q] = *reinterpret_cast<const uint32_t*>(&h0);
+                  hv[F16 ? t : 0][2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                  hv[F16 ? t : 0][8 + 2 * q] = *reinterpret_cast<const uint32_t*>(&l0);
+                  hv[F16 ? t : 0][8 + 2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+                }
+              } else {                                                       // K padding
+#pragma unroll
+                for (int t = 0; t < TR; ++t) hv[F16 ? t : 0][2 * q] = hv[F16 ? t : 0][2 * q + 1] = hv[F16 ? t : 0][8 + 2 * q] = hv[F16 ? t : 0][8 + 2 * q + 1] = 0u;
+              }
+            }
+          }
+        } else if (warp_active && c4 < C4)
           tc_dw_compute<CINP, TR, PS>(buf + my_off + c4 * 4, s_dww + c4 * 4, s_dwb + c4 * 4, row_pitch, mask_l, mask_r, acc);
         if (UNIT == 2) {
           if (warp_active && c4 + 1 < C4) {
@@ -551,7 +590,10 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
         }
         if (warp_active) {
           const uint32_t acol = tlane + colA0 + s * (TR * 16) + half * 4;
-          if (UNIT == 2) tc_dw_store2<TR>(acc, acc1, acol);
+          if (F16) {
+#pragma unroll
+            for (int t = 0; t < TR; ++t) tmem_st16(acol + t * 16, hv[F16 ? t : 0]);
+          } else if (UNIT == 2) tc_dw_store2<TR>(acc, acc1, acol);
           else if (c4 < C4) tc_dw_store<TR>(acc, acol);
           else tc_zero_chunk<TR>(acol);
         }
@@ -572,6 +614,7 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       // =============================================================== epilogue warps
       const int centre0 = my_off + row_pitch + PS;
       const int eset = (warp - W_EPI) >> 2;
+      uint32_t guard = 0u;
       int i = 0, b = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
         const int d = i & 1;
@@ -584,7 +627,8 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
 #pragma unroll
           for (int t = 0; t < TR; ++t)
             if (t % NESETS == eset)
-              tc_epilogue_pixel<C4, NG, N16>(buf + centre0 + t * row_pitch, tlane + d * (TR * N16) + t * N16, s_pwb, active);
+              tc_epilogue_pixel<C4, NG, N16, F16 ? 1 : 0>(buf + centre0 + t * row_pitch, tlane + d * (TR * N16) + t * N16, s_pwb, active, p.unscale,
+                                                          &guard);
           tc_fence_before();
           fence_async_smem();
         }
@@ -593,12 +637,13 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
         if (tid == W_EPI * 32) stamp(i, 4);
         if (++b == NBUF) b = 0;
       }
+      if (F16 && guard && p.status) atomicOr(p.status, 4u);
     }
   } else if (lane_id == 0) {
     if (issuer_of_warp >= 0) {
       // =============================================================== MMA issuers (accumulator rows t % NISS == issuer)
       const int issuer = issuer_of_warp;
-      const uint32_t idesc = tc_idesc_tf32(N16);
+      const uint32_t idesc = F16 ? ((1u << 4) | ((uint32_t)(N16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : tc_idesc_tf32(N16);
       const uint64_t desc_fixed = tc_bdesc_fixed(N16);
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
       uint32_t use = 0;
@@ -625,9 +670,15 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
             if (t % NISS != issuer) continue;
             const uint32_t dc = tmem_base + d * (TR * N16) + t * N16;
             const uint32_t a = tmem_base + colA0 + (s * TR + t) * 16;
-            mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
-            mma_tf32_ts(dc, a, dlo, idesc, 1u);
-            mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+            if (F16) {
+              mma_f16_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+              mma_f16_ts(dc, a, dlo, idesc, 1u);
+              mma_f16_ts(dc, a + 8, dhi, idesc, 1u);
+            } else {
+              mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
+              mma_tf32_ts(dc, a, dlo, idesc, 1u);
+              mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+            }
           }
           tc_commit(&bar_aempty[s]);
         }
@@ -1303,7 +1354,10 @@ template <int CINP, int COUTP, int TR, int NSETS, int NESETS, int UNIT, int NISS
 int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, const BlockWeights& w, const TcCfg& tc, cudaStream_t st) {
   using G = TcGeom<CINP, COUTP>;
   TcdParams p;
-  p.dww = w.dww; p.dwb = w.dwb; p.pwb = w.pwb; p.bhi = w.bhi; p.blo = w.blo;
+  p.dww = w.dww; p.dwb = w.dwb; p.pwb = w.pwb;
+  p.bhi = UNIT == 4 ? w.hhi : w.bhi; p.blo = UNIT == 4 ? w.hlo : w.blo;
+  p.unscale = UNIT == 4 ? w.h_unscale : 1.f;
+  p.status = (unsigned int*)h->status.p;
   p.W = W; p.H = H; p.BH = tc.BH; p.IWB = tc.IWB; p.row_pitch = tc.IWB * G::PS; p.img_pitch = (tc.BH + 2) * p.row_pitch;
   p.NI = tc.ni; p.B = B;
   p.bands_per_img = ceil_div(H, tc.BH);
@@ -1320,7 +1374,7 @@ int launch_deep(hp_ctx* h, const float* in, float* out, int B, int H, int W, con
   HP_REQUIRE(p.lanes >= 1 && p.lanes <= 128 && tc.BH % TR == 0 && (tc.IWB * G::PS) % 32 == 0 && tc.IWB >= W && tc.IWB <= 256 &&
                  tc.BH + 2 <= 256 && tc.ni >= 1 && tc.ni <= 256 && (tc.ni == 1 || p.bands_per_img == 1) && tc.nbuf >= 2 &&
                  tc.nbuf <= TCD_MAXB && tc.NSTG >= 2 && tc.NSTG <= TC_MAX_STG && 2 * TR * G::N16 + tc.NSTG * TR * 16 <= 512 &&
-                 (tc.IWB > W || W % 8 == 0) && tc.nsets <= tc.NSTG * (tc.unit == 2 ? 1 : 2),
+                 (tc.IWB > W || W % 8 == 0) && tc.nsets <= tc.NSTG * (tc.unit >= 2 ? 1 : 2),
              HP_ERR_INVALID, "tc deep block <%d,%d>: bad geometry TR %d BH %d IWB %d W %d NI %d nbuf %d nstg %d", CINP, COUTP, TR, tc.BH,
              tc.IWB, W, tc.ni, tc.nbuf, tc.NSTG);
   CUtensorMap tin, tout;
@@ -1450,6 +1504,9 @@ int launch_tc_cfg(hp_ctx* h, const float* in, float* out, int B, int H, int W, c
     if (tc.TR == TR_ && tc.nsets == NSETS_ && tc.npipe == NESETS_ && tc.unit == UNIT_ && tc.niss == NISS_ && tc.place == PLACE_) \
       return launch_deep<CINP, COUTP, TR_, NSETS_, NESETS_, UNIT_, NISS_, PLACE_>(h, in, out, B, H, W, w, tc, st);
   if (tc.nbuf > 0) {   // warp-specialised kernel: npipe carries the number of epilogue warp sets
+    // (the split-fp16 form of this kernel, UNIT 4, is not instantiated: measured at 96 x 96, batch 4096, blocks 0-5 took 2.30 ms
+    // instead of 1.69 ms -- 16-channel units leave one of the two depthwise sets idle a third of the time at K = 24 and these
+    // blocks are bound by the depthwise shared-memory traffic, not by the hand-offs; profiles/r02/chain_f16_96b.log)
     TCD_CASE(4, 2, 2, 1, 1, 0) TCD_CASE(4, 3, 2, 1, 1, 0) TCD_CASE(2, 2, 2, 1, 1, 0) TCD_CASE(2, 3, 2, 1, 1, 0) TCD_CASE(4, 2, 1, 1, 1, 0)
     TCD_CASE(2, 3, 1, 1, 1, 0) TCD_CASE(2, 2, 2, 2, 1, 0) TCD_CASE(2, 3, 2, 2, 1, 0) TCD_CASE(2, 4, 1, 2, 1, 0) TCD_CASE(4, 2, 2, 2, 1, 0)
     TCD_CASE(4, 3, 2, 2, 1, 0) TCD_CASE(4, 2, 2, 2, 2, 0) TCD_CASE(4, 2, 2, 2, 4, 0) TCD_CASE(4, 3, 2, 2, 2, 0) TCD_CASE(2, 3, 2, 2, 2, 0)
@@ -1505,6 +1562,38 @@ void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, floa
 }
 
 int hp_tc_weight_floats(int cinp, int coutp) { return ((cinp + 7) / 8 * 8) * ((coutp + 15) / 16 * 16); }
+
+int hp_tc_weight_floats_f16(int cinp, int coutp) { return ((cinp + 15) / 16 * 16) * ((coutp + 15) / 16 * 16) / 2; }
+
+float hp_tc_split_weights_f16(const float* pww, int cinp, int coutp, float* hhi_f, float* hlo_f) {
+  const int K16 = (cinp + 15) / 16 * 16, N16 = (coutp + 15) / 16 * 16;
+  uint16_t* hhi = reinterpret_cast<uint16_t*>(hhi_f);
+  uint16_t* hlo = reinterpret_cast<uint16_t*>(hlo_f);
+  float wmax = 0.f;
+  for (int i = 0; i < cinp * coutp; ++i) {
+    const float a = fabsf(pww[i]);
+    if (a > wmax && a < INFINITY) wmax = a;
+  }
+  int shift = 0;
+  if (wmax > 0.f) {
+    int e;
+    frexpf(wmax, &e);                      // wmax = m * 2^e, m in [0.5, 1)
+    shift = 13 - e;                        // wmax * 2^shift in [2^12, 2^13)
+    if (shift > 100) shift = 100;
+    if (shift < -100) shift = -100;
+  }
+  const float scale = ldexpf(1.f, shift);
+  for (int k = 0; k < K16; ++k)
+    for (int n = 0; n < N16; ++n) {
+      const float wv = (k < cinp && n < coutp) ? pww[k * coutp + n] * scale : 0.f;
+      const uint16_t hi = hp_f32_to_f16_rn(wv);
+      const uint16_t lo = hp_f32_to_f16_rn(wv - hp_f16_to_f32(hi));
+      const size_t idx = ((size_t)(k / 8) * N16 + n) * 8 + (k % 8);
+      hhi[idx] = hi;
+      hlo[idx] = lo;
+    }
+  return ldexpf(1.f, -shift);
+}
 
 // Row width (pixels) of a halo buffer of the warp-specialised kernel: no halo columns when W is a multiple of 8,
 // otherwise at least one zero column on the right and rows of a multiple of 128 bytes.

@@ -80,6 +80,8 @@ static inline int chan_pad(int c) { return (c + 3) & ~3; }
 struct BlockWeights {
   const float *dww, *dwb, *pww, *pwb;  // [9][CINP], [CINP], [CINP][COUTP], [COUTP] (zero padded)
   const float *bhi, *blo;              // pointwise weights split into TF32 hi / lo parts, [K8/4][N16][4] (blocks_tc.cu)
+  const float *hhi, *hlo;              // the same weights times 2^h_shift split into fp16 hi / lo parts, [K16/8][N16][8 halves] (chain kernel)
+  float h_unscale;                     // 2^-h_shift: applied to the accumulator in the epilogue
   const float* h_dw;                   // HOST copy of [9][CINP] dww + [CINP] dwb: passed as kernel-parameter constants
 };
 
@@ -212,6 +214,13 @@ int hp_launch_block_tc_s2(hp_ctx* h, int blk, const float* in, float* out, int B
                           const BlockWeights& w, const TcCfg& tc, cudaStream_t st);
 void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, float* blo);
 int hp_tc_weight_floats(int cinp, int coutp);
+// fp16 split of the pointwise weights for the chain kernel (kind::f16 MMAs, K = 16 per instruction): w * 2^shift = hi + lo with
+// the power of two chosen so that the largest weight lands in [2^12, 2^13) -- the lo parts then stay normal fp16 numbers;
+// returns 2^-shift.  Storage: K16 * N16 halves per part (two per float slot).
+int hp_tc_weight_floats_f16(int cinp, int coutp);
+float hp_tc_split_weights_f16(const float* pww, int cinp, int coutp, float* hhi, float* hlo);
+unsigned short hp_f32_to_f16_rn(float f);
+float hp_f16_to_f32(unsigned short h);
 bool hp_tc_choose(int blk, int H, int W, TcCfg* tc);
 int hp_launch_block_tc(hp_ctx* h, int blk, const float* in, float* out, int B, int H, int W, const BlockWeights& w,
                        const TcCfg& tc, cudaStream_t st);

@@ -260,16 +260,30 @@ class UnifiedModel:
         xt = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(ctx.torch_device)
         if xt.dim() != 4 or xt.shape[-1] != 3:
             raise ValueError(f"expected input (B,H,W,3), got {tuple(xt.shape)}")
-        o = self.forward_device(xt)
+        # The tensor-core stem and the fused chain kernels multiply split-fp16 operands: an input (|x| > 65504, inf, NaN) or a
+        # depthwise output of blocks 6-15 outside the fp16 range raises a status flag instead of a silent inf; the batch is then
+        # redone with the fp32 stem / the 3xTF32 chain kernels, which have no such limit.
+        L = _lib.lib()
         flags = C.c_uint(0)
-        _lib.check(_lib.lib().hp_backbone_status(ctx.handle, C.byref(flags), ctx.stream_ptr()))
-        if flags.value & 1:
-            # an input outside the fp16 range of the tensor-core stem (|x| > 65504, inf, NaN): redo the batch with the fp32 stem
-            _lib.check(_lib.lib().hp_debug_set_stem_tc(ctx.handle, -1, 0, 0, 0))
-            try:
+        stem_fp32 = chain_tf32 = False
+        try:
+            for _ in range(3):
                 o = self.forward_device(xt)
-            finally:
-                _lib.check(_lib.lib().hp_debug_set_stem_tc(ctx.handle, 0, 0, 0, 0))
+                _lib.check(L.hp_backbone_status(ctx.handle, C.byref(flags), ctx.stream_ptr()))
+                redo = False
+                if (flags.value & 1) and not stem_fp32:
+                    stem_fp32 = redo = True
+                    _lib.check(L.hp_debug_set_stem_tc(ctx.handle, -1, 0, 0, 0))
+                if (flags.value & 4) and not chain_tf32:
+                    chain_tf32 = redo = True
+                    _lib.check(L.hp_debug_set_chain(ctx.handle, 2 + 4, 0, 0))
+                if not redo:
+                    break
+        finally:
+            if stem_fp32:
+                _lib.check(L.hp_debug_set_stem_tc(ctx.handle, 0, 0, 0, 0))
+            if chain_tf32:
+                _lib.check(L.hp_debug_set_chain(ctx.handle, 2, 0, 0))
         B = xt.shape[0]
         A16 = o["feat16"].shape[1] * o["feat16"].shape[2] * 2
         cls, loc = o["cls"].cpu().numpy(), o["loc"].cpu().numpy()

@@ -88,6 +88,9 @@ int hp_backbone_forward(hp_handle h, const float* x, int B, int H, int W,
  * `stream`, returns the word and clears it; hp_debug_set_stem_tc(h, -1, 0, 0, 0) selects the fp32 CUDA-core stem, which has
  * no such limit (the Python layer re-runs a flagged batch that way).  The uint8 entry points cannot trigger it. */
 #define HP_STATUS_STEM_RANGE 1u
+#define HP_STATUS_CHAIN_RANGE 4u    /* a depthwise output of blocks 6-15 does not fit fp16 (|a| >= 65520): the fused chain kernels multiply
+                                     * split-fp16 operands; hp_debug_set_chain(h, 2 + 4, 0, 0) selects their 3xTF32 form, which has no such
+                                     * limit (the Python layer re-runs a flagged batch that way) */
 #define HP_STATUS_P2P_TIMEOUT 2u    /* a rank of the peer-memory gradient exchange waited ~2 s for a peer (see hp_p2p_open) */
 int hp_backbone_status(hp_handle h, unsigned int* flags_host, void* stream);
 
@@ -294,7 +297,8 @@ int hp_debug_tile_report(hp_handle h, int* report16x8);
 /* tensor-core stem kernel: band height, input buffers, output stages, gather warp sets (0 = automatic; BH = -1 keeps the
  * stem on the CUDA-core kernel) */
 int hp_debug_set_stem_tc(hp_handle h, int BH, int nbuf, int nout, int nsets);
-/* cross-block fusion (blocks 6-10 and 12-15 as one persistent kernel each): mode 1 = on (default), 0 = one kernel per block;
+/* cross-block fusion (blocks 6-10 and 12-15 as one persistent kernel each): mode 0 = one kernel per block, 1 = chains, 2 = chains
+ * with the stride-2 block 11 riding on the first one (default); + 4 = 3xTF32 products instead of split fp16;
  * nsets / niss override the worker warp sets / MMA issuer threads of the chain kernel (0 = default) */
 int hp_debug_set_chain(hp_handle h, int mode, int nsets, int niss);
 /* watchdog record of the chain kernels since the last call: out8_host[0] != 0 -> a barrier wait timed out ({1, barrier id, parity,

@@ -222,11 +222,15 @@ def test_tensor_core_block_geometries(geom, size, batch):
     assert ran >= 1 or size == 128, f"geometry {geom} ran on no block"
 
 
-@pytest.mark.parametrize("cfg", [(0, 0, 0, 0), (0, 2, 2, 2 + 32), (4, 3, 2, 3 + 32), (0, 4, 3, 4 + 32), (0, 0, 0, 3)])   # BH, nbuf, nout, nsets (+ 16 x issuers)
+# BH, nbuf, nout, gather sets + 16 x issuers (+ 128 / 512: two / three epilogue sets; + 256: the first-generation kernel, where + 128
+# places the issuers on SM sub-partition 3)
+@pytest.mark.parametrize("cfg", [(0, 0, 0, 0), (0, 2, 2, 2 + 32), (4, 3, 2, 3 + 32 + 128), (0, 4, 3, 4 + 32), (0, 0, 0, 3 + 48 + 512),
+                                 (0, 0, 0, 256), (0, 2, 2, 2 + 32 + 128 + 256), (4, 3, 2, 3 + 32 + 256)])
 @pytest.mark.parametrize("size,batch", [(96, 37), (88, 5), (128, 3), (64, 2), (120, 2)])
 def test_tensor_core_stem(cfg, size, batch):
-    """The implicit-GEMM (tcgen05, 3xTF32) stem reproduces the naive CUDA stem for every pipeline geometry
-    (band height, input buffers, output stages, gather warp sets); 88 and 120 give partial last bands."""
+    """The implicit-GEMM (tcgen05, split fp16) stem reproduces the naive CUDA stem for every pipeline geometry of both
+    generations (band height, input buffers, output stages, gather / epilogue warp sets, issuers); 88 and 120 give partial
+    last bands and partial M-tiles."""
     from hpose_b200 import _lib
     from hpose_b200.unified import pack_backbone, random_backbone
     ctx = _ctx()
@@ -348,5 +352,42 @@ def test_stem_input_range_is_guarded():
             w[f"{name}/{k}"] = v
     with torch.no_grad():
         ref = [t.numpy() for t in KerasGraph(m.config(), to_torch(w, torch.float64))(torch.tensor(bad, dtype=torch.float64))]
+    for got, want in zip(out, ref):
+        assert np.isfinite(got).all() and rel_err(got, want) < 1e-4
+
+
+
+def test_chain_fp16_range_is_guarded():
+    """The fused chain kernels (blocks 6-15) multiply split-fp16 operands.  A depthwise output beyond the fp16 range (here: the
+    depthwise kernel of block 8 scaled by 3e6, everything finite in fp32) sets HP_STATUS_CHAIN_RANGE instead of clamping an inf
+    to zero in the ReLU, and the host model re-runs the batch with the 3xTF32 chain kernels: outputs match the float64 oracle."""
+    from hpose_b200 import _lib, keras_spec as K, train_88
+    from hpose_b200.attention_model import se_transformer_regr_head
+    from hpose_b200.unified import UnifiedModel, random_backbone
+    ctx = _ctx()
+    K.reset_names(); K.set_seed(4)
+    h16 = train_88.create_model()
+    K.reset_names()
+    bbw = random_backbone(seed=4, bias_scale=0.1)
+    x = np.random.default_rng(2).uniform(-1, 1, (2, 96, 96, 3)).astype(np.float32)
+    flags = C.c_uint(7)
+    status = lambda: (_lib.check(_lib.lib().hp_backbone_status(ctx.handle, C.byref(flags), ctx.stream_ptr())), flags.value)[1]
+    m = UnifiedModel(bbw, h16, se_transformer_regr_head(input_channels=96))
+    m.forward_device(torch.from_numpy(x).cuda())
+    assert status() == 0
+    big = dict(bbw)
+    big["depthwise_conv2d_8/depthwise_kernel"] = bbw["depthwise_conv2d_8/depthwise_kernel"] * np.float32(3e6)
+    big["conv2d_9/kernel"] = bbw["conv2d_9/kernel"] * np.float32(1e-6)          # the pointwise conv behind it brings the values back
+    mb = UnifiedModel(big, h16, se_transformer_regr_head(input_channels=96))
+    mb.forward_device(torch.from_numpy(x).cuda())
+    assert status() == 4 and status() == 0                                      # reported once, then cleared
+    out = mb(x)
+    assert status() == 0
+    w = dict(big)
+    for name, head in (("model", mb.head16), ("model_10", mb.head8)):
+        for k, v in head.get_weights_dict().items():
+            w[f"{name}/{k}"] = v
+    with torch.no_grad():
+        ref = [t.numpy() for t in KerasGraph(mb.config(), to_torch(w, torch.float64))(torch.tensor(x, dtype=torch.float64))]
     for got, want in zip(out, ref):
         assert np.isfinite(got).all() and rel_err(got, want) < 1e-4

@@ -78,7 +78,7 @@ def timing(ctx, S, B, iters=5):
     L = _lib.lib()
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand((B, S, S, 3), generator=g, device="cuda") * 2 - 1
-    for mode, nsets, niss in ((0, 0, 0), (1, 0, 0), (2, 0, 0), (2, 4, 2)):
+    for mode, nsets, niss in ((0, 0, 0), (1, 0, 0), (2, 0, 0), (2, 4, 2), (6, 0, 0), (6, 4, 2)):   # + 4: 3xTF32 instead of split fp16
         _lib.check(L.hp_debug_set_chain(ctx.handle, mode, nsets, niss))
         per = np.zeros(18, np.float32)
         for _ in range(2):
