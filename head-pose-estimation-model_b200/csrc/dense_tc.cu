@@ -498,13 +498,17 @@ static int dense_tc_launch(hp_ctx* h, const float* x, int M, int K, int ldx, con
   // sets are 20-25 % faster than 1, more than 2 change nothing
   int ns = (!tail && p.N16 <= 32) ? 3 : 2, ne = (!tail && p.N16 <= 32) ? 1 : 2;
   // measured (profiles/r01/dense_issuers_sweep.log): 2 issuers 110 -> 90 us on the 88 -> 34 detector head, 37.5 -> 32.5 us on 96 -> 64;
-  // the fused narrow layer prefers 4 accumulator buffers and one issuer (115 vs 127 us)
-  int want_iss = tail ? 1 : 2;
+  // the fused narrow layer keeps one issuer and 4 accumulator buffers: alone it runs faster with two (profiles/r02/dense_nd_sweep.log:
+  // 88 -> 64 -> 3 113 -> 89.5 us), inside a step slower (launch list of a bench step: 116.8 -> 126.1 us)
+  int want_iss = tail ? 1 : 2, nd_env = 0;
   {
-    static const char* env = getenv("HP_DENSE_TC_SETS");
+    static const char* env = getenv("HP_DENSE_TC_SETS");   // <gather sets><epilogue sets>[issuers[accumulators]]
     if (env && env[0] >= '1' && env[0] <= '3' && env[1] >= '1' && env[1] <= '2') {
       ns = env[0] - '0'; ne = env[1] - '0';
-      if (env[2] == '1' || env[2] == '2') want_iss = env[2] - '0';
+      if (env[2] == '1' || env[2] == '2') {
+        want_iss = env[2] - '0';
+        if (env[3] == '2' || env[3] == '4') nd_env = env[3] - '0';
+      }
     }
   }
   // Two issuing threads: one thread issues a tcgen05.mma only every ~110 clk next to the worker warps and nothing else is
@@ -512,19 +516,24 @@ static int dense_tc_launch(hp_ctx* h, const float* x, int M, int K, int ldx, con
   // an mbarrier waiter may be one phase ahead at most, so consecutive units of a gather set within one ring must be at most
   // nstg ring slots apart: checked by walking the round-robin schedule.
   if (want_iss == 2) {
-    const int nd2 = 2;
-    int stg = (512 - nd2 * p.N16) / (2 * 16 * p.ku);
-    if (stg > DT_MAXSTG) stg = DT_MAXSTG;
-    bool safe = stg >= 2;
-    for (int x = 0; x < ns && safe; ++x) {
-      long long last[2] = {-1, -1};
-      for (long long g = x; g < 16ll * p.upt; g += ns) {
-        const long long i = g / p.upt, u = g - i * p.upt, r = i & 1, q = (i >> 1) * p.upt + u;
-        if (last[r] >= 0 && q - last[r] > stg) safe = false;
-        last[r] = q;
+    // each issuer's tiles (i, i + 2, ...) use the accumulators i % nd: with nd = 2 an issuer owned ONE accumulator and its MMAs
+    // waited for the epilogue of its previous tile (tools/dense_trace.py: 5.5 K clk of MMAs + 1.2 K of hand-off per issuer and
+    // pair of tiles); 4 accumulators give every issuer two when they fit next to two rings of >= 2 stages
+    for (int nd2 = 4; nd2 >= 2 && p.niss != 2; nd2 -= 2) {
+      if (nd_env > 0 && nd2 != nd_env) continue;
+      int stg = (512 - nd2 * p.N16) / (2 * 16 * p.ku);
+      if (stg > DT_MAXSTG) stg = DT_MAXSTG;
+      bool safe = stg >= 2;
+      for (int x = 0; x < ns && safe; ++x) {
+        long long last[2] = {-1, -1};
+        for (long long g = x; g < 16ll * p.upt; g += ns) {
+          const long long i = g / p.upt, u = g - i * p.upt, r = i & 1, q = (i >> 1) * p.upt + u;
+          if (last[r] >= 0 && q - last[r] > stg) safe = false;
+          last[r] = q;
+        }
       }
+      if (safe && ns <= stg * 2) { p.niss = 2; p.nstg = stg; p.nd = nd2; }
     }
-    if (safe) { p.niss = 2; p.nstg = stg; p.nd = nd2; }
   }
   HP_REQUIRE(p.nd * p.N16 + p.niss * p.nstg * 16 * p.ku <= 512 && p.upt >= 3 && p.KPAD <= 256 && ns <= p.nstg * (p.niss == 2 ? 2 : 1),
              HP_ERR_UNSUPPORTED, "dense tc: layer %dx%d too large", K, N);

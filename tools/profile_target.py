@@ -22,6 +22,8 @@ _lib.check(lib.hp_backbone_load_weights(ctx.handle, flat.ctypes.data, flat.size,
 for item in filter(None, os.environ.get("TC_GEOM", "").split(";")):
     blk, vals = item.split(":")
     _lib.check(lib.hp_debug_set_tc(ctx.handle, int(blk), *[int(v) for v in vals.split(",")]))
+if os.environ.get("STEM_CFG"):   # tensor-core stem geometry: "BH,nbuf,nout,sets" as in hp_debug_set_stem_tc
+    _lib.check(lib.hp_debug_set_stem_tc(ctx.handle, *[int(v) for v in os.environ["STEM_CFG"].split(",")]))
 x = torch.rand((B, size, size, 3), device="cuda") * 2 - 1
 A = lib.hp_num_anchors(size, size)
 cls = torch.empty((B, A), device="cuda")
