@@ -360,27 +360,37 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
       const uint64_t desc_fixed = tc_bdesc_fixed(N16);
       const uint32_t bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
       uint32_t use = 0;                                              // index of the unit within this issuer's ring
+      // every instruction of this loop is on the critical path (a lone warp retires a dependent instruction every ~5 clk and
+      // shares its sub-partition with four worker warps: 166 clk per MMA measured, tools/dense_trace.py): descriptors and TMEM
+      // addresses advance by additions, the waits are bare try_wait loops, the trace test is hoisted
+      const bool traced = p.trace != nullptr && blockIdx.x == 0;
+      const uint64_t dhi0 = desc_fixed | (uint64_t)((bhi_addr >> 4) & 0x3FFF), dlo0 = desc_fixed | (uint64_t)((blo_addr >> 4) & 0x3FFF);
+      const uint32_t kstep_desc = (2u * (uint32_t)N16 * 16u) >> 4;  // one k-step of W in descriptor units; no carry out of the address field
+      const uint32_t stage_cols = 16u * (uint32_t)p.ku;
+      const uint32_t a_ring = tmem_base + colA0 + (uint32_t)(ring * NSTG) * stage_cols;
+      const int KU = p.ku, UPT = p.upt;
       for (int i = ring; i < my_tiles; i += p.niss) {
         const int d = i % ND;
         if (i >= ND) {
-          mbar_wait(&bar_dempty[d], ((i / ND) - 1) & 1);
+          mbar_wait_lean(&bar_dempty[d], ((i / ND) - 1) & 1);
           tc_fence_after();
         }
-        if (i > 0) stamp(i, 11);
+        if (traced && i > 0) stamp(i, 11);
+        const uint32_t dc = tmem_base + d * N16;
+        uint64_t dhi = dhi0, dlo = dlo0;
+        int ks = 0;
 #pragma unroll 1
-        for (int u = 0; u < p.upt; ++u, ++use) {
+        for (int u = 0; u < UPT; ++u, ++use) {
           const uint32_t s = use % NSTG;
           mbar_wait_lean(&bar_afull[ring * DT_MAXSTG + s], (use / NSTG) & 1);
           tc_fence_after();
-          if (u == 0) stamp(i, 10);
-          if (u == p.upt - 1) stamp(i, 9);
-          const uint32_t dc = tmem_base + d * N16;
-          for (int kk = 0; kk < p.ku && u * p.ku + kk < KS; ++kk) {
-            const int ks = u * p.ku + kk;
-            const uint32_t koff = (uint32_t)ks * 2u * N16 * 16u;
-            const uint64_t dhi = desc_fixed | (uint64_t)(((bhi_addr + koff) >> 4) & 0x3FFF);
-            const uint64_t dlo = desc_fixed | (uint64_t)(((blo_addr + koff) >> 4) & 0x3FFF);
-            const uint32_t a = tmem_base + colA0 + (ring * NSTG + s) * (16 * p.ku) + kk * 16;
+          if (traced) {
+            if (u == 0) stamp(i, 10);
+            if (u == UPT - 1) stamp(i, 9);
+          }
+          uint32_t a = a_ring + s * stage_cols;
+#pragma unroll 1
+          for (int kk = 0; kk < KU && ks < KS; ++kk, ++ks, a += 16, dhi += kstep_desc, dlo += kstep_desc) {
             mma_tf32_ts(dc, a, dhi, idesc, ks > 0 ? 1u : 0u);
             mma_tf32_ts(dc, a, dlo, idesc, 1u);
             mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
@@ -388,7 +398,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tm_in, DenseTcParams p) {
           tc_commit(&bar_aempty[ring * DT_MAXSTG + s]);
         }
         tc_commit(&bar_dfull[d]);
-        stamp(i, 7);
+        if (traced) stamp(i, 7);
       }
     } else if (warp == W_LOAD) {
       // =============================================================== TMA loader

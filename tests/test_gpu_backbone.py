@@ -226,7 +226,7 @@ def test_tensor_core_block_geometries(geom, size, batch):
 # places the issuers on SM sub-partition 3)
 @pytest.mark.parametrize("cfg", [(0, 0, 0, 0), (0, 2, 2, 2 + 32), (4, 3, 2, 3 + 32 + 128), (0, 4, 3, 4 + 32), (0, 0, 0, 3 + 48 + 512),
                                  (0, 0, 0, 256), (0, 2, 2, 2 + 32 + 128 + 256), (4, 3, 2, 3 + 32 + 256)])
-@pytest.mark.parametrize("size,batch", [(96, 37), (88, 5), (128, 3), (64, 2), (120, 2)])
+@pytest.mark.parametrize("size,batch", [(96, 37), (88, 5), (128, 3), (64, 2), (120, 2), (100, 2), (104, 2), (160, 1)])
 def test_tensor_core_stem(cfg, size, batch):
     """The implicit-GEMM (tcgen05, split fp16) stem reproduces the naive CUDA stem for every pipeline geometry of both
     generations (band height, input buffers, output stages, gather / epilogue warp sets, issuers); 88 and 120 give partial
