@@ -7,16 +7,20 @@
 // Reference semantics per block (graph called at BlazePoser/blazeFaceDetectorH5.py:272):
 //   out = ReLU(Conv1x1(DepthwiseConv3x3_SAME(x) + b_dw) + b_pw + channel_pad(x)).
 //
-// Tile layout in shared memory: [NI][H+1][W+1][PS floats] -- one zero row BELOW every image and one zero pixel at the
-// end of every row (TMA zero-fills them: the box is H+1 rows x W+1 pixels from (0, 0); a TMA store must not start at a
-// negative coordinate -- measured: illegal instruction -- so the padding sits on the high side), and a zero row + pixel in
-// front of the first image.  Every 3x3 tap of every pixel is then a plain address, no masks: the left neighbour of x = 0 is
-// the pad pixel of the row above, row -1 is the zero row of the image before (or the lead row), row H the image's own.  PS = odd number of 16-byte chunks >= the widest
-// block of the chain (bank-conflict-free for lanes that own neighbouring columns); the output of a block overwrites its
-// input pixel (C_out >= C_in).
+// Tile layout in shared memory: [NI][H+1][W][PS floats] -- one zero row BELOW every image (TMA zero-fills it: the box is
+// H+1 rows from row 0; a TMA store must not start at a negative coordinate -- measured: illegal instruction -- so the padding
+// sits on the high side) and a zero row + pixel in front of the first image.  Every vertical tap of every pixel is then a
+// plain address: row -1 is the zero row of the image before (or the lead row), row H the image's own.  There is NO padding
+// pixel between rows: the left tap of x = 0 / the right tap of x = W-1 read the neighbouring row's end pixel and are
+// multiplied by a zeroed depthwise weight (per-lane factors on the three weights of that column).  Why: with PS = an odd
+// number of 16-byte chunks (>= the widest block of the chain) the bank group of a pixel is its linear index mod 8, and
+// with W + 1 pixels per row the strips of a 12 x 12 map collided (5.3 wavefronts per LDS.128 instead of 4; 7 at 6 x 6).
+// Lanes are dealt to pixel columns by a host-side table (chain_lane_table) so that every quarter warp -- the 8 lanes that
+// share a shared-memory wavefront of a 128-bit access -- touches 8 different bank groups whenever the geometry allows it.
+// The output of a block overwrites its input pixel (C_out >= C_in).
 //
 // Work decomposition (lane <-> TMEM lane <-> pixel column, as in blaze_block_deep_kernel): lane l owns column x of strip
-// yq of image im (l = (im * strips + yq) * W + x) and the TR output pixels (yq*TR + t, x); pixel t of every lane forms
+// yq of image im ((im, yq, x) = lane_tab[l]) and the TR output pixels (yq*TR + t, x); pixel t of every lane forms
 // M-tile t, so one tile of the chain is TR M-tiles of at most 128 rows.  Per block ("step"):
 //   DW phase : unit = one k-step (8 channels) for all TR M-tiles: sliding 3x3 window down the column -> TF32 hi / lo ->
 //              tcgen05.st into the A stage of the warp set; units are dealt round-robin to NSETS sets of 4 warps.
@@ -27,6 +31,8 @@
 //              (M-tile, 32 accumulator columns): tcgen05.ld + bias + skip -> ReLU -> st.shared over the input pixel.
 // The same worker warps run both phases; the next step's DW phase starts when all epilogue units have arrived.
 #include <cuda_fp16.h>
+
+#include <vector>
 
 #include "tc_common.cuh"
 
@@ -57,7 +63,10 @@ struct ChainParams {
   int Ho, Wo, tail_lpi, tail_lanes, pad_t, pad_l;   // output map, lanes per image / in use, SAME padding of the depthwise conv
   int H, W, NI, B, n_tiles;
   int lanes, lpi;                 // TMEM lanes in use, lanes per image (= strips * W)
-  int row_pitch;                  // (W + 1) * PS floats
+  int row_pitch;                  // W * PS floats
+  // lane -> pixel column: im | strip << 8 | x << 16 (chain blocks) and im | oy << 8 | ox << 16 (tail block), dealt so that the
+  // quarter warps are free of shared-memory bank conflicts where the geometry allows it (chain_lane_table)
+  uint32_t lane_tab[128], tail_tab[128];
   uint32_t load_bytes;
   int off_w, w_floats, off_ring, off_zero, zero_floats, off_tile;   // shared-memory layout in floats
   long long* trace;               // optional clock stamps of CTA 0: 8 per step
@@ -104,6 +113,24 @@ __device__ __forceinline__ void ch_wait_lean(uint32_t addr, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@!p bra CH_WAIT_%=;\n\t}"
       ::"r"(addr), "r"(parity) : "memory");
+}
+
+// One arrival per WARP: 512 per-thread arrivals on one mbarrier are 512 serialised shared-memory atomics (measured: a hand-off
+// round trip of the empty pipeline cost ~1.4 K clk).  __syncwarp orders the lanes' shared-memory / TMEM accesses (each lane has
+// executed its own tcgen05.wait / fences) before the elected lane's releasing arrive.
+#ifndef HP_CHAIN_DWEXP
+#define HP_CHAIN_DWEXP 0          // timing experiments on the depthwise phase (see the uses); 0 in every shipped build
+#endif
+#ifndef HP_CHAIN_WARP_ARRIVE
+#define HP_CHAIN_WARP_ARRIVE 1
+#endif
+__device__ __forceinline__ void ch_arrive(uint64_t* bar, int lane_id) {
+#if HP_CHAIN_WARP_ARRIVE
+  __syncwarp();
+  if (lane_id == 0) mbar_arrive(bar);
+#else
+  mbar_arrive(bar);
+#endif
 }
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -172,11 +199,12 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   if (tid == 0) {
     *s_abort = 0u;
     mbar_init(bar_tile_full, 1);
-    mbar_init(bar_tile_done, NWORK);
+    constexpr uint32_t NARRIVE = HP_CHAIN_WARP_ARRIVE ? NWORK / 32 : NWORK;   // arrivals of the worker warps per phase
+    mbar_init(bar_tile_done, NARRIVE);
     mbar_init(bar_dfull, NISS);
-    mbar_init(bar_epi, NWORK);
-    mbar_init(bar_tail_done, NWORK);
-    mbar_init(bar_afull, NWORK);
+    mbar_init(bar_epi, NARRIVE);
+    mbar_init(bar_tail_done, NARRIVE);
+    mbar_init(bar_afull, NARRIVE);
     mbar_init(bar_aempty, NISS);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_wfull[s], 1);
@@ -228,13 +256,14 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
     const bool active = lane < p.lanes;
     const bool warp_active = wq * 32 < p.lanes;
-    const int l = active ? lane : 0;
-    const int im = l / p.lpi, l2 = l - im * p.lpi;
-    const int yq = l2 / p.W, x = l2 - yq * p.W;
+    const uint32_t lt = p.lane_tab[active ? lane : 0];
+    const int im = (int)(lt & 255u), yq = (int)((lt >> 8) & 255u), x = (int)(lt >> 16);
     const int row_pitch = p.row_pitch;
+    // SAME padding left / right: the taps of column x - 1 (x + 1) of the first (last) column get a zero weight
+    const float fL = x == 0 ? 0.f : 1.f, fR = x == p.W - 1 ? 0.f : 1.f;
     // top-left tap of the window of output row yq*TR: buffer row im*(H+1) + yq*TR - 1 (= image row yq*TR - 1; row -1 of the
     // buffer is the lead zero row), column x - 1
-    const float* win = tile + ((im * (p.H + 1) + yq * TR - 1) * (p.W + 1) + x - 1) * PS;
+    const float* win = tile + ((im * (p.H + 1) + yq * TR - 1) * p.W + x - 1) * PS;
     float* centre0 = const_cast<float*>(win) + row_pitch + PS;
     uint32_t g0 = 0, e0 = 0;     // global round counter / epilogue unit counter
     uint32_t guard = 0u;         // F16: set when an accumulator of this lane is inf / NaN
@@ -267,6 +296,11 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               float4 w[9];
 #pragma unroll
               for (int k = 0; k < 9; ++k) w[k] = ld4(wp + k * cin);
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                w[ky * 3 + 0] = scale4(w[ky * 3 + 0], fL);
+                w[ky * 3 + 2] = scale4(w[ky * 3 + 2], fR);
+              }
               const float4 bias = ld4(wp + 9 * cin);
 #pragma unroll
               for (int t = 0; t < TR; ++t) acc[half][t] = bias;
@@ -274,7 +308,19 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 #pragma unroll
               for (int rr = 0; rr < TR + 2; ++rr) {
                 const float* row = wc + rr * row_pitch;
+#if HP_CHAIN_DWEXP == 2      // timing experiment: arithmetic without the data loads
+                const float4 v0 = make_float4(acc[half][0].y, acc[half][0].x, (float)rr, acc[half][0].w), v1 = v0, v2 = v0;
+#else
                 const float4 v0 = ld4(row), v1 = ld4(row + PS), v2 = ld4(row + 2 * PS);
+#endif
+#if HP_CHAIN_DWEXP == 1      // timing experiment: data loads with next to no arithmetic
+                {
+                  const int t = rr < TR ? rr : TR - 1;
+                  acc[half][t].x = __uint_as_float((__float_as_uint(acc[half][t].x) ^ __float_as_uint(v0.x) ^ __float_as_uint(v1.x)) ^ (__float_as_uint(v2.x) ^ __float_as_uint(v0.y) ^ __float_as_uint(v1.y)));
+                  acc[half][t].y = __uint_as_float((__float_as_uint(acc[half][t].y) ^ __float_as_uint(v2.y) ^ __float_as_uint(v0.z)) ^ (__float_as_uint(v1.z) ^ __float_as_uint(v2.z) ^ __float_as_uint(v0.w)));
+                  acc[half][t].z = __uint_as_float(__float_as_uint(acc[half][t].z) ^ __float_as_uint(v1.w) ^ __float_as_uint(v2.w));
+                }
+#else
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                   const int t = rr - ky;
@@ -284,6 +330,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                     acc[half][t] = fma4(v2, w[ky * 3 + 2], acc[half][t]);
                   }
                 }
+#endif
               }
             }
           }
@@ -301,11 +348,16 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
+#if HP_CHAIN_DWEXP == 3      // timing experiment: no fp16 split
+                  hi[e] = __float_as_uint(f[2 * e]) & 0x3fff3fffu;
+                  lo[e] = __float_as_uint(f[2 * e + 1]) & 0x3fff3fffu;
+#else
                   const __half2 h2 = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
                   const float2 back = __half22float2(h2);
                   const __half2 l2 = __floats2half2_rn(f[2 * e] - back.x, f[2 * e + 1] - back.y);
                   hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
                   lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+#endif
                 }
                 tmem_st4(acol + t * 16, hi[0], hi[1], hi[2], hi[3]);
                 tmem_st4(acol + t * 16 + 8, lo[0], lo[1], lo[2], lo[3]);
@@ -338,7 +390,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
           }
-          mbar_arrive(bar_afull);
+          ch_arrive(bar_afull, lane_id);
         }
         if (tid == 0) stamp(step, 1);
         // ---------------- epilogue units (M-tile t, 32 accumulator columns) with (e0 + unit) % NSETS == set
@@ -390,8 +442,8 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           if (b == nblk - 1) fence_async_smem();           // the tile leaves through the async proxy (TMA store)
         }
         e0 += (uint32_t)n_eu;
-        mbar_arrive(bar_epi);
-        if (b == nblk - 1) mbar_arrive(bar_tile_done);
+        ch_arrive(bar_epi, lane_id);
+        if (b == nblk - 1) ch_arrive(bar_tile_done, lane_id);
         if (tid == 0) stamp(step, 3);
       }
       if (p.tail) {
@@ -406,11 +458,18 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         const float* s_pwb = s_dww + 10 * cin;
         const bool active2 = lane < p.tail_lanes;
         const bool warp_active2 = wq * 32 < p.tail_lanes;
-        const int l3 = active2 ? lane : 0;
-        const int im2 = l3 / p.tail_lpi, r2 = l3 - im2 * p.tail_lpi;
-        const int oy = r2 / p.Wo, ox = r2 - oy * p.Wo;
-        const float* win2 = tile + ((im2 * (p.H + 1) + 2 * oy - p.pad_t) * (p.W + 1) + 2 * ox - p.pad_l) * PS;
-        const float* pool = tile + ((im2 * (p.H + 1) + 2 * oy) * (p.W + 1) + 2 * ox) * PS;
+        const uint32_t lt2 = p.tail_tab[active2 ? lane : 0];
+        const int im2 = (int)(lt2 & 255u), oy = (int)((lt2 >> 8) & 255u), ox = (int)(lt2 >> 16);
+        const float* win2 = tile + ((im2 * (p.H + 1) + 2 * oy - p.pad_t) * p.W + 2 * ox - p.pad_l) * PS;
+        const float* pool = tile + ((im2 * (p.H + 1) + 2 * oy) * p.W + 2 * ox) * PS;
+        // window columns 2 ox - pad_l + kx outside the image take a zero weight; the pool window's second column may fall off an odd map
+        float fk[3];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int col = 2 * ox - p.pad_l + kx;
+          fk[kx] = (col >= 0 && col < p.W) ? 1.f : 0.f;
+        }
+        const bool pool2 = 2 * ox + 1 < p.W;
         ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
         tc_fence_after();
         if (tid == 0) stamp(step, 0);
@@ -429,7 +488,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) a = fma4(ld4(win2 + ky * row_pitch + kx * PS + c), ld4(wp + (ky * 3 + kx) * cin), a);
+                for (int kx = 0; kx < 3; ++kx) a = fma4(ld4(win2 + ky * row_pitch + kx * PS + c), scale4(ld4(wp + (ky * 3 + kx) * cin), fk[kx]), a);
               acc[half] = a;
             }
           }
@@ -472,7 +531,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
           }
-          mbar_arrive(bar_afull);
+          ch_arrive(bar_afull, lane_id);
         }
         if (tid == 0) stamp(step, 1);
         ch_wait(bar_dfull, step & 1, 4, s_abort, step);
@@ -510,8 +569,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                                : make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
                                              __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
                 if (j < C4) {
-                  const float4 p00 = ld4(pool + j * 4), p01 = ld4(pool + PS + j * 4);
-                  const float4 p10 = ld4(pool + row_pitch + j * 4), p11 = ld4(pool + row_pitch + PS + j * 4);
+                  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  const float4 p00 = ld4(pool + j * 4), p01 = pool2 ? ld4(pool + PS + j * 4) : z4;
+                  const float4 p10 = ld4(pool + row_pitch + j * 4), p11 = pool2 ? ld4(pool + row_pitch + PS + j * 4) : z4;
                   o.x += fmaxf(fmaxf(p00.x, p01.x), fmaxf(p10.x, p11.x));
                   o.y += fmaxf(fmaxf(p00.y, p01.y), fmaxf(p10.y, p11.y));
                   o.z += fmaxf(fmaxf(p00.z, p01.z), fmaxf(p10.z, p11.z));
@@ -525,8 +585,8 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           tc_fence_before();
         }
         e0 += (uint32_t)ncg;
-        mbar_arrive(bar_epi);
-        mbar_arrive(bar_tail_done);
+        ch_arrive(bar_epi, lane_id);
+        ch_arrive(bar_tail_done, lane_id);
         if (tid == 0) stamp(step, 3);
         ++step;
       }
@@ -722,15 +782,15 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
       ChainCfg c;
       c.TR = TR; c.NI = NI; c.PS = PS; c.lanes = NI * lpi; c.lpi = lpi;
       c.nsets = 4; c.niss = 1;   // measured at 96 x 96, batch 4096: 1 issuer 0.589 ms, 2 issuers 0.609, 3 issuers 0.659 (every extra issuer adds its commits to each round)
-      const int lead = tc_align_up((W + 2) * PS, 32);     // zero row above the first image + the left neighbour of its first pixel
+      const int lead = tc_align_up((W + 1) * PS, 32);     // zero row above the first image + the left neighbour of its first pixel
       const int rows = NI * (H + 1) + TR;                 // image rows + their zero rows, slack for partial strips
       int off = CH_BAR_FLOATS;
       c.off_w = off; off = tc_align_up(off + w_floats, 32);
       c.off_ring = off; off += CH_RING * CH_SLOT_FLOATS;
       c.off_zero = off; off += lead;
       c.off_tile = off;
-      c.tile_floats = rows * (W + 1) * PS;
-      off += c.tile_floats + PS;                          // one more pixel: the right neighbour of the last pad pixel
+      c.tile_floats = rows * W * PS;
+      off += c.tile_floats + PS;                          // one more pixel: the right neighbour of the last pixel
       c.zero_floats = off - c.off_zero;
       c.w_floats = w_floats;
       c.smem = (size_t)off * sizeof(float);
@@ -745,6 +805,34 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
   if (best_cost >= 1e30) return false;
   *cfg = best;
   return true;
+}
+
+// Deal pixel columns to lanes.  pix[i] = linear pixel index (in pixels of PS floats) of the first tap of entry i, code[i] = its
+// packed coordinates.  With PS = an odd number of 16-byte chunks the bank group of a 128-bit access is pix mod 8, and the 8
+// lanes of a quarter warp share the wavefronts of an LDS.128 / STS.128: every group of 8 consecutive lanes gets entries with
+// different residues while the supply lasts (greedy: largest residue classes first), so that an access costs 4 wavefronts
+// per warp instead of up to 8.  The groups are filled densely: lanes [0, n) are in use.
+static void chain_lane_table(const std::vector<int>& pix, const std::vector<uint32_t>& code, uint32_t* tab) {
+  std::vector<int> bucket[8];
+  const int n = (int)pix.size();
+  for (int i = n - 1; i >= 0; --i) bucket[((pix[i] % 8) + 8) % 8].push_back(i);   // pop_back() hands them out in natural order
+  int lane = 0;
+  while (lane < n) {
+    int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int want = n - lane < 8 ? n - lane : 8;
+    for (int k = 0; k < want; ++k) {
+      // the class with the lowest multiplicity in this group, then the fullest one
+      int best = -1;
+      for (int r = 0; r < 8; ++r) {
+        if (bucket[r].empty()) continue;
+        if (best < 0 || used[r] < used[best] || (used[r] == used[best] && bucket[r].size() > bucket[best].size())) best = r;
+      }
+      tab[lane++] = code[bucket[best].back()];
+      bucket[best].pop_back();
+      used[best]++;
+    }
+  }
+  for (; lane < 128; ++lane) tab[lane] = 0u;
 }
 
 int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out, int B, int H, int W, const ChainCfg& cfg,
@@ -792,13 +880,35 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
     same_pad(H, 3, 2, &o_, &pb); p.pad_t = pb;
     same_pad(W, 3, 2, &o_, &pb); p.pad_l = pb;
     HP_REQUIRE(p.tail_lanes <= 128 && p.pad_t <= 1 && p.pad_l <= 1, HP_ERR_INVALID, "chain: tail block on %dx%d does not fit one M-tile", H, W);
+    std::vector<int> pix;
+    std::vector<uint32_t> code;
+    for (int im = 0; im < cfg.NI; ++im)
+      for (int oy = 0; oy < p.Ho; ++oy)
+        for (int ox = 0; ox < p.Wo; ++ox) {
+          pix.push_back((im * (H + 1) + 2 * oy) * W + 2 * ox);
+          code.push_back((uint32_t)im | ((uint32_t)oy << 8) | ((uint32_t)ox << 16));
+        }
+    chain_lane_table(pix, code, p.tail_tab);
+  }
+  {
+    const int strips = ceil_div(H, cfg.TR);
+    HP_REQUIRE(cfg.NI * strips * W == cfg.lanes && cfg.NI < 256 && strips < 256 && W < 256, HP_ERR_INVALID, "chain: lane count %d does not match %d x %d x %d", cfg.lanes, cfg.NI, strips, W);
+    std::vector<int> pix;
+    std::vector<uint32_t> code;
+    for (int im = 0; im < cfg.NI; ++im)
+      for (int yq = 0; yq < strips; ++yq)
+        for (int x = 0; x < W; ++x) {
+          pix.push_back((im * (H + 1) + yq * cfg.TR) * W + x);
+          code.push_back((uint32_t)im | ((uint32_t)yq << 8) | ((uint32_t)x << 16));
+        }
+    chain_lane_table(pix, code, p.lane_tab);
   }
   HP_REQUIRE(w_off <= cfg.w_floats, HP_ERR_STATE, "chain: weight area too small (%d > %d floats)", w_off, cfg.w_floats);
   p.H = H; p.W = W; p.NI = cfg.NI; p.B = B;
   p.n_tiles = ceil_div(B, cfg.NI);
   p.lanes = cfg.lanes; p.lpi = cfg.lpi;
-  p.row_pitch = (W + 1) * cfg.PS;
-  p.load_bytes = (uint32_t)((size_t)cfg.NI * (H + 1) * (W + 1) * cfg.PS * sizeof(float));
+  p.row_pitch = W * cfg.PS;
+  p.load_bytes = (uint32_t)((size_t)cfg.NI * (H + 1) * W * cfg.PS * sizeof(float));
   p.off_w = cfg.off_w; p.w_floats = cfg.w_floats; p.off_ring = cfg.off_ring; p.off_zero = cfg.off_zero; p.zero_floats = cfg.zero_floats;
   p.off_tile = cfg.off_tile;
   p.trace = h->tc_trace; p.trace_steps = h->tc_trace_tiles;
@@ -823,7 +933,7 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
     const cuuint64_t sin_[3] = {(cuuint64_t)cin0 * 4, (cuuint64_t)W * cin0 * 4, (cuuint64_t)H * W * cin0 * 4};
     const cuuint64_t dout[4] = {(cuuint64_t)coutL, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t sout[3] = {(cuuint64_t)coutL * 4, (cuuint64_t)W * coutL * 4, (cuuint64_t)H * W * coutL * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)cfg.PS, (cuuint32_t)(W + 1), (cuuint32_t)(H + 1), (cuuint32_t)cfg.NI};
+    const cuuint32_t box[4] = {(cuuint32_t)cfg.PS, (cuuint32_t)W, (cuuint32_t)(H + 1), (cuuint32_t)cfg.NI};
     HP_TRY(tc_make_map4(&tin, in, din, sin_, box));
     HP_TRY(tc_make_map4(&tout, out, dout, sout, box));
   }

@@ -989,13 +989,18 @@ blaze_block_small_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
 // 9 tap offsets of a lane need no boundary logic at all, and the max-pool of the skip path reads 4 of the same pixels
 // (rows / columns + pad_t / + pad_l; the zero fill is harmless there because block inputs are ReLU outputs, >= 0).
 // Depthwise -> TF32 hi / lo -> TMEM A ring (work unit = `ku` k-steps), one accumulator row per lane, epilogue into a
-// separate output staging buffer (the output has different geometry: not in place) -> TMA store.  The input pixel stride is
-// an odd number of 16-byte chunks, but neighbouring lanes are TWO input pixels apart: depthwise LDS.128 are 2-way bank
-// conflicted (accepted: still ~2x faster than the CUDA-core kernel, which is FMA-issue bound).
+// separate output staging buffer (the output has different geometry: not in place) -> TMA store.
+// Neighbouring lanes are TWO input pixels apart, and with a pixel stride of an odd number of 16-byte chunks that is an even
+// number of chunks: every depthwise / max-pool LDS.128 of the dense band was 2-way bank conflicted (8 wavefronts instead of
+// 4; ncu: 77 % of the shared-memory wavefront budget on block 2).  The band therefore arrives as TWO boxes with a traversal
+// stride of 2 pixels (cuTensorMapEncodeTiled elementStrides): the EVEN band columns 0, 2, .., 2 Wo form plane E, the ODD ones
+// plane O, each stored densely [2R+1][Wo+1][PSI].  Tap kx = 0 of lane x is E[x], kx = 1 is O[x], kx = 2 is E[x+1]:
+// neighbouring lanes are ONE pixel apart in every access.
 struct Tcs2Params {
   const float *pwb, *bhi, *blo;
   int Wo, Ho, R, rows, bands_per_img, n_tiles, pad_t, pad_l;
-  int IWB, row_pitch;                        // input box: IWB = 2 Wo + 1 pixels per row, row_pitch = IWB * PSI floats
+  int IWB, row_pitch;                        // planes: IWB = Wo + 1 pixels per row, row_pitch = IWB * PSI floats
+  int plane_floats;                          // plane O follows plane E at this offset
   int nstg, nbuf, ku, upt;
   uint32_t load_bytes;
   int off_b, off_w, off_out, out_floats, off_in, in_floats;
@@ -1080,7 +1085,8 @@ blaze_block_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     const bool active = lane < p.rows;
     const bool warp_active = wq * 32 < p.rows;
     const int yl = active ? lane / p.Wo : 0, xl = active ? lane - yl * p.Wo : 0;
-    const int win0 = (2 * yl * p.IWB + 2 * xl) * PSI;             // top-left tap of the 3x3 window in the input band
+    const int win0 = (2 * yl * p.IWB + xl) * PSI;                 // top-left tap of the 3x3 window: band row 2 yl, E[xl]
+    const int koff1 = p.plane_floats, koff2 = PSI;                // taps kx = 1 (O[xl]) and kx = 2 (E[xl + 1]) relative to kx = 0
     if (warp < W_EPI) {
       // =============================================================== depthwise sets (units of ku k-steps, global round-robin)
       const int set = warp >> 2;
@@ -1113,7 +1119,7 @@ blaze_block_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
             float4 a0 = ld4(dwc.b + c), a1 = two ? ld4(dwc.b + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-              const float* q = buf + ((t / 3) * p.IWB + (t % 3)) * PSI + c;
+              const float* q = buf + (t / 3) * p.row_pitch + ((t % 3) == 0 ? 0 : (t % 3) == 1 ? koff1 : koff2) + c;
               a0 = fma4(ld4(q), ld4(dwc.w + t * CINP + c), a0);
               if (two) a1 = fma4(ld4(q + 4), ld4(dwc.w + t * CINP + c + 4), a1);
             }
@@ -1138,11 +1144,15 @@ blaze_block_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     } else {
       // =============================================================== epilogue sets: tile i belongs to set i % NESETS
       const int eset = (warp - W_EPI) >> 2;
-      const int skip0 = win0 + (p.pad_t * p.IWB + p.pad_l) * PSI;  // image pixel (2 y, 2 x): the 2x2 max-pool window starts here
+      // 2x2 max-pool window of the skip path: image pixels (2 y + {0, 1}, 2 x + {0, 1}) = band columns 2 xl + pad_l + {0, 1}:
+      // E[xl], O[xl] (pad_l = 0) or O[xl], E[xl + 1] (pad_l = 1)
+      const int skip0 = win0 + p.pad_t * p.row_pitch + (p.pad_l ? koff1 : 0);
+      const int skip1 = win0 + p.pad_t * p.row_pitch + (p.pad_l ? koff2 : koff1);
       constexpr int NGRP = (NG + 7) / 8;
       for (int i = eset; i < my_tiles; i += NESETS) {
         const int d = i & 1, b = i % NBUF, ob = i & 1;
         const float* win = bufs + b * p.in_floats + skip0;
+        const float* win1 = bufs + b * p.in_floats + skip1;
         float* opix = obufs + ob * p.out_floats + lane * PSO;
         mbar_wait(&bar_dfull[d], (i >> 1) & 1);
         tc_fence_after();
@@ -1173,8 +1183,8 @@ blaze_block_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
                 float4 o = make_float4(__uint_as_float(v[g][jj * 4 + 0]) + bb.x, __uint_as_float(v[g][jj * 4 + 1]) + bb.y,
                                        __uint_as_float(v[g][jj * 4 + 2]) + bb.z, __uint_as_float(v[g][jj * 4 + 3]) + bb.w);
                 if (j < C4) {
-                  const float4 s0 = ld4(win + j * 4), s1 = ld4(win + PSI + j * 4);
-                  const float4 s2 = ld4(win + p.row_pitch + j * 4), s3 = ld4(win + p.row_pitch + PSI + j * 4);
+                  const float4 s0 = ld4(win + j * 4), s1 = ld4(win1 + j * 4);
+                  const float4 s2 = ld4(win + p.row_pitch + j * 4), s3 = ld4(win1 + p.row_pitch + j * 4);
                   o.x += fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x)); o.y += fmaxf(fmaxf(s0.y, s1.y), fmaxf(s2.y, s3.y));
                   o.z += fmaxf(fmaxf(s0.z, s1.z), fmaxf(s2.z, s3.z)); o.w += fmaxf(fmaxf(s0.w, s1.w), fmaxf(s2.w, s3.w));
                 }
@@ -1239,8 +1249,9 @@ blaze_block_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         if (i >= NBUF) mbar_wait(&bar_free[b], ((i / NBUF) - 1) & 1);
         int img, y0;
         tile_coords(tile, img, y0);
-        mbar_expect_tx(&bar_full[b], p.load_bytes);
-        tma_load_4d(bufs + b * p.in_floats, &tm_in, &bar_full[b], 0, -p.pad_l, 2 * y0 - p.pad_t, img);
+        mbar_expect_tx(&bar_full[b], 2u * p.load_bytes);
+        tma_load_4d(bufs + b * p.in_floats, &tm_in, &bar_full[b], 0, -p.pad_l, 2 * y0 - p.pad_t, img);                       // plane E
+        tma_load_4d(bufs + b * p.in_floats + p.plane_floats, &tm_in, &bar_full[b], 0, 1 - p.pad_l, 2 * y0 - p.pad_t, img);   // plane O
         stamp(i, 0);
         if (++b == NBUF) b = 0;
       }
@@ -1286,12 +1297,13 @@ int get_encode() {
 }
 
 // NHWC float tensor [N][H][W][C] with box [bn][bh][bw][bc]; bc may exceed C (padded pixel stride in smem)
-int make_map(CUtensorMap* tm, const float* base, int N, int H, int W, int C, int bn, int bh, int bw, int bc) {
+// wstride > 1: every wstride-th pixel of a row is loaded (bw pixels land densely in shared memory)
+int make_map(CUtensorMap* tm, const float* base, int N, int H, int W, int C, int bn, int bh, int bw, int bc, int wstride = 1) {
   HP_TRY(get_encode());
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)(bw * wstride), (cuuint32_t)bh, (cuuint32_t)bn};   // traversal extent: bw * wstride
+  cuuint32_t estr[4] = {1, (cuuint32_t)wstride, 1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1434,8 +1446,9 @@ int launch_small(hp_ctx* h, const float* in, float* out, int B, int H, int W, co
 inline size_t tcs2_layout(int cinp, int coutp, int Wo, int R, int nbuf, Tcs2Params* p) {
   const int C4 = cinp / 4, NG = coutp / 4, K8 = (cinp + 7) / 8 * 8, N16 = (coutp + 15) / 16 * 16;
   const int PSI = (C4 | 1) * 4, PSO = (NG | 1) * 4;
-  p->IWB = 2 * Wo + 1;
+  p->IWB = Wo + 1;
   p->row_pitch = p->IWB * PSI;
+  p->plane_floats = align_up((2 * R + 1) * p->row_pitch, 32);   // TMA destinations are 128-byte aligned
   int off = TC_BAR_FLOATS;
   p->off_b = off;
   off = align_up(off + 2 * K8 * N16, 32);
@@ -1445,7 +1458,7 @@ inline size_t tcs2_layout(int cinp, int coutp, int Wo, int R, int nbuf, Tcs2Para
   p->out_floats = align_up(R * Wo * PSO, 256);
   off += 2 * p->out_floats;
   p->off_in = off;
-  p->in_floats = align_up((2 * R + 1) * p->row_pitch, 256);
+  p->in_floats = align_up(2 * p->plane_floats, 256);
   p->load_bytes = (uint32_t)((size_t)(2 * R + 1) * p->row_pitch * sizeof(float));
   return (size_t)(off + nbuf * p->in_floats) * sizeof(float);
 }
@@ -1466,12 +1479,12 @@ int launch_s2(hp_ctx* h, const float* in, float* out, int B, int Hi, int Wi, int
   const size_t smem = tcs2_layout(CINP, COUTP, Wo, tc.BH, tc.nbuf, &p);
   HP_REQUIRE(smem <= 227 * 1024, HP_ERR_INVALID, "tc stride-2 block <%d,%d>: %zu bytes of shared memory needed", CINP, COUTP, smem);
   HP_REQUIRE(p.rows >= 1 && p.rows <= 128 && tc.nbuf >= 2 && tc.nbuf <= TCD_MAXB && tc.NSTG >= 2 && tc.NSTG <= TC_MAX_STG &&
-                 tc.unit >= 1 && tc.unit <= 2 && tc.nsets <= tc.NSTG && 2 * G::N16 + tc.NSTG * 16 * tc.unit <= 512 && p.IWB <= 256 &&
+                 tc.unit >= 1 && tc.unit <= 2 && tc.nsets <= tc.NSTG && 2 * G::N16 + tc.NSTG * 16 * tc.unit <= 512 && 2 * p.IWB <= 256 &&
                  2 * tc.BH + 1 <= 256 && pad_t >= 0 && pad_t <= 1 && pad_l >= 0 && pad_l <= 1,
              HP_ERR_INVALID, "tc stride-2 block <%d,%d>: bad geometry %dx%d R %d nbuf %d nstg %d", CINP, COUTP, Ho, Wo, tc.BH, tc.nbuf, tc.NSTG);
   HP_REQUIRE(w.h_dw != nullptr, HP_ERR_STATE, "tc stride-2 block: host copy of the depthwise weights missing");
   CUtensorMap tin, tout;
-  HP_TRY(make_map(&tin, in, B, Hi, Wi, CINP, 1, 2 * tc.BH + 1, p.IWB, PSI));
+  HP_TRY(make_map(&tin, in, B, Hi, Wi, CINP, 1, 2 * tc.BH + 1, p.IWB, PSI, 2));
   HP_TRY(make_map(&tout, out, B, Ho, Wo, COUTP, 1, tc.BH, Wo, PSO));
   DwConst<CINP> dwc;
   memcpy(dwc.w, w.h_dw, sizeof(dwc));
@@ -1692,7 +1705,7 @@ bool hp_tcs2_geometry(int blk, int Ho, int Wo, int nsets, int esets, TcCfg* tc) 
   const int N16 = (coutp + 15) / 16 * 16;
   if (kBlazeBlocks[blk].stride != 2 || Wo < 1 || Wo > 127 || Ho < 1) return false;
   TcCfg t;
-  t.TR = 1; t.nsets = nsets; t.npipe = esets; t.niss = 1; t.place = 0; t.ni = 1; t.IWB = 2 * Wo + 1;
+  t.TR = 1; t.nsets = nsets; t.npipe = esets; t.niss = 1; t.place = 0; t.ni = 1; t.IWB = Wo + 1;
   t.unit = 2;
   t.NSTG = TC_MAX_STG;
   if (2 * N16 + t.NSTG * 16 * t.unit > 512) return false;

@@ -120,6 +120,11 @@ __device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
   const float2 hi = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(c.z, c.w));
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
+__device__ __forceinline__ float4 scale4(float4 a, float f) {
+  const float2 lo = __fmul2_rn(make_float2(a.x, a.y), make_float2(f, f));
+  const float2 hi = __fmul2_rn(make_float2(a.z, a.w), make_float2(f, f));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 
 
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
