@@ -116,9 +116,12 @@ __device__ __forceinline__ void tc_zero_chunk(uint32_t acol) {   // K padding (o
 // All column groups are requested before the single tcgen05.wait::ld (the TMEM load latency is paid once per pixel).
 // F16: the accumulator carries the power-of-two scale of the fp16 weights (multiplied out here) and, when a depthwise output did
 // not fit fp16, inf / NaN in every column: column 0 is tested (guard).
-template <int C4, int NG, int N16, int F16 = 0>
+// BREG = 1: the pointwise bias comes from the caller's registers (breg[NG], loaded once per kernel) instead of one warp-uniform
+// LDS.128 per 4 channels and pixel -- a broadcast LDS.128 costs the 4 shared-memory wavefronts of a full-width one, a third of
+// the epilogue's shared-memory traffic (bias + skip + store).
+template <int C4, int NG, int N16, int F16 = 0, int BREG = 0>
 __device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, const float* s_pwb, bool active, float us = 1.f,
-                                                  uint32_t* guard = nullptr) {
+                                                  uint32_t* guard = nullptr, const float4* breg = nullptr) {
   constexpr int NGRP = (NG + 7) / 8;   // 32-column groups that hold real output channels
   uint32_t v[NGRP][32];
 #pragma unroll
@@ -140,7 +143,7 @@ __device__ __forceinline__ void tc_epilogue_pixel(float* cpix, uint32_t dcol, co
     for (int jj = 0; jj < 8; ++jj) {
       const int j = g * 8 + jj;
       if (j < NG) {
-        const float4 bb = ld4(s_pwb + j * 4);
+        const float4 bb = BREG ? breg[j] : ld4(s_pwb + j * 4);
         float4 o = F16 ? make_float4(fmaf(__uint_as_float(v[g][jj * 4 + 0]), us, bb.x), fmaf(__uint_as_float(v[g][jj * 4 + 1]), us, bb.y),
                                      fmaf(__uint_as_float(v[g][jj * 4 + 2]), us, bb.z), fmaf(__uint_as_float(v[g][jj * 4 + 3]), us, bb.w))
                        : make_float4(__uint_as_float(v[g][jj * 4 + 0]) + bb.x, __uint_as_float(v[g][jj * 4 + 1]) + bb.y,
@@ -385,6 +388,9 @@ blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 // the pixel-per-lane kernel took ~9.5K clk per tile against 3.5K clk of input wavefronts).  From the constant bank they do not touch the
 // shared-memory pipe at all.  (Tried in the band kernel too: there the weights are reused over TR rows and the constant
 // loads cost more than they save -- blocks 0 / 1 went from 0.43 to 0.45 ms -- so it keeps them in shared memory.)
+#ifndef HP_TC_BREG_MAX
+#define HP_TC_BREG_MAX 8
+#endif
 template <int CINP>
 struct DwConst {
   float w[9 * CINP];
@@ -615,6 +621,12 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       const int centre0 = my_off + row_pitch + PS;
       const int eset = (warp - W_EPI) >> 2;
       uint32_t guard = 0u;
+      constexpr int BREG = (NG <= HP_TC_BREG_MAX) ? 1 : 0;          // the bias of up to 32 output channels lives in registers
+      float4 breg[BREG ? NG : 1];
+      if (BREG) {
+#pragma unroll
+        for (int j = 0; j < (BREG ? NG : 1); ++j) breg[j] = ld4(s_pwb + j * 4);
+      }
       int i = 0, b = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
         const int d = i & 1;
@@ -627,8 +639,8 @@ blaze_block_deep_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
 #pragma unroll
           for (int t = 0; t < TR; ++t)
             if (t % NESETS == eset)
-              tc_epilogue_pixel<C4, NG, N16, F16 ? 1 : 0>(buf + centre0 + t * row_pitch, tlane + d * (TR * N16) + t * N16, s_pwb, active, p.unscale,
-                                                          &guard);
+              tc_epilogue_pixel<C4, NG, N16, F16 ? 1 : 0, BREG>(buf + centre0 + t * row_pitch, tlane + d * (TR * N16) + t * N16, s_pwb, active, p.unscale,
+                                                                &guard, breg);
           tc_fence_before();
           fence_async_smem();
         }
