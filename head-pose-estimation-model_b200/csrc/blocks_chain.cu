@@ -171,7 +171,10 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   uint64_t* bar_wfull = bars + 6;                        // [2] weight slices of round R (ring half R & 1) have landed
   uint64_t* bar_wempty = bars + 8;                       // [2] issuers (commit): ring half R & 1 may be overwritten
   uint64_t* bar_tail_done = bars + 10;                   // all worker threads: the tail block has read the tile for the last time
-  static_assert(2 * NSETS <= CH_RING && 11 * 8 + 8 <= CH_BAR_FLOATS * 4, "weight ring / barrier block");
+  // bar_dfull[t] = bars + 2 (t = 0), bars + 11, bars + 12: the accumulator of M-tile t is complete.  The last round of a step is
+  // issued tile by tile with one commit per tile, so the epilogue of tile 0 runs while the MMAs of tiles 1, 2 drain.
+  static_assert(TR <= 3, "d_full barriers");
+  static_assert(2 * NSETS <= CH_RING && 13 * 8 + 8 <= CH_BAR_FLOATS * 4, "weight ring / barrier block");
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem) + (CH_BAR_FLOATS - 1);
   volatile uint32_t* s_abort = reinterpret_cast<uint32_t*>(smem) + (CH_BAR_FLOATS - 2);
   float* s_w = smem + p.off_w;
@@ -201,7 +204,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     mbar_init(bar_tile_full, 1);
     constexpr uint32_t NARRIVE = HP_CHAIN_WARP_ARRIVE ? NWORK / 32 : NWORK;   // arrivals of the worker warps per phase
     mbar_init(bar_tile_done, NARRIVE);
-    mbar_init(bar_dfull, NISS);
+    mbar_init(bar_dfull, 1);
+    mbar_init(bars + 11, 1);
+    mbar_init(bars + 12, 1);
     mbar_init(bar_epi, NARRIVE);
     mbar_init(bar_tail_done, NARRIVE);
     mbar_init(bar_afull, NARRIVE);
@@ -393,51 +398,66 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           ch_arrive(bar_afull, lane_id);
         }
         if (tid == 0) stamp(step, 1);
-        // ---------------- epilogue units (M-tile t, 32 accumulator columns) with (e0 + unit) % NSETS == set
-        ch_wait(bar_dfull, step & 1, 4, s_abort, step);
-        tc_fence_after();
-        if (tid == 0) stamp(step, 2);
-        const int ncg = (n16 + 31) >> 5, n_eu = TR * ncg;
+        // ---------------- epilogue units: 8 accumulator columns of ALL TR M-tiles, dealt to the sets with (e0 + unit) % NSETS == set.
+        // The bias of a unit is loaded once for the TR pixels (a warp-uniform LDS.128 costs the 4 wavefronts of a full-width one:
+        // with one bias load per pixel a third of the epilogue's shared-memory traffic was bias).  The first unit of a set takes
+        // the M-tiles as their accumulators complete (d_full per tile), later units load all TR rows before one tcgen05.wait.
         const int C4 = cin >> 2, NG = cb.cout >> 2;
+        const int n_eu = (NG + 1) >> 1;
+        (void)n16;
         if (warp_active) {
+          const float us = cb.unscale;
+          auto finish = [&](int t, int j, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, const float4& bb) {
+            if (j < NG && !(p.exp_ & 2)) {
+              float* cpix = centre0 + t * row_pitch;
+              float4 o = F16 ? make_float4(fmaf(__uint_as_float(x0), us, bb.x), fmaf(__uint_as_float(x1), us, bb.y), fmaf(__uint_as_float(x2), us, bb.z),
+                                           fmaf(__uint_as_float(x3), us, bb.w))
+                             : make_float4(__uint_as_float(x0) + bb.x, __uint_as_float(x1) + bb.y, __uint_as_float(x2) + bb.z, __uint_as_float(x3) + bb.w);
+              if (j < C4) {
+                const float4 sk = ld4(cpix + j * 4);
+                o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+              }
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              if (active && (yq * TR + t < p.H)) st4(cpix + j * 4, o);
+            }
+          };
           int u = (int)((NSETS + set - (e0 % NSETS)) % NSETS);
+          bool first = true;
 #pragma unroll 1
           for (; u < n_eu; u += NSETS) {
-            const int t = u / ncg, cg = u - t * ncg;
-            float* cpix = centre0 + t * row_pitch;
-            const bool valid = active && (yq * TR + t < p.H);
-            const uint32_t dcol = tlane + t * CH_DSTRIDE + cg * 32;
-            uint32_t v[32];
-            if (cg * 32 + 32 <= n16) {
-              tmem_ld32(dcol, v);
+            const int j0 = 2 * u;
+            const float4 b0 = ld4(s_pwb + j0 * 4);
+            const float4 b1 = (j0 + 1 < NG) ? ld4(s_pwb + j0 * 4 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t dcol = tlane + (uint32_t)u * 8u;
+            if (first) {
+              first = false;
+#pragma unroll
+              for (int t = 0; t < TR; ++t) {
+                ch_wait(t == 0 ? bar_dfull : bars + 10 + t, step & 1, 4, s_abort, step);
+                tc_fence_after();
+                if (t == 0 && tid == 0) stamp(step, 2);
+                uint32_t v[8];
+                tmem_ld8(dcol + t * CH_DSTRIDE, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // an fp16 infinity among the A operands of this pixel makes every accumulator column inf or NaN: test one
+                if (F16 && u == 0 && active && (yq * TR + t < p.H) && (v[0] & 0x7F800000u) == 0x7F800000u) guard = 1u;
+                finish(t, j0, v[0], v[1], v[2], v[3], b0);
+                finish(t, j0 + 1, v[4], v[5], v[6], v[7], b1);
+              }
             } else {
-              uint32_t hlf[16];
-              tmem_ld16(dcol, hlf);
+              uint32_t v[TR][8];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // an fp16 infinity among the A operands of this pixel makes every accumulator column inf or NaN: test one
-            if (F16 && cg == 0 && valid && (v[0] & 0x7F800000u) == 0x7F800000u) guard = 1u;
-            const float us = cb.unscale;
+              for (int t = 0; t < TR; ++t) tmem_ld8(dcol + t * CH_DSTRIDE, v[t]);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const int j = cg * 8 + jj;
-              if (j < NG && !(p.exp_ & 2)) {
-                const float4 bb = ld4(s_pwb + j * 4);
-                float4 o = F16 ? make_float4(fmaf(__uint_as_float(v[jj * 4 + 0]), us, bb.x), fmaf(__uint_as_float(v[jj * 4 + 1]), us, bb.y),
-                                             fmaf(__uint_as_float(v[jj * 4 + 2]), us, bb.z), fmaf(__uint_as_float(v[jj * 4 + 3]), us, bb.w))
-                               : make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
-                                             __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
-                if (j < C4) {
-                  const float4 sk = ld4(cpix + j * 4);
-                  o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
-                }
-                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                if (valid) st4(cpix + j * 4, o);
+              for (int t = 0; t < TR; ++t) {
+                if (F16 && u == 0 && active && (yq * TR + t < p.H) && (v[t][0] & 0x7F800000u) == 0x7F800000u) guard = 1u;
+                finish(t, j0, v[t][0], v[t][1], v[t][2], v[t][3], b0);
+                finish(t, j0 + 1, v[t][4], v[t][5], v[t][6], v[t][7], b1);
               }
             }
           }
+          if (first && tid == 0) stamp(step, 2);
           tc_fence_before();
           if (b == nblk - 1) fence_async_smem();           // the tile leaves through the async proxy (TMA store)
         }
@@ -602,7 +622,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       const int issuer = warp - W_ISS0;
       const uint32_t ring_addr = smem_u32(s_ring);
       const uint32_t wfull_addr = smem_u32(bar_wfull), afull_addr = smem_u32(bar_afull);
-      const uint32_t wempty_addr = smem_u32(bar_wempty), aempty_addr = smem_u32(bar_aempty);
+      const uint32_t wempty_addr = smem_u32(bar_wempty), aempty_addr = smem_u32(bar_aempty), dfull_addr = smem_u32(bar_dfull);
       uint32_t R = 0;                                                     // global round counter
       int step = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -626,38 +646,53 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               if (traced && r == 0) stamp(step, 4);
               const int nk8 = KS - r * NSETS < NSETS ? KS - r * NSETS : NSETS;
               const int nk = F16 ? (nk8 + 1) >> 1 : nk8;                     // MMA k-steps (A stages, weight slices) of this round
-              uint64_t dhi = desc_hi0 + (uint64_t)(half * NSETS * ((CH_SLOT_FLOATS * 4) >> 4));   // the ring stays below 256 KB: no carry
-              uint32_t a0 = tmem_base + colA0;
-#pragma unroll 1
-              for (int j = 0; j < nk; ++j, dhi += (CH_SLOT_FLOATS * 4) >> 4, a0 += STAGE) {
+              const uint64_t dhi0 = desc_hi0 + (uint64_t)(half * NSETS * ((CH_SLOT_FLOATS * 4) >> 4));   // the ring stays below 256 KB: no carry
+              auto mma3 = [&](int t, int j, uint64_t dhi, uint32_t a0) {
                 const uint64_t dlo = dhi + lo_off;
                 const uint32_t acc_flag = (r | j) ? 1u : 0u;
+                const uint32_t dc = tmem_base + t * CH_DSTRIDE;
+                const uint32_t a = a0 + t * 16;
+                if (F16) {
+                  mma_f16_ts(dc, a, dhi, idesc, acc_flag);
+                  mma_f16_ts(dc, a, dlo, idesc, 1u);
+                  mma_f16_ts(dc, a + 8, dhi, idesc, 1u);
+                } else {
+                  mma_tf32_ts(dc, a, dhi, idesc, acc_flag);
+                  mma_tf32_ts(dc, a, dlo, idesc, 1u);
+                  mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+                }
+              };
+              if (r + 1 < rounds) {
+                uint64_t dhi = dhi0;
+                uint32_t a0 = tmem_base + colA0;
+#pragma unroll 1
+                for (int j = 0; j < nk; ++j, dhi += (CH_SLOT_FLOATS * 4) >> 4, a0 += STAGE) {
 #pragma unroll
-                for (int t = 0; t < TR; ++t) {
-                  if (t % NISS != issuer || no_mma || t >= trn) continue;
-                  const uint32_t dc = tmem_base + t * CH_DSTRIDE;
-                  const uint32_t a = a0 + t * 16;
-                  if (F16) {
-                    mma_f16_ts(dc, a, dhi, idesc, acc_flag);
-                    mma_f16_ts(dc, a, dlo, idesc, 1u);
-                    mma_f16_ts(dc, a + 8, dhi, idesc, 1u);
-                  } else {
-                    mma_tf32_ts(dc, a, dhi, idesc, acc_flag);
-                    mma_tf32_ts(dc, a, dlo, idesc, 1u);
-                    mma_tf32_ts(dc, a + 8, dhi, idesc, 1u);
+                  for (int t = 0; t < TR; ++t) {
+                    if (t % NISS != issuer || no_mma || t >= trn) continue;
+                    mma3(t, j, dhi, a0);
                   }
                 }
+              } else {
+                // last round of the step: M-tile by M-tile (the k order within a tile is unchanged), one d_full per tile
+#pragma unroll
+                for (int t = 0; t < TR; ++t) {
+                  if (t % NISS != issuer) continue;
+                  if (!no_mma && t < trn) {
+                    uint64_t dhi = dhi0;
+                    uint32_t a0 = tmem_base + colA0;
+#pragma unroll 1
+                    for (int j = 0; j < nk; ++j, dhi += (CH_SLOT_FLOATS * 4) >> 4, a0 += STAGE) mma3(t, j, dhi, a0);
+                  }
+                  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t == 0 ? dfull_addr : dfull_addr + (8 + t) * 8) : "memory");
+                }
+                if (traced) stamp(step, 5);
               }
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(aempty_addr) : "memory");
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(wempty_addr + half * 8) : "memory");
             }
             __syncwarp();
           }
-          if (leader) {
-            tc_commit(bar_dfull);
-            if (traced) stamp(step, 5);
-          }
-          __syncwarp();
         }
       }
     } else if (warp == W_WLOAD) {
