@@ -64,7 +64,7 @@ struct ChainParams {
   int H, W, NI, B, n_tiles;
   int lanes, lpi;                 // TMEM lanes in use, lanes per image (= strips * W)
   int row_pitch;                  // W * PS floats
-  // lane -> pixel column: im | strip << 8 | x << 16 (chain blocks) and im | oy << 8 | ox << 16 (tail block), dealt so that the
+  // lane -> pixel column: im | strip << 8 | x << 16 (chain blocks) and im | oy << 8 | ox << 16 | swapped order << 31 (tail block), dealt so that the
   // quarter warps are free of shared-memory bank conflicts where the geometry allows it (chain_lane_table)
   uint32_t lane_tab[128], tail_tab[128];
   uint32_t load_bytes;
@@ -479,7 +479,11 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         const bool active2 = lane < p.tail_lanes;
         const bool warp_active2 = wq * 32 < p.tail_lanes;
         const uint32_t lt2 = p.tail_tab[active2 ? lane : 0];
-        const int im2 = (int)(lt2 & 255u), oy = (int)((lt2 >> 8) & 255u), ox = (int)(lt2 >> 16);
+        const int im2 = (int)(lt2 & 255u), oy = (int)((lt2 >> 8) & 255u), ox = (int)((lt2 >> 16) & 255u);
+        // neighbouring lanes are two input pixels = an even number of 16-byte chunks apart: only 4 of the 8 bank groups are hit.
+        // Every second lane of a bank group (swp) takes the 4-channel halves of a k-step, and the two columns of the pool window,
+        // in the opposite order -- one chunk / one pixel further is the other parity -- which makes the LDS.128 conflict-free.
+        const int swp = (int)(lt2 >> 31);
         const float* win2 = tile + ((im2 * (p.H + 1) + 2 * oy - p.pad_t) * p.W + 2 * ox - p.pad_l) * PS;
         const float* pool = tile + ((im2 * (p.H + 1) + 2 * oy) * p.W + 2 * ox) * PS;
         // window columns 2 ox - pad_l + kx outside the image take a zero weight; the pool window's second column may fall off an odd map
@@ -490,6 +494,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           fk[kx] = (col >= 0 && col < p.W) ? 1.f : 0.f;
         }
         const bool pool2 = 2 * ox + 1 < p.W;
+        const float* pool_a = swp ? pool + PS : pool;             // first / second column of the pool window in this lane's order
+        const float* pool_b = swp ? pool : pool + PS;
+        const bool pool_va = swp ? pool2 : true, pool_vb = swp ? true : pool2;
         ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
         tc_fence_after();
         if (tid == 0) stamp(step, 0);
@@ -502,7 +509,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           if (has) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              const int c = ks * 8 + half * 4;
+              const int c = ks * 8 + (half ^ swp) * 4;
               const float* wp = s_dww + c;
               float4 a = ld4(wp + 9 * cin);
 #pragma unroll
@@ -510,6 +517,11 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) a = fma4(ld4(win2 + ky * row_pitch + kx * PS + c), scale4(ld4(wp + (ky * 3 + kx) * cin), fk[kx]), a);
               acc[half] = a;
+            }
+            if (swp) {                                      // back to channel order
+              const float4 t4 = acc[0];
+              acc[0] = acc[1];
+              acc[1] = t4;
             }
           }
           if (g0 >= 1) {
@@ -557,41 +569,34 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         ch_wait(bar_dfull, step & 1, 4, s_abort, step);
         tc_fence_after();
         if (tid == 0) stamp(step, 2);
-        const int ncg = (n16 + 31) >> 5;
+        (void)n16;
         const int C4 = cin >> 2, NG = cb.cout >> 2;
+        const int n_eu = (NG + 1) >> 1;                           // units of 8 accumulator columns, dealt to the sets like the chain blocks' units
         const long long img = (long long)(blockIdx.x + (long long)it * gridDim.x) * p.NI + im2;
         const bool valid2 = active2 && img < p.B;
         float* dst = p.tail_out + ((img * p.Ho + oy) * p.Wo + ox) * (long long)cb.cout;
         if (warp_active2) {
+          const float us = cb.unscale;
           int u = (int)((NSETS + set - (e0 % NSETS)) % NSETS);
 #pragma unroll 1
-          for (; u < ncg; u += NSETS) {
-            const uint32_t dcol = tlane + u * 32;
-            uint32_t v[32];
-            if (u * 32 + 32 <= n16) {
-              tmem_ld32(dcol, v);
-            } else {
-              uint32_t hlf[16];
-              tmem_ld16(dcol, hlf);
-#pragma unroll
-              for (int e = 0; e < 16; ++e) { v[e] = hlf[e]; v[16 + e] = 0u; }
-            }
+          for (; u < n_eu; u += NSETS) {
+            uint32_t v[8];
+            tmem_ld8(tlane + (uint32_t)u * 8u, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (F16 && u == 0 && valid2 && (v[0] & 0x7F800000u) == 0x7F800000u) guard = 1u;
-            const float us = cb.unscale;
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const int j = u * 8 + jj;
+            for (int q = 0; q < 2; ++q) {
+              const int j = 2 * u + q;
               if (j < NG) {
                 const float4 bb = ld4(s_pwb + j * 4);
-                float4 o = F16 ? make_float4(fmaf(__uint_as_float(v[jj * 4 + 0]), us, bb.x), fmaf(__uint_as_float(v[jj * 4 + 1]), us, bb.y),
-                                             fmaf(__uint_as_float(v[jj * 4 + 2]), us, bb.z), fmaf(__uint_as_float(v[jj * 4 + 3]), us, bb.w))
-                               : make_float4(__uint_as_float(v[jj * 4 + 0]) + bb.x, __uint_as_float(v[jj * 4 + 1]) + bb.y,
-                                             __uint_as_float(v[jj * 4 + 2]) + bb.z, __uint_as_float(v[jj * 4 + 3]) + bb.w);
+                float4 o = F16 ? make_float4(fmaf(__uint_as_float(v[q * 4 + 0]), us, bb.x), fmaf(__uint_as_float(v[q * 4 + 1]), us, bb.y),
+                                             fmaf(__uint_as_float(v[q * 4 + 2]), us, bb.z), fmaf(__uint_as_float(v[q * 4 + 3]), us, bb.w))
+                               : make_float4(__uint_as_float(v[q * 4 + 0]) + bb.x, __uint_as_float(v[q * 4 + 1]) + bb.y,
+                                             __uint_as_float(v[q * 4 + 2]) + bb.z, __uint_as_float(v[q * 4 + 3]) + bb.w);
                 if (j < C4) {
                   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                  const float4 p00 = ld4(pool + j * 4), p01 = pool2 ? ld4(pool + PS + j * 4) : z4;
-                  const float4 p10 = ld4(pool + row_pitch + j * 4), p11 = pool2 ? ld4(pool + row_pitch + PS + j * 4) : z4;
+                  const float4 p00 = pool_va ? ld4(pool_a + j * 4) : z4, p01 = pool_vb ? ld4(pool_b + j * 4) : z4;
+                  const float4 p10 = pool_va ? ld4(pool_a + row_pitch + j * 4) : z4, p11 = pool_vb ? ld4(pool_b + row_pitch + j * 4) : z4;
                   o.x += fmaxf(fmaxf(p00.x, p01.x), fmaxf(p10.x, p11.x));
                   o.y += fmaxf(fmaxf(p00.y, p01.y), fmaxf(p10.y, p11.y));
                   o.z += fmaxf(fmaxf(p00.z, p01.z), fmaxf(p10.z, p11.z));
@@ -604,7 +609,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           }
           tc_fence_before();
         }
-        e0 += (uint32_t)ncg;
+        e0 += (uint32_t)n_eu;
         ch_arrive(bar_epi, lane_id);
         ch_arrive(bar_tail_done, lane_id);
         if (tid == 0) stamp(step, 3);
@@ -847,7 +852,10 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
 // lanes of a quarter warp share the wavefronts of an LDS.128 / STS.128: every group of 8 consecutive lanes gets entries with
 // different residues while the supply lasts (greedy: largest residue classes first), so that an access costs 4 wavefronts
 // per warp instead of up to 8.  The groups are filled densely: lanes [0, n) are in use.
-static void chain_lane_table(const std::vector<int>& pix, const std::vector<uint32_t>& code, uint32_t* tab) {
+// second_bit != 0: every second lane of a residue class within its group of 8 gets that bit set (the stride-2 tail block only
+// has even residues -- at least two lanes per class -- and lets those lanes walk the two 16-byte halves of a k-step, and the
+// two columns of the max-pool window, in the opposite order: one chunk further, the other bank group).
+static void chain_lane_table(const std::vector<int>& pix, const std::vector<uint32_t>& code, uint32_t* tab, uint32_t second_bit = 0u) {
   std::vector<int> bucket[8];
   const int n = (int)pix.size();
   for (int i = n - 1; i >= 0; --i) bucket[((pix[i] % 8) + 8) % 8].push_back(i);   // pop_back() hands them out in natural order
@@ -862,7 +870,7 @@ static void chain_lane_table(const std::vector<int>& pix, const std::vector<uint
         if (bucket[r].empty()) continue;
         if (best < 0 || used[r] < used[best] || (used[r] == used[best] && bucket[r].size() > bucket[best].size())) best = r;
       }
-      tab[lane++] = code[bucket[best].back()];
+      tab[lane++] = code[bucket[best].back()] | ((used[best] & 1) ? second_bit : 0u);
       bucket[best].pop_back();
       used[best]++;
     }
@@ -923,7 +931,7 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
           pix.push_back((im * (H + 1) + 2 * oy) * W + 2 * ox);
           code.push_back((uint32_t)im | ((uint32_t)oy << 8) | ((uint32_t)ox << 16));
         }
-    chain_lane_table(pix, code, p.tail_tab);
+    chain_lane_table(pix, code, p.tail_tab, 0x80000000u);
   }
   {
     const int strips = ceil_div(H, cfg.TR);
