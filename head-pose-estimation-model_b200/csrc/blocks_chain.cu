@@ -118,6 +118,15 @@ __device__ __forceinline__ void ch_wait_lean(uint32_t addr, uint32_t parity) {
 // One arrival per WARP: 512 per-thread arrivals on one mbarrier are 512 serialised shared-memory atomics (measured: a hand-off
 // round trip of the empty pipeline cost ~1.4 K clk).  __syncwarp orders the lanes' shared-memory / TMEM accesses (each lane has
 // executed its own tcgen05.wait / fences) before the elected lane's releasing arrive.
+// HP_CHAIN_SETSYNC = 1: the warp sets run through the blocks of a tile independently.  Set s owns the channel groups
+// u = s, s + NSETS, ... of EVERY block, in the epilogue (accumulator columns 8 u ..) as in the depthwise phase (k-step u), and the
+// depthwise conv of a channel group only reads that group: a set needs nothing but its own epilogue output, so a named barrier
+// of its 128 threads replaces the CTA-wide "epilogue done" barrier between the blocks.  Sets that finish their epilogue units
+// early start the next block's depthwise round while the others are still in the (latency-bound) epilogue; only the issuer waits
+// for all of them (the first MMA of the next block overwrites the accumulators they read).
+#ifndef HP_CHAIN_SETSYNC
+#define HP_CHAIN_SETSYNC 1
+#endif
 #ifndef HP_CHAIN_DWEXP
 #define HP_CHAIN_DWEXP 0          // timing experiments on the depthwise phase (see the uses); 0 in every shipped build
 #endif
@@ -280,7 +289,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         const float* s_dww = s_w + cb.w_off;
         const float* s_pwb = s_dww + 10 * cin;
         if (b == 0) ch_wait(bar_tile_full, it & 1, 1, s_abort, step);
-        else ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
+        else if (!HP_CHAIN_SETSYNC) ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
         tc_fence_after();
         if (tid == 0) stamp(step, 0);
         // ---------------- depthwise rounds: in round r this set computes k-step r * NSETS + set (if the block has it)
@@ -421,7 +430,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               if (active && (yq * TR + t < p.H)) st4(cpix + j * 4, o);
             }
           };
-          int u = (int)((NSETS + set - (e0 % NSETS)) % NSETS);
+          int u = HP_CHAIN_SETSYNC ? set : (int)((NSETS + set - (e0 % NSETS)) % NSETS);
           bool first = true;
 #pragma unroll 1
           for (; u < n_eu; u += NSETS) {
@@ -462,6 +471,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           if (b == nblk - 1) fence_async_smem();           // the tile leaves through the async proxy (TMA store)
         }
         e0 += (uint32_t)n_eu;
+        if (HP_CHAIN_SETSYNC) named_bar_sync(1 + set, 128);   // this set's channel groups of the block are in the tile (all 4 warps, active or not)
         ch_arrive(bar_epi, lane_id);
         if (b == nblk - 1) ch_arrive(bar_tile_done, lane_id);
         if (tid == 0) stamp(step, 3);
@@ -497,7 +507,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         const float* pool_a = swp ? pool + PS : pool;             // first / second column of the pool window in this lane's order
         const float* pool_b = swp ? pool : pool + PS;
         const bool pool_va = swp ? pool2 : true, pool_vb = swp ? true : pool2;
-        ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
+        if (!HP_CHAIN_SETSYNC) ch_wait(bar_epi, (step - 1) & 1, 2, s_abort, step);
         tc_fence_after();
         if (tid == 0) stamp(step, 0);
         const int rounds = (KS + NSETS - 1) / NSETS;
@@ -577,7 +587,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         float* dst = p.tail_out + ((img * p.Ho + oy) * p.Wo + ox) * (long long)cb.cout;
         if (warp_active2) {
           const float us = cb.unscale;
-          int u = (int)((NSETS + set - (e0 % NSETS)) % NSETS);
+          int u = HP_CHAIN_SETSYNC ? set : (int)((NSETS + set - (e0 % NSETS)) % NSETS);
 #pragma unroll 1
           for (; u < n_eu; u += NSETS) {
             uint32_t v[8];
@@ -627,7 +637,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       const int issuer = warp - W_ISS0;
       const uint32_t ring_addr = smem_u32(s_ring);
       const uint32_t wfull_addr = smem_u32(bar_wfull), afull_addr = smem_u32(bar_afull);
-      const uint32_t wempty_addr = smem_u32(bar_wempty), aempty_addr = smem_u32(bar_aempty), dfull_addr = smem_u32(bar_dfull);
+      const uint32_t wempty_addr = smem_u32(bar_wempty), aempty_addr = smem_u32(bar_aempty), dfull_addr = smem_u32(bar_dfull), epi_addr = smem_u32(bar_epi);
       uint32_t R = 0;                                                     // global round counter
       int step = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -641,6 +651,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           const bool traced = p.trace != nullptr && blockIdx.x == 0 && leader && issuer == 0;
           const bool no_mma = (p.exp_ & 4) != 0;
           const int rounds = (KS + NSETS - 1) / NSETS;
+          // the first MMA of the step overwrites accumulators that the epilogue of the previous step reads (the workers
+          // themselves no longer wait for each other between the blocks of a tile)
+          if (HP_CHAIN_SETSYNC && b > 0) ch_wait_lean(epi_addr, (uint32_t)(step - 1) & 1u);
 #pragma unroll 1
           for (int r = 0; r < rounds; ++r, ++R) {
             const uint32_t half = R & 1u;
