@@ -841,7 +841,7 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
       // with 3 sets, profiles/r01/tc_sweep_s2_96.log).  Output maps under 100 pixels (block 11: 36 of 128 lanes per 6 x 6 image,
       // 67 KB of split weights next to 62 KB input bands) are no faster than the CUDA-core kernel and stay there unless asked for.
       if (tv[0] > 0 || Ho * Wo >= 100)
-        use_tc_s2 = hp_tcs2_geometry(i, Ho, Wo, tv[0] > 0 && tv[4] > 0 ? tv[4] : 2, tv[0] > 0 && tv[3] > 0 ? tv[3] : 2, &tcc);
+        use_tc_s2 = hp_tcs2_geometry(i, Ho, Wo, tv[0] > 0 && tv[4] > 0 ? tv[4] : 2, tv[0] > 0 && tv[3] > 0 ? tv[3] : 2, &tcc, tv[0] > 0 ? tv[2] : 0);
       HP_REQUIRE(use_tc_s2 || tv[0] == 0, HP_ERR_INVALID, "tc override for block %d: the stride-2 kernel does not fit a %dx%d map", i, Ho, Wo);
       if (use_tc_s2 && tv[0] > 0) {
         if (tv[5] >= 2 && tv[5] < tcc.nbuf) tcc.nbuf = tv[5];

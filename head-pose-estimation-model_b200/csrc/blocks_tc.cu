@@ -1712,7 +1712,7 @@ bool hp_tcs_geometry(int blk, int H, int W, int nsets, int esets, TcCfg* tc) {
 
 // Geometry of the stride-2 tensor-core kernel: the tallest band of output rows (R Wo <= 128 lanes) whose input band fits
 // shared memory at least twice next to the split weights and two output staging tiles.
-bool hp_tcs2_geometry(int blk, int Ho, int Wo, int nsets, int esets, TcCfg* tc) {
+bool hp_tcs2_geometry(int blk, int Ho, int Wo, int nsets, int esets, TcCfg* tc, int force_R) {
   const int cinp = chan_pad(kBlazeBlocks[blk].cin), coutp = chan_pad(kBlazeBlocks[blk].cout);
   const int N16 = (coutp + 15) / 16 * 16;
   if (kBlazeBlocks[blk].stride != 2 || Wo < 1 || Wo > 127 || Ho < 1) return false;
@@ -1723,13 +1723,27 @@ bool hp_tcs2_geometry(int blk, int Ho, int Wo, int nsets, int esets, TcCfg* tc) 
   if (2 * N16 + t.NSTG * 16 * t.unit > 512) return false;
   int Rmax = 128 / Wo;
   if (Rmax > Ho) Rmax = Ho;
+  if (force_R > 0) {                                               // tuning: explicit band height, as many buffers as fit (at most 4)
+    if (force_R > Rmax) return false;
+    for (int want = TCD_MAXB; want >= 2; --want) {
+      Tcs2Params p;
+      if (tcs2_layout(cinp, coutp, Wo, force_R, want, &p) <= 227 * 1024) {
+        t.BH = force_R; t.nbuf = want;
+        *tc = t;
+        return true;
+      }
+    }
+    return false;
+  }
   // three input bands in flight beat taller bands (the band cycle load -> depthwise -> epilogue is latency bound: block 2
-  // went from 5.3K clk per 120-pixel tile with 2 buffers to 3 buffers of 96 pixels), as long as >= 60 % of the rows remain
+  // went from 5.3K clk per 120-pixel tile with 2 buffers to 3 buffers of 96 pixels), as long as >= 40 % of the rows remain
+  // (tools/s2_sweep.py: block 5 at 88 x 88 input 0.179 ms with 2 bands of 6 rows in 2 buffers -> 0.130 in 3 buffers; at 128 x 128
+  // 0.266 ms with 8 rows in 2 buffers -> 0.242 with 4 rows in 3)
   for (int want = 3; want >= 2; --want)
     for (int R = Rmax; R >= 1; --R) {
       const int bands = ceil_div(Ho, R);
       const int Rb = ceil_div(Ho, bands);                       // equally tall bands
-      if (want == 3 && Rb * 10 < Rmax * 6) break;
+      if (want == 3 && Rb * 10 < Rmax * 4) break;
       Tcs2Params p;
       if (tcs2_layout(cinp, coutp, Wo, Rb, want, &p) <= 227 * 1024) {
         t.BH = Rb; t.nbuf = want;

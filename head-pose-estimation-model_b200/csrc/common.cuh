@@ -209,7 +209,7 @@ struct TcCfg {
 bool hp_tc_fits(int blk, int H, int W, const TcCfg& tc);
 bool hp_tcd_geometry(int blk, int H, int W, int TR, int nsets, int esets, TcCfg* tc);
 bool hp_tcs_geometry(int blk, int H, int W, int nsets, int esets, TcCfg* tc);
-bool hp_tcs2_geometry(int blk, int Ho, int Wo, int nsets, int esets, TcCfg* tc);
+bool hp_tcs2_geometry(int blk, int Ho, int Wo, int nsets, int esets, TcCfg* tc, int force_R = 0);
 int hp_launch_block_tc_s2(hp_ctx* h, int blk, const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, int pad_t, int pad_l,
                           const BlockWeights& w, const TcCfg& tc, cudaStream_t st);
 void hp_tc_split_weights(const float* pww, int cinp, int coutp, float* bhi, float* blo);
