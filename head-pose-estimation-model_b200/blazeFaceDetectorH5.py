@@ -294,22 +294,36 @@ class blazeFaceDetector:
         14.4 KB per frame whatever was found).
 
         Buffer lifetime: three result slots rotate and at most two batches are in flight, so a yielded dict stays valid
-        until the generator has been advanced TWICE more (the slot being refilled is never the one just handed out)."""
+        until the generator has been advanced TWICE more (the slot being refilled is never the one just handed out).
+        The slots (device input / result tensors, PINNED host result tensors, streams, events) belong to the detector and
+        are reused by later ``detect_stream`` calls with the same ``packed`` / ``chunks``: pinning ~60 MB of host memory per
+        slot costs ~6 ms, which a serving loop must not pay per call.  Results of an earlier call are therefore overwritten by
+        the next one -- copy what has to live longer.  (A second generator started while one is still running gets private slots.)"""
         import torch
         dev = self.ctx.torch_device
         comp = torch.cuda.current_stream(dev)
-        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        s_rec = torch.cuda.Stream(dev)                    # second-phase record copies: must not queue behind the NEXT batch's read-back
         chunks = 1 if packed else max(1, int(chunks))
         NS = 3
-        d_in = [[None] * chunks for _ in range(NS)]
-        d_out = [[None] * chunks for _ in range(NS)]      # device result tensors, reused: slot b is idle once its read-back is done
-        ev_read = [[None] * chunks for _ in range(NS)]
-        h_out = [None] * NS
-        ev_in = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(NS)]
-        ev_comp = [[torch.cuda.Event() for _ in range(chunks)] for _ in range(NS)]
-        used = [[False] * chunks for _ in range(NS)]
-        ev_out = [torch.cuda.Event() for _ in range(NS)]
+        cache = self.__dict__.setdefault("_stream_slots", {})
+        st = cache.get((bool(packed), chunks))
+        if st is None or st["busy"]:
+            st = {"busy": False,
+                  "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                  "s_rec": torch.cuda.Stream(dev),      # second-phase record copies: must not queue behind the NEXT batch's read-back
+                  "d_in": [[None] * chunks for _ in range(NS)],
+                  "d_out": [[None] * chunks for _ in range(NS)],   # device result tensors, reused: slot b is idle once its read-back is done
+                  "ev_read": [[None] * chunks for _ in range(NS)],
+                  "h_out": [None] * NS,
+                  "ev_in": [[torch.cuda.Event() for _ in range(chunks)] for _ in range(NS)],
+                  "ev_comp": [[torch.cuda.Event() for _ in range(chunks)] for _ in range(NS)],
+                  "used": [[False] * chunks for _ in range(NS)],
+                  "ev_out": [torch.cuda.Event() for _ in range(NS)]}
+            if (bool(packed), chunks) not in cache or not cache[(bool(packed), chunks)]["busy"]:
+                cache[(bool(packed), chunks)] = st
+        st["busy"] = True
+        s_in, s_out, s_rec = st["s_in"], st["s_out"], st["s_rec"]
+        d_in, d_out, ev_read, h_out = st["d_in"], st["d_out"], st["ev_read"], st["h_out"]
+        ev_in, ev_comp, used, ev_out = st["ev_in"], st["ev_comp"], st["used"], st["ev_out"]
         meta = [None] * NS
         pending = []                                      # slots whose results are still on their way to the host
         L = _lib.lib()
@@ -333,6 +347,18 @@ class blazeFaceDetector:
             return {"total": int(hdr[0]), "count": hdr[_lib.HP_RESULT_HEADER_INTS:_lib.HP_RESULT_HEADER_INTS + B],
                     "faces": raw[faces_off:faces_off + written * FACE_DTYPE.itemsize].view(FACE_DTYPE)}
 
+        n = 0
+        try:
+            yield from self._detect_stream_loop(host_batches, max_faces, keys, chunks, packed, st, finish, pending, meta, comp, L, m, NS)
+        finally:
+            st["busy"] = False
+
+    def _detect_stream_loop(self, host_batches, max_faces, keys, chunks, packed, st, finish, pending, meta, comp, L, m, NS):
+        import torch
+        dev = self.ctx.torch_device
+        s_in, s_out = st["s_in"], st["s_out"]
+        d_in, d_out, ev_read, h_out = st["d_in"], st["d_out"], st["ev_read"], st["h_out"]
+        ev_in, ev_comp, used, ev_out = st["ev_in"], st["ev_comp"], st["used"], st["ev_out"]
         n = 0
         for hb in host_batches:
             b = n % NS

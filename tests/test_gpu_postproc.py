@@ -192,6 +192,44 @@ def test_detect_stream_matches_detect_device(chunks):
                 assert np.array_equal(g[k][i, :c], w[k][i, :c]), (k, i)
 
 
+def test_detect_stream_reuses_its_pinned_slots():
+    """A second detect_stream call on the same detector reuses the pinned host result tensors of the first one (pinning ~60 MB
+    per slot costs milliseconds: a serving loop must not pay it per call) and returns the same results; a generator started
+    while another one is still running gets private slots."""
+    import torch
+    from hpose_b200 import keras_spec as K, train_88
+    from hpose_b200.attention_model import se_transformer_regr_head
+    from hpose_b200.blazeFaceDetectorH5 import blazeFaceDetector
+    from hpose_b200.unified import UnifiedModel, random_backbone
+    K.reset_names(); K.set_seed(11)
+    head16 = train_88.create_model()
+    K.reset_names()
+    head8 = se_transformer_regr_head(input_channels=96)
+    det = blazeFaceDetector(model=UnifiedModel(random_backbone(seed=4, bias_scale=0.1), head16, head8), inputSize=96)
+    rng = np.random.default_rng(5)
+    host = [torch.from_numpy(rng.integers(0, 256, size=(64, 96, 96, 3), dtype=np.uint8)).pin_memory() for _ in range(5)]
+    runs, ptrs = [], []
+    for _ in range(2):
+        got, pp = [], set()
+        for res in det.detect_stream(iter(host)):
+            got.append({k: res[k].numpy().copy() for k in res})
+            pp.add(res["boxes"].data_ptr())
+        runs.append(got)
+        ptrs.append(pp)
+    assert ptrs[0] == ptrs[1] and len(ptrs[0]) == 3
+    for a, b in zip(*runs):
+        assert np.array_equal(a["count"], b["count"])
+        for i, c in enumerate(a["count"]):
+            for k in ("boxes", "scores", "poses", "keypoints"):
+                assert np.array_equal(a[k][i, :c], b[k][i, :c]), (k, i)
+    # two generators at the same time: the second one must not share the first one's slots
+    g1, g2 = det.detect_stream(iter(host)), det.detect_stream(iter(host))
+    r1, r2 = next(g1), next(g2)
+    assert r1["boxes"].data_ptr() != r2["boxes"].data_ptr()
+    assert np.array_equal(r1["count"].numpy(), r2["count"].numpy())
+    g1.close(); g2.close()
+
+
 def test_kept_anchors_against_fp64_oracle_logits():
     """north_star asks for bit-exact kept-anchor indices against the reference path.  Here the whole CUDA path (fp32 logits from
     the tensor-core backbone -> CUDA decode + NMS) is compared with the float64 oracle graph -> numpy post-processing on the
