@@ -169,6 +169,7 @@ _PROTOS = {
     "hp_debug_set_stem_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hp_debug_set_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "hp_debug_chain_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hp_debug_chain_describe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hp_debug_tc_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hp_debug_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

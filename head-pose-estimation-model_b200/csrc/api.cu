@@ -165,6 +165,10 @@ int hp_debug_chain_status(hp_handle h, unsigned int* out8_host) {
   HP_REQUIRE(out8_host != nullptr, HP_ERR_INVALID, "hp_debug_chain_status: null pointer");
   return hp_chain_status(out8_host);
 }
+int hp_debug_chain_describe(int first, int nblk, int H, int W, int tail, unsigned int* out264_host) {
+  HP_REQUIRE(out264_host != nullptr, HP_ERR_INVALID, "hp_debug_chain_describe: null pointer");
+  return hp_chain_describe(first, nblk, H, W, tail, out264_host);
+}
 int hp_debug_tc_trace(hp_handle h, long long* dev_buf, int max_tiles) {
   HP_REQUIRE(h, HP_ERR_INVALID, "null handle");
   h->tc_trace = dev_buf; h->tc_trace_tiles = dev_buf ? max_tiles : 0;

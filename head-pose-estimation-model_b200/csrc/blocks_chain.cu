@@ -891,6 +891,49 @@ static void chain_lane_table(const std::vector<int>& pix, const std::vector<uint
   for (; lane < 128; ++lane) tab[lane] = 0u;
 }
 
+// lane -> pixel column tables of the chain kernel for an H x W map (host only)
+static void chain_tables(int H, int W, int TR, int NI, bool tail, uint32_t* lane_tab, uint32_t* tail_tab) {
+  const int strips = ceil_div(H, TR);
+  std::vector<int> pix;
+  std::vector<uint32_t> code;
+  for (int im = 0; im < NI; ++im)
+    for (int yq = 0; yq < strips; ++yq)
+      for (int x = 0; x < W; ++x) {
+        pix.push_back((im * (H + 1) + yq * TR) * W + x);
+        code.push_back((uint32_t)im | ((uint32_t)yq << 8) | ((uint32_t)x << 16));
+      }
+  chain_lane_table(pix, code, lane_tab);
+  if (!tail) return;
+  pix.clear();
+  code.clear();
+  const int Ho = ceil_div(H, 2), Wo = ceil_div(W, 2);
+  for (int im = 0; im < NI; ++im)
+    for (int oy = 0; oy < Ho; ++oy)
+      for (int ox = 0; ox < Wo; ++ox) {
+        pix.push_back((im * (H + 1) + 2 * oy) * W + 2 * ox);
+        code.push_back((uint32_t)im | ((uint32_t)oy << 8) | ((uint32_t)ox << 16));
+      }
+  chain_lane_table(pix, code, tail_tab, 0x80000000u);
+}
+
+// Host-side geometry of the chain kernel for blocks [first, first + nblk) (+ the stride-2 block behind them when tail != 0) on an
+// H x W map, without touching the device: out[0..7] = {TR, NI, PS, lanes, tail lanes, shared-memory bytes, 0, 0}, out[8..135] = lane table,
+// out[136..263] = tail table.  Returns HP_ERR_UNSUPPORTED when the chain kernel does not apply.
+int hp_chain_describe(int first, int nblk, int H, int W, int tail, unsigned int* out264) {
+  ChainCfg cfg;
+  const int tail_blk = tail ? first + nblk : -1;
+  if (!hp_chain_geometry(first, nblk, nblk, H, W, &cfg, tail_blk)) {
+    hp_set_error("chain %d..%d does not apply to a %dx%d map", first, first + nblk - 1, H, W);
+    return HP_ERR_UNSUPPORTED;
+  }
+  memset(out264, 0, 264 * sizeof(unsigned int));
+  out264[0] = cfg.TR; out264[1] = cfg.NI; out264[2] = cfg.PS; out264[3] = cfg.lanes;
+  out264[4] = tail ? cfg.NI * ceil_div(H, 2) * ceil_div(W, 2) : 0;
+  out264[5] = (unsigned int)cfg.smem;
+  chain_tables(H, W, cfg.TR, cfg.NI, tail != 0, out264 + 8, out264 + 136);
+  return HP_OK;
+}
+
 int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out, int B, int H, int W, const ChainCfg& cfg,
                     cudaStream_t st, int tail_blk, float* tail_out) {
   const Backbone& bb = h->bb;
@@ -936,28 +979,11 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
     same_pad(H, 3, 2, &o_, &pb); p.pad_t = pb;
     same_pad(W, 3, 2, &o_, &pb); p.pad_l = pb;
     HP_REQUIRE(p.tail_lanes <= 128 && p.pad_t <= 1 && p.pad_l <= 1, HP_ERR_INVALID, "chain: tail block on %dx%d does not fit one M-tile", H, W);
-    std::vector<int> pix;
-    std::vector<uint32_t> code;
-    for (int im = 0; im < cfg.NI; ++im)
-      for (int oy = 0; oy < p.Ho; ++oy)
-        for (int ox = 0; ox < p.Wo; ++ox) {
-          pix.push_back((im * (H + 1) + 2 * oy) * W + 2 * ox);
-          code.push_back((uint32_t)im | ((uint32_t)oy << 8) | ((uint32_t)ox << 16));
-        }
-    chain_lane_table(pix, code, p.tail_tab, 0x80000000u);
   }
   {
     const int strips = ceil_div(H, cfg.TR);
     HP_REQUIRE(cfg.NI * strips * W == cfg.lanes && cfg.NI < 256 && strips < 256 && W < 256, HP_ERR_INVALID, "chain: lane count %d does not match %d x %d x %d", cfg.lanes, cfg.NI, strips, W);
-    std::vector<int> pix;
-    std::vector<uint32_t> code;
-    for (int im = 0; im < cfg.NI; ++im)
-      for (int yq = 0; yq < strips; ++yq)
-        for (int x = 0; x < W; ++x) {
-          pix.push_back((im * (H + 1) + yq * cfg.TR) * W + x);
-          code.push_back((uint32_t)im | ((uint32_t)yq << 8) | ((uint32_t)x << 16));
-        }
-    chain_lane_table(pix, code, p.lane_tab);
+    chain_tables(H, W, cfg.TR, cfg.NI, tail_blk >= 0, p.lane_tab, p.tail_tab);
   }
   HP_REQUIRE(w_off <= cfg.w_floats, HP_ERR_STATE, "chain: weight area too small (%d > %d floats)", w_off, cfg.w_floats);
   p.H = H; p.W = W; p.NI = cfg.NI; p.B = B;

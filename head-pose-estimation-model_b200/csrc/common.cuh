@@ -234,6 +234,7 @@ struct ChainCfg {
 };
 bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg, int tail_blk = -1);
 int hp_chain_status(unsigned int out[8]);
+int hp_chain_describe(int first, int nblk, int H, int W, int tail, unsigned int* out264);
 int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out, int B, int H, int W, const ChainCfg& cfg,
                     cudaStream_t st, int tail_blk = -1, float* tail_out = nullptr);
 

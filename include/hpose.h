@@ -304,6 +304,11 @@ int hp_debug_set_chain(hp_handle h, int mode, int nsets, int niss);
 /* watchdog record of the chain kernels since the last call: out8_host[0] != 0 -> a barrier wait timed out ({1, barrier id, parity,
  * thread, CTA, step}); synchronises the device and clears the record */
 int hp_debug_chain_status(hp_handle h, unsigned int* out8_host);
+/* host-only (no device needed): geometry of the chain kernel for blocks [first, first + nblk) (+ the stride-2 block behind them when
+ * tail != 0) on an H x W map: out[0..5] = {rows per lane, images per tile, pixel stride in floats, lanes, tail lanes, shared-memory bytes},
+ * out[8..135] = lane table (image | strip << 8 | column << 16 per TMEM lane), out[136..263] = tail table (image | oy << 8 | ox << 16 |
+ * swapped order << 31); HP_ERR_UNSUPPORTED when the chain kernel does not apply */
+int hp_debug_chain_describe(int first, int nblk, int H, int W, int tail, unsigned int* out264_host);
 /* device buffer of max_tiles x 12 clock64 stamps written by CTA 0 of the warp-specialised tensor-core kernel (NULL = off) */
 int hp_debug_tc_trace(hp_handle h, long long* dev_buf, int max_tiles);
 int hp_debug_set_tc(hp_handle h, int blk, int TR, int NSTG, int BH, int npipe, int nsets, int nbuf);

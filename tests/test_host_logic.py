@@ -285,3 +285,66 @@ def test_real_unified_h5_files_load():
                 assert np.array_equal(v, w[f"model/{k}"])
             for k, v in u.head8.get_weights_dict().items():
                 assert np.array_equal(v, w[f"model_10/{k}"])
+
+
+def _chain_desc(built_lib, first, nblk, H, W, tail):
+    lib = ctypes.CDLL(built_lib)
+    out = np.zeros(264, np.uint32)
+    rc = lib.hp_debug_chain_describe(first, nblk, H, W, tail, out.ctypes.data_as(ctypes.c_void_p))
+    return rc, out
+
+
+@pytest.mark.parametrize("size", [64, 88, 96, 100, 104, 128])
+def test_chain_lane_tables_cover_every_pixel_column_once(built_lib, size):
+    """Host logic of the chain kernels (csrc/blocks_chain.cu: chain_lane_table): every TMEM lane in use owns exactly one
+    (image, strip, column) of the tile / one output pixel of the stride-2 tail block, nothing twice, nothing missing."""
+    H16, H8 = -(-size // 8), -(-size // 16)
+    for first, nblk, H, tail in ((6, 5, H16, 1), (12, 4, H8, 0)):
+        rc, d = _chain_desc(built_lib, first, nblk, H, H, tail)
+        assert rc == 0, (size, first)
+        TR, NI, PS, lanes, tail_lanes, smem = [int(v) for v in d[:6]]
+        assert smem <= 227 * 1024 and 1 <= lanes <= 128 and PS % 8 == 4
+        strips = -(-H // TR)
+        got = {(int(v) & 255, (int(v) >> 8) & 255, int(v) >> 16) for v in d[8:8 + lanes]}
+        assert got == {(im, s, x) for im in range(NI) for s in range(strips) for x in range(H)}
+        assert not d[8 + lanes:136].any()
+        if tail:
+            Ho = -(-H // 2)
+            assert tail_lanes == NI * Ho * Ho <= 128
+            got = {(int(v) & 255, (int(v) >> 8) & 255, (int(v) >> 16) & 255) for v in d[136:136 + tail_lanes]}
+            assert got == {(im, y, x) for im in range(NI) for y in range(Ho) for x in range(Ho)}
+
+
+def _wavefronts(residues):
+    """shared-memory wavefronts of one LDS.128 of a warp: the 8 lanes of a quarter warp share a wavefront unless two of them hit the
+    same bank group (16-byte chunk index mod 8)"""
+    tot = 0
+    for q in range(0, len(residues), 8):
+        grp = residues[q:q + 8]
+        tot += max(grp.count(r) for r in set(grp))
+    return tot
+
+
+def test_chain_lane_tables_are_bank_conflict_free_at_96(built_lib):
+    """At the headline size (12 x 12 and 6 x 6 maps) the lane tables make every 128-bit shared-memory access of the chain kernels
+    conflict-free: the bank group of a pixel is (linear pixel index x odd chunk count) mod 8, the tail block's swapped lanes start
+    one 16-byte chunk further."""
+    for first, nblk, H, tail in ((6, 5, 12, 1), (12, 4, 6, 0)):
+        rc, d = _chain_desc(built_lib, first, nblk, H, H, tail)
+        assert rc == 0
+        TR, NI, PS, lanes, tail_lanes = [int(v) for v in d[:5]]
+        chunks = PS // 4
+        assert chunks % 2 == 1
+        res = []
+        for v in d[8:8 + lanes]:
+            im, s, x = int(v) & 255, (int(v) >> 8) & 255, int(v) >> 16
+            res.append((((im * (H + 1) + s * TR) * H + x) * chunks) % 8)
+        # 12 x 12: 4 wavefronts per warp; 6 x 6 (7 images of 18 lanes): the residue classes are not equally full, one group has two lanes
+        # in a class (17 wavefronts for 126 lanes; the natural lane order needs 31)
+        assert _wavefronts(res) <= -(-lanes // 8) + (1 if H == 6 else 0), (H, res)
+        if tail:
+            res = []
+            for v in d[136:136 + tail_lanes]:
+                im, y, x, swp = int(v) & 255, (int(v) >> 8) & 255, (int(v) >> 16) & 255, int(v) >> 31
+                res.append((((im * (H + 1) + 2 * y) * H + 2 * x) * chunks + swp) % 8)
+            assert _wavefronts(res) == -(-tail_lanes // 8), res
