@@ -860,37 +860,6 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
   return true;
 }
 
-// Deal pixel columns to lanes.  pix[i] = linear pixel index (in pixels of PS floats) of the first tap of entry i, code[i] = its
-// packed coordinates.  With PS = an odd number of 16-byte chunks the bank group of a 128-bit access is pix mod 8, and the 8
-// lanes of a quarter warp share the wavefronts of an LDS.128 / STS.128: every group of 8 consecutive lanes gets entries with
-// different residues while the supply lasts (greedy: largest residue classes first), so that an access costs 4 wavefronts
-// per warp instead of up to 8.  The groups are filled densely: lanes [0, n) are in use.
-// second_bit != 0: every second lane of a residue class within its group of 8 gets that bit set (the stride-2 tail block only
-// has even residues -- at least two lanes per class -- and lets those lanes walk the two 16-byte halves of a k-step, and the
-// two columns of the max-pool window, in the opposite order: one chunk further, the other bank group).
-static void chain_lane_table(const std::vector<int>& pix, const std::vector<uint32_t>& code, uint32_t* tab, uint32_t second_bit = 0u) {
-  std::vector<int> bucket[8];
-  const int n = (int)pix.size();
-  for (int i = n - 1; i >= 0; --i) bucket[((pix[i] % 8) + 8) % 8].push_back(i);   // pop_back() hands them out in natural order
-  int lane = 0;
-  while (lane < n) {
-    int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int want = n - lane < 8 ? n - lane : 8;
-    for (int k = 0; k < want; ++k) {
-      // the class with the lowest multiplicity in this group, then the fullest one
-      int best = -1;
-      for (int r = 0; r < 8; ++r) {
-        if (bucket[r].empty()) continue;
-        if (best < 0 || used[r] < used[best] || (used[r] == used[best] && bucket[r].size() > bucket[best].size())) best = r;
-      }
-      tab[lane++] = code[bucket[best].back()] | ((used[best] & 1) ? second_bit : 0u);
-      bucket[best].pop_back();
-      used[best]++;
-    }
-  }
-  for (; lane < 128; ++lane) tab[lane] = 0u;
-}
-
 // lane -> pixel column tables of the chain kernel for an H x W map (host only)
 static void chain_tables(int H, int W, int TR, int NI, bool tail, uint32_t* lane_tab, uint32_t* tail_tab) {
   const int strips = ceil_div(H, TR);
@@ -902,7 +871,7 @@ static void chain_tables(int H, int W, int TR, int NI, bool tail, uint32_t* lane
         pix.push_back((im * (H + 1) + yq * TR) * W + x);
         code.push_back((uint32_t)im | ((uint32_t)yq << 8) | ((uint32_t)x << 16));
       }
-  chain_lane_table(pix, code, lane_tab);
+  tc_lane_table(pix, code, lane_tab);
   if (!tail) return;
   pix.clear();
   code.clear();
@@ -913,7 +882,7 @@ static void chain_tables(int H, int W, int TR, int NI, bool tail, uint32_t* lane
         pix.push_back((im * (H + 1) + 2 * oy) * W + 2 * ox);
         code.push_back((uint32_t)im | ((uint32_t)oy << 8) | ((uint32_t)ox << 16));
       }
-  chain_lane_table(pix, code, tail_tab, 0x80000000u);
+  tc_lane_table(pix, code, tail_tab, 0x80000000u);
 }
 
 // Host-side geometry of the chain kernel for blocks [first, first + nblk) (+ the stride-2 block behind them when tail != 0) on an

@@ -1,5 +1,6 @@
 // Device-side PTX helpers shared by the tensor-core kernels (blocks_tc.cu, stem_tc.cu): mbarrier, TMA, tcgen05.
 #pragma once
+#include <vector>
 #include <cuda.h>
 
 #include "common.cuh"
@@ -190,3 +191,34 @@ inline int tc_make_map4(CUtensorMap* tm, const float* base, const cuuint64_t dim
 inline int tc_align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 }  // namespace
+
+// Deal pixel columns to lanes.  pix[i] = linear pixel index (in pixels of PS floats) of the first tap of entry i, code[i] = its
+// packed coordinates.  With PS = an odd number of 16-byte chunks the bank group of a 128-bit access is pix mod 8, and the 8
+// lanes of a quarter warp share the wavefronts of an LDS.128 / STS.128: every group of 8 consecutive lanes gets entries with
+// different residues while the supply lasts (greedy: largest residue classes first), so that an access costs 4 wavefronts
+// per warp instead of up to 8.  The groups are filled densely: lanes [0, n) are in use.
+// second_bit != 0: every second lane of a residue class within its group of 8 gets that bit set (the stride-2 tail block only
+// has even residues -- at least two lanes per class -- and lets those lanes walk the two 16-byte halves of a k-step, and the
+// two columns of the max-pool window, in the opposite order: one chunk further, the other bank group).
+inline void tc_lane_table(const std::vector<int>& pix, const std::vector<uint32_t>& code, uint32_t* tab, uint32_t second_bit = 0u) {
+  std::vector<int> bucket[8];
+  const int n = (int)pix.size();
+  for (int i = n - 1; i >= 0; --i) bucket[((pix[i] % 8) + 8) % 8].push_back(i);   // pop_back() hands them out in natural order
+  int lane = 0;
+  while (lane < n) {
+    int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int want = n - lane < 8 ? n - lane : 8;
+    for (int k = 0; k < want; ++k) {
+      // the class with the lowest multiplicity in this group, then the fullest one
+      int best = -1;
+      for (int r = 0; r < 8; ++r) {
+        if (bucket[r].empty()) continue;
+        if (best < 0 || used[r] < used[best] || (used[r] == used[best] && bucket[r].size() > bucket[best].size())) best = r;
+      }
+      tab[lane++] = code[bucket[best].back()] | ((used[best] & 1) ? second_bit : 0u);
+      bucket[best].pop_back();
+      used[best]++;
+    }
+  }
+  for (; lane < 128; ++lane) tab[lane] = 0u;
+}
