@@ -1785,8 +1785,13 @@ bool hp_tc_choose(int blk, int H, int W, TcCfg* tc) {
   if (H * W <= 128) return hp_tcs_geometry(blk, H, W, 3, 2, tc);   // pixel-per-lane kernel (blocks 6-15 on 6 x 6 ... 11 x 11 maps)
   if (W < 12) return false;
   const int n16 = (chan_pad(kBlazeBlocks[blk].cout) + 15) / 16 * 16;
-  if (n16 == 48 && hp_tcd_geometry(blk, H, W, 2, 3, 1, &a)) {   // blocks 3, 4: 2 rows, 3 depthwise sets, issuers on sub-partition 3
-    a.unit = 2; a.niss = 2; a.place = 1;
+  if (n16 == 48 && hp_tcd_geometry(blk, H, W, 2, 3, 1, &a)) {   // blocks 3, 4: 2 rows, 3 depthwise sets
+    // up to 96 lanes: one epilogue set, issuers on the free sub-partition 3 (0.181 / 0.203 ms at 96 x 96 input against 0.181 / 0.216 with
+    // two epilogue sets); with 128 lanes (128 x 128 input) that sub-partition is busy: two epilogue sets, unplaced issuers (0.277 / 0.379
+    // -> 0.269 / 0.354 ms)
+    const bool wide = (a.BH / a.TR) * W * a.ni > 96;
+    if (wide && !hp_tcd_geometry(blk, H, W, 2, 3, 2, &a)) return false;
+    a.unit = 2; a.niss = 2; a.place = wide ? 0 : 1;
     if (hp_tc_fits(blk, H, W, a)) { *tc = a; return true; }
   }
   // tiles of at most 96 lanes leave TMEM sub-partition 3 (and its scheduler) to the issuer warps: one epilogue set is then enough and
