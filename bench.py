@@ -667,9 +667,10 @@ def main():
                 "layers": layers}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cps, dt = cpu_reference_run(S, args.cpu_sample, 2, threads)
+            n_cpu = max(args.cpu_sample, 1024)        # ~10 s of CPU work: a quarter of the GPU batch, twice
+            cps, dt = cpu_reference_run(S, n_cpu, 2, threads)
             line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{args.cpu_sample} crops, best of 2; restated CPU path (TensorFlow/Keras "
+                                    "sample": f"{n_cpu} crops, best of 2; restated CPU path (TensorFlow/Keras "
                                               "unavailable): torch-CPU fp32 graph + numpy decode/NMS"}
         if world == 1 and not args.no_extras:
             line["sustained"] = sustained_run(args, det, x)
