@@ -368,7 +368,8 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 #else
                   const __half2 h2 = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
                   const float2 back = __half22float2(h2);
-                  const __half2 l2 = __floats2half2_rn(f[2 * e] - back.x, f[2 * e + 1] - back.y);
+                  const float2 rest = __ffma2_rn(back, make_float2(-1.f, -1.f), make_float2(f[2 * e], f[2 * e + 1]));   // f - back, one packed FMA
+                  const __half2 l2 = __floats2half2_rn(rest.x, rest.y);
                   hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
                   lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
 #endif
@@ -547,7 +548,8 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               for (int e = 0; e < 4; ++e) {
                 const __half2 h2 = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
                 const float2 back = __half22float2(h2);
-                const __half2 l2 = __floats2half2_rn(f[2 * e] - back.x, f[2 * e + 1] - back.y);
+                const float2 rest = __ffma2_rn(back, make_float2(-1.f, -1.f), make_float2(f[2 * e], f[2 * e + 1]));
+                const __half2 l2 = __floats2half2_rn(rest.x, rest.y);
                 hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
                 lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
               }

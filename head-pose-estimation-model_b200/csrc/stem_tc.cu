@@ -501,7 +501,10 @@ stem_flat_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
               const float2 q = *reinterpret_cast<const float2*>(sr + ky * p.WB + 2 * e);
               const __half2 hi = __floats2half2_rn(q.x, q.y);
               const float2 back = __half22float2(hi);
-              const __half2 lo = __floats2half2_rn(q.x - back.x, q.y - back.y);
+              // q - back as ONE packed FMA (back * -1 is exact, so the rounding is that of the subtraction): the gather warps are
+              // bound by issue slots (ncu: 75 % issue-active), not by the FMA pipe
+              const float2 rest = __ffma2_rn(back, make_float2(-1.f, -1.f), q);
+              const __half2 lo = __floats2half2_rn(rest.x, rest.y);
               v[e] = *reinterpret_cast<const uint32_t*>(&hi);
               v[8 + e] = *reinterpret_cast<const uint32_t*>(&lo);
             }
