@@ -162,6 +162,14 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   constexpr uint32_t colA0 = TR * CH_DSTRIDE;          // TMEM: D_0 .. D_{TR-1}, then one A stage of TR * 16 columns per set
   constexpr uint32_t STAGE = TR * 16;
   static_assert(colA0 + NSETS * STAGE <= 512, "TMEM budget");
+  // F16: only NSETS / 2 A stages are in use; the columns behind them hold the max-pooled skip values of the tail block (one column
+  // per input channel of the lane's output pixel)
+  constexpr uint32_t colPool = colA0 + (NSETS / 2) * STAGE;
+  static_assert(!F16 || colPool + 96 <= 512, "TMEM budget (pool columns)");
+  // Early release of the tile by the tail block (see there).  Only in the TR = 2 instantiations: with TR = 3 the kernel sits at its
+  // 96-register cap and the few extra live values made ptxas spill inside the latency-bound epilogue of the chain blocks
+  // (chain 6-11 at 96 x 96: 0.606 -> 0.69 ms; at 128 x 128, TR = 2: 0.983 -> 0.958).
+  constexpr bool EARLY = F16 && TR == 2;
   static_assert(NISS >= 1 && NISS <= 3 && NISS <= TR, "issuers");
   static_assert(!F16 || NSETS % 2 == 0, "two worker sets share an A stage of 16 channels");
   constexpr int NWORK = 128 * NSETS;
@@ -577,13 +585,41 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           }
           ch_arrive(bar_afull, lane_id);
         }
+        (void)n16;
+        const int C4 = cin >> 2, NG = cb.cout >> 2;
+        const int n_eu = (NG + 1) >> 1;                           // units of 8 accumulator columns, dealt to the sets like the chain blocks' units
+        if (EARLY) {
+          // The 2x2 max-pool of the skip path is taken now, while the MMAs of the last round drain, and parked in spare TMEM columns of
+          // the lane: the epilogue below then reads nothing of the tile, which is released here -- the next tile's TMA load (~3 K clk)
+          // hides behind the tail block's epilogue instead of following it.
+          if (warp_active2) {
+#pragma unroll 1
+            for (int u = set; 2 * u < C4; u += NSETS) {
+              uint32_t pw8[8];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int j = 2 * u + q;
+                float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < C4) {
+                  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  const float4 p00 = pool_va ? ld4(pool_a + j * 4) : z4, p01 = pool_vb ? ld4(pool_b + j * 4) : z4;
+                  const float4 p10 = pool_va ? ld4(pool_a + row_pitch + j * 4) : z4, p11 = pool_vb ? ld4(pool_b + row_pitch + j * 4) : z4;
+                  m = make_float4(fmaxf(fmaxf(p00.x, p01.x), fmaxf(p10.x, p11.x)), fmaxf(fmaxf(p00.y, p01.y), fmaxf(p10.y, p11.y)),
+                                  fmaxf(fmaxf(p00.z, p01.z), fmaxf(p10.z, p11.z)), fmaxf(fmaxf(p00.w, p01.w), fmaxf(p10.w, p11.w)));
+                }
+                pw8[q * 4 + 0] = __float_as_uint(m.x); pw8[q * 4 + 1] = __float_as_uint(m.y);
+                pw8[q * 4 + 2] = __float_as_uint(m.z); pw8[q * 4 + 3] = __float_as_uint(m.w);
+              }
+              tmem_st8(tlane + colPool + (uint32_t)u * 8u, pw8);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+          ch_arrive(bar_tail_done, lane_id);                      // nothing below reads the tile
+        }
         if (tid == 0) stamp(step, 1);
         ch_wait(bar_dfull, step & 1, 4, s_abort, step);
         tc_fence_after();
         if (tid == 0) stamp(step, 2);
-        (void)n16;
-        const int C4 = cin >> 2, NG = cb.cout >> 2;
-        const int n_eu = (NG + 1) >> 1;                           // units of 8 accumulator columns, dealt to the sets like the chain blocks' units
         const long long img = (long long)(blockIdx.x + (long long)it * gridDim.x) * p.NI + im2;
         const bool valid2 = active2 && img < p.B;
         float* dst = p.tail_out + ((img * p.Ho + oy) * p.Wo + ox) * (long long)cb.cout;
@@ -592,8 +628,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           int u = HP_CHAIN_SETSYNC ? set : (int)((NSETS + set - (e0 % NSETS)) % NSETS);
 #pragma unroll 1
           for (; u < n_eu; u += NSETS) {
-            uint32_t v[8];
+            uint32_t v[8], pk[8];
             tmem_ld8(tlane + (uint32_t)u * 8u, v);
+            if (EARLY && 2 * u < C4) tmem_ld8(tlane + colPool + (uint32_t)u * 8u, pk);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (F16 && u == 0 && valid2 && (v[0] & 0x7F800000u) == 0x7F800000u) guard = 1u;
 #pragma unroll
@@ -605,7 +642,12 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                                              fmaf(__uint_as_float(v[q * 4 + 2]), us, bb.z), fmaf(__uint_as_float(v[q * 4 + 3]), us, bb.w))
                                : make_float4(__uint_as_float(v[q * 4 + 0]) + bb.x, __uint_as_float(v[q * 4 + 1]) + bb.y,
                                              __uint_as_float(v[q * 4 + 2]) + bb.z, __uint_as_float(v[q * 4 + 3]) + bb.w);
-                if (j < C4) {
+                if (EARLY) {
+                  if (j < C4) {
+                    o.x += __uint_as_float(pk[q * 4 + 0]); o.y += __uint_as_float(pk[q * 4 + 1]);
+                    o.z += __uint_as_float(pk[q * 4 + 2]); o.w += __uint_as_float(pk[q * 4 + 3]);
+                  }
+                } else if (j < C4) {
                   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                   const float4 p00 = pool_va ? ld4(pool_a + j * 4) : z4, p01 = pool_vb ? ld4(pool_b + j * 4) : z4;
                   const float4 p10 = pool_va ? ld4(pool_a + row_pitch + j * 4) : z4, p11 = pool_vb ? ld4(pool_b + row_pitch + j * 4) : z4;
@@ -623,7 +665,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         }
         e0 += (uint32_t)n_eu;
         ch_arrive(bar_epi, lane_id);
-        ch_arrive(bar_tail_done, lane_id);
+        if (!EARLY) ch_arrive(bar_tail_done, lane_id);
         if (tid == 0) stamp(step, 3);
         ++step;
       }
@@ -655,7 +697,9 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           const int rounds = (KS + NSETS - 1) / NSETS;
           // the first MMA of the step overwrites accumulators that the epilogue of the previous step reads (the workers
           // themselves no longer wait for each other between the blocks of a tile)
-          if (HP_CHAIN_SETSYNC && b > 0) ch_wait_lean(epi_addr, (uint32_t)(step - 1) & 1u);
+          // (also across tiles: the tail block releases the tile before its epilogue, so the first block of the next tile can be
+          // under way while a set still reads the tail's accumulator)
+          if (HP_CHAIN_SETSYNC && step > 0) ch_wait_lean(epi_addr, (uint32_t)(step - 1) & 1u);
 #pragma unroll 1
           for (int r = 0; r < rounds; ++r, ++R) {
             const uint32_t half = R & 1u;
