@@ -170,6 +170,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   // 96-register cap and the few extra live values made ptxas spill inside the latency-bound epilogue of the chain blocks
   // (chain 6-11 at 96 x 96: 0.606 -> 0.69 ms; at 128 x 128, TR = 2: 0.983 -> 0.958).
   constexpr bool EARLY = F16 && TR == 2;
+  static_assert(!EARLY || HP_CHAIN_SETSYNC, "the parked pool values rely on epilogue unit u belonging to the set that ran k-step u");
   static_assert(NISS >= 1 && NISS <= 3 && NISS <= TR, "issuers");
   static_assert(!F16 || NSETS % 2 == 0, "two worker sets share an A stage of 16 channels");
   constexpr int NWORK = 128 * NSETS;
