@@ -166,10 +166,14 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   // per input channel of the lane's output pixel)
   constexpr uint32_t colPool = colA0 + (NSETS / 2) * STAGE;
   static_assert(!F16 || colPool + 96 <= 512, "TMEM budget (pool columns)");
-  // Early release of the tile by the tail block (see there).  Only in the TR = 2 instantiations: with TR = 3 the kernel sits at its
-  // 96-register cap and the few extra live values made ptxas spill inside the latency-bound epilogue of the chain blocks
-  // (chain 6-11 at 96 x 96: 0.606 -> 0.69 ms; at 128 x 128, TR = 2: 0.983 -> 0.958).
-  constexpr bool EARLY = F16 && TR == 2;
+  // Early release of the tile by the tail block (see there).  Only in the TR = 2 instantiations (128 x 128 input: 0.983 -> 0.955 ms).
+  // With TR = 3 (96 x 96 input) it is slower, 0.606 -> 0.69 .. 0.74 ms, with or without extra spills (-DHP_CHAIN_EARLY_TR3=1): the sets
+  // drift further apart across the tile boundary, the epilogue of one set then runs against the depthwise loads of the others (every
+  // epilogue of the tile takes 5.6-8.4 K clk instead of 3.2-4.6 K) and the slowest set paces every round.
+#ifndef HP_CHAIN_EARLY_TR3
+#define HP_CHAIN_EARLY_TR3 0
+#endif
+  constexpr bool EARLY = F16 && (TR == 2 || HP_CHAIN_EARLY_TR3);
   static_assert(!EARLY || HP_CHAIN_SETSYNC, "the parked pool values rely on epilogue unit u belonging to the set that ran k-step u");
   static_assert(NISS >= 1 && NISS <= 3 && NISS <= TR, "issuers");
   static_assert(!F16 || NSETS % 2 == 0, "two worker sets share an A stage of 16 channels");
@@ -595,23 +599,13 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           // hides behind the tail block's epilogue instead of following it.
           if (warp_active2) {
 #pragma unroll 1
-            for (int u = set; 2 * u < C4; u += NSETS) {
-              uint32_t pw8[8];
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int j = 2 * u + q;
-                float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < C4) {
-                  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                  const float4 p00 = pool_va ? ld4(pool_a + j * 4) : z4, p01 = pool_vb ? ld4(pool_b + j * 4) : z4;
-                  const float4 p10 = pool_va ? ld4(pool_a + row_pitch + j * 4) : z4, p11 = pool_vb ? ld4(pool_b + row_pitch + j * 4) : z4;
-                  m = make_float4(fmaxf(fmaxf(p00.x, p01.x), fmaxf(p10.x, p11.x)), fmaxf(fmaxf(p00.y, p01.y), fmaxf(p10.y, p11.y)),
-                                  fmaxf(fmaxf(p00.z, p01.z), fmaxf(p10.z, p11.z)), fmaxf(fmaxf(p00.w, p01.w), fmaxf(p10.w, p11.w)));
-                }
-                pw8[q * 4 + 0] = __float_as_uint(m.x); pw8[q * 4 + 1] = __float_as_uint(m.y);
-                pw8[q * 4 + 2] = __float_as_uint(m.z); pw8[q * 4 + 3] = __float_as_uint(m.w);
-              }
-              tmem_st8(tlane + colPool + (uint32_t)u * 8u, pw8);
+            for (int j = 2 * set; j < C4; j += (j & 1) ? 2 * NSETS - 1 : 1) {   // the float4 groups 2 u, 2 u + 1 of this set's units u
+              const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 p00 = pool_va ? ld4(pool_a + j * 4) : z4, p01 = pool_vb ? ld4(pool_b + j * 4) : z4;
+              const float4 p10 = pool_va ? ld4(pool_a + row_pitch + j * 4) : z4, p11 = pool_vb ? ld4(pool_b + row_pitch + j * 4) : z4;
+              tmem_st4(tlane + colPool + (uint32_t)j * 4u, __float_as_uint(fmaxf(fmaxf(p00.x, p01.x), fmaxf(p10.x, p11.x))),
+                       __float_as_uint(fmaxf(fmaxf(p00.y, p01.y), fmaxf(p10.y, p11.y))), __float_as_uint(fmaxf(fmaxf(p00.z, p01.z), fmaxf(p10.z, p11.z))),
+                       __float_as_uint(fmaxf(fmaxf(p00.w, p01.w), fmaxf(p10.w, p11.w))));
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           }
