@@ -780,13 +780,15 @@ int hp_backbone_run(hp_ctx* h, const float* x, int B, int H, int W, float* feat1
       bool plain = true;
       for (int b = i; b <= last; ++b) plain = plain && h->tc_override[b][0] == 0 && h->tile_override[b][0] == 0;
       ChainCfg ccfg;
+      // the split-fp16 kernels need half the weight ring of the 3xTF32 ones (the same test as in hp_launch_chain)
+      const bool chain_f16 = !(h->chain_mode & 4) && (h->chain_cfg[0] <= 0 || h->chain_cfg[0] % 2 == 0) && h->chain_cfg[1] <= 2;
       // block 11 (stride 2, 12x12x88 -> 6x6x96 at 96x96 input) rides on the chain 6-10: it is computed from the resident tile
       // while the tile's TMA store is in flight (chain_mode 2 = default; 1 = chains without the tail)
       int tail_blk = -1;
       if (i == 6 && last == 10 && (h->chain_mode & 3) >= 2 && (stop_after_blk < 0 || stop_after_blk > 10) && h->tc_override[11][0] == 0 &&
-          h->tile_override[11][0] == 0 && plain && hp_chain_geometry(i, chain_nblk, chain_nblk, hs[i + 1], ws[i + 1], &ccfg, 11))
+          h->tile_override[11][0] == 0 && plain && hp_chain_geometry(i, chain_nblk, chain_nblk, hs[i + 1], ws[i + 1], &ccfg, 11, chain_f16))
         tail_blk = 11;
-      if (plain && (tail_blk >= 0 || hp_chain_geometry(i, last - i + 1, chain_nblk, hs[i + 1], ws[i + 1], &ccfg))) {
+      if (plain && (tail_blk >= 0 || hp_chain_geometry(i, last - i + 1, chain_nblk, hs[i + 1], ws[i + 1], &ccfg, -1, chain_f16))) {
         if (h->chain_cfg[0] > 0) ccfg.nsets = h->chain_cfg[0];
         if (h->chain_cfg[1] > 0) ccfg.niss = h->chain_cfg[1] < ccfg.TR ? h->chain_cfg[1] : ccfg.TR;
         float* cout_buf = (last == 10) ? feat16 : (last == 15) ? feat8 : bb.act[pp ^ 1].f();

@@ -178,6 +178,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   static_assert(NISS >= 1 && NISS <= 3 && NISS <= TR, "issuers");
   static_assert(!F16 || NSETS % 2 == 0, "two worker sets share an A stage of 16 channels");
   constexpr int NWORK = 128 * NSETS;
+  constexpr int RING_HALF = F16 ? NSETS / 2 : NSETS;   // weight slices per round (= per ring half)
 
   extern __shared__ __align__(1024) float smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -705,7 +706,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               if (traced && r == 0) stamp(step, 4);
               const int nk8 = KS - r * NSETS < NSETS ? KS - r * NSETS : NSETS;
               const int nk = F16 ? (nk8 + 1) >> 1 : nk8;                     // MMA k-steps (A stages, weight slices) of this round
-              const uint64_t dhi0 = desc_hi0 + (uint64_t)(half * NSETS * ((CH_SLOT_FLOATS * 4) >> 4));   // the ring stays below 256 KB: no carry
+              const uint64_t dhi0 = desc_hi0 + (uint64_t)(half * RING_HALF * ((CH_SLOT_FLOATS * 4) >> 4));   // the ring stays below 256 KB: no carry
               auto mma3 = [&](int t, int j, uint64_t dhi, uint32_t a0) {
                 const uint64_t dlo = dhi + lo_off;
                 const uint32_t acc_flag = (r | j) ? 1u : 0u;
@@ -772,7 +773,7 @@ blaze_chain_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               mbar_expect_tx(&bar_wfull[half], (uint32_t)nk * 2u * half_bytes);
               for (int j = 0; j < nk; ++j) {
                 const int ks = (F16 ? (r * NSETS) >> 1 : r * NSETS) + j;
-                float* dst = s_ring + (half * NSETS + j) * CH_SLOT_FLOATS;
+                float* dst = s_ring + (half * RING_HALF + j) * CH_SLOT_FLOATS;
                 bulk_g2s(dst, cb.bhi + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[half]);
                 bulk_g2s(dst + cb.n16 * 8, cb.blo + (size_t)ks * cb.n16 * 8, half_bytes, &bar_wfull[half]);
               }
@@ -844,7 +845,7 @@ int hp_chain_status(unsigned int out[8]) {
 
 // Geometry of the chain kernel for blocks [first, first + nblk) on an H x W map: rows per lane TR, images per tile NI.
 // Returns false when the chain kernel does not apply (the per-block kernels are used instead).
-bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg, int tail_blk) {
+bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg, int tail_blk, bool f16) {
   if (nblk < 1 || nblk > CH_MAXBLK || first < 0 || first + nblk > 16 || H < 2 || W < 2 || W > 64) return false;
   // chain_nblk >= nblk: length of the full chain (a truncated chain, used to read intermediate activations, keeps the geometry
   // -- pixel stride, rows per lane, images per tile -- of the full one)
@@ -880,7 +881,8 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
       const int rows = NI * (H + 1) + TR;                 // image rows + their zero rows, slack for partial strips
       int off = CH_BAR_FLOATS;
       c.off_w = off; off = tc_align_up(off + w_floats, 32);
-      c.off_ring = off; off += CH_RING * CH_SLOT_FLOATS;
+      c.ring_slots = f16 ? CH_RING / 2 : CH_RING;        // split fp16: NSETS / 2 slices of 16 channels per round, two rounds in flight
+      c.off_ring = off; off += c.ring_slots * CH_SLOT_FLOATS;
       c.off_zero = off; off += lead;
       c.off_tile = off;
       c.tile_floats = rows * W * PS;
@@ -891,6 +893,8 @@ bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainC
       if (c.smem > 227 * 1024) continue;
       if (tail_blk >= 0 && NI * ceil_div(H, 2) * ceil_div(W, 2) > 128) continue;
       // cost: warp-instructions ~ active warps * M-tiles per image; more images per tile amortise the per-step bubbles
+      // (preferring TR = 3 for its fewer shared-memory loads per output was measured: 6 x 6 maps with 10 images per tile 0.151 -> 0.149 ms,
+      // 16 x 16 and 8 x 8 maps at 128 x 128 input 0.961 -> 1.169 / 0.258 -> 0.279 ms: the cost below stays)
       const double cost = (double)ceil_div(c.lanes, 32) * TR / NI + 0.05 * TR / NI;
       if (cost < best_cost) { best_cost = cost; best = c; }
       break;                                              // the largest NI that fits is the best one for this TR
@@ -950,6 +954,8 @@ int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out,
   ChainParams p;
   memset(&p, 0, sizeof(p));
   const bool f16 = !(h->chain_mode & 4) && cfg.nsets % 2 == 0 && cfg.niss <= 2;   // chain_mode + 4: 3xTF32 products
+  HP_REQUIRE(cfg.ring_slots >= (f16 ? cfg.nsets : 2 * cfg.nsets), HP_ERR_STATE, "chain: weight ring of %d slices is too small for the %s kernel",
+             cfg.ring_slots, f16 ? "split-fp16" : "3xTF32");
   p.status = (unsigned int*)h->status.p;
   p.nblk = nblk;
   int w_off = 0;

@@ -229,10 +229,11 @@ int hp_launch_block_tc(hp_ctx* h, int blk, const float* in, float* out, int B, i
 // images resident in shared memory across the blocks, pointwise weights streamed through a ring of k-step slices)
 struct ChainCfg {
   int TR, NI, PS, lanes, lpi, nsets, niss;
+  int ring_slots;                 // weight ring: 4 slices (split-fp16 kernels: two 16-channel slices per round) or 8 (3xTF32)
   int off_w, w_floats, off_ring, off_zero, zero_floats, off_tile, tile_floats;   // shared-memory layout (floats)
   size_t smem;
 };
-bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg, int tail_blk = -1);
+bool hp_chain_geometry(int first, int nblk, int chain_nblk, int H, int W, ChainCfg* cfg, int tail_blk = -1, bool f16 = true);
 int hp_chain_status(unsigned int out[8]);
 int hp_chain_describe(int first, int nblk, int H, int W, int tail, unsigned int* out264);
 int hp_launch_chain(hp_ctx* h, int first, int nblk, const float* in, float* out, int B, int H, int W, const ChainCfg& cfg,
