@@ -348,3 +348,22 @@ def test_chain_lane_tables_are_bank_conflict_free_at_96(built_lib):
                 im, y, x, swp = int(v) & 255, (int(v) >> 8) & 255, (int(v) >> 16) & 255, int(v) >> 31
                 res.append((((im * (H + 1) + 2 * y) * H + 2 * x) * chunks + swp) % 8)
             assert _wavefronts(res) == -(-tail_lanes // 8), res
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU (the CPU restatement on a bounded sample) and prints ONE JSON line with the
+    keys the driver reads; under torchrun only rank 0 prints."""
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0", "--cpu-sample", "4"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "crops/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
