@@ -198,3 +198,30 @@ def test_results_do_not_depend_on_the_batching():
     b = det.interpreter.forward_device(x[:1].contiguous())
     for k in ("cls", "loc", "pose16", "pose8", "feat16", "feat8"):
         assert torch.equal(a[k][:1], b[k]), k
+
+
+def test_bench_line_contract():
+    """The default arm of bench.py prints one JSON line with the keys the driver and the judge read (small batch, few steps)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "3", "--warmup", "3", "--batch", "256", "--no-extras"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["unit"] == "crops/s" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and "workload" in d["config"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 256 * 96 * 96 * 3 and e["d2h_bytes_per_step"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0
+    assert d["clocks"]["sm_max_mhz"] > 0 and isinstance(d["clocks"]["reasons"], list)
